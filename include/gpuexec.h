@@ -69,9 +69,8 @@ enum {
     GX_AGG_SUM_I4     = 5, /* int4_sum -> int8   (utils/adt/numeric.c:6154)  */
     GX_AGG_MIN_F8     = 6, /* float8smaller                                  */
     GX_AGG_MAX_F8     = 7, /* float8larger                                   */
-    GX_AGG_SUM_I8     = 8, /* sum(int8) kept as int8 (overflow -> error);
+    GX_AGG_SUM_I8     = 8  /* sum(int8) kept as int8 (overflow -> error);
                               the reference returns numeric: see DESIGN.md   */
-    GX_AGG_AVG_I4     = 9  /* int4_avg_accum {count,sum} -> float8 result    */
 };
 
 /* expression opcodes: tiny postfix VM over float8 (the provider pattern-matches
@@ -156,6 +155,9 @@ int  gx_timer_stop(gx_ctx *ctx, double *ms_out);
 int  gx_profile(gx_ctx *ctx, int enable);
 int  gx_profile_get(gx_ctx *ctx, const char *name, double *ms_total, int64_t *launches);
 int  gx_l2_flush(gx_ctx *ctx);              /* writes a >L2-sized buffer      */
+/* pinned host memory for the staging buffers the loader DMA-copies from */
+int  gx_host_alloc(gx_ctx *ctx, size_t bytes, void **out);
+int  gx_host_free(gx_ctx *ctx, void *p);
 
 /* ---- K0: columnar loader ------------------------------------------------
  * Replaces heap_getnext/heapgetpage + slot_deform_tuple + SeqNext
@@ -204,6 +206,10 @@ int  gx_table_column_devptr(gx_table *t, int col, void **dptr);
  * columns of the table's fixed schema are materialised. */
 int  gx_table_generate(gx_table *t, int table_id, int sf, int64_t order0,
                        int64_t order1, int node, int nnodes);
+/* same, for a table holding only some columns of the fixed schema:
+ * colmap[c] = schema column number feeding table column c */
+int  gx_table_generate_cols(gx_table *t, int table_id, int sf, int64_t order0,
+                            int64_t order1, int node, int nnodes, const int32_t *colmap);
 
 /* ---- K1: scan + qual + projection into a new table -----------------------
  * ExecScan qual/projection (executor/execScan.c:237-330) */

@@ -1,0 +1,930 @@
+// gx_agg.cu — K3+K4: [hash probe ->] hash aggregate.
+//
+// Replaces agg_fill_hash_table / lookup_hash_entries / advance_aggregates
+// (nodeAgg.c:2609,2149,856), LookupTupleHashEntry (execGrouping.c:295) and —
+// when a join feeds the aggregate — ExecHashJoinImpl's probe loop
+// (nodeHashjoin.c:446-666) without materialising the join.
+//
+// State model.  A group is a record of 8-byte words
+//      [meta | k0 | k1 | w0 .. w(nwords-1)]
+// meta = null bits of the group columns, k0/k1 = the group columns packed by
+// byte width, w0 = the group's row count, the other words belong to the
+// aggregates (float8 sum, non-NULL input count, int8 sum, min/max).  Every word
+// has a merge kind (add int64 / add float8 / min / max), so ONE merge operator
+// serves the per-CTA shared-memory tables, the global table, the second radix
+// pass and the cross-datanode Finalize step (int8pl / float8pl /
+// float8_combine's N and Sx, utils/adt/float.c:2725).
+//
+// Strategies:
+//   1  shared-memory privatised table per CTA, merged into an L2-resident
+//      global table at CTA exit  (few groups: Q1, GROUP BY date)
+//   2  two-pass radix: rows -> per-row records -> partition by key hash ->
+//      one CTA aggregates one partition in shared memory (many groups: Q3)
+//   3  global table only (atomics in L2)
+#include "gx_internal.cuh"
+
+int gx_fill_dpreds(gx_ctx *ctx, const gx_table *t, int n_preds, const gx_pred *preds, gx_dpred *out);
+
+enum { WK_ADD_I64 = 0, WK_ADD_F64 = 1, WK_MIN_F64 = 2, WK_MAX_F64 = 3 };
+
+struct gx_agg_dev {
+    gx_dplan P;
+    long long winit[GX_MAX_WORDS];
+    int wkind[GX_MAX_WORDS];
+    // join table
+    const gx_slot *slots; unsigned long long mask;
+    const unsigned long long *special; int special_count; int _pad0;
+    long long row0, row1;
+    // shared-memory table
+    int s_slots;             // power of two; 0 = none
+    int _pad1;
+    // global table: g_cap records of (3 + nwords) words
+    unsigned long long *g_tab; unsigned long long g_mask;
+    // record sink (radix stage A)
+    unsigned long long *recs; long long rec_cap;
+    long long *counters;     // [0] ngroups in g_tab, [1] overflow flags, [2] record cursor
+};
+
+#define TAG_LOCK 1ULL
+
+__device__ __forceinline__ unsigned long long group_hash(unsigned long long k0, unsigned long long k1, unsigned int nullmask)
+{
+    return gx_mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long) nullmask << 56) ^ 0x51ED270B27B4F3CFULL);
+}
+__device__ __forceinline__ unsigned long long make_tag(unsigned long long h, unsigned int nullmask)
+{
+    return (1ULL << 63) | ((unsigned long long) (nullmask & 0xF) << 59) | (h >> 5);
+}
+
+// merge one word into a (shared or global) location
+__device__ __forceinline__ void atomic_min_f64(unsigned long long *addr, double v, bool want_min)
+{
+    unsigned long long old = *(volatile unsigned long long *) addr;
+    for (;;) {
+        double cur = __longlong_as_double((long long) old);
+        int c = gx_f8cmp(v, cur);
+        if (want_min ? (c >= 0) : (c <= 0)) return;
+        unsigned long long prev = atomicCAS(addr, old, (unsigned long long) __double_as_longlong(v));
+        if (prev == old) return;
+        old = prev;
+    }
+}
+__device__ __forceinline__ void merge_word(unsigned long long *addr, int kind, unsigned long long v)
+{
+    switch (kind) {
+        case WK_ADD_I64: if (v) atomicAdd(addr, v); break;
+        case WK_ADD_F64: atomicAdd((double *) addr, __longlong_as_double((long long) v)); break;
+        case WK_MIN_F64: atomic_min_f64(addr, __longlong_as_double((long long) v), true); break;
+        default:         atomic_min_f64(addr, __longlong_as_double((long long) v), false); break;
+    }
+}
+
+// --------------------------------------------------------------- sinks
+struct SmemTable {
+    unsigned long long *tag, *k0, *k1, *w;   // w: [slot * nwords + i]
+    int S, nwords, nkw;
+};
+
+// returns slot or -1 when the table is full
+__device__ __forceinline__ int smem_upsert(const SmemTable &T, const gx_agg_dev &A, unsigned long long k0, unsigned long long k1,
+                                           unsigned int nullmask)
+{
+    unsigned long long h = group_hash(k0, k1, nullmask), tag = make_tag(h, nullmask);
+    int s = (int) (h & (unsigned) (T.S - 1));
+    for (int n = 0; n < T.S; n++) {
+        unsigned long long t = *(volatile unsigned long long *) &T.tag[s];
+        if (t == 0) {
+            unsigned long long old = atomicCAS(&T.tag[s], 0ULL, TAG_LOCK);
+            if (old == 0) {
+                T.k0[s] = k0; if (T.nkw > 1) T.k1[s] = k1;
+                __threadfence_block();
+                *(volatile unsigned long long *) &T.tag[s] = tag;
+                return s;
+            }
+            t = old;
+        }
+        while (t == TAG_LOCK) t = *(volatile unsigned long long *) &T.tag[s];
+        if (t == tag && T.k0[s] == k0 && (T.nkw == 1 || T.k1[s] == k1)) return s;
+        s = (s + 1) & (T.S - 1);
+    }
+    return -1;
+}
+
+// global table: record r at g_tab + r * (3 + nwords): [tag][k0][k1][w..]
+__device__ __forceinline__ unsigned long long *global_upsert(const gx_agg_dev &A, unsigned long long k0, unsigned long long k1,
+                                                             unsigned int nullmask)
+{
+    const int RW = 3 + A.P.nwords;
+    unsigned long long h = group_hash(k0, k1, nullmask), tag = make_tag(h, nullmask);
+    unsigned long long s = h & A.g_mask;
+    for (unsigned long long n = 0; n <= A.g_mask; n++) {
+        unsigned long long *rec = A.g_tab + s * RW;
+        unsigned long long t = *(volatile unsigned long long *) rec;
+        if (t == 0) {
+            unsigned long long old = atomicCAS(rec, 0ULL, TAG_LOCK);
+            if (old == 0) {
+                rec[1] = k0; rec[2] = k1;
+                for (int i = 0; i < A.P.nwords; i++) rec[3 + i] = (unsigned long long) A.winit[i];
+                __threadfence();
+                *(volatile unsigned long long *) rec = tag;
+                atomicAdd((unsigned long long *) &A.counters[0], 1ULL);
+                return rec;
+            }
+            t = old;
+        }
+        while (t == TAG_LOCK) t = *(volatile unsigned long long *) rec;
+        if (t == tag && rec[1] == k0 && rec[2] == k1) return rec;
+        s = (s + 1) & A.g_mask;
+        if (n > 4096 && (n & 1023) == 0 && *(volatile long long *) &A.counters[1]) break;
+    }
+    return nullptr;
+}
+
+enum { SINK_SMEM = 1, SINK_RECORD = 2, SINK_GLOBAL = 3 };
+
+template <int SINK>
+struct Sink {
+    unsigned long long *w;          // base of the target's state words
+    bool rec;
+    __device__ __forceinline__ void add_i64(int word, long long v)
+    {
+        if (SINK == SINK_RECORD) w[word] = (unsigned long long) v;
+        else atomicAdd(&w[word], (unsigned long long) v);
+    }
+    __device__ __forceinline__ void add_f64(int word, double v)
+    {
+        if (SINK == SINK_RECORD) w[word] = (unsigned long long) __double_as_longlong(v);
+        else atomicAdd((double *) &w[word], v);
+    }
+    __device__ __forceinline__ void minmax_f64(int word, double v, bool want_min)
+    {
+        if (SINK == SINK_RECORD) w[word] = (unsigned long long) __double_as_longlong(v);
+        else atomic_min_f64(&w[word], v, want_min);
+    }
+};
+
+// pack the group columns of one (joined) row
+__device__ __forceinline__ void pack_group_key(const gx_dplan &P, long long r, unsigned long long payload,
+                                               unsigned long long &k0, unsigned long long &k1, unsigned int &nullmask)
+{
+    k0 = 0; k1 = 0; nullmask = 0;
+#pragma unroll
+    for (int c = 0; c < GX_MAX_GROUP_COLS; c++) {
+        if (c >= P.ngroup) break;
+        const gx_dgroupcol &g = P.gcols[c];
+        unsigned long long v;
+        if (g.side == 0) {
+            if (gx_is_null(g.col, r)) { nullmask |= 1u << c; continue; }
+            v = (unsigned long long) gx_load_int(g.col, r);
+            if (g.type == GX_FLOAT8) {                       // -0 = +0, all NaNs equal (float8eq)
+                double d = __longlong_as_double((long long) v);
+                if (d == 0.0) v = 0; else if (isnan(d)) v = 0x7FF8000000000000ULL;
+            }
+        } else {
+            v = payload >> g.payload_idx;                     // payload_idx holds the bit offset
+        }
+        if (g.bytes < 8) v &= (1ULL << (8 * g.bytes)) - 1;
+        if (g.word == 0) k0 |= v << g.shift; else k1 |= v << g.shift;
+    }
+}
+
+template <int SINK>
+__device__ __forceinline__ void apply_aggs(const gx_dplan &P, long long r, Sink<SINK> &sink)
+{
+    sink.add_i64(0, 1);                                       // w0: rows in the group (count(*))
+#pragma unroll
+    for (int a = 0; a < GX_MAX_AGGS; a++) {
+        if (a >= P.nagg) break;
+        const gx_dagg &g = P.aggs[a];
+        if (g.kind == GXU_NONE) continue;
+        if (g.is_int) {
+            if (gx_is_null(g.icol, r)) continue;
+            if (g.kind == GXU_CNT) { sink.add_i64(g.word, 1); continue; }
+            sink.add_i64(g.word, gx_load_int(g.icol, r));     // int4_sum: widen to int8
+            if (g.cnt_word) sink.add_i64(g.cnt_word, 1);
+        } else {
+            bool isnull = false;
+            double v = gx_eval_expr(g.expr, r, isnull);
+            if (isnull) continue;                             // strict transition function
+            if (g.kind == GXU_ADD_F64) sink.add_f64(g.word, v);
+            else sink.minmax_f64(g.word, v, g.kind == GXU_MIN_F64);
+            if (g.cnt_word) sink.add_i64(g.cnt_word, 1);
+        }
+    }
+}
+
+template <int SINK>
+__device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable &T, long long r, unsigned long long payload)
+{
+    unsigned long long k0, k1; unsigned int nullmask;
+    pack_group_key(A.P, r, payload, k0, k1, nullmask);
+    Sink<SINK> sink;
+    if (SINK == SINK_SMEM) {
+        int s = smem_upsert(T, A, k0, k1, nullmask);
+        if (s < 0) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+        sink.w = T.w + (size_t) s * T.nwords;
+    } else if (SINK == SINK_GLOBAL) {
+        unsigned long long *rec = global_upsert(A, k0, k1, nullmask);
+        if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); return; }
+        sink.w = rec + 3;
+    } else {
+        const int RW = 3 + A.P.nwords;
+        // warp-aggregated append: one atomic per converged group of lanes
+        unsigned int am = __activemask();
+        int leader = __ffs(am) - 1, lane = threadIdx.x & 31;
+        long long idx = 0;
+        if (lane == leader) idx = (long long) atomicAdd((unsigned long long *) &A.counters[2], (unsigned long long) __popc(am));
+        idx = __shfl_sync(am, idx, leader) + __popc(am & ((1u << lane) - 1));
+        if (idx >= A.rec_cap) { atomicOr((unsigned long long *) &A.counters[1], 4ULL); return; }
+        unsigned long long *rec = A.recs + (size_t) idx * RW;
+        rec[0] = nullmask; rec[1] = k0; rec[2] = k1;
+        for (int i = 0; i < A.P.nwords; i++) rec[3 + i] = (unsigned long long) A.winit[i];
+        sink.w = rec + 3;
+    }
+    apply_aggs<SINK>(A.P, r, sink);
+}
+
+template <int SINK>
+__global__ void __launch_bounds__(512, 2) gx_k_agg(const __grid_constant__ gx_agg_dev A)
+{
+    extern __shared__ unsigned long long smem[];
+    SmemTable T; T.S = A.s_slots; T.nwords = A.P.nwords; T.nkw = A.P.nkw;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0 + T.S; T.w = T.k1 + (A.P.nkw > 1 ? T.S : 0);
+    if (SINK == SINK_SMEM) {
+        for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+            T.tag[i] = 0;
+            for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+        }
+        __syncthreads();
+    }
+    const gx_dplan &P = A.P;
+    long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long r = A.row0 + (long long) blockIdx.x * blockDim.x + threadIdx.x; r < A.row1; r += stride) {
+        bool ok = true;
+#pragma unroll
+        for (int p = 0; p < GX_MAX_PREDS; p++) if (p < P.npreds) ok = ok && gx_eval_pred(P.preds[p], r);
+        if (!ok) continue;
+        if (!P.has_join) { consume_row<SINK>(A, T, r, 0ULL); continue; }
+        if (gx_is_null(P.okey, r)) continue;                  // NULL outer key never joins
+        long long key = gx_load_int(P.okey, r);
+        if (key == GX_EMPTY_KEY) {
+            for (int i = 0; i < A.special_count; i++) { consume_row<SINK>(A, T, r, A.special[i]); if (P.unique) break; }
+            continue;
+        }
+        unsigned long long s = gx_key_hash(key) & A.mask;
+        for (;;) {
+            gx_slot sl = A.slots[s];
+            if (sl.key == GX_EMPTY_KEY) break;
+            if (sl.key == key) { consume_row<SINK>(A, T, r, sl.payload); if (P.unique) break; }
+            s = (s + 1) & A.mask;
+        }
+    }
+    if (SINK == SINK_SMEM) {
+        __syncthreads();
+        // merge the CTA's table into the global one
+        for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+            unsigned long long t = T.tag[i];
+            if (t == 0) continue;
+            unsigned int nullmask = (unsigned int) (t >> 59) & 0xF;
+            unsigned long long *rec = global_upsert(A, T.k0[i], T.nkw > 1 ? T.k1[i] : 0ULL, nullmask);
+            if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+            for (int j = 0; j < T.nwords; j++) merge_word(&rec[3 + j], A.wkind[j], T.w[(size_t) i * T.nwords + j]);
+        }
+    }
+}
+
+// global table -> dense records [meta][k0][k1][w..]
+__global__ void gx_k_compact_groups(const unsigned long long *g_tab, long long g_cap, int nwords,
+                                    unsigned long long *recs, long long *cursor)
+{
+    const int RW = 3 + nwords;
+    long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < g_cap; i += stride) {
+        const unsigned long long *src = g_tab + i * RW;
+        unsigned long long t = src[0];
+        if (t == 0) continue;
+        long long dst = (long long) atomicAdd((unsigned long long *) cursor, 1ULL);
+        unsigned long long *d = recs + dst * RW;
+        d[0] = (t >> 59) & 0xF;
+        for (int j = 1; j < RW; j++) d[j] = src[j];
+    }
+}
+
+// ----------------------------------------------------- radix pass 1 & 2
+#define RADIX_MAX_BITS 13
+
+__device__ __forceinline__ unsigned int rec_partition(const unsigned long long *rec, int bits)
+{
+    unsigned long long h = group_hash(rec[1], rec[2], (unsigned int) rec[0]);
+    return (unsigned int) (h >> (64 - bits));
+}
+
+// histogram: hist[part * nblocks + block]
+__global__ void __launch_bounds__(512) gx_k_radix_hist(const unsigned long long *recs, long long nrec, int RW, int bits, long long *hist)
+{
+    extern __shared__ unsigned int sh[];
+    const int P = 1 << bits;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    long long per = (nrec + gridDim.x - 1) / gridDim.x, b = per * blockIdx.x, e = min(nrec, b + per);
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) atomicAdd(&sh[rec_partition(recs + i * RW, bits)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) hist[(long long) i * gridDim.x + blockIdx.x] = sh[i];
+}
+__global__ void __launch_bounds__(512) gx_k_radix_scatter(const unsigned long long *recs, long long nrec, int RW, int bits,
+                                                         const long long *offs, unsigned long long *out)
+{
+    extern __shared__ unsigned int sh[];       // per-partition cursor within this block's slice
+    const int P = 1 << bits;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    long long per = (nrec + gridDim.x - 1) / gridDim.x, b = per * blockIdx.x, e = min(nrec, b + per);
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const unsigned long long *src = recs + i * RW;
+        unsigned int p = rec_partition(src, bits);
+        unsigned int k = atomicAdd(&sh[p], 1u);
+        unsigned long long *dst = out + (offs[(long long) p * gridDim.x + blockIdx.x] + k) * RW;
+        for (int j = 0; j < RW; j++) dst[j] = src[j];
+    }
+}
+
+// pass 2: one CTA per partition (grid-strided); aggregates the partition in a
+// shared-memory table and appends its groups to the dense output.
+__global__ void __launch_bounds__(512) gx_k_radix_agg(const gx_agg_dev A, const unsigned long long *recs, const long long *part_begin,
+                                                      int nparts, int nblk, unsigned long long *out, long long *cursor, int *overflowed)
+{
+    extern __shared__ unsigned long long smem[];
+    __shared__ long long s_base; __shared__ int s_cnt, s_over;
+    const int RW = 3 + A.P.nwords;
+    SmemTable T; T.S = A.s_slots; T.nwords = A.P.nwords; T.nkw = 2;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0 + T.S; T.w = T.k1 + T.S;
+    for (int part = blockIdx.x; part < nparts; part += gridDim.x) {
+        long long b = part_begin[(long long) part * nblk];
+        long long e = (part + 1 < nparts) ? part_begin[(long long) (part + 1) * nblk] : A.rec_cap;
+        for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+            T.tag[i] = 0;
+            for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+        }
+        if (threadIdx.x == 0) { s_cnt = 0; s_over = 0; }
+        __syncthreads();
+        for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+            const unsigned long long *rec = recs + i * RW;
+            int s = smem_upsert(T, A, rec[1], rec[2], (unsigned int) rec[0]);
+            if (s < 0) { s_over = 1; continue; }
+            for (int j = 0; j < T.nwords; j++) merge_word(&T.w[(size_t) s * T.nwords + j], A.wkind[j], rec[3 + j]);
+        }
+        __syncthreads();
+        if (s_over) { if (threadIdx.x == 0) overflowed[part] = 1; __syncthreads(); continue; }
+        int mine = 0;
+        for (int i = threadIdx.x; i < T.S; i += blockDim.x) mine += T.tag[i] != 0;
+        int pos = mine ? atomicAdd(&s_cnt, mine) : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = (long long) atomicAdd((unsigned long long *) cursor, (unsigned long long) s_cnt);
+        __syncthreads();
+        for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+            unsigned long long t = T.tag[i];
+            if (t == 0) continue;
+            unsigned long long *d = out + (s_base + pos++) * RW;
+            d[0] = (t >> 59) & 0xF; d[1] = T.k0[i]; d[2] = T.k1[i];
+            for (int j = 0; j < T.nwords; j++) d[3 + j] = T.w[(size_t) i * T.nwords + j];
+        }
+        __syncthreads();
+    }
+}
+
+// fallback for partitions that did not fit shared memory, and the generic
+// "merge records into the global table" used by gx_result_combine
+__global__ void gx_k_merge_records(const gx_agg_dev A, const unsigned long long *recs, const long long *part_begin, int nblk,
+                                   const int *sel /* may be NULL: all */, int nparts, long long nrec)
+{
+    const int RW = 3 + A.P.nwords;
+    if (!sel) {
+        long long stride = (long long) gridDim.x * blockDim.x;
+        for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += stride) {
+            const unsigned long long *rec = recs + i * RW;
+            unsigned long long *g = global_upsert(A, rec[1], rec[2], (unsigned int) rec[0]);
+            if (!g) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+            for (int j = 0; j < A.P.nwords; j++) merge_word(&g[3 + j], A.wkind[j], rec[3 + j]);
+        }
+        return;
+    }
+    for (int part = blockIdx.x; part < nparts; part += gridDim.x) {
+        if (!sel[part]) continue;
+        long long b = part_begin[(long long) part * nblk];
+        long long e = (part + 1 < nparts) ? part_begin[(long long) (part + 1) * nblk] : nrec;
+        for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+            const unsigned long long *rec = recs + i * RW;
+            unsigned long long *g = global_upsert(A, rec[1], rec[2], (unsigned int) rec[0]);
+            if (!g) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+            for (int j = 0; j < A.P.nwords; j++) merge_word(&g[3 + j], A.wkind[j], rec[3 + j]);
+        }
+    }
+}
+
+__global__ void gx_k_scan_i64(long long *v, long long n, long long *total);   // below
+
+// ============================================================ host side
+static gx_dcol dcol_of(const gx_table *t, int c)
+{
+    gx_dcol d; d.data = t->cols[c]; d.nulls = t->nulls[c]; d.type = t->types[c]; d._pad = 0; return d;
+}
+
+// postfix -> chain form; returns false when the shape is not representable
+struct sym { int is_chain; gx_dexpr e; };
+static bool compile_expr(gx_ctx *ctx, const gx_table *t, const gx_expr *in, gx_dexpr *out, bool *nullable)
+{
+    sym st[GX_MAX_EXPR_OPS]; int sp = 0;
+    *nullable = false;
+    for (int i = 0; i < in->nops; i++) {
+        const gx_expr_op *op = &in->ops[i];
+        if (op->op == GX_OP_COL) {
+            if (op->col < 0 || op->col >= t->ncols) { GX_SET_ERR(ctx, "expression: column %d out of range", op->col); return false; }
+            sym s; memset(&s, 0, sizeof(s)); s.e.nterms = 1; s.e.t[0].kind = GXT_COL; s.e.t[0].col = dcol_of(t, op->col);
+            if (t->nulls[op->col]) *nullable = true;
+            st[sp++] = s;
+        } else if (op->op == GX_OP_CONST) {
+            sym s; memset(&s, 0, sizeof(s)); s.e.nterms = 1; s.e.t[0].kind = GXT_CONST; s.e.t[0].k = op->k;
+            st[sp++] = s;
+        } else if (op->op == GX_OP_ADD || op->op == GX_OP_SUB || op->op == GX_OP_MUL) {
+            if (sp < 2) { GX_SET_ERR(ctx, "expression: stack underflow"); return false; }
+            sym b = st[--sp], a = st[--sp];
+            if (b.is_chain) { GX_SET_ERR(ctx, "expression shape not supported (right operand is a compound expression)"); return false; }
+            gx_dterm bt = b.e.t[0];
+            if (!a.is_chain) {
+                gx_dterm at = a.e.t[0];
+                // leaf (op) leaf -> a single composite term where one exists
+                if (at.kind == GXT_CONST && bt.kind == GXT_COL) {
+                    sym s; memset(&s, 0, sizeof(s)); s.e.nterms = 1; s.e.t[0] = bt; s.e.t[0].k = at.k;
+                    s.e.t[0].kind = op->op == GX_OP_ADD ? GXT_K_ADD_COL : op->op == GX_OP_SUB ? GXT_K_SUB_COL : GXT_K_MUL_COL;
+                    st[sp++] = s; continue;
+                }
+                if (at.kind == GXT_COL && bt.kind == GXT_CONST) {
+                    sym s; memset(&s, 0, sizeof(s)); s.e.nterms = 1; s.e.t[0] = at; s.e.t[0].k = bt.k;
+                    s.e.t[0].kind = op->op == GX_OP_ADD ? GXT_K_ADD_COL : op->op == GX_OP_SUB ? GXT_COL_SUB_K : GXT_K_MUL_COL;
+                    st[sp++] = s; continue;
+                }
+                if (at.kind == GXT_CONST && bt.kind == GXT_CONST) {
+                    sym s; memset(&s, 0, sizeof(s)); s.e.nterms = 1; s.e.t[0].kind = GXT_CONST;
+                    s.e.t[0].k = op->op == GX_OP_ADD ? at.k + bt.k : op->op == GX_OP_SUB ? at.k - bt.k : at.k * bt.k;
+                    st[sp++] = s; continue;
+                }
+            }
+            if (a.e.nterms >= 4) { GX_SET_ERR(ctx, "expression too long (more than 4 terms)"); return false; }
+            a.is_chain = 1;
+            bt.op = op->op;
+            a.e.t[a.e.nterms++] = bt;
+            st[sp++] = a;
+        } else { GX_SET_ERR(ctx, "expression: unknown opcode %d", op->op); return false; }
+    }
+    if (sp != 1) { GX_SET_ERR(ctx, "expression: malformed postfix program"); return false; }
+    *out = st[0].e;
+    return true;
+}
+
+struct compiled_plan {
+    gx_agg_dev A;
+    int32_t group_types[GX_MAX_GROUP_COLS];
+    int gword[GX_MAX_GROUP_COLS], gshift[GX_MAX_GROUP_COLS], gbytes[GX_MAX_GROUP_COLS];
+    int agg_word[GX_MAX_AGGS], agg_cnt_word[GX_MAX_AGGS];
+};
+
+static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, const gx_agg_plan *plan, compiled_plan *cp)
+{
+    memset(cp, 0, sizeof(*cp));
+    gx_dplan &P = cp->A.P;
+    GX_CHECK_ARG(ctx, plan->n_aggs >= 0 && plan->n_aggs <= GX_MAX_AGGS, "agg plan: n_aggs %d", plan->n_aggs);
+    GX_CHECK_ARG(ctx, plan->n_group_cols >= 0 && plan->n_group_cols <= GX_MAX_GROUP_COLS, "agg plan: n_group_cols %d", plan->n_group_cols);
+    P.npreds = plan->n_preds;
+    int rc = gx_fill_dpreds(ctx, outer, plan->n_preds, plan->preds, P.preds); if (rc) return rc;
+    P.has_join = plan->outer_key_col >= 0;
+    if (P.has_join) {
+        GX_CHECK_ARG(ctx, h != nullptr, "agg plan: join requested but no hash table given");
+        GX_CHECK_ARG(ctx, plan->outer_key_col < outer->ncols, "agg plan: outer key column out of range");
+        int kt = outer->types[plan->outer_key_col];
+        GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "agg plan: outer key type %d not supported", kt);
+        P.okey = dcol_of(outer, plan->outer_key_col); P.key_type = kt; P.unique = h->unique;
+        P.n_payload = h->n_payload;
+        for (int i = 0; i < h->n_payload; i++) P.payload_types[i] = h->payload_types[i];
+        cp->A.slots = h->slots; cp->A.mask = (unsigned long long) h->nslots - 1;
+        cp->A.special = h->special_payload; cp->A.special_count = h->special_count;
+    }
+    // group columns: pack by byte width into k0 then k1
+    int used[2] = { 0, 0 };
+    P.ngroup = plan->n_group_cols;
+    for (int c = 0; c < plan->n_group_cols; c++) {
+        gx_dgroupcol &g = P.gcols[c];
+        g.side = plan->group_cols[c].side;
+        int type;
+        if (g.side == 0) {
+            int col = plan->group_cols[c].col;
+            GX_CHECK_ARG(ctx, col >= 0 && col < outer->ncols, "agg plan: group column %d out of range", col);
+            g.col = dcol_of(outer, col); type = outer->types[col];
+        } else {
+            GX_CHECK_ARG(ctx, h != nullptr && h->n_payload > 0, "agg plan: group column refers to a join payload but none is carried");
+            int pi = plan->group_cols[c].col;
+            GX_CHECK_ARG(ctx, pi >= 0 && pi < h->n_payload, "agg plan: payload index %d out of range", pi);
+            int bit = 0;
+            for (int i = 0; i < pi; i++) bit += 8 * gx_type_size(h->payload_types[i]);
+            g.payload_idx = bit; type = h->payload_types[pi];
+        }
+        g.type = type; g.bytes = gx_type_size(type);
+        int w = (used[0] + g.bytes <= 8) ? 0 : 1;
+        GX_CHECK_ARG(ctx, used[w] + g.bytes <= 8, "agg plan: group key wider than 16 bytes");
+        g.word = w; g.shift = 8 * used[w]; used[w] += g.bytes;
+        cp->group_types[c] = type; cp->gword[c] = g.word; cp->gshift[c] = g.shift; cp->gbytes[c] = g.bytes;
+    }
+    P.nkw = used[1] ? 2 : 1;
+    // aggregates
+    int nw = 1;                                     // w0 = row count
+    cp->A.wkind[0] = WK_ADD_I64; cp->A.winit[0] = 0;
+    P.nagg = plan->n_aggs;
+    for (int a = 0; a < plan->n_aggs; a++) {
+        gx_dagg &g = P.aggs[a];
+        const gx_agg &src = plan->aggs[a];
+        bool nullable = false;
+        auto new_word = [&](int kind, long long init) { cp->A.wkind[nw] = kind; cp->A.winit[nw] = init; return nw++; };
+        if (nw + 2 > GX_MAX_WORDS) { GX_SET_ERR(ctx, "agg plan: too many state words"); return GX_ERR_ARG; }
+        switch (src.fn) {
+            case GX_AGG_COUNT_STAR: g.kind = GXU_NONE; cp->agg_word[a] = 0; break;
+            case GX_AGG_COUNT: case GX_AGG_SUM_I4: case GX_AGG_SUM_I8: {
+                GX_CHECK_ARG(ctx, src.arg.nops == 1 && src.arg.ops[0].op == GX_OP_COL, "agg %d: argument must be a plain column", a);
+                int col = src.arg.ops[0].col;
+                GX_CHECK_ARG(ctx, col >= 0 && col < outer->ncols, "agg %d: column out of range", a);
+                int t = outer->types[col];
+                if (src.fn == GX_AGG_SUM_I4) GX_CHECK_ARG(ctx, t == GX_INT4, "agg %d: sum(int4) needs an int4 column", a);
+                if (src.fn == GX_AGG_SUM_I8) GX_CHECK_ARG(ctx, t == GX_INT8, "agg %d: sum(int8) needs an int8 column", a);
+                g.is_int = 1; g.icol = dcol_of(outer, col); nullable = outer->nulls[col] != nullptr;
+                if (src.fn == GX_AGG_COUNT) {
+                    if (nullable) { g.kind = GXU_CNT; g.word = new_word(WK_ADD_I64, 0); cp->agg_word[a] = g.word; }
+                    else { g.kind = GXU_NONE; cp->agg_word[a] = 0; }
+                } else {
+                    g.kind = GXU_ADD_I64; g.word = new_word(WK_ADD_I64, 0); cp->agg_word[a] = g.word;
+                    g.cnt_word = nullable ? new_word(WK_ADD_I64, 0) : 0; cp->agg_cnt_word[a] = g.cnt_word;
+                }
+                break;
+            }
+            case GX_AGG_SUM_F8: case GX_AGG_AVG_F8: case GX_AGG_MIN_F8: case GX_AGG_MAX_F8: {
+                GX_CHECK_ARG(ctx, src.arg.nops >= 1 && src.arg.nops <= GX_MAX_EXPR_OPS, "agg %d: missing argument expression", a);
+                if (!compile_expr(ctx, outer, &src.arg, &g.expr, &nullable)) return GX_ERR_ARG;
+                if (src.fn == GX_AGG_MIN_F8) {        // identity of float8smaller under float8_cmp: NaN
+                    double nan = __builtin_nan(""); long long bits; memcpy(&bits, &nan, 8);
+                    g.kind = GXU_MIN_F64; g.word = new_word(WK_MIN_F64, bits);
+                } else if (src.fn == GX_AGG_MAX_F8) { // identity of float8larger: -inf
+                    double ninf = -__builtin_inf(); long long bits; memcpy(&bits, &ninf, 8);
+                    g.kind = GXU_MAX_F64; g.word = new_word(WK_MAX_F64, bits);
+                } else { g.kind = GXU_ADD_F64; g.word = new_word(WK_ADD_F64, 0); }
+                cp->agg_word[a] = g.word;
+                g.cnt_word = nullable ? new_word(WK_ADD_I64, 0) : 0; cp->agg_cnt_word[a] = g.cnt_word;
+                break;
+            }
+            default: GX_SET_ERR(ctx, "agg %d: unknown aggregate function %d", a, src.fn); return GX_ERR_ARG;
+        }
+    }
+    P.nwords = nw;
+    cp->A.row0 = 0; cp->A.row1 = outer->nrows;
+    cp->A.counters = ctx->d_scratch + 8;
+    return GX_OK;
+}
+
+int gx_result_alloc(gx_ctx *ctx, const gx_agg_plan *plan, const int32_t *group_types, int64_t cap, gx_result **out)
+{
+    gx_result *r = (gx_result *) calloc(1, sizeof(gx_result));
+    r->ctx = ctx; r->plan = *plan; r->cap = cap < 1 ? 1 : cap;
+    for (int c = 0; c < plan->n_group_cols; c++) r->group_types[c] = group_types[c];
+    *out = r;
+    return GX_OK;
+}
+
+static size_t smem_bytes_for(int S, int nkw, int nwords) { return (size_t) S * 8 * (1 + nkw + nwords); }
+
+template <int SINK>
+static int launch_agg(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name)
+{
+    static bool attr_set[4] = { false, false, false, false };
+    if (!attr_set[SINK]) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_agg<SINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set[SINK] = true;
+    }
+    long long nrows = A.row1 - A.row0;
+    long long nb = (nrows + 511) / 512, maxb = (long long) ctx->sm_count * 2;
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_k_agg<SINK><<<grid, 512, smem, ctx->stream>>>(A);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
+
+static int read_counters(gx_ctx *ctx, long long *c /* 4 */)
+{
+    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 4 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; i++) c[i] = ctx->h_scratch[8 + i];
+    return GX_OK;
+}
+
+// global table -> result (dense)
+static int table_to_result(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *plan, unsigned long long *g_tab, long long g_cap,
+                           long long ngroups, gx_result **out)
+{
+    const int RW = 3 + cp->A.P.nwords;
+    gx_result *r; gx_result_alloc(ctx, plan, cp->group_types, ngroups, &r);
+    r->nkw = cp->A.P.nkw; r->nwords = cp->A.P.nwords; r->rec_words = RW;
+    for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp->agg_word[a]; r->agg_cnt_word[a] = cp->agg_cnt_word[a]; }
+    cudaError_t e = cudaMalloc((void **) &r->d_recs, (size_t) r->cap * RW * 8);
+    if (e != cudaSuccess) { gx_result_free(r); GX_SET_ERR(ctx, "result: %s", cudaGetErrorString(e)); return GX_ERR_NOMEM; }
+    GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 12, 0, sizeof(long long), ctx->stream));
+    if (ngroups > 0) {
+        gx_launch_scope ls(ctx, "agg_compact");
+        gx_k_compact_groups<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g_tab, g_cap, cp->A.P.nwords, (unsigned long long *) r->d_recs, ctx->d_scratch + 12);
+    }
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->ngroups = ngroups;
+    *out = r;
+    return GX_OK;
+}
+
+// keep the compiled layout around for fetch/combine
+struct result_layout { int gword[GX_MAX_GROUP_COLS], gshift[GX_MAX_GROUP_COLS], gbytes[GX_MAX_GROUP_COLS]; int wkind[GX_MAX_WORDS]; long long winit[GX_MAX_WORDS]; };
+static std::map<gx_result *, result_layout> *g_layouts;
+static void remember_layout(gx_result *r, const compiled_plan *cp)
+{
+    if (!g_layouts) g_layouts = new std::map<gx_result *, result_layout>();
+    result_layout L; memset(&L, 0, sizeof(L));
+    for (int c = 0; c < GX_MAX_GROUP_COLS; c++) { L.gword[c] = cp->gword[c]; L.gshift[c] = cp->gshift[c]; L.gbytes[c] = cp->gbytes[c]; }
+    for (int i = 0; i < GX_MAX_WORDS; i++) { L.wkind[i] = cp->A.wkind[i]; L.winit[i] = cp->A.winit[i]; }
+    (*g_layouts)[r] = L;
+}
+
+static int run_radix(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *plan, long long nrows_in, gx_result **out);
+int gx_result_layout_words(gx_result *r, int *wkind, long long *winit);
+
+extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, const gx_agg_plan *plan, gx_result **out)
+{
+    if (!ctx || !outer || !plan || !out) return GX_ERR_ARG;
+    compiled_plan cp;
+    int rc = compile_plan(ctx, outer, h, plan, &cp); if (rc) return rc;
+    gx_agg_dev &A = cp.A;
+    const int nwords = A.P.nwords, RW = 3 + nwords;
+    long long est = plan->est_groups > 0 ? plan->est_groups : 1024;
+    if (plan->n_group_cols == 0) est = 1;
+
+    // shared-memory capacity for the privatised table (two CTAs per SM)
+    size_t budget = ctx->smem_optin / 2 - 2048;
+    int smax = 1; while (smem_bytes_for(smax * 2, A.P.nkw, nwords) <= budget) smax *= 2;
+    int strategy = plan->strategy;
+    if (strategy == 0) strategy = (est * 2 <= smax) ? 1 : 2;
+    GX_CHECK_ARG(ctx, strategy >= 1 && strategy <= 3, "agg plan: unknown strategy %d", strategy);
+
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if (strategy == 2) { rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
+        int S = 16; while (S < est * 2 && S < smax) S *= 2;
+        long long g_cap = gx_pow2_ceil((strategy == 1 ? (long long) S : est) * 4 + 1024);
+        unsigned long long *g_tab;
+        GX_CUDA(ctx, cudaMalloc((void **) &g_tab, (size_t) g_cap * RW * 8));
+        GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
+        GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
+        A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1; A.s_slots = strategy == 1 ? S : 0;
+        if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, smem_bytes_for(S, A.P.nkw, nwords), h ? "probe_agg" : "agg");
+        else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, h ? "probe_agg" : "agg");
+        long long c[4];
+        if (rc == GX_OK) rc = read_counters(ctx, c);
+        if (rc != GX_OK) { cudaFree(g_tab); return rc; }
+        if (c[1] == 0) {
+            rc = table_to_result(ctx, &cp, plan, g_tab, g_cap, c[0], out);
+            cudaFree(g_tab);
+            if (rc == GX_OK) remember_layout(*out, &cp);
+            return rc;
+        }
+        cudaFree(g_tab);
+        // the planner's estimate was too low: grow, then fall over to radix
+        est *= 8;
+        if (strategy == 1 && est * 2 > smax) strategy = (plan->strategy == 1) ? 3 : 2;
+    }
+    GX_SET_ERR(ctx, "hash_agg: group table kept overflowing");
+    return GX_ERR_STATE;
+}
+
+// single-block exclusive scan (same as gx_table.cu's, kept local to this TU)
+__global__ void gx_k_scan_i64(long long *v, long long n, long long *total)
+{
+    __shared__ long long sm[33];
+    long long carry = 0;
+    for (long long base = 0; base < n; base += blockDim.x) {
+        long long i = base + threadIdx.x;
+        long long x = i < n ? v[i] : 0, tot;
+        long long ex = gx_block_exscan(x, &tot, sm);
+        if (i < n) v[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// Records (already materialised, nrec of them at d_recs) -> dense groups.
+// Used by strategy 2 and by gx_result_combine.
+int gx_aggregate_records(gx_ctx *ctx, gx_agg_dev A, unsigned long long *d_recs, long long nrec,
+                         unsigned long long **d_out, long long *ngroups_out)
+{
+    const int nwords = A.P.nwords, RW = 3 + nwords;
+    *d_out = nullptr; *ngroups_out = 0;
+    if (nrec == 0) return GX_OK;
+    // pass-2 table: as large as one CTA's shared memory allows
+    size_t budget = ctx->smem_optin - 1024;
+    int S2 = 16; while (smem_bytes_for(S2 * 2, 2, nwords) <= budget) S2 *= 2;
+    int bits = 0; while (bits < RADIX_MAX_BITS && (nrec >> bits) > S2 / 4) bits++;
+    const int P = 1 << bits;
+    unsigned nblk = (unsigned) (ctx->sm_count * 2);
+    if ((long long) nblk * 512 > nrec) nblk = (unsigned) ((nrec + 511) / 512);
+    long long *d_hist; unsigned long long *d_part, *d_groups; int *d_over;
+    GX_CUDA(ctx, cudaMalloc((void **) &d_hist, (size_t) P * nblk * sizeof(long long)));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_part, (size_t) nrec * RW * 8));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_groups, (size_t) nrec * RW * 8));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_over, (size_t) P * sizeof(int)));
+    GX_CUDA(ctx, cudaMemsetAsync(d_over, 0, (size_t) P * sizeof(int), ctx->stream));
+    GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 12, 0, sizeof(long long), ctx->stream));
+    static bool attr = false;
+    if (!attr) { GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin)); attr = true; }
+    {
+        gx_launch_scope ls(ctx, "radix_partition", 3);
+        gx_k_radix_hist<<<nblk, 512, P * sizeof(unsigned), ctx->stream>>>(d_recs, nrec, RW, bits, d_hist);
+        gx_k_scan_i64<<<1, 1024, 0, ctx->stream>>>(d_hist, (long long) P * nblk, nullptr);
+        gx_k_radix_scatter<<<nblk, 512, P * sizeof(unsigned), ctx->stream>>>(d_recs, nrec, RW, bits, d_hist, d_part);
+    }
+    A.s_slots = S2; A.rec_cap = nrec;
+    {
+        gx_launch_scope ls(ctx, "radix_agg");
+        unsigned grid = (unsigned) (P < ctx->sm_count ? P : ctx->sm_count);
+        gx_k_radix_agg<<<grid, 512, smem_bytes_for(S2, 2, nwords), ctx->stream>>>(A, d_part, d_hist, P, (int) nblk, d_groups, ctx->d_scratch + 12, d_over);
+    }
+    GX_CUDA(ctx, cudaGetLastError());
+    // partitions that overflowed shared memory go through a global table
+    int *h_over = (int *) malloc((size_t) P * sizeof(int));
+    long long *h_hist0 = (long long *) malloc((size_t) P * sizeof(long long));
+    GX_CUDA(ctx, cudaMemcpyAsync(h_over, d_over, (size_t) P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaMemcpy2DAsync(h_hist0, sizeof(long long), d_hist, (size_t) nblk * sizeof(long long), sizeof(long long), P, cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 12, ctx->d_scratch + 12, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    long long ngroups = ctx->h_scratch[12];
+    long long over_recs = 0; int nover = 0;
+    for (int p = 0; p < P; p++) if (h_over[p]) { nover++; over_recs += ((p + 1 < P) ? h_hist0[p + 1] : nrec) - h_hist0[p]; }
+    free(h_over); free(h_hist0);
+    int rc = GX_OK;
+    if (nover) {
+        long long g_cap = gx_pow2_ceil(over_recs * 2 + 1024);
+        unsigned long long *g_tab;
+        GX_CUDA(ctx, cudaMalloc((void **) &g_tab, (size_t) g_cap * RW * 8));
+        GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
+        GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
+        A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
+        {
+            gx_launch_scope ls(ctx, "radix_overflow", 2);
+            gx_k_merge_records<<<ctx->sm_count * 2, 512, 0, ctx->stream>>>(A, d_part, d_hist, (int) nblk, d_over, P, nrec);
+            GX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch + 12, ctx->h_scratch + 12, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+            gx_k_compact_groups<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g_tab, g_cap, nwords, d_groups, ctx->d_scratch + 12);
+        }
+        long long c[4];
+        rc = read_counters(ctx, c);
+        if (rc == GX_OK && c[1]) { GX_SET_ERR(ctx, "radix overflow table overflowed"); rc = GX_ERR_STATE; }
+        if (rc == GX_OK) ngroups += c[0];
+        cudaFree(g_tab);
+    }
+    cudaFree(d_hist); cudaFree(d_part); cudaFree(d_over);
+    if (rc != GX_OK) { cudaFree(d_groups); return rc; }
+    *d_out = d_groups; *ngroups_out = ngroups;
+    return GX_OK;
+}
+
+// Finalize step of gx_result_combine: merge received partial records by key.
+int gx_combine_records(gx_ctx *ctx, gx_result *r, unsigned long long *d_recs, long long nrec,
+                       unsigned long long **d_out, long long *ngroups_out)
+{
+    gx_agg_dev A; memset(&A, 0, sizeof(A));
+    A.P.nwords = r->nwords; A.P.nkw = 2;
+    int rc = gx_result_layout_words(r, A.wkind, A.winit); if (rc) { GX_SET_ERR(ctx, "combine: unknown result"); return rc; }
+    A.counters = ctx->d_scratch + 8;
+    return gx_aggregate_records(ctx, A, d_recs, nrec, d_out, ngroups_out);
+}
+
+static int run_radix(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *plan, long long nrows_in, gx_result **out)
+{
+    gx_agg_dev &A = cp->A;
+    const int nwords = A.P.nwords, RW = 3 + nwords;
+    // stage A: one record per (joined, qualifying) row.  Capacity: rows in for a
+    // unique build; otherwise count first with the record sink disabled.
+    long long cap = nrows_in;
+    unsigned long long *d_recs = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        GX_CUDA(ctx, cudaMalloc((void **) &d_recs, (size_t) (cap > 0 ? cap : 1) * RW * 8));
+        GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
+        A.recs = d_recs; A.rec_cap = cap; A.s_slots = 0;
+        int rc = launch_agg<SINK_RECORD>(ctx, A, 0, A.P.has_join ? "probe_records" : "scan_records");
+        long long c[4];
+        if (rc == GX_OK) rc = read_counters(ctx, c);
+        if (rc != GX_OK) { cudaFree(d_recs); return rc; }
+        if (!(c[1] & 4)) { cap = c[2]; break; }
+        cudaFree(d_recs); d_recs = nullptr;
+        cap = c[2];                                   // exact need (N:M join fan-out)
+        if (pass == 1) { GX_SET_ERR(ctx, "radix: record buffer overflow"); return GX_ERR_STATE; }
+    }
+    unsigned long long *d_groups; long long ngroups;
+    int rc = gx_aggregate_records(ctx, A, d_recs, cap, &d_groups, &ngroups);
+    cudaFree(d_recs);
+    if (rc) return rc;
+    gx_result *r; gx_result_alloc(ctx, plan, cp->group_types, ngroups, &r);
+    r->nkw = A.P.nkw; r->nwords = nwords; r->rec_words = RW;
+    for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp->agg_word[a]; r->agg_cnt_word[a] = cp->agg_cnt_word[a]; }
+    r->d_recs = (long long *) d_groups; r->ngroups = ngroups; r->cap = ngroups;
+    if (!d_groups) { GX_CUDA(ctx, cudaMalloc((void **) &r->d_recs, 64)); }
+    *out = r;
+    return GX_OK;
+}
+
+// ------------------------------------------------------------ results
+extern "C" int64_t gx_result_ngroups(const gx_result *r)
+{
+    if (!r) return -1;
+    // a plain aggregate over zero rows still returns one row (agg_retrieve_direct)
+    if (r->plan.n_group_cols == 0 && r->ngroups == 0) return 1;
+    return r->ngroups;
+}
+
+extern "C" void gx_result_free(gx_result *r)
+{
+    if (!r) return;
+    if (g_layouts) g_layouts->erase(r);
+    if (r->d_recs) cudaFree(r->d_recs);
+    if (r->d_nullmask) cudaFree(r->d_nullmask);
+    free(r);
+}
+
+// accessors for gx_comm.cu (combine across datanodes)
+int gx_result_layout_words(gx_result *r, int *wkind, long long *winit)
+{
+    if (!g_layouts || !g_layouts->count(r)) return GX_ERR_STATE;
+    const result_layout &L = (*g_layouts)[r];
+    for (int i = 0; i < GX_MAX_WORDS; i++) { wkind[i] = L.wkind[i]; winit[i] = L.winit[i]; }
+    return GX_OK;
+}
+
+// finalize_aggregates (nodeAgg.c:1363) on the host: the result is tiny next to
+// the input.  float8_avg = Sx / N, NULL when N == 0 (float.c:2991-3008).
+extern "C" int gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_out, double *agg_out, uint8_t *null_out)
+{
+    if (!r) return GX_ERR_ARG;
+    gx_ctx *ctx = r->ctx;
+    const int ng = r->plan.n_group_cols, na = r->plan.n_aggs, RW = r->rec_words;
+    if (ng == 0 && r->ngroups == 0) {
+        GX_CHECK_ARG(ctx, max_groups >= 1, "result_fetch: buffer too small");
+        for (int a = 0; a < na; a++) {
+            int fn = r->plan.aggs[a].fn;
+            bool is_count = fn == GX_AGG_COUNT_STAR || fn == GX_AGG_COUNT;
+            long long zero = 0; memcpy(&agg_out[a], &zero, 8);
+            if (null_out) null_out[a] = is_count ? 0 : 1;
+        }
+        return GX_OK;
+    }
+    GX_CHECK_ARG(ctx, max_groups >= r->ngroups, "result_fetch: buffer holds %lld groups, result has %lld", (long long) max_groups, (long long) r->ngroups);
+    if (r->ngroups == 0) return GX_OK;
+    GX_CHECK_ARG(ctx, g_layouts && g_layouts->count(r), "result_fetch: unknown result");
+    const result_layout &L = (*g_layouts)[r];
+    unsigned long long *h = (unsigned long long *) malloc((size_t) r->ngroups * RW * 8);
+    cudaError_t e = cudaMemcpyAsync(h, r->d_recs, (size_t) r->ngroups * RW * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); GX_SET_ERR(ctx, "result_fetch: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    for (int64_t g = 0; g < r->ngroups; g++) {
+        const unsigned long long *rec = h + (size_t) g * RW, *w = rec + 3;
+        unsigned int nullmask = (unsigned int) rec[0];
+        for (int c = 0; c < ng; c++) {
+            bool isnull = (nullmask >> c) & 1;
+            unsigned long long v = (L.gword[c] == 0 ? rec[1] : rec[2]) >> L.gshift[c];
+            long long sv;
+            switch (r->group_types[c]) {
+                case GX_INT4: case GX_DATE: sv = (long long) (int32_t) (uint32_t) v; break;
+                case GX_CHAR: sv = (long long) (int8_t) (uint8_t) v; break;
+                default: sv = (long long) v; break;
+            }
+            key_out[g * ng + c] = isnull ? 0 : sv;
+            if (null_out) null_out[g * (ng + na) + c] = isnull;
+        }
+        for (int a = 0; a < na; a++) {
+            int fn = r->plan.aggs[a].fn, word = r->agg_word[a], cw = r->agg_cnt_word[a];
+            long long cnt = (long long) w[cw];                 // cw == 0 -> group row count
+            uint8_t isnull = 0; double res = 0.0; long long ires = 0; bool is_int = false;
+            switch (fn) {
+                case GX_AGG_COUNT_STAR: ires = (long long) w[0]; is_int = true; break;
+                case GX_AGG_COUNT: ires = (long long) w[word]; is_int = true; break;
+                case GX_AGG_SUM_I4: case GX_AGG_SUM_I8: ires = (long long) w[word]; is_int = true; isnull = cnt == 0; break;
+                case GX_AGG_AVG_F8: { double sx; memcpy(&sx, &w[word], 8); if (cnt == 0) isnull = 1; else res = sx / (double) cnt; break; }
+                default: { memcpy(&res, &w[word], 8); isnull = cnt == 0; break; }
+            }
+            if (isnull) { res = 0.0; ires = 0; }
+            if (is_int) memcpy(&agg_out[g * na + a], &ires, 8); else agg_out[g * na + a] = res;
+            if (null_out) null_out[g * (ng + na) + ng + a] = isnull;
+            // float8pl's CHECKFLOATVAL: a finite-input sum that reached infinity is an ERROR in the reference
+            if (!is_int && !isnull && (fn == GX_AGG_SUM_F8 || fn == GX_AGG_AVG_F8) && __builtin_isinf(res)) {
+                free(h); GX_SET_ERR(ctx, "value out of range: overflow"); return GX_ERR_OVERFLOW;
+            }
+        }
+    }
+    free(h);
+    return GX_OK;
+}

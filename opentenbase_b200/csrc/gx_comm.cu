@@ -1,0 +1,448 @@
+// gx_comm.cu — K5: SHARD routing, partition-by-datanode, NCCL all-to-all
+// redistribute, and the cross-datanode combine of partial aggregate states.
+//
+// Replaces the reference's redistribute step: GetDataRouting / EvaluateHashkey /
+// GetNodeIndexByHashValue (execFragment.c:2360, locator.c:1611, shardmap.c:1147),
+// FragmentSendTuple -> FnPage -> FN sender process -> TCP -> FN receiver ->
+// TupleQueueThread (execFragment.c:2148, src/backend/forward/, tqueueThread.c).
+// One datanode per GPU; rows travel as column slices over NVLink, counts are
+// exchanged first (they replace FragmentSendCompleteMsg, execFragment.c:2953).
+#include <dlfcn.h>
+#include "gx_internal.cuh"
+
+// ---- NCCL through dlopen: the same libnccl.so.2 the host process already has
+// (torch's bundled copy under torchrun; the system one in a PG backend).
+typedef struct { char internal[128]; } gx_ncclUniqueId;
+typedef int (*fn_ncclGetUniqueId)(gx_ncclUniqueId *);
+typedef int (*fn_ncclCommInitRank)(void **, int, gx_ncclUniqueId, int);
+typedef int (*fn_ncclCommDestroy)(void *);
+typedef int (*fn_ncclSend)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclRecv)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclGroup)(void);
+typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef const char *(*fn_ncclGetErrorString)(int);
+enum { GX_NCCL_INT8 = 0, GX_NCCL_INT64 = 4 };
+
+struct gx_nccl_api {
+    void *dl;
+    fn_ncclGetUniqueId GetUniqueId; fn_ncclCommInitRank CommInitRank; fn_ncclCommDestroy CommDestroy;
+    fn_ncclSend Send; fn_ncclRecv Recv; fn_ncclGroup GroupStart, GroupEnd; fn_ncclAllGather AllGather;
+    fn_ncclGetErrorString GetErrorString;
+};
+static gx_nccl_api g_nccl; static bool g_nccl_loaded = false;
+
+static int load_nccl(gx_ctx *ctx)
+{
+    if (g_nccl_loaded) return GX_OK;
+    void *dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) { GX_SET_ERR(ctx, "cannot load libnccl.so.2: %s", dlerror()); return GX_ERR_NCCL; }
+    g_nccl.dl = dl;
+#define SYM(f) g_nccl.f = (fn_nccl##f) dlsym(dl, "nccl" #f); if (!g_nccl.f) { GX_SET_ERR(ctx, "libnccl lacks nccl" #f); return GX_ERR_NCCL; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllGather) SYM(GetErrorString)
+#undef SYM
+    g_nccl.GroupStart = (fn_ncclGroup) dlsym(dl, "ncclGroupStart");
+    g_nccl.GroupEnd = (fn_ncclGroup) dlsym(dl, "ncclGroupEnd");
+    if (!g_nccl.GroupStart || !g_nccl.GroupEnd) { GX_SET_ERR(ctx, "libnccl lacks ncclGroupStart/End"); return GX_ERR_NCCL; }
+    g_nccl_loaded = true;
+    return GX_OK;
+}
+#define GX_NCCL(ctx, call) do { int r__ = (call); if (r__ != 0) { \
+    GX_SET_ERR(ctx, "NCCL error %d at %s:%d: %s", r__, __FILE__, __LINE__, g_nccl.GetErrorString(r__)); return GX_ERR_NCCL; } } while (0)
+
+extern "C" int gx_comm_unique_id(void *uid_out)
+{
+    if (!uid_out) return GX_ERR_ARG;
+    gx_ctx *noctx = nullptr;
+    int rc = load_nccl(noctx); if (rc) return rc;
+    gx_ncclUniqueId id;
+    GX_NCCL(noctx, g_nccl.GetUniqueId(&id));
+    memcpy(uid_out, &id, sizeof(id));
+    return GX_OK;
+}
+
+extern "C" int gx_set_shardmap(gx_ctx *ctx, const int32_t *shardmap, int nnodes)
+{
+    if (!ctx) return GX_ERR_ARG;
+    GX_CHECK_ARG(ctx, nnodes >= 1 && nnodes <= GX_MAX_NODES, "set_shardmap: nnodes %d out of range", nnodes);
+    int32_t map[GX_SHARD_MAP_SHARD_NUM];
+    for (int i = 0; i < GX_SHARD_MAP_SHARD_NUM; i++) {
+        map[i] = shardmap ? shardmap[i] : i % nnodes;            // default: catalog/pgxc_shard_map.c:93
+        GX_CHECK_ARG(ctx, map[i] >= 0 && map[i] < nnodes, "set_shardmap: shard %d -> node %d out of range", i, map[i]);
+    }
+    GX_CUDA(ctx, cudaMemcpyAsync(ctx->d_shardmap, map, sizeof(map), cudaMemcpyHostToDevice, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->nnodes = nnodes;
+    return GX_OK;
+}
+
+extern "C" int gx_comm_init(gx_ctx *ctx, int rank, int nranks, const void *uid)
+{
+    if (!ctx || !uid) return GX_ERR_ARG;
+    GX_CHECK_ARG(ctx, nranks >= 1 && rank >= 0 && rank < nranks, "comm_init: bad rank %d/%d", rank, nranks);
+    int rc = load_nccl(ctx); if (rc) return rc;
+    gx_ncclUniqueId id; memcpy(&id, uid, sizeof(id));
+    void *comm = nullptr;
+    GX_CUDA(ctx, cudaSetDevice(ctx->device));
+    GX_NCCL(ctx, g_nccl.CommInitRank(&comm, nranks, id, rank));
+    ctx->nccl = &g_nccl; ctx->comm = comm; ctx->rank = rank; ctx->nranks = nranks;
+    if (ctx->nnodes != nranks) return gx_set_shardmap(ctx, nullptr, nranks);
+    return GX_OK;
+}
+extern "C" int gx_comm_rank(const gx_ctx *ctx, int *rank, int *nranks)
+{
+    if (!ctx) return GX_ERR_ARG;
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    return GX_OK;
+}
+extern "C" void gx_comm_destroy(gx_ctx *ctx)
+{
+    if (ctx && ctx->comm && ctx->nccl) { ctx->nccl->CommDestroy(ctx->comm); ctx->comm = nullptr; ctx->nranks = 1; ctx->rank = 0; }
+}
+
+// ------------------------------------------------------------- routing
+struct gx_route_args {
+    gx_dcol key; long long nrows; const int32_t *shardmap; int nnodes; int _pad;
+    unsigned char *dest;            // per-row destination
+    long long *hist;                // hist[node * nblocks + block]
+};
+
+__device__ __forceinline__ int route_row(const gx_route_args &a, long long r)
+{
+    bool isnull = gx_is_null(a.key, r);
+    long long datum = isnull ? 0 : gx_load_int(a.key, r);
+    return a.shardmap[gx_shard_index(gx_route_hash(a.key.type, datum, isnull))];
+}
+
+__global__ void __launch_bounds__(256) gx_k_route_hist(gx_route_args a)
+{
+    __shared__ unsigned int sh[GX_MAX_NODES];
+    if (threadIdx.x < GX_MAX_NODES) sh[threadIdx.x] = 0;
+    __syncthreads();
+    long long per = (a.nrows + gridDim.x - 1) / gridDim.x, b = per * blockIdx.x, e = min(a.nrows, b + per);
+    for (long long r = b + threadIdx.x; r < e; r += blockDim.x) {
+        int d = route_row(a, r);
+        a.dest[r] = (unsigned char) d;
+        atomicAdd(&sh[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < a.nnodes) a.hist[(long long) threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+}
+
+struct gx_scatter_args {
+    long long nrows; int ncols, nnodes;
+    const unsigned char *dest; const long long *offs;
+    gx_dcol in[GX_MAX_COLS]; void *out[GX_MAX_COLS]; uint8_t *out_nulls[GX_MAX_COLS];
+};
+// Row order inside a destination is unspecified (as with the reference's FN pages).
+__global__ void __launch_bounds__(256) gx_k_route_scatter(gx_scatter_args a)
+{
+    __shared__ unsigned int cur[GX_MAX_NODES];
+    if (threadIdx.x < GX_MAX_NODES) cur[threadIdx.x] = 0;
+    __syncthreads();
+    long long per = (a.nrows + gridDim.x - 1) / gridDim.x, b = per * blockIdx.x, e = min(a.nrows, b + per);
+    const int lane = threadIdx.x & 31;
+    for (long long r0 = b; r0 < e; r0 += blockDim.x) {
+        long long r = r0 + threadIdx.x;
+        bool valid = r < e;
+        int d = valid ? a.dest[r] : -1;
+        if (valid) {
+            unsigned int m = __match_any_sync(__activemask(), d);
+            int leader = __ffs(m) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(&cur[d], (unsigned int) __popc(m));
+            base = __shfl_sync(m, base, leader);
+            long long dst = a.offs[(long long) d * gridDim.x + blockIdx.x] + base + __popc(m & ((1u << lane) - 1));
+            for (int c = 0; c < a.ncols; c++) {
+                switch (a.in[c].type) {
+                    case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = ((const int *) a.in[c].data)[r]; break;
+                    case GX_CHAR: ((signed char *) a.out[c])[dst] = ((const signed char *) a.in[c].data)[r]; break;
+                    default: ((long long *) a.out[c])[dst] = ((const long long *) a.in[c].data)[r]; break;
+                }
+                if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
+            }
+        }
+    }
+}
+
+__global__ void gx_k_scan_i64(long long *v, long long n, long long *total);   // gx_agg.cu
+
+static int route_setup(gx_ctx *ctx, const gx_table *in, int key_col, gx_route_args *a, unsigned *nblk_out)
+{
+    GX_CHECK_ARG(ctx, key_col >= 0 && key_col < in->ncols, "route: key column %d out of range", key_col);
+    int kt = in->types[key_col];
+    GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "route: distribution column type %d not supported (int4/int8/date)", kt);
+    memset(a, 0, sizeof(*a));
+    a->key.data = in->cols[key_col]; a->key.nulls = in->nulls[key_col]; a->key.type = kt;
+    a->nrows = in->nrows; a->shardmap = ctx->d_shardmap; a->nnodes = ctx->nnodes;
+    unsigned nblk = (unsigned) (ctx->sm_count * 4);
+    if ((long long) nblk * 256 > in->nrows) nblk = (unsigned) ((in->nrows + 255) / 256);
+    if (nblk == 0) nblk = 1;
+    *nblk_out = nblk;
+    GX_CUDA(ctx, cudaMalloc((void **) &a->dest, (size_t) (in->nrows > 0 ? in->nrows : 1)));
+    GX_CUDA(ctx, cudaMalloc((void **) &a->hist, (size_t) ctx->nnodes * nblk * sizeof(long long)));
+    return GX_OK;
+}
+
+extern "C" int gx_route(gx_ctx *ctx, const gx_table *in, int key_col, int32_t *host_dest_out)
+{
+    if (!ctx || !in || !host_dest_out) return GX_ERR_ARG;
+    gx_route_args a; unsigned nblk;
+    int rc = route_setup(ctx, in, key_col, &a, &nblk); if (rc) return rc;
+    { gx_launch_scope ls(ctx, "route"); gx_k_route_hist<<<nblk, 256, 0, ctx->stream>>>(a); }
+    unsigned char *h = (unsigned char *) malloc((size_t) in->nrows + 1);
+    cudaError_t e = cudaMemcpyAsync(h, a.dest, (size_t) in->nrows, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    for (int64_t i = 0; i < in->nrows; i++) host_dest_out[i] = h[i];
+    free(h); cudaFree(a.dest); cudaFree(a.hist);
+    if (e != cudaSuccess) { GX_SET_ERR(ctx, "route: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    return GX_OK;
+}
+
+// partition rows by destination node into a new table; counts[node] on the host
+static int partition_impl(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out, int64_t *host_counts)
+{
+    gx_route_args a; unsigned nblk;
+    int rc = route_setup(ctx, in, key_col, &a, &nblk); if (rc) return rc;
+    bool hn[GX_MAX_COLS];
+    for (int c = 0; c < in->ncols; c++) hn[c] = in->nulls[c] != nullptr;
+    gx_table *t;
+    rc = gx_table_alloc_like(ctx, in->ncols, in->types, hn, in->nrows, &t);
+    if (rc) { cudaFree(a.dest); cudaFree(a.hist); return rc; }
+    gx_scatter_args s; memset(&s, 0, sizeof(s));
+    s.nrows = in->nrows; s.ncols = in->ncols; s.nnodes = ctx->nnodes; s.dest = a.dest; s.offs = a.hist;
+    for (int c = 0; c < in->ncols; c++) {
+        s.in[c].data = in->cols[c]; s.in[c].nulls = in->nulls[c]; s.in[c].type = in->types[c];
+        s.out[c] = t->cols[c]; s.out_nulls[c] = t->nulls[c];
+    }
+    long long *h_offs = (long long *) malloc((size_t) ctx->nnodes * sizeof(long long));
+    {
+        gx_launch_scope ls(ctx, "partition", 3);
+        gx_k_route_hist<<<nblk, 256, 0, ctx->stream>>>(a);
+        gx_k_scan_i64<<<1, 1024, 0, ctx->stream>>>(a.hist, (long long) ctx->nnodes * nblk, nullptr);
+        // node offsets = scanned hist at (node, block 0)
+        cudaMemcpy2DAsync(h_offs, sizeof(long long), a.hist, (size_t) nblk * sizeof(long long), sizeof(long long), ctx->nnodes,
+                          cudaMemcpyDeviceToHost, ctx->stream);
+        gx_k_route_scatter<<<nblk, 256, 0, ctx->stream>>>(s);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(a.dest); cudaFree(a.hist);
+    if (e != cudaSuccess) { free(h_offs); gx_table_free(t); GX_SET_ERR(ctx, "partition: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    for (int n = 0; n < ctx->nnodes; n++)
+        host_counts[n] = ((n + 1 < ctx->nnodes) ? h_offs[n + 1] : in->nrows) - h_offs[n];
+    free(h_offs);
+    t->nrows = in->nrows;
+    *out = t;
+    return GX_OK;
+}
+
+extern "C" int gx_partition_by_node(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out, int64_t *host_counts)
+{
+    if (!ctx || !in || !out || !host_counts) return GX_ERR_ARG;
+    return partition_impl(ctx, in, key_col, out, host_counts);
+}
+
+// all-to-all of byte slices: sendbuf split by sendcnt (bytes), recvbuf by recvcnt
+static int alltoallv_bytes(gx_ctx *ctx, const char *sendbuf, const int64_t *sendoff, const int64_t *sendcnt,
+                           char *recvbuf, const int64_t *recvoff, const int64_t *recvcnt)
+{
+    GX_NCCL(ctx, g_nccl.GroupStart());
+    for (int p = 0; p < ctx->nranks; p++) {
+        if (sendcnt[p]) GX_NCCL(ctx, g_nccl.Send(sendbuf + sendoff[p], (size_t) sendcnt[p], GX_NCCL_INT8, p, ctx->comm, ctx->stream));
+        if (recvcnt[p]) GX_NCCL(ctx, g_nccl.Recv(recvbuf + recvoff[p], (size_t) recvcnt[p], GX_NCCL_INT8, p, ctx->comm, ctx->stream));
+    }
+    GX_NCCL(ctx, g_nccl.GroupEnd());
+    return GX_OK;
+}
+
+// exchange a small int64 vector: every rank learns every rank's vector
+static int allgather_i64(gx_ctx *ctx, const int64_t *mine, int n, int64_t *all /* nranks*n */)
+{
+    long long *d_in, *d_out;
+    GX_CUDA(ctx, cudaMalloc((void **) &d_in, (size_t) n * 8));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_out, (size_t) n * 8 * ctx->nranks));
+    GX_CUDA(ctx, cudaMemcpyAsync(d_in, mine, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GX_NCCL(ctx, g_nccl.AllGather(d_in, d_out, (size_t) n, GX_NCCL_INT64, ctx->comm, ctx->stream));
+    GX_CUDA(ctx, cudaMemcpyAsync(all, d_out, (size_t) n * 8 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return GX_OK;
+}
+
+extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out)
+{
+    if (!ctx || !in || !out) return GX_ERR_ARG;
+    const int N = ctx->nranks;
+    GX_CHECK_ARG(ctx, ctx->nnodes == N, "redistribute: shard map covers %d nodes but the communicator has %d ranks", ctx->nnodes, N);
+    int64_t counts[GX_MAX_NODES + 1];
+    gx_table *part;
+    int rc = partition_impl(ctx, in, key_col, &part, counts); if (rc) return rc;
+    if (N == 1 || !ctx->comm) { *out = part; return GX_OK; }
+    // counts first (+ which columns carry NULL arrays, so every rank agrees)
+    int64_t nullbits = 0;
+    for (int c = 0; c < in->ncols; c++) if (in->nulls[c]) nullbits |= 1LL << c;
+    counts[N] = nullbits;
+    int64_t *all = (int64_t *) malloc((size_t) N * (N + 1) * 8);
+    rc = allgather_i64(ctx, counts, N + 1, all);
+    if (rc) { free(all); gx_table_free(part); return rc; }
+    int64_t sendoff[GX_MAX_NODES], recvcnt[GX_MAX_NODES], recvoff[GX_MAX_NODES], total = 0, anynull = 0;
+    for (int p = 0; p < N; p++) {
+        sendoff[p] = p ? sendoff[p - 1] + counts[p - 1] : 0;
+        recvcnt[p] = all[(size_t) p * (N + 1) + ctx->rank];
+        recvoff[p] = total; total += recvcnt[p];
+        anynull |= all[(size_t) p * (N + 1) + N];
+    }
+    free(all);
+    bool hn[GX_MAX_COLS];
+    for (int c = 0; c < in->ncols; c++) hn[c] = (anynull >> c) & 1;
+    gx_table *t;
+    rc = gx_table_alloc_like(ctx, in->ncols, in->types, hn, total, &t);
+    if (rc) { gx_table_free(part); return rc; }
+    {
+        gx_launch_scope ls(ctx, "alltoall", in->ncols);
+        for (int c = 0; c < in->ncols && rc == GX_OK; c++) {
+            int sz = gx_type_size(in->types[c]);
+            int64_t so[GX_MAX_NODES], sc[GX_MAX_NODES], ro[GX_MAX_NODES], rcn[GX_MAX_NODES];
+            for (int p = 0; p < N; p++) { so[p] = sendoff[p] * sz; sc[p] = counts[p] * sz; ro[p] = recvoff[p] * sz; rcn[p] = recvcnt[p] * sz; }
+            rc = alltoallv_bytes(ctx, (const char *) part->cols[c], so, sc, (char *) t->cols[c], ro, rcn);
+            if (rc == GX_OK && hn[c]) {
+                // a rank without a NULL array for this column sends zeros
+                uint8_t *src = part->nulls[c];
+                uint8_t *tmp = nullptr;
+                if (!src) { cudaMalloc((void **) &tmp, (size_t) (in->nrows > 0 ? in->nrows : 1)); cudaMemsetAsync(tmp, 0, (size_t) in->nrows, ctx->stream); src = tmp; }
+                rc = alltoallv_bytes(ctx, (const char *) src, sendoff, counts, (char *) t->nulls[c], recvoff, recvcnt);
+                if (tmp) { cudaStreamSynchronize(ctx->stream); cudaFree(tmp); }
+            }
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    gx_table_free(part);
+    if (rc) { gx_table_free(t); return rc; }
+    if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "redistribute: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    t->nrows = total;
+    *out = t;
+    return GX_OK;
+}
+
+// ------------------------------------------- Finalize across datanodes
+struct gx_agg_dev;
+int gx_result_layout_words(gx_result *r, int *wkind, long long *winit);
+int gx_combine_records(gx_ctx *ctx, gx_result *r, unsigned long long *d_recs, long long nrec,
+                       unsigned long long **d_out, long long *ngroups_out);   // gx_agg.cu
+
+__global__ void gx_k_rec_dest_hist(const unsigned long long *recs, long long nrec, int RW, int nranks,
+                                   unsigned char *dest, long long *hist)
+{
+    __shared__ unsigned int sh[GX_MAX_NODES];
+    if (threadIdx.x < GX_MAX_NODES) sh[threadIdx.x] = 0;
+    __syncthreads();
+    long long per = (nrec + gridDim.x - 1) / gridDim.x, b = per * blockIdx.x, e = min(nrec, b + per);
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const unsigned long long *rec = recs + i * RW;
+        unsigned long long h = gx_mix64(rec[1] ^ (rec[2] * 0x9E3779B97F4A7C15ULL) ^ (rec[0] << 56));
+        int d = (int) (h % (unsigned long long) nranks);
+        dest[i] = (unsigned char) d;
+        atomicAdd(&sh[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < nranks) hist[(long long) threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void gx_k_rec_scatter(const unsigned long long *recs, long long nrec, int RW, const unsigned char *dest,
+                                 const long long *offs, unsigned long long *out)
+{
+    __shared__ unsigned int cur[GX_MAX_NODES];
+    if (threadIdx.x < GX_MAX_NODES) cur[threadIdx.x] = 0;
+    __syncthreads();
+    long long per = (nrec + gridDim.x - 1) / gridDim.x, b = per * blockIdx.x, e = min(nrec, b + per);
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+        int d = dest[i];
+        unsigned int k = atomicAdd(&cur[d], 1u);
+        unsigned long long *dst = out + (offs[(long long) d * gridDim.x + blockIdx.x] + k) * RW;
+        const unsigned long long *src = recs + i * RW;
+        for (int j = 0; j < RW; j++) dst[j] = src[j];
+    }
+}
+
+extern "C" int gx_result_combine(gx_ctx *ctx, gx_result *r)
+{
+    if (!ctx || !r) return GX_ERR_ARG;
+    const int N = ctx->nranks;
+    if (N == 1 || !ctx->comm || r->finalized_across) return GX_OK;
+    const int RW = r->rec_words;
+    long long nrec = r->ngroups;
+    unsigned nblk = (unsigned) ctx->sm_count;
+    if ((long long) nblk * 256 > nrec) nblk = (unsigned) ((nrec + 255) / 256);
+    if (nblk == 0) nblk = 1;
+    unsigned char *d_dest; long long *d_hist; unsigned long long *d_send;
+    GX_CUDA(ctx, cudaMalloc((void **) &d_dest, (size_t) (nrec > 0 ? nrec : 1)));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_hist, (size_t) N * nblk * 8));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_send, (size_t) (nrec > 0 ? nrec : 1) * RW * 8));
+    long long h_offs[GX_MAX_NODES];
+    {
+        gx_launch_scope ls(ctx, "combine_partition", 3);
+        gx_k_rec_dest_hist<<<nblk, 256, 0, ctx->stream>>>((const unsigned long long *) r->d_recs, nrec, RW, N, d_dest, d_hist);
+        gx_k_scan_i64<<<1, 1024, 0, ctx->stream>>>(d_hist, (long long) N * nblk, nullptr);
+        cudaMemcpy2DAsync(h_offs, 8, d_hist, (size_t) nblk * 8, 8, N, cudaMemcpyDeviceToHost, ctx->stream);
+        gx_k_rec_scatter<<<nblk, 256, 0, ctx->stream>>>((const unsigned long long *) r->d_recs, nrec, RW, d_dest, d_hist, d_send);
+    }
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t counts[GX_MAX_NODES], sendoff[GX_MAX_NODES], recvcnt[GX_MAX_NODES], recvoff[GX_MAX_NODES], total = 0;
+    for (int p = 0; p < N; p++) { sendoff[p] = h_offs[p]; counts[p] = ((p + 1 < N) ? h_offs[p + 1] : nrec) - h_offs[p]; }
+    int64_t *all = (int64_t *) malloc((size_t) N * N * 8);
+    int rc = allgather_i64(ctx, counts, N, all);
+    if (rc == GX_OK) {
+        for (int p = 0; p < N; p++) { recvcnt[p] = all[(size_t) p * N + ctx->rank]; recvoff[p] = total; total += recvcnt[p]; }
+    }
+    free(all);
+    unsigned long long *d_recv = nullptr;
+    if (rc == GX_OK) {
+        GX_CUDA(ctx, cudaMalloc((void **) &d_recv, (size_t) (total > 0 ? total : 1) * RW * 8));
+        int64_t so[GX_MAX_NODES], sc[GX_MAX_NODES], ro[GX_MAX_NODES], rcn[GX_MAX_NODES];
+        for (int p = 0; p < N; p++) { so[p] = sendoff[p] * RW * 8; sc[p] = counts[p] * RW * 8; ro[p] = recvoff[p] * RW * 8; rcn[p] = recvcnt[p] * RW * 8; }
+        gx_launch_scope ls(ctx, "alltoall");
+        rc = alltoallv_bytes(ctx, (const char *) d_send, so, sc, (char *) d_recv, ro, rcn);
+    }
+    if (rc == GX_OK) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) { GX_SET_ERR(ctx, "combine: %s", cudaGetErrorString(e)); rc = GX_ERR_CUDA; } }
+    cudaFree(d_dest); cudaFree(d_hist); cudaFree(d_send);
+    if (rc) { if (d_recv) cudaFree(d_recv); return rc; }
+    unsigned long long *d_groups; long long ngroups;
+    rc = gx_combine_records(ctx, r, d_recv, total, &d_groups, &ngroups);
+    cudaFree(d_recv);
+    if (rc) return rc;
+    cudaFree(r->d_recs);
+    if (!d_groups) { GX_CUDA(ctx, cudaMalloc((void **) &d_groups, 64)); }
+    r->d_recs = (long long *) d_groups; r->ngroups = ngroups; r->cap = ngroups; r->finalized_across = 1;
+    return GX_OK;
+}
+
+// ------------------------------------------------- debug hash entry point
+__global__ void gx_k_debug_hash(int which, const long long *in, long long n, unsigned int *out)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long v = in[i];
+    unsigned int h;
+    switch (which) {
+        case 1: h = gx_hashint4((int) v); break;
+        case 2: h = gx_hashint8(v); break;
+        case 3: h = gx_crc32c_u64((unsigned long long) (long long) (int) v); break;   // hashint4new: widen to int64
+        case 4: h = gx_crc32c_u64((unsigned long long) v); break;                     // hashint8new
+        default: h = gx_murmurhash32((unsigned int) v); break;
+    }
+    out[i] = h;
+}
+extern "C" int gx_debug_hash(gx_ctx *ctx, int which, const int64_t *host_in, int64_t n, uint32_t *host_out)
+{
+    if (!ctx || !host_in || !host_out || n < 0) return GX_ERR_ARG;
+    if (n == 0) return GX_OK;
+    long long *d_in; unsigned int *d_out;
+    GX_CUDA(ctx, cudaMalloc((void **) &d_in, (size_t) n * 8));
+    GX_CUDA(ctx, cudaMalloc((void **) &d_out, (size_t) n * 4));
+    GX_CUDA(ctx, cudaMemcpyAsync(d_in, host_in, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    { gx_launch_scope ls(ctx, "debug_hash"); gx_k_debug_hash<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(which, d_in, n, d_out); }
+    GX_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return GX_OK;
+}

@@ -1,0 +1,332 @@
+// gx_internal.cuh — internal structures and device helpers of libgpuexec.so.
+// sm_100a only.  No CPU fallback anywhere: every entry point needs a live ctx.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <map>
+#include "../../include/gpuexec.h"
+
+#define GX_EMPTY_KEY   ((long long) 0x8000000000000000LL)   /* INT64_MIN marks an empty join slot */
+#define GX_MAX_NODES   64
+
+// ---------------------------------------------------------------- host side
+struct gx_prof_entry { double ms; int64_t launches; };
+
+struct gx_nccl_api;   // gx_comm.cu
+
+struct gx_ctx {
+    int device;
+    int sm_count, cc_major, cc_minor;
+    size_t hbm_bytes;
+    size_t smem_optin;           // max dynamic smem per block
+    cudaStream_t stream;         // all kernels
+    cudaStream_t copy_stream;    // H2D staging
+    cudaEvent_t ev_t0, ev_t1;    // gx_timer_*
+    cudaEvent_t ev_p0, ev_p1;    // per-kernel profiling
+    char err[512];
+    int64_t launches;
+    int profile;
+    std::map<std::string, gx_prof_entry> *prof;
+    void *l2flush_buf; size_t l2flush_bytes;
+    // pinned staging ring for pageable host buffers
+    void *stage[2]; size_t stage_bytes; cudaEvent_t stage_ev[2];
+    // small device scratch (counters / flags)
+    long long *d_scratch;        // 64 x int64
+    long long *h_scratch;        // pinned mirror
+    // routing
+    int32_t *d_shardmap; int nnodes;
+    // communicator
+    gx_nccl_api *nccl; void *comm; int rank, nranks;
+};
+
+struct gx_table {
+    gx_ctx *ctx;
+    int ncols;
+    int32_t types[GX_MAX_COLS];
+    void *cols[GX_MAX_COLS];
+    uint8_t *nulls[GX_MAX_COLS];     // NULL when the column has no NULLs
+    int64_t nrows, capacity;
+};
+
+struct gx_slot { long long key; unsigned long long payload; };   // 16 B
+
+struct gx_hash {
+    gx_ctx *ctx;
+    gx_slot *slots;
+    int64_t nslots;                 // power of two
+    int64_t nentries;
+    int key_type;
+    int n_payload;                  // 0: payload = build row number
+    int32_t payload_types[GX_MAX_PAYLOAD];
+    int unique;
+    // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
+    unsigned long long *special_payload; int special_cap; int special_count;
+};
+
+// A group-state record: [k0][k1][w0..w(nwords-1)], 8-byte words.
+// w0 is always the group's row count.
+#define GX_MAX_WORDS 18
+
+struct gx_result {
+    gx_ctx *ctx;
+    gx_agg_plan plan;
+    int32_t group_types[GX_MAX_GROUP_COLS];
+    int nkw;                         // key words (1 or 2)
+    int nwords;                      // state words
+    int rec_words;                   // 2 + nwords (k0,k1 always present in records)
+    // per-agg state layout
+    int agg_word[GX_MAX_AGGS];       // first word of the aggregate's state
+    int agg_cnt_word[GX_MAX_AGGS];   // word holding its non-NULL input count (may be 0 = row count)
+    long long *d_recs;               // ngroups * rec_words (dense, partial states)
+    unsigned int *d_nullmask;        // ngroups (group-key null bits)
+    int64_t ngroups, cap;
+    int finalized_across;            // combined over the communicator already
+};
+
+#define GX_SET_ERR(ctx, ...) do { if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+                                  gx_set_global_err(__VA_ARGS__); } while (0)
+void gx_set_global_err(const char *fmt, ...);
+
+#define GX_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    GX_SET_ERR(ctx, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    return (e__ == cudaErrorMemoryAllocation) ? GX_ERR_NOMEM : GX_ERR_CUDA; } } while (0)
+
+#define GX_CHECK_ARG(ctx, cond, ...) do { if (!(cond)) { GX_SET_ERR(ctx, __VA_ARGS__); return GX_ERR_ARG; } } while (0)
+
+// launch accounting + optional per-kernel CUDA-event timing
+struct gx_launch_scope {
+    gx_ctx *ctx; const char *name;
+    gx_launch_scope(gx_ctx *c, const char *n, int nlaunch = 1) : ctx(c), name(n) {
+        ctx->launches += nlaunch;
+        if (ctx->profile) cudaEventRecord(ctx->ev_p0, ctx->stream);
+    }
+    ~gx_launch_scope() {
+        if (ctx->profile) {
+            cudaEventRecord(ctx->ev_p1, ctx->stream);
+            cudaEventSynchronize(ctx->ev_p1);
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_p0, ctx->ev_p1);
+            gx_prof_entry &e = (*ctx->prof)[name];
+            e.ms += ms; e.launches += 1;
+        }
+    }
+};
+
+static inline int gx_type_size(int t)
+{
+    switch (t) { case GX_INT4: case GX_DATE: return 4; case GX_INT8: case GX_FLOAT8: return 8; case GX_CHAR: return 1; }
+    return 0;
+}
+static inline int64_t gx_pow2_ceil(int64_t x) { int64_t p = 1; while (p < x) p <<= 1; return p; }
+
+int gx_table_alloc_like(gx_ctx *ctx, int ncols, const int32_t *types, const bool *has_nulls,
+                        int64_t capacity, gx_table **out);
+int gx_result_alloc(gx_ctx *ctx, const gx_agg_plan *plan, const int32_t *group_types, int64_t cap, gx_result **out);
+
+// device-side plan descriptors -------------------------------------------
+struct gx_dcol { const void *data; const uint8_t *nulls; int type; int _pad; };
+
+struct gx_dpred { gx_dcol col; int op; int _pad; long long ival; double fval; };
+
+// chain-form expression: acc = term0; acc = acc (op) term_i
+enum { GXT_COL = 1, GXT_CONST = 2, GXT_K_SUB_COL = 3, GXT_K_ADD_COL = 4, GXT_K_MUL_COL = 5, GXT_COL_SUB_K = 6 };
+struct gx_dterm { int op; int kind; gx_dcol col; double k; };
+struct gx_dexpr { int nterms; int _pad; gx_dterm t[4]; };
+
+enum { GXU_NONE = 0, GXU_ADD_F64 = 1, GXU_ADD_I64 = 2, GXU_MIN_F64 = 3, GXU_MAX_F64 = 4, GXU_CNT = 5 };
+struct gx_dagg {
+    int kind;          // GXU_*
+    int word;          // state word receiving the value
+    int cnt_word;      // word receiving +1 per non-NULL input (0 = none: w0 row count serves)
+    int is_int;        // value is an integer column (SUM_I4/I8, COUNT(col))
+    gx_dexpr expr;     // float8 argument (kind F64) ...
+    gx_dcol icol;      // ... or integer argument column
+};
+
+struct gx_dgroupcol { int side; int type; gx_dcol col; int payload_idx; int word; int shift; int bytes; int _pad; };
+
+struct gx_dplan {
+    int npreds, nagg, ngroup, nkw;
+    int nwords, has_join, key_type, unique;
+    gx_dpred preds[GX_MAX_PREDS];
+    gx_dcol okey;                       // outer join key column
+    gx_dgroupcol gcols[GX_MAX_GROUP_COLS];
+    gx_dagg aggs[GX_MAX_AGGS];
+    int payload_types[GX_MAX_PAYLOAD];
+    int n_payload; int _pad;
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- device side
+
+__device__ __forceinline__ unsigned int gx_rotl32(unsigned int x, int k) { return __funnelshift_l(x, x, k); }
+
+// final() of Bob Jenkins' lookup3 as used by hash_uint32()
+// (reference: src/backend/access/hash/hashfunc.c:593-602, 1044-1058)
+__device__ __forceinline__ unsigned int gx_hash_uint32(unsigned int k)
+{
+    unsigned int a, b, c;
+    a = b = c = 0x9e3779b9u + 4u + 3923095u;
+    a += k;
+    c ^= b; c -= gx_rotl32(b, 14);
+    a ^= c; a -= gx_rotl32(c, 11);
+    b ^= a; b -= gx_rotl32(a, 25);
+    c ^= b; c -= gx_rotl32(b, 16);
+    a ^= c; a -= gx_rotl32(c, 4);
+    b ^= a; b -= gx_rotl32(a, 14);
+    c ^= b; c -= gx_rotl32(b, 24);
+    return c;
+}
+// hashint8(): fold hi into lo (hashfunc.c:92-110)
+__device__ __forceinline__ unsigned int gx_hashint8(long long v)
+{
+    unsigned int lo = (unsigned int) v, hi = (unsigned int) ((unsigned long long) v >> 32);
+    lo ^= (v >= 0) ? hi : ~hi;
+    return gx_hash_uint32(lo);
+}
+__device__ __forceinline__ unsigned int gx_hashint4(int v) { return gx_hash_uint32((unsigned int) v); }
+
+// CRC32C of the 8 little-endian bytes of v, bitwise (hash_any_new, hashfunc.c:112)
+__device__ __forceinline__ unsigned int gx_crc32c_u64(unsigned long long v)
+{
+    unsigned int crc = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        crc ^= (unsigned int) (v >> (8 * i)) & 0xFFu;
+#pragma unroll
+        for (int j = 0; j < 8; j++) crc = (crc >> 1) ^ (0x82F63B78u & (0u - (crc & 1u)));
+    }
+    return crc ^ 0xFFFFFFFFu;
+}
+__device__ __forceinline__ unsigned int gx_murmurhash32(unsigned int h)
+{
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16; return h;
+}
+// internal bucket hash of the join / group tables (need not match the reference:
+// SURVEY.md §2 row 7): murmur3 fmix64
+__device__ __forceinline__ unsigned long long gx_mix64(unsigned long long h)
+{
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33; return h;
+}
+
+// SHARD routing, bit-exact (locator.c:1611, shardmap.c:1147): one distribution column
+__device__ __forceinline__ int gx_shard_index(unsigned int hashvalue)
+{
+    int h = (int) hashvalue;
+    unsigned int mag = (h < 0) ? (0u - (unsigned int) h) : (unsigned int) h;
+    int a = (int) mag;                       // abs(INT_MIN) stays INT_MIN
+    return a % GX_SHARD_MAP_SHARD_NUM;       // INT_MIN % 4096 == 0
+}
+__device__ __forceinline__ unsigned int gx_route_hash(int type, long long datum, bool isnull)
+{
+    unsigned int hashkey = 0;                // rotl1(0) == 0
+    if (!isnull) hashkey ^= (type == GX_INT8) ? gx_hashint8(datum) : gx_hashint4((int) datum);
+    return hashkey;
+}
+
+// typed column access ------------------------------------------------------
+__device__ __forceinline__ long long gx_load_int(const gx_dcol &c, long long r)
+{
+    switch (c.type) {
+        case GX_INT4: case GX_DATE: return (long long) __ldg((const int *) c.data + r);
+        case GX_INT8: return __ldg((const long long *) c.data + r);
+        case GX_CHAR: return (long long) __ldg((const signed char *) c.data + r);
+        default: return __ldg((const long long *) c.data + r);     // FLOAT8 bit pattern
+    }
+}
+__device__ __forceinline__ double gx_load_f64(const gx_dcol &c, long long r)
+{
+    switch (c.type) {
+        case GX_FLOAT8: return __ldg((const double *) c.data + r);
+        case GX_INT4: case GX_DATE: return (double) __ldg((const int *) c.data + r);      // i4tod
+        case GX_INT8: return (double) __ldg((const long long *) c.data + r);              // i8tod
+        default: return (double) __ldg((const signed char *) c.data + r);
+    }
+}
+__device__ __forceinline__ bool gx_is_null(const gx_dcol &c, long long r)
+{
+    return c.nulls != nullptr && __ldg(c.nulls + r) != 0;
+}
+
+// float8_cmp_internal: NaN sorts above everything and equals itself (float.c:1160)
+__device__ __forceinline__ int gx_f8cmp(double a, double b)
+{
+    if (isnan(a)) return isnan(b) ? 0 : 1;
+    if (isnan(b)) return -1;
+    return a > b ? 1 : (a < b ? -1 : 0);
+}
+__device__ __forceinline__ bool gx_op_holds(int op, int c)
+{
+    switch (op) {
+        case GX_LT: return c < 0;  case GX_LE: return c <= 0; case GX_EQ: return c == 0;
+        case GX_GE: return c >= 0; case GX_GT: return c > 0;  default: return c != 0;
+    }
+}
+__device__ __forceinline__ bool gx_eval_pred(const gx_dpred &p, long long r)
+{
+    if (gx_is_null(p.col, r)) return false;          // strict operator: NULL fails the qual
+    int c;
+    if (p.col.type == GX_FLOAT8) c = gx_f8cmp(gx_load_f64(p.col, r), p.fval);
+    else if (p.col.type == GX_CHAR) {                // charlt etc. compare as uint8
+        unsigned char x = (unsigned char) gx_load_int(p.col, r), y = (unsigned char) p.ival;
+        c = x > y ? 1 : (x < y ? -1 : 0);
+    } else { long long x = gx_load_int(p.col, r); c = x > p.ival ? 1 : (x < p.ival ? -1 : 0); }
+    return gx_op_holds(p.op, c);
+}
+
+// IEEE fp64 ops that ptxas must never contract into FMA: the reference computes
+// float8mul/float8pl/float8mi as separate correctly-rounded operations.
+__device__ __forceinline__ double gx_apply(int op, double a, double b)
+{
+    return op == GX_OP_ADD ? __dadd_rn(a, b) : (op == GX_OP_SUB ? __dsub_rn(a, b) : __dmul_rn(a, b));
+}
+__device__ __forceinline__ double gx_eval_term(const gx_dterm &t, long long r, bool &isnull)
+{
+    switch (t.kind) {
+        case GXT_CONST: return t.k;
+        case GXT_COL: isnull |= gx_is_null(t.col, r); return gx_load_f64(t.col, r);
+        case GXT_K_SUB_COL: isnull |= gx_is_null(t.col, r); return __dsub_rn(t.k, gx_load_f64(t.col, r));
+        case GXT_K_ADD_COL: isnull |= gx_is_null(t.col, r); return __dadd_rn(t.k, gx_load_f64(t.col, r));
+        case GXT_K_MUL_COL: isnull |= gx_is_null(t.col, r); return __dmul_rn(t.k, gx_load_f64(t.col, r));
+        default: isnull |= gx_is_null(t.col, r); return __dsub_rn(gx_load_f64(t.col, r), t.k);
+    }
+}
+__device__ __forceinline__ double gx_eval_expr(const gx_dexpr &e, long long r, bool &isnull)
+{
+    double acc = gx_eval_term(e.t[0], r, isnull);
+#pragma unroll
+    for (int i = 1; i < 4; i++)
+        if (i < e.nterms) acc = gx_apply(e.t[i].op, acc, gx_eval_term(e.t[i], r, isnull));
+    return acc;
+}
+
+// join-table probe -------------------------------------------------------
+__device__ __forceinline__ unsigned long long gx_key_hash(long long key) { return gx_mix64((unsigned long long) key); }
+
+// block-wide exclusive scan of one value per thread (blockDim.x <= 1024)
+__device__ __forceinline__ long long gx_block_exscan(long long v, long long *total, long long *smem /* 33 */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) smem[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = (lane < (int) ((blockDim.x + 31) >> 5)) ? smem[lane] : 0, z = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+        smem[lane] = z - w;
+        if (lane == 31) smem[32] = z;
+    }
+    __syncthreads();
+    long long res = smem[wid] + x - v;
+    *total = smem[32];
+    __syncthreads();
+    return res;
+}
+#endif  // __CUDACC__

@@ -1,0 +1,296 @@
+// gx_join.cu — K2 open-addressing hash build and K3 probe (materialising).
+//
+// Table: power-of-two array of 16-byte slots {int64 key, uint64 payload},
+// linear probing, load factor in (0.33, 0.67].  Empty = key INT64_MIN; rows
+// whose key IS INT64_MIN live in a small side list.  The payload holds up to
+// eight bytes of carried build-side columns (or the build row number), so a
+// probe hit costs one 32-byte sector and no second gather.
+//
+// Replaces MultiExecPrivateHash / ExecHashTableInsert (nodeHash.c:157,1828:
+// chained buckets of MinimalTuple copies in 32 KB chunks) and
+// ExecScanHashBucket / ExecHashJoinImpl (nodeHash.c:2174, nodeHashjoin.c:186).
+#include "gx_internal.cuh"
+
+int gx_fill_dpreds(gx_ctx *ctx, const gx_table *t, int n_preds, const gx_pred *preds, gx_dpred *out);
+
+struct gx_build_args {
+    gx_dcol key;
+    int npreds, n_payload;
+    gx_dpred preds[GX_MAX_PREDS];
+    gx_dcol payload[GX_MAX_PAYLOAD];
+    long long nrows;
+    gx_slot *slots; unsigned long long mask;
+    unsigned long long *special; int special_cap;
+    long long *counters;          // [0] entries inserted, [1] special count
+};
+
+__device__ __forceinline__ unsigned long long pack_payload(const gx_build_args &a, long long r)
+{
+    if (a.n_payload == 0) return (unsigned long long) r;
+    unsigned long long p = 0; int shift = 0;
+#pragma unroll
+    for (int i = 0; i < GX_MAX_PAYLOAD; i++) {
+        if (i >= a.n_payload) break;
+        int t = a.payload[i].type;
+        unsigned long long v = (unsigned long long) gx_load_int(a.payload[i], r);
+        int bytes = (t == GX_INT8 || t == GX_FLOAT8) ? 8 : (t == GX_CHAR ? 1 : 4);
+        if (bytes < 8) v &= (1ULL << (8 * bytes)) - 1;
+        p |= v << shift;
+        shift += 8 * bytes;
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(256) gx_k_hash_build(gx_build_args a)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    long long inserted = 0;
+    for (long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x; r < a.nrows; r += stride) {
+        bool ok = !gx_is_null(a.key, r);               // hashStrict: NULL keys never match
+#pragma unroll
+        for (int p = 0; p < GX_MAX_PREDS; p++) if (p < a.npreds) ok = ok && gx_eval_pred(a.preds[p], r);
+        if (!ok) continue;
+        long long key = gx_load_int(a.key, r);
+        unsigned long long payload = pack_payload(a, r);
+        if (key == GX_EMPTY_KEY) {
+            int idx = (int) atomicAdd((unsigned long long *) &a.counters[1], 1ULL);
+            if (idx < a.special_cap) a.special[idx] = payload;
+            continue;
+        }
+        unsigned long long s = gx_key_hash(key) & a.mask;
+        for (;;) {
+            long long old = (long long) atomicCAS((unsigned long long *) &a.slots[s].key,
+                                                  (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key);
+            if (old == GX_EMPTY_KEY) { a.slots[s].payload = payload; break; }
+            s = (s + 1) & a.mask;
+        }
+        inserted++;
+    }
+    // one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, o);
+    if ((threadIdx.x & 31) == 0 && inserted) atomicAdd((unsigned long long *) &a.counters[0], (unsigned long long) inserted);
+}
+
+__global__ void gx_k_fill_slots(gx_slot *slots, long long n)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    // 16-byte stores
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        longlong2 v; v.x = GX_EMPTY_KEY; v.y = 0;
+        ((longlong2 *) slots)[i] = v;
+    }
+}
+
+extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, int n_preds, const gx_pred *preds,
+                             int n_payload, const int32_t *payload_cols, int unique, gx_hash **out)
+{
+    if (!ctx || !inner || !out) return GX_ERR_ARG;
+    GX_CHECK_ARG(ctx, key_col >= 0 && key_col < inner->ncols, "hash_build: key column %d out of range", key_col);
+    int kt = inner->types[key_col];
+    GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "hash_build: key type %d not hashable here (int4/int8/date only)", kt);
+    GX_CHECK_ARG(ctx, n_payload >= 0 && n_payload <= GX_MAX_PAYLOAD, "hash_build: n_payload %d", n_payload);
+    gx_build_args a; memset(&a, 0, sizeof(a));
+    a.key.data = inner->cols[key_col]; a.key.nulls = inner->nulls[key_col]; a.key.type = kt;
+    a.npreds = n_preds; a.n_payload = n_payload; a.nrows = inner->nrows;
+    int rc = gx_fill_dpreds(ctx, inner, n_preds, preds, a.preds); if (rc) return rc;
+    int bytes = 0;
+    gx_hash *h = (gx_hash *) calloc(1, sizeof(gx_hash));
+    h->ctx = ctx; h->key_type = kt; h->n_payload = n_payload; h->unique = unique;
+    for (int i = 0; i < n_payload; i++) {
+        int c = payload_cols[i];
+        if (c < 0 || c >= inner->ncols) { free(h); GX_SET_ERR(ctx, "hash_build: payload column %d out of range", c); return GX_ERR_ARG; }
+        if (inner->nulls[c]) { free(h); GX_SET_ERR(ctx, "hash_build: nullable payload column %d not supported in-slot", c); return GX_ERR_ARG; }
+        a.payload[i].data = inner->cols[c]; a.payload[i].nulls = nullptr; a.payload[i].type = inner->types[c];
+        h->payload_types[i] = inner->types[c];
+        bytes += gx_type_size(inner->types[c]);
+    }
+    if (bytes > 8) { free(h); GX_SET_ERR(ctx, "hash_build: payload columns total %d bytes > 8", bytes); return GX_ERR_ARG; }
+
+    int64_t want = inner->nrows + inner->nrows / 2 + 16;       // load factor <= 0.67
+    h->nslots = gx_pow2_ceil(want);
+    h->special_cap = 1 << 16;
+    cudaError_t e = cudaMalloc((void **) &h->slots, (size_t) h->nslots * sizeof(gx_slot));
+    if (e == cudaSuccess) e = cudaMalloc((void **) &h->special_payload, (size_t) h->special_cap * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        GX_SET_ERR(ctx, "hash_build: cudaMalloc of %lld slots failed: %s", (long long) h->nslots, cudaGetErrorString(e));
+        gx_hash_free(h);
+        return GX_ERR_NOMEM;
+    }
+    a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
+    a.special = h->special_payload; a.special_cap = h->special_cap;
+    a.counters = ctx->d_scratch;
+    GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
+    {
+        gx_launch_scope ls(ctx, "build_clear");
+        gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots);
+    }
+    if (inner->nrows > 0) {
+        gx_launch_scope ls(ctx, "build");
+        long long nb = (inner->nrows + 255) / 256;
+        long long maxb = (long long) ctx->sm_count * 8;
+        gx_k_hash_build<<<(unsigned) (nb < maxb ? nb : maxb), 256, 0, ctx->stream>>>(a);
+    }
+    GX_CUDA(ctx, cudaGetLastError());
+    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h->nentries = ctx->h_scratch[0] + ctx->h_scratch[1];
+    h->special_count = (int) ctx->h_scratch[1];
+    if (h->special_count > h->special_cap) {
+        GX_SET_ERR(ctx, "hash_build: %d rows carry key INT64_MIN (side list holds %d)", h->special_count, h->special_cap);
+        gx_hash_free(h);
+        return GX_ERR_ARG;
+    }
+    *out = h;
+    return GX_OK;
+}
+
+extern "C" int64_t gx_hash_nentries(const gx_hash *h) { return h ? h->nentries : -1; }
+extern "C" int64_t gx_hash_nslots(const gx_hash *h) { return h ? h->nslots : -1; }
+extern "C" void gx_hash_free(gx_hash *h)
+{
+    if (!h) return;
+    if (h->slots) cudaFree(h->slots);
+    if (h->special_payload) cudaFree(h->special_payload);
+    free(h);
+}
+
+// ------------------------------------------------------------ K3 probe
+struct gx_probe_args {
+    gx_dcol key;
+    int npreds, n_out_outer, n_payload, unique;
+    gx_dpred preds[GX_MAX_PREDS];
+    long long nrows;
+    const gx_slot *slots; unsigned long long mask;
+    const unsigned long long *special; int special_count;
+    gx_dcol out_src[GX_MAX_COLS];
+    void *out[GX_MAX_COLS];
+    uint8_t *out_nulls[GX_MAX_COLS];
+    int payload_types[GX_MAX_PAYLOAD];
+    long long *cursor;             // global output cursor
+    long long out_cap;
+    int count_only; int _pad;
+};
+
+__device__ __forceinline__ void emit_row(const gx_probe_args &a, long long dst, long long r, unsigned long long payload)
+{
+    for (int c = 0; c < a.n_out_outer; c++) {
+        switch (a.out_src[c].type) {
+            case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = ((const int *) a.out_src[c].data)[r]; break;
+            case GX_CHAR: ((signed char *) a.out[c])[dst] = ((const signed char *) a.out_src[c].data)[r]; break;
+            default: ((long long *) a.out[c])[dst] = ((const long long *) a.out_src[c].data)[r]; break;
+        }
+        if (a.out_nulls[c]) a.out_nulls[c][dst] = a.out_src[c].nulls ? a.out_src[c].nulls[r] : 0;
+    }
+    if (a.n_payload == 0) { ((long long *) a.out[a.n_out_outer])[dst] = (long long) payload; return; }
+    int shift = 0;
+    for (int i = 0; i < a.n_payload; i++) {
+        int t = a.payload_types[i]; void *o = a.out[a.n_out_outer + i];
+        switch (t) {
+            case GX_INT4: case GX_DATE: ((int *) o)[dst] = (int) (payload >> shift); shift += 32; break;
+            case GX_CHAR: ((signed char *) o)[dst] = (signed char) (payload >> shift); shift += 8; break;
+            default: ((long long *) o)[dst] = (long long) payload; shift += 64; break;
+        }
+    }
+}
+
+// One pass.  Each thread walks its row's probe sequence; matches are appended
+// through a warp-aggregated cursor (join output order is unspecified in the
+// reference as well).  count_only sizes the output for non-unique builds.
+__global__ void __launch_bounds__(256) gx_k_hash_probe(gx_probe_args a)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    long long nloop = (a.nrows + stride - 1) / stride;
+    long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    for (long long it = 0; it < nloop; it++, r += stride) {
+        bool ok = r < a.nrows && !gx_is_null(a.key, r);
+        if (ok) {
+#pragma unroll
+            for (int p = 0; p < GX_MAX_PREDS; p++) if (p < a.npreds) ok = ok && gx_eval_pred(a.preds[p], r);
+        }
+        long long key = ok ? gx_load_int(a.key, r) : 0;
+        // walk: the warp iterates until every lane has exhausted its chain
+        unsigned long long s = gx_key_hash(key) & a.mask;
+        bool special = ok && key == GX_EMPTY_KEY;
+        int sp_i = 0;
+        bool active = ok;
+        while (__any_sync(0xffffffffu, active)) {
+            bool hit = false; unsigned long long payload = 0;
+            if (active) {
+                if (special) {
+                    if (sp_i < a.special_count) { hit = true; payload = a.special[sp_i++]; if (a.unique) active = false; }
+                    else active = false;
+                } else {
+                    gx_slot sl = a.slots[s];
+                    if (sl.key == GX_EMPTY_KEY) active = false;
+                    else {
+                        if (sl.key == key) { hit = true; payload = sl.payload; if (a.unique) active = false; }
+                        s = (s + 1) & a.mask;
+                    }
+                }
+            }
+            unsigned int m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                long long base = 0;
+                if (lane == 0) base = (long long) atomicAdd((unsigned long long *) a.cursor, (unsigned long long) __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit && !a.count_only) {
+                    long long dst = base + __popc(m & ((1u << lane) - 1));
+                    if (dst < a.out_cap) emit_row(a, dst, r, payload);
+                }
+            }
+        }
+    }
+}
+
+extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, int n_preds, const gx_pred *preds,
+                             const gx_hash *h, int n_out_outer, const int32_t *out_outer_cols, gx_table **out)
+{
+    if (!ctx || !outer || !h || !out) return GX_ERR_ARG;
+    GX_CHECK_ARG(ctx, key_col >= 0 && key_col < outer->ncols, "hash_probe: key column %d out of range", key_col);
+    int kt = outer->types[key_col];
+    GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "hash_probe: key type %d not supported", kt);
+    int n_pay_out = h->n_payload ? h->n_payload : 1;
+    GX_CHECK_ARG(ctx, n_out_outer >= 0 && n_out_outer + n_pay_out <= GX_MAX_COLS, "hash_probe: too many output columns");
+    gx_probe_args a; memset(&a, 0, sizeof(a));
+    a.key.data = outer->cols[key_col]; a.key.nulls = outer->nulls[key_col]; a.key.type = kt;
+    a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique;
+    a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
+    a.special = h->special_payload; a.special_count = h->special_count;
+    int rc = gx_fill_dpreds(ctx, outer, n_preds, preds, a.preds); if (rc) return rc;
+    int32_t types[GX_MAX_COLS]; bool hn[GX_MAX_COLS];
+    for (int c = 0; c < n_out_outer; c++) {
+        int oc = out_outer_cols[c];
+        GX_CHECK_ARG(ctx, oc >= 0 && oc < outer->ncols, "hash_probe: output column %d out of range", oc);
+        a.out_src[c].data = outer->cols[oc]; a.out_src[c].nulls = outer->nulls[oc]; a.out_src[c].type = outer->types[oc];
+        types[c] = outer->types[oc]; hn[c] = outer->nulls[oc] != nullptr;
+    }
+    if (h->n_payload == 0) { types[n_out_outer] = GX_INT8; hn[n_out_outer] = false; }
+    for (int i = 0; i < h->n_payload; i++) { types[n_out_outer + i] = h->payload_types[i]; hn[n_out_outer + i] = false; a.payload_types[i] = h->payload_types[i]; }
+    a.cursor = ctx->d_scratch + 2;
+    long long nb = (outer->nrows + 255) / 256, maxb = (long long) ctx->sm_count * 8;
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    long long out_cap = outer->nrows;
+    if (!h->unique) {
+        // size the output first
+        a.count_only = 1; a.out_cap = 0;
+        GX_CUDA(ctx, cudaMemsetAsync(a.cursor, 0, sizeof(long long), ctx->stream));
+        { gx_launch_scope ls(ctx, "probe_count"); gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a); }
+        GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, a.cursor, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        out_cap = ctx->h_scratch[0];
+    }
+    gx_table *t;
+    rc = gx_table_alloc_like(ctx, n_out_outer + n_pay_out, types, hn, out_cap, &t); if (rc) return rc;
+    for (int c = 0; c < t->ncols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
+    a.count_only = 0; a.out_cap = out_cap;
+    GX_CUDA(ctx, cudaMemsetAsync(a.cursor, 0, sizeof(long long), ctx->stream));
+    { gx_launch_scope ls(ctx, "probe"); gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a); }
+    cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, a.cursor, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "hash_probe: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    t->nrows = ctx->h_scratch[0] < out_cap ? ctx->h_scratch[0] : out_cap;
+    *out = t;
+    return GX_OK;
+}

@@ -1,0 +1,544 @@
+// gx_table.cu — K0 columnar loader (host columns, raw heap pages, synthetic
+// generator) and K1 scan/qual/projection.
+#include "gx_internal.cuh"
+#include "../../include/gx_tpch_gen.h"
+
+// --------------------------------------------------------------- lifecycle
+int gx_table_alloc_like(gx_ctx *ctx, int ncols, const int32_t *types, const bool *has_nulls,
+                        int64_t capacity, gx_table **out)
+{
+    GX_CHECK_ARG(ctx, ncols > 0 && ncols <= GX_MAX_COLS, "table: ncols %d out of range", ncols);
+    gx_table *t = (gx_table *) calloc(1, sizeof(gx_table));
+    t->ctx = ctx; t->ncols = ncols; t->capacity = capacity < 1 ? 1 : capacity;
+    for (int c = 0; c < ncols; c++) {
+        int sz = gx_type_size(types[c]);
+        if (!sz) { free(t); GX_SET_ERR(ctx, "table: column %d has unknown type %d", c, types[c]); return GX_ERR_ARG; }
+        t->types[c] = types[c];
+        cudaError_t e = cudaMalloc(&t->cols[c], (size_t) t->capacity * sz + 32);
+        if (e == cudaSuccess && has_nulls && has_nulls[c]) {
+            e = cudaMalloc((void **) &t->nulls[c], (size_t) t->capacity + 32);
+            if (e == cudaSuccess) e = cudaMemsetAsync(t->nulls[c], 0, (size_t) t->capacity, ctx->stream);
+        }
+        if (e != cudaSuccess) {
+            GX_SET_ERR(ctx, "table: cudaMalloc of %lld rows failed: %s", (long long) t->capacity, cudaGetErrorString(e));
+            gx_table_free(t);
+            return GX_ERR_NOMEM;
+        }
+    }
+    *out = t;
+    return GX_OK;
+}
+
+extern "C" int gx_table_create(gx_ctx *ctx, int ncols, const int32_t *types, int64_t capacity_rows, gx_table **out)
+{
+    if (!ctx || !types || !out) return GX_ERR_ARG;
+    return gx_table_alloc_like(ctx, ncols, types, nullptr, capacity_rows, out);
+}
+
+extern "C" void gx_table_free(gx_table *t)
+{
+    if (!t) return;
+    for (int c = 0; c < t->ncols; c++) { if (t->cols[c]) cudaFree(t->cols[c]); if (t->nulls[c]) cudaFree(t->nulls[c]); }
+    free(t);
+}
+extern "C" int64_t gx_table_nrows(const gx_table *t) { return t ? t->nrows : -1; }
+extern "C" int gx_table_ncols(const gx_table *t) { return t ? t->ncols : -1; }
+extern "C" int gx_table_truncate(gx_table *t) { if (!t) return GX_ERR_ARG; t->nrows = 0; return GX_OK; }
+extern "C" int gx_table_column_devptr(gx_table *t, int col, void **dptr)
+{
+    if (!t || col < 0 || col >= t->ncols || !dptr) return GX_ERR_ARG;
+    *dptr = t->cols[col];
+    return GX_OK;
+}
+
+static int ensure_null_array(gx_table *t, int c)
+{
+    if (t->nulls[c]) return GX_OK;
+    GX_CUDA(t->ctx, cudaMalloc((void **) &t->nulls[c], (size_t) t->capacity + 32));
+    GX_CUDA(t->ctx, cudaMemsetAsync(t->nulls[c], 0, (size_t) t->capacity, t->ctx->stream));
+    return GX_OK;
+}
+
+extern "C" int gx_table_append_columns(gx_table *t, const void *const *host_cols,
+                                       const uint8_t *const *host_nulls, int64_t nrows)
+{
+    if (!t || !host_cols || nrows < 0) return GX_ERR_ARG;
+    gx_ctx *ctx = t->ctx;
+    GX_CHECK_ARG(ctx, t->nrows + nrows <= t->capacity, "append_columns: %lld + %lld rows exceed capacity %lld",
+                 (long long) t->nrows, (long long) nrows, (long long) t->capacity);
+    if (nrows == 0) return GX_OK;
+    for (int c = 0; c < t->ncols; c++) {
+        int sz = gx_type_size(t->types[c]);
+        GX_CHECK_ARG(ctx, host_cols[c] != nullptr, "append_columns: column %d is NULL", c);
+        GX_CUDA(ctx, cudaMemcpyAsync((char *) t->cols[c] + (size_t) t->nrows * sz, host_cols[c], (size_t) nrows * sz,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        if (host_nulls && host_nulls[c]) {
+            int rc = ensure_null_array(t, c); if (rc) return rc;
+            GX_CUDA(ctx, cudaMemcpyAsync(t->nulls[c] + t->nrows, host_nulls[c], (size_t) nrows,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    t->nrows += nrows;
+    return GX_OK;
+}
+
+extern "C" int gx_table_read_column(gx_table *t, int col, int64_t row0, int64_t nrows, void *host_out, uint8_t *host_nulls_out)
+{
+    if (!t || col < 0 || col >= t->ncols || row0 < 0 || nrows < 0 || row0 + nrows > t->nrows) return GX_ERR_ARG;
+    gx_ctx *ctx = t->ctx;
+    int sz = gx_type_size(t->types[col]);
+    if (host_out && nrows)
+        GX_CUDA(ctx, cudaMemcpyAsync(host_out, (char *) t->cols[col] + (size_t) row0 * sz, (size_t) nrows * sz, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_nulls_out && nrows) {
+        if (t->nulls[col]) GX_CUDA(ctx, cudaMemcpyAsync(host_nulls_out, t->nulls[col] + row0, (size_t) nrows, cudaMemcpyDeviceToHost, ctx->stream));
+        else memset(host_nulls_out, 0, (size_t) nrows);
+    }
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GX_OK;
+}
+
+// ------------------------------------------------------------ block scan
+// exclusive scan of n int64 values in place; total written to *total
+__global__ void gx_k_scan_inplace(long long *v, long long n, long long *total)
+{
+    __shared__ long long sm[33];
+    long long carry = 0;
+    for (long long base = 0; base < n; base += blockDim.x) {
+        long long i = base + threadIdx.x;
+        long long x = i < n ? v[i] : 0, tot;
+        long long ex = gx_block_exscan(x, &tot, sm);
+        if (i < n) v[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// ------------------------------------------------------------- generator
+struct gx_gen_args {
+    int table_id, sf, node, nnodes;
+    long long o0, o1, base_row;
+    const int32_t *shardmap;
+    void *cols[GXG_L_NCOLS];
+};
+
+__device__ __forceinline__ int gen_rows_of(const gx_gen_args &a, long long i)
+{
+    if (a.table_id == GXG_T_CUSTOMER) {
+        if (a.nnodes > 1) {
+            int node = a.shardmap[gx_shard_index(gx_route_hash(GX_INT4, gxg_c_custkey(i), false))];
+            if (node != a.node) return 0;
+        }
+        return 1;
+    }
+    if (a.nnodes > 1) {
+        int node = a.shardmap[gx_shard_index(gx_route_hash(GX_INT8, gxg_o_orderkey(i), false))];
+        if (node != a.node) return 0;
+    }
+    return a.table_id == GXG_T_LINEITEM ? gxg_l_nlines(i) : 1;
+}
+
+__global__ void gx_k_gen_count(gx_gen_args a, long long *blocksums)
+{
+    __shared__ long long sm[33];
+    long long i = a.o0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (i < a.o1) ? gen_rows_of(a, i) : 0, tot;
+    gx_block_exscan(n, &tot, sm);
+    if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
+}
+
+__global__ void gx_k_gen_write(gx_gen_args a, const long long *blockoffs)
+{
+    __shared__ long long sm[33];
+    long long i = a.o0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (i < a.o1) ? gen_rows_of(a, i) : 0;
+    long long tot;
+    long long row = a.base_row + blockoffs[blockIdx.x] + gx_block_exscan(n, &tot, sm);
+    if (n == 0) return;
+    if (a.table_id == GXG_T_ORDERS) {
+        if (a.cols[GXG_O_ORDERKEY])     ((long long *) a.cols[GXG_O_ORDERKEY])[row] = gxg_o_orderkey(i);
+        if (a.cols[GXG_O_CUSTKEY])      ((int *) a.cols[GXG_O_CUSTKEY])[row] = gxg_o_custkey(i, a.sf);
+        if (a.cols[GXG_O_ORDERDATE])    ((int *) a.cols[GXG_O_ORDERDATE])[row] = gxg_o_orderdate(i);
+        if (a.cols[GXG_O_SHIPPRIORITY]) ((int *) a.cols[GXG_O_SHIPPRIORITY])[row] = gxg_o_shippriority(i);
+    } else if (a.table_id == GXG_T_CUSTOMER) {
+        if (a.cols[GXG_C_CUSTKEY])    ((int *) a.cols[GXG_C_CUSTKEY])[row] = gxg_c_custkey(i);
+        if (a.cols[GXG_C_MKTSEGMENT]) ((signed char *) a.cols[GXG_C_MKTSEGMENT])[row] = gxg_c_mktsegment(i);
+    } else {
+        long long key = gxg_o_orderkey(i);
+        for (int j = 0; j < n; j++, row++) {
+            if (a.cols[GXG_L_ORDERKEY])      ((long long *) a.cols[GXG_L_ORDERKEY])[row] = key;
+            if (a.cols[GXG_L_QUANTITY])      ((double *) a.cols[GXG_L_QUANTITY])[row] = gxg_l_quantity(i, j);
+            if (a.cols[GXG_L_EXTENDEDPRICE]) ((double *) a.cols[GXG_L_EXTENDEDPRICE])[row] = gxg_l_extendedprice(i, j, a.sf);
+            if (a.cols[GXG_L_DISCOUNT])      ((double *) a.cols[GXG_L_DISCOUNT])[row] = gxg_l_discount(i, j);
+            if (a.cols[GXG_L_TAX])           ((double *) a.cols[GXG_L_TAX])[row] = gxg_l_tax(i, j);
+            if (a.cols[GXG_L_SHIPDATE])      ((int *) a.cols[GXG_L_SHIPDATE])[row] = gxg_l_shipdate(i, j);
+            if (a.cols[GXG_L_RETURNFLAG])    ((signed char *) a.cols[GXG_L_RETURNFLAG])[row] = gxg_l_returnflag(i, j);
+            if (a.cols[GXG_L_LINESTATUS])    ((signed char *) a.cols[GXG_L_LINESTATUS])[row] = gxg_l_linestatus(i, j);
+        }
+    }
+}
+
+static const int32_t k_schema_orders[GXG_O_NCOLS] = { GX_INT8, GX_INT4, GX_DATE, GX_INT4 };
+static const int32_t k_schema_lineitem[GXG_L_NCOLS] = { GX_INT8, GX_FLOAT8, GX_FLOAT8, GX_FLOAT8, GX_FLOAT8, GX_DATE, GX_CHAR, GX_CHAR };
+static const int32_t k_schema_customer[GXG_C_NCOLS] = { GX_INT4, GX_CHAR };
+
+// The table's columns must be a prefix-compatible subset of the fixed schema:
+// the table is created with the full schema's column count; columns whose
+// type is passed as the schema type are materialised.  To skip a column the
+// caller creates the table with capacity and then frees nothing — skipping is
+// expressed through gx_table_generate_cols() below.
+static int generate_impl(gx_table *t, int table_id, int sf, int64_t o0, int64_t o1, int node, int nnodes, const int32_t *colmap)
+{
+    gx_ctx *ctx = t->ctx;
+    const int32_t *schema; int nschema;
+    switch (table_id) {
+        case GXG_T_ORDERS: schema = k_schema_orders; nschema = GXG_O_NCOLS; break;
+        case GXG_T_LINEITEM: schema = k_schema_lineitem; nschema = GXG_L_NCOLS; break;
+        case GXG_T_CUSTOMER: schema = k_schema_customer; nschema = GXG_C_NCOLS; break;
+        default: GX_SET_ERR(ctx, "generate: unknown table id %d", table_id); return GX_ERR_ARG;
+    }
+    GX_CHECK_ARG(ctx, sf >= 1 && o0 >= 0 && o1 >= o0, "generate: bad range");
+    GX_CHECK_ARG(ctx, nnodes >= 1 && node >= 0 && node < nnodes, "generate: bad node %d/%d", node, nnodes);
+    GX_CHECK_ARG(ctx, nnodes == 1 || nnodes == ctx->nnodes, "generate: nnodes %d != installed shard map (%d); call gx_set_shardmap first", nnodes, ctx->nnodes);
+    gx_gen_args a; memset(&a, 0, sizeof(a));
+    a.table_id = table_id; a.sf = sf; a.node = node; a.nnodes = nnodes; a.o0 = o0; a.o1 = o1; a.base_row = t->nrows;
+    a.shardmap = ctx->d_shardmap;
+    for (int c = 0; c < t->ncols; c++) {
+        int sc = colmap ? colmap[c] : c;
+        GX_CHECK_ARG(ctx, sc >= 0 && sc < nschema && schema[sc] == t->types[c], "generate: table column %d does not match schema column %d", c, sc);
+        a.cols[sc] = t->cols[c];
+    }
+    long long n = o1 - o0;
+    if (n == 0) return GX_OK;
+    const int BS = 256;
+    long long nblocks = (n + BS - 1) / BS;
+    long long *d_sums;
+    GX_CUDA(ctx, cudaMalloc(&d_sums, (size_t) nblocks * sizeof(long long)));
+    {
+        gx_launch_scope ls(ctx, "generate", 3);
+        gx_k_gen_count<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
+        gx_k_scan_inplace<<<1, 1024, 0, ctx->stream>>>(d_sums, nblocks, ctx->d_scratch);
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_sums); GX_SET_ERR(ctx, "generate: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    long long total = ctx->h_scratch[0];
+    if (t->nrows + total > t->capacity) {
+        cudaFree(d_sums);
+        GX_SET_ERR(ctx, "generate: %lld + %lld rows exceed capacity %lld", (long long) t->nrows, total, (long long) t->capacity);
+        return GX_ERR_ARG;
+    }
+    gx_k_gen_write<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sums);
+    if (e != cudaSuccess) { GX_SET_ERR(ctx, "generate: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    t->nrows += total;
+    return GX_OK;
+}
+
+extern "C" int gx_table_generate(gx_table *t, int table_id, int sf, int64_t order0, int64_t order1, int node, int nnodes)
+{
+    if (!t) return GX_ERR_ARG;
+    return generate_impl(t, table_id, sf, order0, order1, node, nnodes, nullptr);
+}
+// colmap[c] = schema column number feeding table column c (bench: only the referenced columns)
+extern "C" int gx_table_generate_cols(gx_table *t, int table_id, int sf, int64_t order0, int64_t order1,
+                                      int node, int nnodes, const int32_t *colmap)
+{
+    if (!t || !colmap) return GX_ERR_ARG;
+    return generate_impl(t, table_id, sf, order0, order1, node, nnodes, colmap);
+}
+
+// ------------------------------------------------------------- K1 filter
+struct gx_filter_args {
+    int npreds, ncols;
+    gx_dpred preds[GX_MAX_PREDS];
+    gx_dcol in[GX_MAX_COLS];
+    void *out[GX_MAX_COLS];
+    uint8_t *out_nulls[GX_MAX_COLS];
+    long long nrows;
+};
+
+#define FILTER_ROWS_PER_THREAD 4
+__device__ __forceinline__ bool filter_pass(const gx_filter_args &a, long long r)
+{
+    bool ok = true;
+#pragma unroll
+    for (int p = 0; p < GX_MAX_PREDS; p++) if (p < a.npreds) ok = ok && gx_eval_pred(a.preds[p], r);
+    return ok;
+}
+__global__ void gx_k_filter_count(gx_filter_args a, long long *blocksums)
+{
+    __shared__ long long sm[33];
+    long long base = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * FILTER_ROWS_PER_THREAD;
+    long long n = 0, tot;
+#pragma unroll
+    for (int k = 0; k < FILTER_ROWS_PER_THREAD; k++) { long long r = base + k; if (r < a.nrows && filter_pass(a, r)) n++; }
+    gx_block_exscan(n, &tot, sm);
+    if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
+}
+__global__ void gx_k_filter_write(gx_filter_args a, const long long *blockoffs)
+{
+    __shared__ long long sm[33];
+    long long base = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * FILTER_ROWS_PER_THREAD;
+    bool keep[FILTER_ROWS_PER_THREAD]; long long n = 0, tot;
+#pragma unroll
+    for (int k = 0; k < FILTER_ROWS_PER_THREAD; k++) { long long r = base + k; keep[k] = r < a.nrows && filter_pass(a, r); n += keep[k]; }
+    long long dst = blockoffs[blockIdx.x] + gx_block_exscan(n, &tot, sm);
+#pragma unroll
+    for (int k = 0; k < FILTER_ROWS_PER_THREAD; k++) {
+        if (!keep[k]) continue;
+        long long r = base + k;
+        for (int c = 0; c < a.ncols; c++) {
+            switch (a.in[c].type) {
+                case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = ((const int *) a.in[c].data)[r]; break;
+                case GX_CHAR: ((signed char *) a.out[c])[dst] = ((const signed char *) a.in[c].data)[r]; break;
+                default: ((long long *) a.out[c])[dst] = ((const long long *) a.in[c].data)[r]; break;
+            }
+            if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
+        }
+        dst++;
+    }
+}
+
+static gx_dcol make_dcol(const gx_table *t, int c)
+{
+    gx_dcol d; d.data = t->cols[c]; d.nulls = t->nulls[c]; d.type = t->types[c]; d._pad = 0; return d;
+}
+int gx_fill_dpreds(gx_ctx *ctx, const gx_table *t, int n_preds, const gx_pred *preds, gx_dpred *out)
+{
+    GX_CHECK_ARG(ctx, n_preds >= 0 && n_preds <= GX_MAX_PREDS, "too many predicates (%d)", n_preds);
+    for (int i = 0; i < n_preds; i++) {
+        GX_CHECK_ARG(ctx, preds[i].col >= 0 && preds[i].col < t->ncols, "predicate %d: column %d out of range", i, preds[i].col);
+        GX_CHECK_ARG(ctx, preds[i].op >= GX_LT && preds[i].op <= GX_NE, "predicate %d: bad operator %d", i, preds[i].op);
+        out[i].col = make_dcol(t, preds[i].col);
+        out[i].op = preds[i].op; out[i]._pad = 0; out[i].ival = preds[i].ival; out[i].fval = preds[i].fval;
+    }
+    return GX_OK;
+}
+
+extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, const gx_pred *preds,
+                              int n_out_cols, const int32_t *out_cols, gx_table **out)
+{
+    if (!ctx || !in || !out || !out_cols) return GX_ERR_ARG;
+    GX_CHECK_ARG(ctx, n_out_cols > 0 && n_out_cols <= GX_MAX_COLS, "scan_filter: bad output column count");
+    gx_filter_args a; memset(&a, 0, sizeof(a));
+    a.npreds = n_preds; a.ncols = n_out_cols; a.nrows = in->nrows;
+    int rc = gx_fill_dpreds(ctx, in, n_preds, preds, a.preds); if (rc) return rc;
+    int32_t types[GX_MAX_COLS]; bool hn[GX_MAX_COLS];
+    for (int c = 0; c < n_out_cols; c++) {
+        GX_CHECK_ARG(ctx, out_cols[c] >= 0 && out_cols[c] < in->ncols, "scan_filter: column %d out of range", out_cols[c]);
+        a.in[c] = make_dcol(in, out_cols[c]); types[c] = in->types[out_cols[c]]; hn[c] = in->nulls[out_cols[c]] != nullptr;
+    }
+    const int BS = 256;
+    long long rows_per_block = (long long) BS * FILTER_ROWS_PER_THREAD;
+    long long nblocks = (in->nrows + rows_per_block - 1) / rows_per_block;
+    long long total = 0;
+    long long *d_sums = nullptr;
+    if (nblocks > 0) {
+        GX_CUDA(ctx, cudaMalloc(&d_sums, (size_t) nblocks * sizeof(long long)));
+        {
+            gx_launch_scope ls(ctx, "filter", 2);
+            gx_k_filter_count<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
+            gx_k_scan_inplace<<<1, 1024, 0, ctx->stream>>>(d_sums, nblocks, ctx->d_scratch);
+        }
+        cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d_sums); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+        total = ctx->h_scratch[0];
+    }
+    gx_table *t;
+    rc = gx_table_alloc_like(ctx, n_out_cols, types, hn, total, &t);
+    if (rc) { if (d_sums) cudaFree(d_sums); return rc; }
+    if (nblocks > 0) {
+        for (int c = 0; c < n_out_cols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
+        {
+            gx_launch_scope ls(ctx, "filter", 1);
+            gx_k_filter_write<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_sums);
+        if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    }
+    t->nrows = total;
+    *out = t;
+    return GX_OK;
+}
+
+// ------------------------------------------------- K0 heap-page deform
+// Page / tuple layout constants of the reference build
+// (storage/bufpage.h:153-175, access/htup_details.h:126-201, storage/itemid.h:24-29):
+#define PG_BLCKSZ       8192
+#define PG_PAGE_HDR     36      // offsetof(PageHeaderData, pd_linp)
+#define PG_PD_LOWER     14
+#define PG_HTH_INFOMASK 40
+#define PG_HTH_HOFF     46
+#define PG_HTH_BITS     47
+#define PG_HEAP_HASNULL 0x0001
+
+struct gx_deform_args {
+    const uint8_t *pages; long long npages;
+    const uint16_t *vis; const int32_t *vis_counts; int vis_stride;
+    int natts, ncols, maxatt;
+    short att_len[64]; signed char att_align[64];
+    signed char col_of_att[64];          // table column fed by attribute a, or -1
+    void *out[GX_MAX_COLS]; uint8_t *out_nulls[GX_MAX_COLS]; int out_type[GX_MAX_COLS];
+    long long base_row;
+};
+
+__device__ __forceinline__ int page_nvisible(const gx_deform_args &a, long long p)
+{
+    if (a.vis_counts) return a.vis_counts[p];
+    const uint8_t *pg = a.pages + p * PG_BLCKSZ;
+    int lines = ((int) *(const uint16_t *) (pg + PG_PD_LOWER) - PG_PAGE_HDR) / 4;
+    int n = 0;
+    for (int i = 0; i < lines; i++) { unsigned int lp = *(const unsigned int *) (pg + PG_PAGE_HDR + 4 * i); n += ((lp >> 15) & 3) == 1; }
+    return n;
+}
+__global__ void gx_k_deform_count(gx_deform_args a, long long *counts)
+{
+    long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.npages) counts[p] = page_nvisible(a, p);
+}
+
+// One warp per page; lane l takes visible tuples l, l+32, ...  Each lane walks
+// its tuple's attributes exactly as slot_deform_tuple does
+// (access/common/heaptuple.c:1518-1614), storing only referenced columns.
+__global__ void gx_k_deform(gx_deform_args a, const long long *pageoffs)
+{
+    long long p = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= a.npages) return;
+    const uint8_t *pg = a.pages + p * PG_BLCKSZ;
+    int lines = ((int) *(const uint16_t *) (pg + PG_PD_LOWER) - PG_PAGE_HDR) / 4;
+    long long row0 = a.base_row + pageoffs[p];
+    int nvis = a.vis_counts ? a.vis_counts[p] : -1;
+    // without a visibility list: k-th LP_NORMAL item; find by scanning (lane-cooperative ballot)
+    int seen = 0;
+    for (int base = 0; (nvis >= 0) ? (base < nvis) : (base < lines); base += 32) {
+        int idx = base + lane;
+        int lineoff = -1, myrow = -1;
+        if (nvis >= 0) {
+            if (idx < nvis) { lineoff = a.vis[p * a.vis_stride + idx]; myrow = idx; }
+        } else {
+            bool normal = false;
+            if (idx < lines) { unsigned int lp = *(const unsigned int *) (pg + PG_PAGE_HDR + 4 * idx); normal = ((lp >> 15) & 3) == 1; }
+            unsigned int m = __ballot_sync(0xffffffffu, normal);
+            if (normal) { lineoff = idx + 1; myrow = seen + __popc(m & ((1u << lane) - 1)); }
+            seen += __popc(m);
+        }
+        if (lineoff < 0) continue;
+        unsigned int lp = *(const unsigned int *) (pg + PG_PAGE_HDR + 4 * (lineoff - 1));
+        const uint8_t *tup = pg + (lp & 0x7FFF);
+        bool hasnulls = (*(const uint16_t *) (tup + PG_HTH_INFOMASK) & PG_HEAP_HASNULL) != 0;
+        const uint8_t *bp = tup + PG_HTH_BITS;
+        const uint8_t *tp = tup + tup[PG_HTH_HOFF];
+        unsigned int off = 0;
+        long long row = row0 + myrow;
+        for (int att = 0; att < a.maxatt; att++) {
+            int c = a.col_of_att[att];
+            if (hasnulls && !(bp[att >> 3] & (1 << (att & 7)))) {
+                if (c >= 0) {
+                    if (a.out_nulls[c]) a.out_nulls[c][row] = 1;
+                    switch (a.out_type[c]) { case GX_INT4: case GX_DATE: ((int *) a.out[c])[row] = 0; break;
+                                             case GX_CHAR: ((signed char *) a.out[c])[row] = 0; break;
+                                             default: ((long long *) a.out[c])[row] = 0; }
+                }
+                continue;
+            }
+            int len = a.att_len[att], al = a.att_align[att];
+            long long v = 0;
+            if (len > 0) {
+                off = (off + al - 1) & ~(unsigned) (al - 1);                 // att_align_nominal
+                if (c >= 0) {
+                    switch (len) {
+                        case 1: v = (long long) (signed char) tp[off]; break;
+                        case 2: v = (long long) *(const short *) (tp + off); break;
+                        case 4: v = (long long) *(const int *) (tp + off); break;
+                        default: v = *(const long long *) (tp + off); break;
+                    }
+                }
+                off += len;
+            } else {
+                if (tp[off] == 0) off = (off + al - 1) & ~(unsigned) (al - 1);   // att_align_pointer
+                uint8_t h = tp[off];
+                unsigned int vsz, hdr;
+                if (h & 1) { vsz = (h >> 1) & 0x7F; hdr = 1; }
+                else { vsz = (((unsigned) tp[off]) | ((unsigned) tp[off + 1] << 8) | ((unsigned) tp[off + 2] << 16) | ((unsigned) tp[off + 3] << 24)) >> 2; vsz &= 0x3FFFFFFF; hdr = 4; }
+                if (c >= 0) v = vsz > hdr ? (long long) (signed char) tp[off + hdr] : 0;  // bpchar(1) -> its byte
+                off += vsz;
+            }
+            if (c >= 0) {
+                if (a.out_nulls[c]) a.out_nulls[c][row] = 0;
+                switch (a.out_type[c]) { case GX_INT4: case GX_DATE: ((int *) a.out[c])[row] = (int) v; break;
+                                         case GX_CHAR: ((signed char *) a.out[c])[row] = (signed char) v; break;
+                                         default: ((long long *) a.out[c])[row] = v; }
+            }
+        }
+    }
+}
+
+extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_t npages, const gx_heap_desc *desc,
+                                          const uint16_t *vis_offsets, const int32_t *vis_counts, int32_t vis_stride)
+{
+    if (!t || !pages || !desc || npages < 0) return GX_ERR_ARG;
+    gx_ctx *ctx = t->ctx;
+    GX_CHECK_ARG(ctx, desc->natts > 0 && desc->natts <= 64, "heap desc: natts %d out of range", desc->natts);
+    GX_CHECK_ARG(ctx, desc->ncols == t->ncols, "heap desc: ncols %d != table ncols %d", desc->ncols, t->ncols);
+    GX_CHECK_ARG(ctx, (vis_offsets == nullptr) == (vis_counts == nullptr), "heap pages: vis_offsets and vis_counts go together");
+    if (npages == 0) return GX_OK;
+    gx_deform_args a; memset(&a, 0, sizeof(a));
+    a.npages = npages; a.natts = desc->natts; a.ncols = desc->ncols; a.vis_stride = vis_stride; a.base_row = t->nrows;
+    for (int i = 0; i < desc->natts; i++) {
+        a.att_len[i] = desc->att_len[i]; a.att_align[i] = desc->att_align[i]; a.col_of_att[i] = -1;
+        GX_CHECK_ARG(ctx, a.att_len[i] == -1 || a.att_len[i] == 1 || a.att_len[i] == 2 || a.att_len[i] == 4 || a.att_len[i] == 8, "heap desc: attribute %d has unsupported attlen %d", i, a.att_len[i]);
+        GX_CHECK_ARG(ctx, a.att_align[i] == 1 || a.att_align[i] == 2 || a.att_align[i] == 4 || a.att_align[i] == 8, "heap desc: attribute %d has bad attalign", i);
+    }
+    for (int c = 0; c < desc->ncols; c++) {
+        int att = desc->attnums[c];
+        GX_CHECK_ARG(ctx, att >= 0 && att < desc->natts, "heap desc: attnum %d out of range", att);
+        a.col_of_att[att] = (signed char) c;
+        if (att + 1 > a.maxatt) a.maxatt = att + 1;
+        int rc = ensure_null_array(t, c); if (rc) return rc;
+        a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; a.out_type[c] = t->types[c];
+    }
+    // stage the raw pages (and visibility lists) in HBM
+    uint8_t *d_pages = nullptr; uint16_t *d_vis = nullptr; int32_t *d_cnt = nullptr; long long *d_offs = nullptr;
+    cudaError_t e = cudaMalloc((void **) &d_pages, (size_t) npages * PG_BLCKSZ);
+    if (e == cudaSuccess) e = cudaMalloc((void **) &d_offs, (size_t) npages * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pages, pages, (size_t) npages * PG_BLCKSZ, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && vis_offsets) {
+        e = cudaMalloc((void **) &d_vis, (size_t) npages * vis_stride * sizeof(uint16_t));
+        if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, (size_t) npages * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_vis, vis_offsets, (size_t) npages * vis_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, vis_counts, (size_t) npages * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    int rc = GX_OK;
+    if (e == cudaSuccess) {
+        a.pages = d_pages; a.vis = d_vis; a.vis_counts = d_cnt;
+        {
+            gx_launch_scope ls(ctx, "deform", 2);
+            gx_k_deform_count<<<(unsigned) ((npages + 255) / 256), 256, 0, ctx->stream>>>(a, d_offs);
+            gx_k_scan_inplace<<<1, 1024, 0, ctx->stream>>>(d_offs, npages, ctx->d_scratch);
+        }
+        e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) {
+            long long total = ctx->h_scratch[0];
+            if (t->nrows + total > t->capacity) {
+                GX_SET_ERR(ctx, "append_heap_pages: %lld + %lld rows exceed capacity %lld", (long long) t->nrows, total, (long long) t->capacity);
+                rc = GX_ERR_ARG;
+            } else {
+                {
+                    gx_launch_scope ls(ctx, "deform", 1);
+                    long long nthreads = npages * 32;
+                    gx_k_deform<<<(unsigned) ((nthreads + 255) / 256), 256, 0, ctx->stream>>>(a, d_offs);
+                }
+                e = cudaStreamSynchronize(ctx->stream);
+                if (e == cudaSuccess) t->nrows += total;
+            }
+        }
+    }
+    cudaFree(d_pages); cudaFree(d_offs); if (d_vis) cudaFree(d_vis); if (d_cnt) cudaFree(d_cnt);
+    if (e != cudaSuccess) { GX_SET_ERR(ctx, "append_heap_pages: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GX_ERR_NOMEM : GX_ERR_CUDA; }
+    return rc;
+}
