@@ -85,7 +85,7 @@ enum {
 };
 
 #define GX_MAX_PREDS      4
-#define GX_MAX_EXPR_OPS   8
+#define GX_MAX_EXPR_OPS   12
 #define GX_MAX_AGGS       8
 #define GX_MAX_GROUP_COLS 4
 #define GX_MAX_PAYLOAD    2

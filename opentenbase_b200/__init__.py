@@ -54,7 +54,7 @@ class GxExprOp(C.Structure):
 
 
 class GxExpr(C.Structure):
-    _fields_ = [("nops", C.c_int32), ("_pad", C.c_int32), ("ops", GxExprOp * 8)]
+    _fields_ = [("nops", C.c_int32), ("_pad", C.c_int32), ("ops", GxExprOp * 12)]
 
 
 class GxAgg(C.Structure):
@@ -89,8 +89,7 @@ class GxHostTable(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile libgpuexec.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    if force or not os.path.exists(LIB_PATH):
-        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s"] + (["-B"] if force else []))
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s"] + (["-B"] if force else []))
     return LIB_PATH
 
 

@@ -37,6 +37,10 @@ struct gx_agg_dev {
     long long row0, row1;
     // shared-memory table
     int s_slots;             // power of two; 0 = none
+    int s_log2;              // log2(s_slots)
+    int s_tagkey;            // 1: the tag word holds the whole (<= 7 byte) key, no k0/k1 arrays
+    int s_gmax;              // lane-private mode: max dense groups per CTA (0 = dense CAS mode)
+    int need_w0;             // maintain w0 (rows per group)?
     int _pad1;
     // global table: g_cap records of (3 + nwords) words
     unsigned long long *g_tab; unsigned long long g_mask;
@@ -80,31 +84,56 @@ __device__ __forceinline__ void merge_word(unsigned long long *addr, int kind, u
 }
 
 // --------------------------------------------------------------- sinks
+// CTA-shared directory (+ dense state words).  Measured on B200
+// (profiles/r01_ubench_agg_update_mechanisms.txt): a CTA-shared table with
+// CAS-loop fp64 adds sustains ~230 G rows/s; for a handful of groups
+// lane-private accumulators ([word][group][lane], bank == lane, no atomics)
+// reach ~440 G rows/s.  Both are used here.
 struct SmemTable {
-    unsigned long long *tag, *k0, *k1, *w;   // w: [slot * nwords + i]
-    int S, nwords, nkw;
+    unsigned long long *tag, *k0, *k1, *w;   // dense: w[slot * nwords + i]; lane-private: see lp_base()
+    unsigned int *gidx;                      // lane-private: slot -> dense group number
+    unsigned int *gcount;                    // lane-private: groups handed out so far
+    int S, log2S, nwords, nkw, tagkey, gmax;
 };
 
-// returns slot or -1 when the table is full
-__device__ __forceinline__ int smem_upsert(const SmemTable &T, const gx_agg_dev &A, unsigned long long k0, unsigned long long k1,
-                                           unsigned int nullmask)
+__device__ __forceinline__ unsigned long long smem_hash(unsigned long long k0, unsigned long long k1, unsigned int nullmask)
 {
-    unsigned long long h = group_hash(k0, k1, nullmask), tag = make_tag(h, nullmask);
-    int s = (int) (h & (unsigned) (T.S - 1));
-    for (int n = 0; n < T.S; n++) {
+    return (k0 ^ (k0 >> 29) ^ (k1 * 0xC2B2AE3D27D4EB4FULL) ^ ((unsigned long long) nullmask << 50)) * 0x9E3779B97F4A7C15ULL;
+}
+
+// returns the slot, or -1 when the table (or the lane-private group budget) is full
+template <bool LP>
+__device__ __forceinline__ int smem_upsert(const SmemTable &T, unsigned long long k0, unsigned long long k1, unsigned int nullmask)
+{
+    unsigned long long h = smem_hash(k0, k1, nullmask);
+    unsigned long long tag = T.tagkey ? ((1ULL << 63) | ((unsigned long long) (nullmask & 0xF) << 59) | (k0 & 0x00FFFFFFFFFFFFFFULL))
+                                      : make_tag(h, nullmask);
+    int s = (int) (h >> (64 - T.log2S));
+    const int maxprobe = T.S < 64 ? T.S : 64;
+    const bool direct = T.tagkey && !LP;          // the tag IS the key: claim with one CAS, no lock phase
+    for (int n = 0; n < maxprobe; n++) {
         unsigned long long t = *(volatile unsigned long long *) &T.tag[s];
-        if (t == 0) {
-            unsigned long long old = atomicCAS(&T.tag[s], 0ULL, TAG_LOCK);
+        if (t == tag) { if (T.tagkey || (T.k0[s] == k0 && (T.nkw == 1 || T.k1[s] == k1))) return s; }
+        else if (t == 0) {
+            unsigned long long old = atomicCAS(&T.tag[s], 0ULL, direct ? tag : TAG_LOCK);
             if (old == 0) {
-                T.k0[s] = k0; if (T.nkw > 1) T.k1[s] = k1;
+                if (direct) return s;
+                if (!T.tagkey) { T.k0[s] = k0; if (T.nkw > 1) T.k1[s] = k1; }
+                if (LP) {
+                    unsigned int gi = atomicAdd(T.gcount, 1u);
+                    T.gidx[s] = gi;                 // gi >= gmax is caught by the caller
+                }
                 __threadfence_block();
                 *(volatile unsigned long long *) &T.tag[s] = tag;
                 return s;
             }
             t = old;
+            while (t == TAG_LOCK) t = *(volatile unsigned long long *) &T.tag[s];
+            if (t == tag && (T.tagkey || (T.k0[s] == k0 && (T.nkw == 1 || T.k1[s] == k1)))) return s;
+        } else if (t == TAG_LOCK) {
+            while (t == TAG_LOCK) t = *(volatile unsigned long long *) &T.tag[s];
+            if (t == tag && (T.tagkey || (T.k0[s] == k0 && (T.nkw == 1 || T.k1[s] == k1)))) return s;
         }
-        while (t == TAG_LOCK) t = *(volatile unsigned long long *) &T.tag[s];
-        if (t == tag && T.k0[s] == k0 && (T.nkw == 1 || T.k1[s] == k1)) return s;
         s = (s + 1) & (T.S - 1);
     }
     return -1;
@@ -140,26 +169,40 @@ __device__ __forceinline__ unsigned long long *global_upsert(const gx_agg_dev &A
     return nullptr;
 }
 
-enum { SINK_SMEM = 1, SINK_RECORD = 2, SINK_GLOBAL = 3 };
+enum { SINK_SMEM = 1, SINK_RECORD = 2, SINK_GLOBAL = 3, SINK_SMEM_LP = 4 };
 
 template <int SINK>
 struct Sink {
     unsigned long long *w;          // base of the target's state words
-    bool rec;
+    int wstride;                    // distance between consecutive words (lane-private: gmax * 32)
+    __device__ __forceinline__ unsigned long long *at(int word) { return w + (size_t) word * wstride; }
+    // +1 on a counter word
+    __device__ __forceinline__ void inc(int word)
+    {
+        if (SINK == SINK_RECORD) *at(word) = 1ULL;
+        else if (SINK == SINK_SMEM_LP) *at(word) += 1ULL;
+        else if (SINK == SINK_SMEM) atomicAdd((unsigned int *) at(word), 1u);   // native ATOMS.ADD.32; < 2^32 rows per CTA
+        else atomicAdd(at(word), 1ULL);
+    }
     __device__ __forceinline__ void add_i64(int word, long long v)
     {
-        if (SINK == SINK_RECORD) w[word] = (unsigned long long) v;
-        else atomicAdd(&w[word], (unsigned long long) v);
+        if (SINK == SINK_RECORD) *at(word) = (unsigned long long) v;
+        else if (SINK == SINK_SMEM_LP) *at(word) += (unsigned long long) v;
+        else atomicAdd(at(word), (unsigned long long) v);
     }
     __device__ __forceinline__ void add_f64(int word, double v)
     {
-        if (SINK == SINK_RECORD) w[word] = (unsigned long long) __double_as_longlong(v);
-        else atomicAdd((double *) &w[word], v);
+        if (SINK == SINK_RECORD) *at(word) = (unsigned long long) __double_as_longlong(v);
+        else if (SINK == SINK_SMEM_LP) { double *p = (double *) at(word); *p = __dadd_rn(*p, v); }
+        else atomicAdd((double *) at(word), v);
     }
     __device__ __forceinline__ void minmax_f64(int word, double v, bool want_min)
     {
-        if (SINK == SINK_RECORD) w[word] = (unsigned long long) __double_as_longlong(v);
-        else atomic_min_f64(&w[word], v, want_min);
+        if (SINK == SINK_RECORD) *at(word) = (unsigned long long) __double_as_longlong(v);
+        else if (SINK == SINK_SMEM_LP) {
+            double *p = (double *) at(word); int c = gx_f8cmp(v, *p);
+            if (want_min ? (c < 0) : (c > 0)) *p = v;
+        } else atomic_min_f64(at(word), v, want_min);
     }
 };
 
@@ -189,9 +232,9 @@ __device__ __forceinline__ void pack_group_key(const gx_dplan &P, long long r, u
 }
 
 template <int SINK>
-__device__ __forceinline__ void apply_aggs(const gx_dplan &P, long long r, Sink<SINK> &sink)
+__device__ __forceinline__ void apply_aggs(const gx_dplan &P, bool need_w0, long long r, Sink<SINK> &sink)
 {
-    sink.add_i64(0, 1);                                       // w0: rows in the group (count(*))
+    if (need_w0 || SINK == SINK_RECORD) sink.inc(0);          // w0: rows in the group (count(*))
 #pragma unroll
     for (int a = 0; a < GX_MAX_AGGS; a++) {
         if (a >= P.nagg) break;
@@ -199,16 +242,16 @@ __device__ __forceinline__ void apply_aggs(const gx_dplan &P, long long r, Sink<
         if (g.kind == GXU_NONE) continue;
         if (g.is_int) {
             if (gx_is_null(g.icol, r)) continue;
-            if (g.kind == GXU_CNT) { sink.add_i64(g.word, 1); continue; }
+            if (g.kind == GXU_CNT) { sink.inc(g.word); continue; }
             sink.add_i64(g.word, gx_load_int(g.icol, r));     // int4_sum: widen to int8
-            if (g.cnt_word) sink.add_i64(g.cnt_word, 1);
+            if (g.cnt_word) sink.inc(g.cnt_word);
         } else {
             bool isnull = false;
             double v = gx_eval_expr(g.expr, r, isnull);
             if (isnull) continue;                             // strict transition function
             if (g.kind == GXU_ADD_F64) sink.add_f64(g.word, v);
             else sink.minmax_f64(g.word, v, g.kind == GXU_MIN_F64);
-            if (g.cnt_word) sink.add_i64(g.cnt_word, 1);
+            if (g.cnt_word) sink.inc(g.cnt_word);
         }
     }
 }
@@ -218,11 +261,18 @@ __device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable
 {
     unsigned long long k0, k1; unsigned int nullmask;
     pack_group_key(A.P, r, payload, k0, k1, nullmask);
-    Sink<SINK> sink;
+    Sink<SINK> sink; sink.wstride = 1;
     if (SINK == SINK_SMEM) {
-        int s = smem_upsert(T, A, k0, k1, nullmask);
+        int s = smem_upsert<false>(T, k0, k1, nullmask);
         if (s < 0) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
         sink.w = T.w + (size_t) s * T.nwords;
+    } else if (SINK == SINK_SMEM_LP) {
+        int s = smem_upsert<true>(T, k0, k1, nullmask);
+        unsigned int gi = s < 0 ? 0xFFFFFFFFu : T.gidx[s];
+        if (gi >= (unsigned) T.gmax) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+        // [warp][word][group][lane]
+        sink.wstride = T.gmax * 32;
+        sink.w = T.w + ((size_t) (threadIdx.x >> 5) * T.nwords * T.gmax + gi) * 32 + (threadIdx.x & 31);
     } else if (SINK == SINK_GLOBAL) {
         unsigned long long *rec = global_upsert(A, k0, k1, nullmask);
         if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); return; }
@@ -241,19 +291,62 @@ __device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable
         for (int i = 0; i < A.P.nwords; i++) rec[3 + i] = (unsigned long long) A.winit[i];
         sink.w = rec + 3;
     }
-    apply_aggs<SINK>(A.P, r, sink);
+    apply_aggs<SINK>(A.P, A.need_w0 != 0, r, sink);
+}
+
+// lane-private merge helper: combine one word over all warps and lanes of the CTA
+__device__ __forceinline__ unsigned long long lp_reduce_word(const SmemTable &T, int nwarps, int word, unsigned int gi, int kind, int lane)
+{
+    unsigned long long acc = 0; bool first = true;
+    for (int wp = 0; wp < nwarps; wp++) {
+        unsigned long long v = T.w[(((size_t) wp * T.nwords + word) * T.gmax + gi) * 32 + lane];
+        if (first) { acc = v; first = false; continue; }
+        switch (kind) {
+            case WK_ADD_I64: acc += v; break;
+            case WK_ADD_F64: acc = (unsigned long long) __double_as_longlong(__dadd_rn(__longlong_as_double((long long) acc), __longlong_as_double((long long) v))); break;
+            case WK_MIN_F64: if (gx_f8cmp(__longlong_as_double((long long) v), __longlong_as_double((long long) acc)) < 0) acc = v; break;
+            default:         if (gx_f8cmp(__longlong_as_double((long long) v), __longlong_as_double((long long) acc)) > 0) acc = v; break;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long v = __shfl_down_sync(0xffffffffu, acc, o);
+        switch (kind) {
+            case WK_ADD_I64: acc += v; break;
+            case WK_ADD_F64: acc = (unsigned long long) __double_as_longlong(__dadd_rn(__longlong_as_double((long long) acc), __longlong_as_double((long long) v))); break;
+            case WK_MIN_F64: if (gx_f8cmp(__longlong_as_double((long long) v), __longlong_as_double((long long) acc)) < 0) acc = v; break;
+            default:         if (gx_f8cmp(__longlong_as_double((long long) v), __longlong_as_double((long long) acc)) > 0) acc = v; break;
+        }
+    }
+    return acc;                                   // valid in lane 0
 }
 
 template <int SINK>
-__global__ void __launch_bounds__(512, 2) gx_k_agg(const __grid_constant__ gx_agg_dev A)
+__global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_agg_dev A)
 {
     extern __shared__ unsigned long long smem[];
-    SmemTable T; T.S = A.s_slots; T.nwords = A.P.nwords; T.nkw = A.P.nkw;
-    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0 + T.S; T.w = T.k1 + (A.P.nkw > 1 ? T.S : 0);
+    constexpr bool IS_SMEM = SINK == SINK_SMEM || SINK == SINK_SMEM_LP;
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = A.P.nkw; T.tagkey = A.s_tagkey; T.gmax = A.s_gmax;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0 + (T.tagkey ? 0 : T.S);
+    unsigned long long *after_keys = T.k1 + ((!T.tagkey && A.P.nkw > 1) ? T.S : 0);
+    T.gidx = nullptr; T.gcount = nullptr; T.w = after_keys;
+    const int nwarps = blockDim.x >> 5;
     if (SINK == SINK_SMEM) {
         for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
             T.tag[i] = 0;
             for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+        }
+        __syncthreads();
+    } else if (SINK == SINK_SMEM_LP) {
+        T.gidx = (unsigned int *) after_keys;                       // S entries (+ the counter), padded to 8 bytes
+        T.gcount = T.gidx + T.S;
+        T.w = after_keys + (T.S + 2) / 2 + 1;
+        for (int i = threadIdx.x; i < T.S; i += blockDim.x) T.tag[i] = 0;
+        if (threadIdx.x == 0) *T.gcount = 0;
+        const int per_warp = T.nwords * T.gmax * 32;
+        for (int i = threadIdx.x; i < per_warp * nwarps; i += blockDim.x) {
+            int word = (i % per_warp) / (T.gmax * 32);
+            T.w[i] = (unsigned long long) A.winit[word];
         }
         __syncthreads();
     }
@@ -279,16 +372,34 @@ __global__ void __launch_bounds__(512, 2) gx_k_agg(const __grid_constant__ gx_ag
             s = (s + 1) & A.mask;
         }
     }
+    if (!IS_SMEM) return;
+    __syncthreads();
+    // merge the CTA's table into the global one
     if (SINK == SINK_SMEM) {
-        __syncthreads();
-        // merge the CTA's table into the global one
         for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
             unsigned long long t = T.tag[i];
             if (t == 0) continue;
             unsigned int nullmask = (unsigned int) (t >> 59) & 0xF;
-            unsigned long long *rec = global_upsert(A, T.k0[i], T.nkw > 1 ? T.k1[i] : 0ULL, nullmask);
+            unsigned long long k0 = T.tagkey ? (t & 0x00FFFFFFFFFFFFFFULL) : T.k0[i];
+            unsigned long long *rec = global_upsert(A, k0, (!T.tagkey && T.nkw > 1) ? T.k1[i] : 0ULL, nullmask);
             if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
             for (int j = 0; j < T.nwords; j++) merge_word(&rec[3 + j], A.wkind[j], T.w[(size_t) i * T.nwords + j]);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int i = wid; i < T.S; i += nwarps) {              // one warp per directory slot
+            unsigned long long t = T.tag[i];
+            if (t == 0) continue;
+            unsigned int gi = T.gidx[i];
+            if (gi >= (unsigned) T.gmax) continue;             // overflow already flagged
+            unsigned int nullmask = (unsigned int) (t >> 59) & 0xF;
+            unsigned long long k0 = T.tagkey ? (t & 0x00FFFFFFFFFFFFFFULL) : T.k0[i];
+            unsigned long long *rec = nullptr;
+            if (lane == 0) rec = global_upsert(A, k0, (!T.tagkey && T.nkw > 1) ? T.k1[i] : 0ULL, nullmask);
+            for (int j = 0; j < T.nwords; j++) {
+                unsigned long long v = lp_reduce_word(T, nwarps, j, gi, A.wkind[j], lane);
+                if (lane == 0) { if (rec) merge_word(&rec[3 + j], A.wkind[j], v); else atomicOr((unsigned long long *) &A.counters[1], 2ULL); }
+            }
         }
     }
 }
@@ -356,7 +467,8 @@ __global__ void __launch_bounds__(512) gx_k_radix_agg(const gx_agg_dev A, const 
     extern __shared__ unsigned long long smem[];
     __shared__ long long s_base; __shared__ int s_cnt, s_over;
     const int RW = 3 + A.P.nwords;
-    SmemTable T; T.S = A.s_slots; T.nwords = A.P.nwords; T.nkw = 2;
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = 2; T.tagkey = 0; T.gmax = 0;
+    T.gidx = nullptr; T.gcount = nullptr;
     T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0 + T.S; T.w = T.k1 + T.S;
     for (int part = blockIdx.x; part < nparts; part += gridDim.x) {
         long long b = part_begin[(long long) part * nblk];
@@ -369,7 +481,7 @@ __global__ void __launch_bounds__(512) gx_k_radix_agg(const gx_agg_dev A, const 
         __syncthreads();
         for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
             const unsigned long long *rec = recs + i * RW;
-            int s = smem_upsert(T, A, rec[1], rec[2], (unsigned int) rec[0]);
+            int s = smem_upsert<false>(T, rec[1], rec[2], (unsigned int) rec[0]);
             if (s < 0) { s_over = 1; continue; }
             for (int j = 0; j < T.nwords; j++) merge_word(&T.w[(size_t) s * T.nwords + j], A.wkind[j], rec[3 + j]);
         }
@@ -486,6 +598,7 @@ struct compiled_plan {
     int32_t group_types[GX_MAX_GROUP_COLS];
     int gword[GX_MAX_GROUP_COLS], gshift[GX_MAX_GROUP_COLS], gbytes[GX_MAX_GROUP_COLS];
     int agg_word[GX_MAX_AGGS], agg_cnt_word[GX_MAX_AGGS];
+    int need_w0;
 };
 
 static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, const gx_agg_plan *plan, compiled_plan *cp)
@@ -545,7 +658,7 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
         auto new_word = [&](int kind, long long init) { cp->A.wkind[nw] = kind; cp->A.winit[nw] = init; return nw++; };
         if (nw + 2 > GX_MAX_WORDS) { GX_SET_ERR(ctx, "agg plan: too many state words"); return GX_ERR_ARG; }
         switch (src.fn) {
-            case GX_AGG_COUNT_STAR: g.kind = GXU_NONE; cp->agg_word[a] = 0; break;
+            case GX_AGG_COUNT_STAR: g.kind = GXU_NONE; cp->agg_word[a] = 0; cp->need_w0 = 1; break;
             case GX_AGG_COUNT: case GX_AGG_SUM_I4: case GX_AGG_SUM_I8: {
                 GX_CHECK_ARG(ctx, src.arg.nops == 1 && src.arg.ops[0].op == GX_OP_COL, "agg %d: argument must be a plain column", a);
                 int col = src.arg.ops[0].col;
@@ -556,7 +669,7 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
                 g.is_int = 1; g.icol = dcol_of(outer, col); nullable = outer->nulls[col] != nullptr;
                 if (src.fn == GX_AGG_COUNT) {
                     if (nullable) { g.kind = GXU_CNT; g.word = new_word(WK_ADD_I64, 0); cp->agg_word[a] = g.word; }
-                    else { g.kind = GXU_NONE; cp->agg_word[a] = 0; }
+                    else { g.kind = GXU_NONE; cp->agg_word[a] = 0; cp->need_w0 = 1; }
                 } else {
                     g.kind = GXU_ADD_I64; g.word = new_word(WK_ADD_I64, 0); cp->agg_word[a] = g.word;
                     g.cnt_word = nullable ? new_word(WK_ADD_I64, 0) : 0; cp->agg_cnt_word[a] = g.cnt_word;
@@ -575,6 +688,7 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
                 } else { g.kind = GXU_ADD_F64; g.word = new_word(WK_ADD_F64, 0); }
                 cp->agg_word[a] = g.word;
                 g.cnt_word = nullable ? new_word(WK_ADD_I64, 0) : 0; cp->agg_cnt_word[a] = g.cnt_word;
+                if (!nullable && src.fn == GX_AGG_AVG_F8) cp->need_w0 = 1;    // N of float8_avg
                 break;
             }
             default: GX_SET_ERR(ctx, "agg %d: unknown aggregate function %d", a, src.fn); return GX_ERR_ARG;
@@ -597,19 +711,23 @@ int gx_result_alloc(gx_ctx *ctx, const gx_agg_plan *plan, const int32_t *group_t
 
 static size_t smem_bytes_for(int S, int nkw, int nwords) { return (size_t) S * 8 * (1 + nkw + nwords); }
 
+static int ilog2(long long x) { int l = 0; while ((1LL << l) < x) l++; return l; }
+
 template <int SINK>
-static int launch_agg(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name)
+static int launch_agg(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name, int threads = 1024)
 {
-    static bool attr_set[4] = { false, false, false, false };
+    static bool attr_set[8] = { false };
     if (!attr_set[SINK]) {
         GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_agg<SINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
         attr_set[SINK] = true;
     }
     long long nrows = A.row1 - A.row0;
-    long long nb = (nrows + 511) / 512, maxb = (long long) ctx->sm_count * 2;
+    long long nb = (nrows + threads - 1) / threads, maxb = (long long) ctx->sm_count;
+    // the shared-memory counters are 32-bit per CTA
+    while ((nrows + maxb - 1) / maxb >= (1LL << 32)) maxb *= 2;
     unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
     gx_launch_scope ls(ctx, name);
-    gx_k_agg<SINK><<<grid, 512, smem, ctx->stream>>>(A);
+    gx_k_agg<SINK><<<grid, threads, smem, ctx->stream>>>(A);
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
@@ -628,7 +746,7 @@ static int table_to_result(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *pl
 {
     const int RW = 3 + cp->A.P.nwords;
     gx_result *r; gx_result_alloc(ctx, plan, cp->group_types, ngroups, &r);
-    r->nkw = cp->A.P.nkw; r->nwords = cp->A.P.nwords; r->rec_words = RW;
+    r->nkw = cp->A.P.nkw; r->nwords = cp->A.P.nwords; r->rec_words = RW; r->need_w0 = cp->need_w0;
     for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp->agg_word[a]; r->agg_cnt_word[a] = cp->agg_cnt_word[a]; }
     cudaError_t e = cudaMalloc((void **) &r->d_recs, (size_t) r->cap * RW * 8);
     if (e != cudaSuccess) { gx_result_free(r); GX_SET_ERR(ctx, "result: %s", cudaGetErrorString(e)); return GX_ERR_NOMEM; }
@@ -668,24 +786,44 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
     long long est = plan->est_groups > 0 ? plan->est_groups : 1024;
     if (plan->n_group_cols == 0) est = 1;
 
-    // shared-memory capacity for the privatised table (two CTAs per SM)
-    size_t budget = ctx->smem_optin / 2 - 2048;
-    int smax = 1; while (smem_bytes_for(smax * 2, A.P.nkw, nwords) <= budget) smax *= 2;
+    // ---- shared-memory plan (strategy 1) -----------------------------------
+    // key bytes <= 7 and one key word: the tag word carries the key itself
+    int keybytes = 0;
+    for (int c = 0; c < plan->n_group_cols; c++) keybytes += cp.gbytes[c];
+    const int tagkey = (A.P.nkw == 1 && keybytes <= 7) ? 1 : 0;
+    const size_t budget = ctx->smem_optin - 1024;
+    auto dense_bytes = [&](long long S) { return (size_t) S * 8 * (1 + (tagkey ? 0 : A.P.nkw) + nwords); };
+    long long smax = 16; while (dense_bytes(smax * 2) <= budget) smax *= 2;
     int strategy = plan->strategy;
-    if (strategy == 0) strategy = (est * 2 <= smax) ? 1 : 2;
+    if (strategy == 0) strategy = (est * 3 / 2 <= smax) ? 1 : 2;
     GX_CHECK_ARG(ctx, strategy >= 1 && strategy <= 3, "agg plan: unknown strategy %d", strategy);
+    A.need_w0 = cp.need_w0;
 
-    for (int attempt = 0; attempt < 6; attempt++) {
+    for (int attempt = 0; attempt < 8; attempt++) {
         if (strategy == 2) { rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
-        int S = 16; while (S < est * 2 && S < smax) S *= 2;
-        long long g_cap = gx_pow2_ceil((strategy == 1 ? (long long) S : est) * 4 + 1024);
+        long long S = 16; while (S < est * 2 && S < smax) S *= 2;
+        // lane-private mode for a handful of groups: [warp][word][group][lane]
+        int gmax = 0, lp_warps = 0; size_t lp_bytes = 0;
+        if (strategy == 1 && est <= 16) {
+            gmax = 8; while (gmax < est * 2) gmax *= 2;              // 8, 16 or 32 groups per CTA
+            S = 4 * gmax;
+            size_t dir = (size_t) S * 8 * (1 + (tagkey ? 0 : A.P.nkw)) + ((S + 2) / 2 + 1) * 8;
+            size_t per_warp = (size_t) nwords * gmax * 32 * 8;
+            lp_warps = (int) ((budget - dir) / per_warp); if (lp_warps > 32) lp_warps = 32;
+            if (lp_warps < 8) { gmax = 0; S = 16; while (S < est * 2 && S < smax) S *= 2; }   // too many words: use the dense table
+            else lp_bytes = dir + per_warp * lp_warps;
+        }
+        long long g_cap = gx_pow2_ceil((strategy == 1 ? S : est) * 4 + 1024);
         unsigned long long *g_tab;
         GX_CUDA(ctx, cudaMalloc((void **) &g_tab, (size_t) g_cap * RW * 8));
         GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
         GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
-        A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1; A.s_slots = strategy == 1 ? S : 0;
-        if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, smem_bytes_for(S, A.P.nkw, nwords), h ? "probe_agg" : "agg");
-        else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, h ? "probe_agg" : "agg");
+        A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
+        A.s_slots = strategy == 1 ? (int) S : 0; A.s_log2 = ilog2(S); A.s_tagkey = tagkey; A.s_gmax = gmax;
+        const char *kname = h ? "probe_agg" : "agg";
+        if (strategy == 1 && gmax) rc = launch_agg<SINK_SMEM_LP>(ctx, A, lp_bytes, kname, lp_warps * 32);
+        else if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, dense_bytes(S), kname);
+        else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, kname);
         long long c[4];
         if (rc == GX_OK) rc = read_counters(ctx, c);
         if (rc != GX_OK) { cudaFree(g_tab); return rc; }
@@ -697,8 +835,8 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         }
         cudaFree(g_tab);
         // the planner's estimate was too low: grow, then fall over to radix
-        est *= 8;
-        if (strategy == 1 && est * 2 > smax) strategy = (plan->strategy == 1) ? 3 : 2;
+        est = est < 16 ? 17 : est * 8;
+        if (strategy == 1 && est * 3 / 2 > smax) strategy = (plan->strategy == 1) ? 3 : 2;
     }
     GX_SET_ERR(ctx, "hash_agg: group table kept overflowing");
     return GX_ERR_STATE;
@@ -742,14 +880,14 @@ int gx_aggregate_records(gx_ctx *ctx, gx_agg_dev A, unsigned long long *d_recs, 
     GX_CUDA(ctx, cudaMemsetAsync(d_over, 0, (size_t) P * sizeof(int), ctx->stream));
     GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 12, 0, sizeof(long long), ctx->stream));
     static bool attr = false;
-    if (!attr) { GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin)); attr = true; }
+    if (!attr) { GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin - 512)); attr = true; }
     {
         gx_launch_scope ls(ctx, "radix_partition", 3);
         gx_k_radix_hist<<<nblk, 512, P * sizeof(unsigned), ctx->stream>>>(d_recs, nrec, RW, bits, d_hist);
         gx_k_scan_i64<<<1, 1024, 0, ctx->stream>>>(d_hist, (long long) P * nblk, nullptr);
         gx_k_radix_scatter<<<nblk, 512, P * sizeof(unsigned), ctx->stream>>>(d_recs, nrec, RW, bits, d_hist, d_part);
     }
-    A.s_slots = S2; A.rec_cap = nrec;
+    A.s_slots = S2; A.s_log2 = ilog2(S2); A.rec_cap = nrec;
     {
         gx_launch_scope ls(ctx, "radix_agg");
         unsigned grid = (unsigned) (P < ctx->sm_count ? P : ctx->sm_count);
@@ -830,7 +968,7 @@ static int run_radix(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *plan, lo
     cudaFree(d_recs);
     if (rc) return rc;
     gx_result *r; gx_result_alloc(ctx, plan, cp->group_types, ngroups, &r);
-    r->nkw = A.P.nkw; r->nwords = nwords; r->rec_words = RW;
+    r->nkw = A.P.nkw; r->nwords = nwords; r->rec_words = RW; r->need_w0 = cp->need_w0;
     for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp->agg_word[a]; r->agg_cnt_word[a] = cp->agg_cnt_word[a]; }
     r->d_recs = (long long *) d_groups; r->ngroups = ngroups; r->cap = ngroups;
     if (!d_groups) { GX_CUDA(ctx, cudaMalloc((void **) &r->d_recs, 64)); }
@@ -907,7 +1045,9 @@ extern "C" int gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_ou
         }
         for (int a = 0; a < na; a++) {
             int fn = r->plan.aggs[a].fn, word = r->agg_word[a], cw = r->agg_cnt_word[a];
-            long long cnt = (long long) w[cw];                 // cw == 0 -> group row count
+            // cw == 0: the argument cannot be NULL, so a group that exists has input;
+            // w0 (rows per group) is only maintained when count(*)/avg need it
+            long long cnt = cw ? (long long) w[cw] : (r->need_w0 ? (long long) w[0] : 1);
             uint8_t isnull = 0; double res = 0.0; long long ires = 0; bool is_int = false;
             switch (fn) {
                 case GX_AGG_COUNT_STAR: ires = (long long) w[0]; is_int = true; break;

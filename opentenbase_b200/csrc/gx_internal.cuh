@@ -86,6 +86,7 @@ struct gx_result {
     unsigned int *d_nullmask;        // ngroups (group-key null bits)
     int64_t ngroups, cap;
     int finalized_across;            // combined over the communicator already
+    int need_w0;                     // w0 (rows per group) is maintained
 };
 
 #define GX_SET_ERR(ctx, ...) do { if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \

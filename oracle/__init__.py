@@ -24,8 +24,8 @@ NP_DTYPES = {GX_INT4: np.int32, GX_INT8: np.int64, GX_FLOAT8: np.float64,
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with gcc (building the checker is not using it)."""
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    # make is incremental and tracks the shared headers: always let it decide
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
 
@@ -51,7 +51,7 @@ class GxExprOp(C.Structure):
 
 
 class GxExpr(C.Structure):
-    _fields_ = [("nops", C.c_int32), ("_pad", C.c_int32), ("ops", GxExprOp * 8)]
+    _fields_ = [("nops", C.c_int32), ("_pad", C.c_int32), ("ops", GxExprOp * 12)]
 
 
 class GxAgg(C.Structure):
