@@ -65,6 +65,7 @@ extern "C" void gx_shutdown(gx_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     gx_comm_destroy(ctx);
     if (ctx->l2flush_buf) cudaFree(ctx->l2flush_buf);
+    if (ctx->prof_pool) { for (int i = 0; i < GX_PROF_POOL; i++) { cudaEventDestroy(ctx->prof_pool[i].a); cudaEventDestroy(ctx->prof_pool[i].b); } free(ctx->prof_pool); }
     for (int i = 0; i < 2; i++) { if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]); if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]); }
     cudaFree(ctx->d_scratch); cudaFreeHost(ctx->h_scratch); cudaFree(ctx->d_shardmap);
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
@@ -111,16 +112,35 @@ extern "C" int gx_timer_stop(gx_ctx *ctx, double *ms_out)
     return GX_OK;
 }
 
+static int prof_resolve(gx_ctx *ctx)
+{
+    if (ctx->prof_used == 0) return GX_OK;
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->prof_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->prof_pool[i].a, ctx->prof_pool[i].b) == cudaSuccess) {
+            gx_prof_entry &e = (*ctx->prof)[ctx->prof_pool[i].name];
+            e.ms += ms; e.launches += 1;
+        }
+    }
+    ctx->prof_used = 0;
+    return GX_OK;
+}
 extern "C" int gx_profile(gx_ctx *ctx, int enable)
 {
     if (!ctx) return GX_ERR_ARG;
+    if (enable && !ctx->prof_pool) {
+        ctx->prof_pool = (gx_prof_rec *) calloc(GX_PROF_POOL, sizeof(gx_prof_rec));
+        for (int i = 0; i < GX_PROF_POOL; i++) { GX_CUDA(ctx, cudaEventCreate(&ctx->prof_pool[i].a)); GX_CUDA(ctx, cudaEventCreate(&ctx->prof_pool[i].b)); }
+    }
+    if (enable) { cudaGetLastError(); ctx->prof_used = 0; ctx->prof->clear(); }
     ctx->profile = enable;
-    if (enable) ctx->prof->clear();
     return GX_OK;
 }
 extern "C" int gx_profile_get(gx_ctx *ctx, const char *name, double *ms_total, int64_t *launches)
 {
     if (!ctx || !name) return GX_ERR_ARG;
+    int rc = prof_resolve(ctx); if (rc) return rc;
     auto it = ctx->prof->find(name);
     if (ms_total) *ms_total = it == ctx->prof->end() ? 0.0 : it->second.ms;
     if (launches) *launches = it == ctx->prof->end() ? 0 : it->second.launches;

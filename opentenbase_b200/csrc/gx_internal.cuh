@@ -16,6 +16,8 @@
 
 // ---------------------------------------------------------------- host side
 struct gx_prof_entry { double ms; int64_t launches; };
+#define GX_PROF_POOL 2048
+struct gx_prof_rec { cudaEvent_t a, b; const char *name; };
 
 struct gx_nccl_api;   // gx_comm.cu
 
@@ -32,6 +34,7 @@ struct gx_ctx {
     int64_t launches;
     int profile;
     std::map<std::string, gx_prof_entry> *prof;
+    gx_prof_rec *prof_pool; int prof_used;      // events recorded, not yet resolved
     void *l2flush_buf; size_t l2flush_bytes;
     // pinned staging ring for pageable host buffers
     void *stage[2]; size_t stage_bytes; cudaEvent_t stage_ev[2];
@@ -102,19 +105,17 @@ void gx_set_global_err(const char *fmt, ...);
 // launch accounting + optional per-kernel CUDA-event timing
 struct gx_launch_scope {
     gx_ctx *ctx; const char *name;
-    gx_launch_scope(gx_ctx *c, const char *n, int nlaunch = 1) : ctx(c), name(n) {
+    int slot;
+    gx_launch_scope(gx_ctx *c, const char *n, int nlaunch = 1) : ctx(c), name(n), slot(-1) {
         ctx->launches += nlaunch;
-        if (ctx->profile) cudaEventRecord(ctx->ev_p0, ctx->stream);
-    }
-    ~gx_launch_scope() {
-        if (ctx->profile) {
-            cudaEventRecord(ctx->ev_p1, ctx->stream);
-            cudaEventSynchronize(ctx->ev_p1);
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_p0, ctx->ev_p1);
-            gx_prof_entry &e = (*ctx->prof)[name];
-            e.ms += ms; e.launches += 1;
+        // events are only recorded here (asynchronously); gx_profile_get() resolves them
+        if (ctx->profile && ctx->prof_used < GX_PROF_POOL) {
+            slot = ctx->prof_used++;
+            ctx->prof_pool[slot].name = name;
+            cudaEventRecord(ctx->prof_pool[slot].a, ctx->stream);
         }
     }
+    ~gx_launch_scope() { if (slot >= 0) cudaEventRecord(ctx->prof_pool[slot].b, ctx->stream); }
 };
 
 static inline int gx_type_size(int t)

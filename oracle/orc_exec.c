@@ -58,9 +58,9 @@ static void arena_free(arena *a)
 }
 
 /* ---------------------------------------------------------- error status */
-static int g_err;
-static double g_last_secs;
-static int64_t g_hs_nbuckets, g_hs_ntuples, g_hs_space;
+static __thread int g_err;
+static __thread double g_last_secs;
+static __thread int64_t g_hs_nbuckets, g_hs_ntuples, g_hs_space;
 double orc_last_exec_seconds(void) { return g_last_secs; }
 static double now_s(void)
 {
