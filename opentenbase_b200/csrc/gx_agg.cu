@@ -294,6 +294,20 @@ __device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable
     apply_aggs<SINK>(A.P, A.need_w0 != 0, r, sink);
 }
 
+// merge a CTA's dense shared-memory table into the global table
+__device__ __forceinline__ void smem_dense_merge(const SmemTable &T, const gx_agg_dev &A)
+{
+    for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+        unsigned long long t = T.tag[i];
+        if (t == 0) continue;
+        unsigned int nullmask = (unsigned int) (t >> 59) & 0xF;
+        unsigned long long k0 = T.tagkey ? (t & 0x00FFFFFFFFFFFFFFULL) : T.k0[i];
+        unsigned long long *rec = global_upsert(A, k0, (!T.tagkey && T.nkw > 1) ? T.k1[i] : 0ULL, nullmask);
+        if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+        for (int j = 0; j < T.nwords; j++) merge_word(&rec[3 + j], A.wkind[j], T.w[(size_t) i * T.nwords + j]);
+    }
+}
+
 // lane-private merge helper: combine one word over all warps and lanes of the CTA
 __device__ __forceinline__ unsigned long long lp_reduce_word(const SmemTable &T, int nwarps, int word, unsigned int gi, int kind, int lane)
 {
@@ -369,22 +383,14 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_a
             gx_slot sl = A.slots[s];
             if (sl.key == GX_EMPTY_KEY) break;
             if (sl.key == key) { consume_row<SINK>(A, T, r, sl.payload); if (P.unique) break; }
-            s = (s + 1) & A.mask;
+            s = gx_next_slot(s, A.mask);
         }
     }
     if (!IS_SMEM) return;
     __syncthreads();
     // merge the CTA's table into the global one
     if (SINK == SINK_SMEM) {
-        for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
-            unsigned long long t = T.tag[i];
-            if (t == 0) continue;
-            unsigned int nullmask = (unsigned int) (t >> 59) & 0xF;
-            unsigned long long k0 = T.tagkey ? (t & 0x00FFFFFFFFFFFFFFULL) : T.k0[i];
-            unsigned long long *rec = global_upsert(A, k0, (!T.tagkey && T.nkw > 1) ? T.k1[i] : 0ULL, nullmask);
-            if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
-            for (int j = 0; j < T.nwords; j++) merge_word(&rec[3 + j], A.wkind[j], T.w[(size_t) i * T.nwords + j]);
-        }
+        smem_dense_merge(T, A);
     } else {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         for (int i = wid; i < T.S; i += nwarps) {              // one warp per directory slot
@@ -402,6 +408,134 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_a
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Specialised kernel for the dominant plan shape (BASELINE configs 2 and 3):
+//   [probe a unique-key join table with an int8 key ->] GROUP BY one 4-byte
+//   column (a scanned int4/date column, or the 4-byte join payload), aggregates
+//   drawn from { count(*), sum/avg(one float8 column) }, no quals, no NULLs.
+// The generic kernel above interprets the plan per row (~220-580 instructions
+// per row measured with ncu, profiles/r01_ncu_generic_kernel.txt): this one is
+// what the same plan compiles to by hand.  Four consecutive rows per thread:
+// 16-byte vector loads, four independent table probes in flight, equal
+// neighbouring keys probed once (TPC-H lineitem is clustered on the order key)
+// and their rows pre-combined in registers before touching shared memory.
+struct gx_fast_args {
+    const long long *okey;      // JOIN: outer key column (int8)
+    const int *gcol;            // !JOIN: group column (int4/date)
+    const double *vcol;         // value column of sum/avg (may be NULL)
+    int sum_word;               // state word of the sum
+    int _pad;
+};
+
+__device__ __forceinline__ longlong2 ld_stream_ll2(const long long *p)
+{
+    longlong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream_i4(const int *p)
+{
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ gx_slot ld_slot(const gx_slot *p)
+{
+    gx_slot s;
+    asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(s.key), "=l"(s.payload) : "l"(p));
+    return s;
+}
+
+template <bool HAS_CNT, bool HAS_SUM>
+__device__ __forceinline__ void fast_flush(const SmemTable &T, const gx_agg_dev &A, int gkey, unsigned int cnt, double sum, int sum_word)
+{
+    int s = smem_upsert<false>(T, (unsigned long long) (unsigned int) gkey, 0ULL, 0u);
+    if (s < 0) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+    unsigned long long *w = T.w + (size_t) s * T.nwords;
+    if (HAS_CNT) atomicAdd((unsigned int *) &w[0], cnt);
+    if (HAS_SUM) atomicAdd((double *) &w[sum_word], sum);
+}
+
+template <bool JOIN, bool HAS_CNT, bool HAS_SUM>
+__global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
+{
+    extern __shared__ unsigned long long smem[];
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = 1; T.tagkey = 1; T.gmax = 0;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0; T.w = T.k0; T.gidx = nullptr; T.gcount = nullptr;
+    for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+        T.tag[i] = 0;
+        for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+    }
+    __syncthreads();
+    const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += stride) {
+        const long long r = A.row0 + (q << 2);
+        int g[4]; bool hit[4]; double v[4];
+        if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+        if (JOIN) {
+            longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+            long long k[4] = { ka.x, ka.y, kb.x, kb.y };
+            gx_slot sl[4]; unsigned long long pos[4];
+            // issue the first probe of every distinct neighbour first: up to four loads in flight
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                pos[i] = gx_key_hash(k[i]) & A.mask;
+                if (i == 0 || k[i] != k[i - 1]) sl[i] = ld_slot(A.slots + pos[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i > 0 && k[i] == k[i - 1]) { g[i] = g[i - 1]; hit[i] = hit[i - 1]; continue; }
+                if (k[i] == GX_EMPTY_KEY) {                    // lives in the side list, never in the table
+                    hit[i] = A.special_count > 0; g[i] = hit[i] ? (int) A.special[0] : 0; continue;
+                }
+                gx_slot c = sl[i]; unsigned long long p = pos[i];
+                while (c.key != k[i] && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
+                hit[i] = c.key == k[i]; g[i] = (int) (unsigned int) c.payload;
+            }
+        } else {
+            int4 gg = ld_stream_i4(F.gcol + r);
+            g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
+            hit[0] = hit[1] = hit[2] = hit[3] = true;
+        }
+        // combine equal neighbours in registers, then one shared-memory update per run
+        int cur = 0; unsigned int cnt = 0; double sum = 0.0; bool open = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!hit[i]) continue;
+            if (open && g[i] == cur) { cnt++; if (HAS_SUM) sum = __dadd_rn(sum, v[i]); continue; }
+            if (open) fast_flush<HAS_CNT, HAS_SUM>(T, A, cur, cnt, sum, F.sum_word);
+            open = true; cur = g[i]; cnt = 1; sum = HAS_SUM ? v[i] : 0.0;
+        }
+        if (open) fast_flush<HAS_CNT, HAS_SUM>(T, A, cur, cnt, sum, F.sum_word);
+    }
+    // the (< 4) rows after the last full vector: one thread each
+    {
+        long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < A.row1) {
+            bool h = true; int gk;
+            if (JOIN) {
+                long long key = F.okey[r];
+                if (key == GX_EMPTY_KEY) { h = A.special_count > 0; gk = h ? (int) A.special[0] : 0; }
+                else {
+                    unsigned long long p = gx_key_hash(key) & A.mask; gx_slot c = ld_slot(A.slots + p);
+                    while (c.key != key && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
+                    h = c.key == key; gk = (int) (unsigned int) c.payload;
+                }
+            } else gk = F.gcol[r];
+            if (h) fast_flush<HAS_CNT, HAS_SUM>(T, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0, F.sum_word);
+        }
+    }
+    __syncthreads();
+    smem_dense_merge(T, A);
 }
 
 // global table -> dense records [meta][k0][k1][w..]
@@ -732,6 +866,35 @@ static int launch_agg(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char 
     return GX_OK;
 }
 
+template <bool JOIN, bool HAS_CNT, bool HAS_SUM>
+static int launch_fast_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t smem, const char *name)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fast<JOIN, HAS_CNT, HAS_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set = true;
+    }
+    long long nvec = (A.row1 - A.row0 + 3) / 4;
+    long long nb = (nvec + 1023) / 1024, maxb = (long long) ctx->sm_count;
+    while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 32)) maxb *= 2;
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_k_fast<JOIN, HAS_CNT, HAS_SUM><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
+static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name)
+{
+    if (join) {
+        if (cnt && sum) return launch_fast_t<true, true, true>(ctx, A, FA, smem, name);
+        if (cnt) return launch_fast_t<true, true, false>(ctx, A, FA, smem, name);
+        return launch_fast_t<true, false, true>(ctx, A, FA, smem, name);
+    }
+    if (cnt && sum) return launch_fast_t<false, true, true>(ctx, A, FA, smem, name);
+    if (cnt) return launch_fast_t<false, true, false>(ctx, A, FA, smem, name);
+    return launch_fast_t<false, false, true>(ctx, A, FA, smem, name);
+}
+
 static int read_counters(gx_ctx *ctx, long long *c /* 4 */)
 {
     GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 4 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -799,6 +962,29 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
     GX_CHECK_ARG(ctx, strategy >= 1 && strategy <= 3, "agg plan: unknown strategy %d", strategy);
     A.need_w0 = cp.need_w0;
 
+    // ---- does the plan have the shape the specialised kernel was written for?
+    gx_fast_args FA; memset(&FA, 0, sizeof(FA));
+    bool fast_ok = plan->n_preds == 0 && plan->n_group_cols == 1 && tagkey && outer->nrows > 0;
+    if (fast_ok) {
+        const gx_dgroupcol &gc = A.P.gcols[0];
+        if (A.P.has_join) {
+            fast_ok = gc.side == 1 && gc.payload_idx == 0 && gc.bytes == 4 && h->unique && A.P.key_type == GX_INT8 && A.P.okey.nulls == nullptr;
+            FA.okey = (const long long *) A.P.okey.data;
+        } else {
+            fast_ok = gc.side == 0 && gc.bytes == 4 && gc.col.nulls == nullptr;
+            FA.gcol = (const int *) gc.col.data;
+        }
+        int nvalue = 0;
+        for (int a = 0; a < plan->n_aggs && fast_ok; a++) {
+            const gx_dagg &ga = A.P.aggs[a];
+            if (plan->aggs[a].fn == GX_AGG_COUNT_STAR) continue;
+            if ((plan->aggs[a].fn == GX_AGG_SUM_F8 || plan->aggs[a].fn == GX_AGG_AVG_F8) && ga.expr.nterms == 1 && ga.expr.t[0].kind == GXT_COL &&
+                ga.expr.t[0].col.type == GX_FLOAT8 && ga.expr.t[0].col.nulls == nullptr && nvalue == 0) {
+                FA.vcol = (const double *) ga.expr.t[0].col.data; FA.sum_word = ga.word; nvalue++;
+            } else fast_ok = false;
+        }
+    }
+
     for (int attempt = 0; attempt < 8; attempt++) {
         if (strategy == 2) { rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
         long long S = 16; while (S < est * 2 && S < smax) S *= 2;
@@ -821,7 +1007,8 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
         A.s_slots = strategy == 1 ? (int) S : 0; A.s_log2 = ilog2(S); A.s_tagkey = tagkey; A.s_gmax = gmax;
         const char *kname = h ? "probe_agg" : "agg";
-        if (strategy == 1 && gmax) rc = launch_agg<SINK_SMEM_LP>(ctx, A, lp_bytes, kname, lp_warps * 32);
+        if (strategy == 1 && !gmax && fast_ok) rc = launch_fast(ctx, A, FA, A.P.has_join != 0, cp.need_w0 != 0, FA.vcol != nullptr, dense_bytes(S), kname);
+        else if (strategy == 1 && gmax) rc = launch_agg<SINK_SMEM_LP>(ctx, A, lp_bytes, kname, lp_warps * 32);
         else if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, dense_bytes(S), kname);
         else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, kname);
         long long c[4];

@@ -13,6 +13,8 @@
 
 #define GX_EMPTY_KEY   ((long long) 0x8000000000000000LL)   /* INT64_MIN marks an empty join slot */
 #define GX_MAX_NODES   64
+#define GX_SUB_LOG2    12                 /* join table: linear probing wraps inside 4096-slot (64 KB) sub-tables */
+#define GX_SUB         (1 << GX_SUB_LOG2)
 
 // ---------------------------------------------------------------- host side
 struct gx_prof_entry { double ms; int64_t launches; };
@@ -308,6 +310,12 @@ __device__ __forceinline__ double gx_eval_expr(const gx_dexpr &e, long long r, b
 
 // join-table probe -------------------------------------------------------
 __device__ __forceinline__ unsigned long long gx_key_hash(long long key) { return gx_mix64((unsigned long long) key); }
+// next slot of a probe sequence: wraps inside the slot's sub-table (or the whole table when it is smaller)
+__device__ __forceinline__ unsigned long long gx_next_slot(unsigned long long s, unsigned long long mask)
+{
+    const unsigned long long w = mask < (GX_SUB - 1) ? mask : (unsigned long long) (GX_SUB - 1);
+    return (s & ~w) | ((s + 1) & w);
+}
 
 // block-wide exclusive scan of one value per thread (blockDim.x <= 1024)
 __device__ __forceinline__ long long gx_block_exscan(long long v, long long *total, long long *smem /* 33 */)

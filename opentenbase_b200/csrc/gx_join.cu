@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) gx_k_hash_build(gx_build_args a)
             long long old = (long long) atomicCAS((unsigned long long *) &a.slots[s].key,
                                                   (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key);
             if (old == GX_EMPTY_KEY) { a.slots[s].payload = payload; break; }
-            s = (s + 1) & a.mask;
+            s = gx_next_slot(s, a.mask);
         }
         inserted++;
     }
@@ -81,6 +81,97 @@ __global__ void gx_k_fill_slots(gx_slot *slots, long long n)
         ((longlong2 *) slots)[i] = v;
     }
 }
+
+
+// ---------------------------------------------------------------------------
+// Bucketed build.  Random CAS into a table much larger than L2 tops out at
+// ~16-21 G inserts/s on B200 (profiles/r01_ubench_random_access.txt): every
+// insert is a DRAM read-modify-write of a sector that was just cleared.  So the
+// table is cut into sub-tables of GX_SUB slots (64 KB); linear probing wraps
+// INSIDE a sub-table (all probe kernels use gx_next_slot()).  Build rows are
+// bucketed by sub-table (sequential read, 16-byte scattered stores that
+// write-combine in L2), then one CTA builds one sub-table entirely in shared
+// memory and streams it out with coalesced 16-byte stores: the table is written
+// exactly once, never read, never cleared, and sees no global atomics.
+struct gx_bbuild_args {
+    gx_build_args b;
+    long long nsub;
+    unsigned int *count;        // [nsub] rows per sub-table
+    long long *offs;            // [nsub] exclusive scan of count
+    unsigned int *cursor;       // [nsub]
+    gx_slot *pairs;
+    int *overflow;
+};
+
+__device__ __forceinline__ bool build_row_ok(const gx_build_args &a, long long r)
+{
+    bool ok = !gx_is_null(a.key, r);
+#pragma unroll
+    for (int p = 0; p < GX_MAX_PREDS; p++) if (p < a.npreds) ok = ok && gx_eval_pred(a.preds[p], r);
+    return ok;
+}
+
+__global__ void __launch_bounds__(256) gx_k_bbuild_count(gx_bbuild_args a)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x; r < a.b.nrows; r += stride) {
+        if (!build_row_ok(a.b, r)) continue;
+        long long key = gx_load_int(a.b.key, r);
+        if (key == GX_EMPTY_KEY) continue;
+        atomicAdd(&a.count[(gx_key_hash(key) & a.b.mask) >> GX_SUB_LOG2], 1u);
+    }
+}
+__global__ void gx_k_bbuild_widen(const unsigned int *count, long long *offs, long long n)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) offs[i] = count[i];
+}
+__global__ void __launch_bounds__(256) gx_k_bbuild_scatter(gx_bbuild_args a)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x; r < a.b.nrows; r += stride) {
+        if (!build_row_ok(a.b, r)) continue;
+        long long key = gx_load_int(a.b.key, r);
+        unsigned long long payload = pack_payload(a.b, r);
+        if (key == GX_EMPTY_KEY) {
+            int idx = (int) atomicAdd((unsigned long long *) &a.b.counters[1], 1ULL);
+            if (idx < a.b.special_cap) a.b.special[idx] = payload;
+            continue;
+        }
+        unsigned long long sub = (gx_key_hash(key) & a.b.mask) >> GX_SUB_LOG2;
+        unsigned int k = atomicAdd(&a.cursor[sub], 1u);
+        longlong2 v; v.x = key; v.y = (long long) payload;
+        ((longlong2 *) a.pairs)[a.offs[sub] + k] = v;
+    }
+}
+// one CTA per sub-table (grid-strided)
+__global__ void __launch_bounds__(256) gx_k_bbuild_fill(gx_bbuild_args a)
+{
+    extern __shared__ gx_slot tab[];               // GX_SUB slots = 64 KB (dynamic: above the 48 KB static limit)
+    for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
+        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
+        __syncthreads();
+        const long long b = a.offs[sub];
+        const unsigned int n = a.count[sub];
+        if (n > GX_SUB) { if (threadIdx.x == 0) *a.overflow = 1; }
+        else {
+            for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+                longlong2 v = ((const longlong2 *) a.pairs)[b + i];
+                unsigned int s = (unsigned int) (gx_key_hash(v.x) & (GX_SUB - 1));
+                for (;;) {
+                    long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v.x);
+                    if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v.y; break; }
+                    s = (s + 1) & (GX_SUB - 1);
+                }
+            }
+        }
+        __syncthreads();
+        longlong2 *dst = (longlong2 *) (a.b.slots + sub * GX_SUB);
+        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { longlong2 v; v.x = tab[i].key; v.y = (long long) tab[i].payload; dst[i] = v; }
+        __syncthreads();
+    }
+}
+__global__ void gx_k_scan_i64(long long *v, long long n, long long *total);   // gx_agg.cu
 
 extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, int n_preds, const gx_pred *preds,
                              int n_payload, const int32_t *payload_cols, int unique, gx_hash **out)
@@ -121,19 +212,63 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     a.special = h->special_payload; a.special_cap = h->special_cap;
     a.counters = ctx->d_scratch;
     GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
-    {
-        gx_launch_scope ls(ctx, "build_clear");
-        gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots);
+    // big tables: bucket by sub-table, build each sub-table in shared memory
+    const char *force = getenv("GX_BUILD_DIRECT");
+    bool bucketed = h->nslots >= 64 * GX_SUB && !(force && force[0] == '1');
+    long long nscattered = -1;
+    if (inner->nrows > 0 && bucketed) {
+        gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
+        ba.b = a; ba.nsub = h->nslots / GX_SUB;
+        cudaError_t e = cudaMalloc((void **) &ba.count, (size_t) ba.nsub * 2 * sizeof(unsigned int) + sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void **) &ba.offs, (size_t) ba.nsub * sizeof(long long));
+        if (e == cudaSuccess) e = cudaMalloc((void **) &ba.pairs, (size_t) inner->nrows * sizeof(gx_slot));
+        if (e != cudaSuccess) {
+            if (ba.count) cudaFree(ba.count); if (ba.offs) cudaFree(ba.offs);
+            GX_SET_ERR(ctx, "hash_build: cudaMalloc of the bucketing buffers failed: %s", cudaGetErrorString(e));
+            gx_hash_free(h);
+            return GX_ERR_NOMEM;
+        }
+        ba.cursor = ba.count + ba.nsub; ba.overflow = (int *) (ba.cursor + ba.nsub);
+        cudaMemsetAsync(ba.count, 0, (size_t) ba.nsub * 2 * sizeof(unsigned int) + sizeof(int), ctx->stream);
+        long long nb = (inner->nrows + 255) / 256, maxb = (long long) ctx->sm_count * 8;
+        unsigned grid = (unsigned) (nb < maxb ? nb : maxb);
+        {
+            gx_launch_scope ls(ctx, "build_bucket", 4);
+            gx_k_bbuild_count<<<grid, 256, 0, ctx->stream>>>(ba);
+            gx_k_bbuild_widen<<<(unsigned) ((ba.nsub + 255) / 256), 256, 0, ctx->stream>>>(ba.count, ba.offs, ba.nsub);
+            gx_k_scan_i64<<<1, 1024, 0, ctx->stream>>>(ba.offs, ba.nsub, ctx->d_scratch + 3);
+            gx_k_bbuild_scatter<<<grid, 256, 0, ctx->stream>>>(ba);
+        }
+        {
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(gx_k_bbuild_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); attr = true; }
+            gx_launch_scope ls(ctx, "build");
+            gx_k_bbuild_fill<<<ctx->sm_count * 3, 256, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+        }
+        int h_over = 0;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_over, ba.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(ba.count); cudaFree(ba.offs); cudaFree(ba.pairs);
+        if (e != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e)); gx_hash_free(h); return GX_ERR_CUDA; }
+        if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
+        else nscattered = ctx->h_scratch[3];
     }
-    if (inner->nrows > 0) {
+    if (inner->nrows > 0 && !bucketed) {
+        GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
+        { gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots); }
         gx_launch_scope ls(ctx, "build");
         long long nb = (inner->nrows + 255) / 256;
         long long maxb = (long long) ctx->sm_count * 8;
         gx_k_hash_build<<<(unsigned) (nb < maxb ? nb : maxb), 256, 0, ctx->stream>>>(a);
+    } else if (inner->nrows == 0) {
+        gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots);
     }
     GX_CUDA(ctx, cudaGetLastError());
     GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nscattered >= 0) ctx->h_scratch[0] = nscattered;
     h->nentries = ctx->h_scratch[0] + ctx->h_scratch[1];
     h->special_count = (int) ctx->h_scratch[1];
     if (h->special_count > h->special_cap) {
@@ -226,7 +361,7 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe(gx_probe_args a)
                     if (sl.key == GX_EMPTY_KEY) active = false;
                     else {
                         if (sl.key == key) { hit = true; payload = sl.payload; if (a.unique) active = false; }
-                        s = (s + 1) & a.mask;
+                        s = gx_next_slot(s, a.mask);
                     }
                 }
             }

@@ -368,8 +368,8 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
 // Page / tuple layout constants of the reference build
 // (storage/bufpage.h:153-175, access/htup_details.h:126-201, storage/itemid.h:24-29):
 #define PG_BLCKSZ       8192
-#define PG_PAGE_HDR     36      // offsetof(PageHeaderData, pd_linp)
-#define PG_PD_LOWER     14
+#define PG_PAGE_HDR     44      // offsetof(PageHeaderData, pd_linp); LocationIndex is uint32 (__OPENTENBASE_C__)
+#define PG_PD_LOWER     16
 #define PG_HTH_INFOMASK 40
 #define PG_HTH_HOFF     46
 #define PG_HTH_BITS     47
@@ -389,7 +389,7 @@ __device__ __forceinline__ int page_nvisible(const gx_deform_args &a, long long 
 {
     if (a.vis_counts) return a.vis_counts[p];
     const uint8_t *pg = a.pages + p * PG_BLCKSZ;
-    int lines = ((int) *(const uint16_t *) (pg + PG_PD_LOWER) - PG_PAGE_HDR) / 4;
+    int lines = ((int) *(const uint32_t *) (pg + PG_PD_LOWER) - PG_PAGE_HDR) / 4;
     int n = 0;
     for (int i = 0; i < lines; i++) { unsigned int lp = *(const unsigned int *) (pg + PG_PAGE_HDR + 4 * i); n += ((lp >> 15) & 3) == 1; }
     return n;
@@ -409,7 +409,7 @@ __global__ void gx_k_deform(gx_deform_args a, const long long *pageoffs)
     int lane = threadIdx.x & 31;
     if (p >= a.npages) return;
     const uint8_t *pg = a.pages + p * PG_BLCKSZ;
-    int lines = ((int) *(const uint16_t *) (pg + PG_PD_LOWER) - PG_PAGE_HDR) / 4;
+    int lines = ((int) *(const uint32_t *) (pg + PG_PD_LOWER) - PG_PAGE_HDR) / 4;
     long long row0 = a.base_row + pageoffs[p];
     int nvis = a.vis_counts ? a.vis_counts[p] : -1;
     // without a visibility list: k-th LP_NORMAL item; find by scanning (lane-cooperative ballot)

@@ -31,10 +31,10 @@ static inline uint32_t Rehash32to32(uint32_t hash)
 static const uint32_t REHASH[8] = { 0x47b6137bU, 0x44974d91U, 0x8824ad5bU, 0xa2b7289dU,
                                     0x705495c7U, 0x2df1424bU, 0x9efc4947U, 0x5c6bfb31U };
 
-/* BlockBloomFilterInit(nrows, fpp = 0.01 at the hash-join call site) */
+/* BlockBloomFilterInit(nrows, fpp = BLOOM_ERROR_RATE 0.05 at the hash-join call site, nodeHash.c:717) */
 orc_bloom *orc_bloom_create(int64_t nrows)
 {
-    int logMemorySize = MinLogSpace(nrows, 0.01);
+    int logMemorySize = MinLogSpace(nrows, 0.05);     /* BLOOM_ERROR_RATE, nodeHash.c:57 */
     int logNumBuckets = logMemorySize - LOG_BUCKET_BYTE_SIZE;
     if (logNumBuckets < 1) logNumBuckets = 1;
     if (logNumBuckets > 20) return NULL;            /* "give up using bloom filter" */

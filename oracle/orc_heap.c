@@ -64,13 +64,18 @@ static inline void wr16(uint8_t *p, uint16_t v) { memcpy(p, &v, 2); }
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 
-/* PageHeaderData field offsets (bufpage.h:153-175, _SHARDING_/_MLS_/GTS on) */
+/* PageHeaderData field offsets (bufpage.h:153-175 with _SHARDING_, _MLS_, GTS and
+ * __OPENTENBASE_C__ on: LocationIndex is uint32, bufpage.h:85-89).  Verified
+ * against the reference's own headers by tests/test_oracle_vs_ref.py:
+ * pd_lsn 0, pd_checksum 8, pd_flags 10, pd_shard 12, pd_lower 16, pd_upper 20,
+ * pd_special 24, pd_pagesize_version 28, pd_algorithm_id 30, pd_prune_ts 32,
+ * pd_prune_xid 40, pd_linp 44. */
 #define PD_FLAGS    10
 #define PD_SHARD    12
-#define PD_LOWER    14
-#define PD_UPPER    16
-#define PD_SPECIAL  18
-#define PD_PAGESIZE_VERSION 20
+#define PD_LOWER    16
+#define PD_UPPER    20
+#define PD_SPECIAL  24
+#define PD_PAGESIZE_VERSION 28
 
 /* PageInit, bufpage.c:42-60 */
 static uint8_t *page_new(orc_rel *r)
@@ -78,9 +83,9 @@ static uint8_t *page_new(orc_rel *r)
     uint8_t *pg;
     if (posix_memalign((void **) &pg, 64, ORC_BLCKSZ)) abort();
     memset(pg, 0, ORC_BLCKSZ);
-    wr16(pg + PD_LOWER, ORC_PAGE_HDR);
-    wr16(pg + PD_UPPER, ORC_BLCKSZ);
-    wr16(pg + PD_SPECIAL, ORC_BLCKSZ);
+    wr32(pg + PD_LOWER, ORC_PAGE_HDR);
+    wr32(pg + PD_UPPER, ORC_BLCKSZ);
+    wr32(pg + PD_SPECIAL, ORC_BLCKSZ);
     wr16(pg + PD_PAGESIZE_VERSION, ORC_BLCKSZ | 4);   /* PG_PAGE_LAYOUT_VERSION 4 */
     if (r->npages == r->pages_cap) {
         r->pages_cap = r->pages_cap ? r->pages_cap * 2 : 64;
@@ -159,14 +164,14 @@ static void rel_insert_tuple(orc_rel *r, const int64_t *values, const uint8_t *i
 
     uint8_t *pg = r->npages ? r->pages[r->npages - 1] : NULL;
     if (pg) {
-        uint32_t lower = rd16(pg + PD_LOWER), upper = rd16(pg + PD_UPPER);
+        uint32_t lower = rd32(pg + PD_LOWER), upper = rd32(pg + PD_UPPER);
         /* PageGetFreeSpace: space minus one new line pointer */
         int32_t freesp = (int32_t) upper - (int32_t) lower - 4;
         if (freesp < (int32_t) alen) pg = NULL;
     }
     if (!pg) pg = page_new(r);
 
-    uint32_t lower = rd16(pg + PD_LOWER), upper = rd16(pg + PD_UPPER);
+    uint32_t lower = rd32(pg + PD_LOWER), upper = rd32(pg + PD_UPPER);
     uint32_t offnum = (lower - ORC_PAGE_HDR) / 4 + 1;           /* 1-based OffsetNumber */
     upper -= alen;
     uint8_t *tup = pg + upper;
@@ -195,8 +200,8 @@ static void rel_insert_tuple(orc_rel *r, const int64_t *values, const uint8_t *i
     /* ItemIdData: lp_off:15, lp_flags:2, lp_len:15 (itemid.h:24-29) */
     uint32_t lp = (upper & 0x7FFF) | ((uint32_t) LP_NORMAL << 15) | ((len & 0x7FFF) << 17);
     wr32(pg + lower, lp);
-    wr16(pg + PD_LOWER, (uint16_t) (lower + 4));
-    wr16(pg + PD_UPPER, (uint16_t) upper);
+    wr32(pg + PD_LOWER, lower + 4);
+    wr32(pg + PD_UPPER, upper);
     r->ntuples++;
 }
 
@@ -233,7 +238,7 @@ int orc_rel_delete_tuple(orc_rel *r, int64_t pageno, int lineoff)
 {
     if (pageno < 0 || pageno >= r->npages) return -1;
     uint8_t *pg = r->pages[pageno];
-    uint32_t nlines = (rd16(pg + PD_LOWER) - ORC_PAGE_HDR) / 4;
+    uint32_t nlines = (rd32(pg + PD_LOWER) - ORC_PAGE_HDR) / 4;
     if (lineoff < 1 || (uint32_t) lineoff > nlines) return -1;
     uint32_t lp = rd32(pg + ORC_PAGE_HDR + 4 * (uint32_t) (lineoff - 1));
     uint8_t *tup = pg + (lp & 0x7FFF);
@@ -260,7 +265,7 @@ static inline int tuple_visible(const uint8_t *tup)
 int orc_heapgetpage(const uint8_t *pg, uint16_t *vistuples)
 {
     int ntup = 0;
-    uint32_t lines = (rd16(pg + PD_LOWER) - ORC_PAGE_HDR) / 4;   /* PageGetMaxOffsetNumber */
+    uint32_t lines = (rd32(pg + PD_LOWER) - ORC_PAGE_HDR) / 4;   /* PageGetMaxOffsetNumber */
     for (uint32_t lineoff = 1; lineoff <= lines; lineoff++) {
         uint32_t lp = rd32(pg + ORC_PAGE_HDR + 4 * (lineoff - 1));
         if (((lp >> 15) & 3) != LP_NORMAL) continue;             /* ItemIdIsNormal */

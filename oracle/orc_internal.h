@@ -7,7 +7,8 @@
 
 #define ORC_BLCKSZ            8192
 #define ORC_MAXALIGN(x)       (((uintptr_t) (x) + 7) & ~(uintptr_t) 7)
-#define ORC_PAGE_HDR          36     /* offsetof(PageHeaderData, pd_linp), bufpage.h:153-175 */
+#define ORC_PAGE_HDR          44     /* offsetof(PageHeaderData, pd_linp), bufpage.h:153-175: LocationIndex is
+                                      * uint32 under __OPENTENBASE_C__ (bufpage.h:85-89); pinned by oracle/_ref */
 #define ORC_HEAP_HDR          47     /* offsetof(HeapTupleHeaderData, t_bits), htup_details.h:165-201 */
 #define ORC_MINIMAL_TUPLE_OFFSET 32  /* ((38 - 4) / 8) * 8, htup_details.h:743-744 */
 #define ORC_BPCHAR1           6      /* heap-side only: bpchar(1), short varlena */

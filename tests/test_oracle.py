@@ -105,7 +105,7 @@ def test_golden_opentenbase_c_aggregation():
 
 def test_heap_pages_round_trip():
     """heap_form_tuple + PageAddItem -> heapgetpage + slot_deform_tuple is the identity,
-    page and tuple headers have the OpenTenBase layout (t_hoff 48, 36-byte page header)."""
+    page and tuple headers have the OpenTenBase layout (t_hoff 48, 44-byte page header)."""
     rng = np.random.default_rng(1)
     n = 3000
     types = [O.GX_INT8, O.GX_INT4, O.ORC_BPCHAR1, O.GX_FLOAT8, O.GX_CHAR, O.GX_DATE]
@@ -117,11 +117,11 @@ def test_heap_pages_round_trip():
     rel = O.Rel(types, cols, nulls)
     assert rel.ntuples == n and rel.npages > 10
     pages = rel.pages().reshape(-1, 8192)
-    pd_lower = pages[:, 14].astype(int) | (pages[:, 15].astype(int) << 8)
-    pd_upper = pages[:, 16].astype(int) | (pages[:, 17].astype(int) << 8)
-    assert (pd_lower >= 36).all() and (pd_upper <= 8192).all() and (pd_lower <= pd_upper).all()
-    assert ((pd_lower - 36) % 4 == 0).all()
-    lp0 = int.from_bytes(pages[0, 36:40].tobytes(), "little")
+    pd_lower = pages[:, 16:20].copy().view(np.uint32)[:, 0].astype(int)      # LocationIndex is uint32 in OpenTenBase-C
+    pd_upper = pages[:, 20:24].copy().view(np.uint32)[:, 0].astype(int)
+    assert (pd_lower >= 44).all() and (pd_upper <= 8192).all() and (pd_lower <= pd_upper).all()
+    assert ((pd_lower - 44) % 4 == 0).all()
+    lp0 = int.from_bytes(pages[0, 44:48].tobytes(), "little")
     off, flags, ln = lp0 & 0x7FFF, (lp0 >> 15) & 3, lp0 >> 17
     assert flags == 1 and off % 8 == 0 and off + ln <= 8192
     assert pages[0, off + 46] in (48, 56)                       # t_hoff: 48 without NULLs (htup_details.h)
