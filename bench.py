@@ -173,6 +173,8 @@ def workload_config(args, world):
 def run_ours(args):
     import opentenbase_b200 as g
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner to stdout otherwise
     dist = None
     if world > 1:
         import torch

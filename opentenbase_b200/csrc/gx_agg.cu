@@ -911,7 +911,7 @@ static int table_to_result(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *pl
     gx_result *r; gx_result_alloc(ctx, plan, cp->group_types, ngroups, &r);
     r->nkw = cp->A.P.nkw; r->nwords = cp->A.P.nwords; r->rec_words = RW; r->need_w0 = cp->need_w0;
     for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp->agg_word[a]; r->agg_cnt_word[a] = cp->agg_cnt_word[a]; }
-    cudaError_t e = cudaMalloc((void **) &r->d_recs, (size_t) r->cap * RW * 8);
+    cudaError_t e = gx_tmp_alloc(ctx, (void **) &r->d_recs, (size_t) r->cap * RW * 8);
     if (e != cudaSuccess) { gx_result_free(r); GX_SET_ERR(ctx, "result: %s", cudaGetErrorString(e)); return GX_ERR_NOMEM; }
     GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 12, 0, sizeof(long long), ctx->stream));
     if (ngroups > 0) {
@@ -987,7 +987,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
 
     for (int attempt = 0; attempt < 8; attempt++) {
         if (strategy == 2) { rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
-        long long S = 16; while (S < est * 2 && S < smax) S *= 2;
+        long long S = 16; while (S * 2 < est * 3 && S < smax) S *= 2;     // load factor <= 0.67
         // lane-private mode for a handful of groups: [warp][word][group][lane]
         int gmax = 0, lp_warps = 0; size_t lp_bytes = 0;
         if (strategy == 1 && est <= 16) {
@@ -1001,7 +1001,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         }
         long long g_cap = gx_pow2_ceil((strategy == 1 ? S : est) * 4 + 1024);
         unsigned long long *g_tab;
-        GX_CUDA(ctx, cudaMalloc((void **) &g_tab, (size_t) g_cap * RW * 8));
+        GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &g_tab, (size_t) g_cap * RW * 8));
         GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
         GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
         A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
@@ -1013,14 +1013,14 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, kname);
         long long c[4];
         if (rc == GX_OK) rc = read_counters(ctx, c);
-        if (rc != GX_OK) { cudaFree(g_tab); return rc; }
+        if (rc != GX_OK) { gx_tmp_free(ctx, g_tab); return rc; }
         if (c[1] == 0) {
             rc = table_to_result(ctx, &cp, plan, g_tab, g_cap, c[0], out);
-            cudaFree(g_tab);
+            gx_tmp_free(ctx, g_tab);
             if (rc == GX_OK) remember_layout(*out, &cp);
             return rc;
         }
-        cudaFree(g_tab);
+        gx_tmp_free(ctx, g_tab);
         // the planner's estimate was too low: grow, then fall over to radix
         est = est < 16 ? 17 : est * 8;
         if (strategy == 1 && est * 3 / 2 > smax) strategy = (plan->strategy == 1) ? 3 : 2;
@@ -1176,8 +1176,8 @@ extern "C" void gx_result_free(gx_result *r)
 {
     if (!r) return;
     if (g_layouts) g_layouts->erase(r);
-    if (r->d_recs) cudaFree(r->d_recs);
-    if (r->d_nullmask) cudaFree(r->d_nullmask);
+    gx_tmp_free(r->ctx, r->d_recs);
+    gx_tmp_free(r->ctx, r->d_nullmask);
     free(r);
 }
 

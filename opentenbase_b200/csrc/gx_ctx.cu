@@ -41,8 +41,21 @@ extern "C" int gx_init(int device, gx_ctx **out)
     ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
     ctx->hbm_bytes = prop.totalGlobalMem;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    // L2 fetch granularity: a random 32-byte sector miss otherwise drags in 64 bytes
+    // (profiles/r01_ncu_fast_probe_and_bucket_build_sf100.csv: 2 sectors per join-table miss)
+    {
+        const char *g = getenv("GX_L2_FETCH");
+        size_t gran = g ? (size_t) atoi(g) : 0;      // measured: 32 is no faster than the default 64 (DRAM is the limit); opt-in only
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     ctx->prof = new std::map<std::string, gx_prof_entry>();
     ctx->nnodes = 1; ctx->rank = 0; ctx->nranks = 1;
+    {   // keep freed temporaries cached in the default pool instead of returning them to the OS
+        cudaMemPool_t pool; unsigned long long thresh = ~0ULL;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+        cudaGetLastError();
+    }
     GX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     GX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     GX_CUDA(ctx, cudaEventCreate(&ctx->ev_t0)); GX_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));

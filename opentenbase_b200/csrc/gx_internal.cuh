@@ -127,6 +127,11 @@ static inline int gx_type_size(int t)
 }
 static inline int64_t gx_pow2_ceil(int64_t x) { int64_t p = 1; while (p < x) p <<= 1; return p; }
 
+// Stream-ordered, pool-cached device allocations for per-query temporaries (join table,
+// bucket buffers, group tables): cudaMalloc/cudaFree of multi-GB blocks cost milliseconds per query.
+static inline cudaError_t gx_tmp_alloc(gx_ctx *ctx, void **p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream); }
+static inline void gx_tmp_free(gx_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
 int gx_table_alloc_like(gx_ctx *ctx, int ncols, const int32_t *types, const bool *has_nulls,
                         int64_t capacity, gx_table **out);
 int gx_result_alloc(gx_ctx *ctx, const gx_agg_plan *plan, const int32_t *group_types, int64_t cap, gx_result **out);

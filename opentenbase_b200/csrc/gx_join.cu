@@ -96,10 +96,8 @@ __global__ void gx_k_fill_slots(gx_slot *slots, long long n)
 struct gx_bbuild_args {
     gx_build_args b;
     long long nsub;
-    unsigned int *count;        // [nsub] rows per sub-table
-    long long *offs;            // [nsub] exclusive scan of count
-    unsigned int *cursor;       // [nsub]
-    gx_slot *pairs;
+    unsigned int *cursor;       // [nsub] rows scattered to each sub-table so far
+    gx_slot *pairs;             // nsub fixed-capacity buckets of GX_SUB pairs (a fuller bucket cannot be built anyway)
     int *overflow;
 };
 
@@ -111,58 +109,59 @@ __device__ __forceinline__ bool build_row_ok(const gx_build_args &a, long long r
     return ok;
 }
 
-__global__ void __launch_bounds__(256) gx_k_bbuild_count(gx_bbuild_args a)
-{
-    long long stride = (long long) gridDim.x * blockDim.x;
-    for (long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x; r < a.b.nrows; r += stride) {
-        if (!build_row_ok(a.b, r)) continue;
-        long long key = gx_load_int(a.b.key, r);
-        if (key == GX_EMPTY_KEY) continue;
-        atomicAdd(&a.count[(gx_key_hash(key) & a.b.mask) >> GX_SUB_LOG2], 1u);
-    }
-}
-__global__ void gx_k_bbuild_widen(const unsigned int *count, long long *offs, long long n)
-{
-    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) offs[i] = count[i];
-}
+// Scatter (key, payload) pairs into their sub-table's bucket.  The position
+// comes from one L2 atomic; the chain load -> atomic -> store is latency bound,
+// so every thread keeps BSCAT rows in flight.
+#define BSCAT 4
 __global__ void __launch_bounds__(256) gx_k_bbuild_scatter(gx_bbuild_args a)
 {
-    long long stride = (long long) gridDim.x * blockDim.x;
-    for (long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x; r < a.b.nrows; r += stride) {
-        if (!build_row_ok(a.b, r)) continue;
-        long long key = gx_load_int(a.b.key, r);
-        unsigned long long payload = pack_payload(a.b, r);
-        if (key == GX_EMPTY_KEY) {
-            int idx = (int) atomicAdd((unsigned long long *) &a.b.counters[1], 1ULL);
-            if (idx < a.b.special_cap) a.b.special[idx] = payload;
-            continue;
+    const long long tile = (long long) blockDim.x * BSCAT;
+    const long long ntiles = (a.b.nrows + tile - 1) / tile;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        long long key[BSCAT]; unsigned long long payload[BSCAT], sub[BSCAT]; unsigned int pos[BSCAT]; bool ok[BSCAT];
+#pragma unroll
+        for (int u = 0; u < BSCAT; u++) {
+            long long r = t * tile + (long long) u * blockDim.x + threadIdx.x;     // coalesced per u
+            ok[u] = r < a.b.nrows && build_row_ok(a.b, r);
+            key[u] = ok[u] ? gx_load_int(a.b.key, r) : 0;
+            payload[u] = ok[u] ? pack_payload(a.b, r) : 0;
         }
-        unsigned long long sub = (gx_key_hash(key) & a.b.mask) >> GX_SUB_LOG2;
-        unsigned int k = atomicAdd(&a.cursor[sub], 1u);
-        longlong2 v; v.x = key; v.y = (long long) payload;
-        ((longlong2 *) a.pairs)[a.offs[sub] + k] = v;
+#pragma unroll
+        for (int u = 0; u < BSCAT; u++) {
+            if (ok[u] && key[u] == GX_EMPTY_KEY) {
+                int idx = (int) atomicAdd((unsigned long long *) &a.b.counters[1], 1ULL);
+                if (idx < a.b.special_cap) a.b.special[idx] = payload[u];
+                ok[u] = false;
+            }
+            sub[u] = (gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2;
+            if (ok[u]) pos[u] = atomicAdd(&a.cursor[sub[u]], 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < BSCAT; u++) {
+            if (!ok[u]) continue;
+            if (pos[u] >= GX_SUB) { *a.overflow = 1; continue; }
+            longlong2 v; v.x = key[u]; v.y = (long long) payload[u];
+            ((longlong2 *) a.pairs)[sub[u] * GX_SUB + pos[u]] = v;
+        }
     }
 }
-// one CTA per sub-table (grid-strided)
-__global__ void __launch_bounds__(256) gx_k_bbuild_fill(gx_bbuild_args a)
+// one CTA per sub-table (grid-strided): build it in shared memory, stream it out
+__global__ void __launch_bounds__(512, 3) gx_k_bbuild_fill(gx_bbuild_args a)
 {
     extern __shared__ gx_slot tab[];               // GX_SUB slots = 64 KB (dynamic: above the 48 KB static limit)
     for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
         for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
         __syncthreads();
-        const long long b = a.offs[sub];
-        const unsigned int n = a.count[sub];
-        if (n > GX_SUB) { if (threadIdx.x == 0) *a.overflow = 1; }
-        else {
-            for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
-                longlong2 v = ((const longlong2 *) a.pairs)[b + i];
-                unsigned int s = (unsigned int) (gx_key_hash(v.x) & (GX_SUB - 1));
-                for (;;) {
-                    long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v.x);
-                    if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v.y; break; }
-                    s = (s + 1) & (GX_SUB - 1);
-                }
+        unsigned int n = a.cursor[sub];
+        if (n > GX_SUB) n = 0;                         // overflowed: the host rebuilds directly
+        const longlong2 *src = (const longlong2 *) a.pairs + sub * GX_SUB;
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+            longlong2 v = src[i];
+            unsigned int s = (unsigned int) (gx_key_hash(v.x) & (GX_SUB - 1));
+            for (;;) {
+                long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v.x);
+                if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v.y; break; }
+                s = (s + 1) & (GX_SUB - 1);
             }
         }
         __syncthreads();
@@ -170,6 +169,15 @@ __global__ void __launch_bounds__(256) gx_k_bbuild_fill(gx_bbuild_args a)
         for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { longlong2 v; v.x = tab[i].key; v.y = (long long) tab[i].payload; dst[i] = v; }
         __syncthreads();
     }
+}
+// entries actually placed = sum of the cursors
+__global__ void gx_k_bbuild_total(const unsigned int *cursor, long long n, long long *total)
+{
+    long long sum = 0;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) sum += cursor[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd((unsigned long long *) total, (unsigned long long) sum);
 }
 __global__ void gx_k_scan_i64(long long *v, long long n, long long *total);   // gx_agg.cu
 
@@ -201,8 +209,8 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     int64_t want = inner->nrows + inner->nrows / 2 + 16;       // load factor <= 0.67
     h->nslots = gx_pow2_ceil(want);
     h->special_cap = 1 << 16;
-    cudaError_t e = cudaMalloc((void **) &h->slots, (size_t) h->nslots * sizeof(gx_slot));
-    if (e == cudaSuccess) e = cudaMalloc((void **) &h->special_payload, (size_t) h->special_cap * sizeof(unsigned long long));
+    cudaError_t e = gx_tmp_alloc(ctx, (void **) &h->slots, (size_t) h->nslots * sizeof(gx_slot));
+    if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &h->special_payload, (size_t) h->special_cap * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         GX_SET_ERR(ctx, "hash_build: cudaMalloc of %lld slots failed: %s", (long long) h->nslots, cudaGetErrorString(e));
         gx_hash_free(h);
@@ -219,38 +227,33 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     if (inner->nrows > 0 && bucketed) {
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
         ba.b = a; ba.nsub = h->nslots / GX_SUB;
-        cudaError_t e = cudaMalloc((void **) &ba.count, (size_t) ba.nsub * 2 * sizeof(unsigned int) + sizeof(int));
-        if (e == cudaSuccess) e = cudaMalloc((void **) &ba.offs, (size_t) ba.nsub * sizeof(long long));
-        if (e == cudaSuccess) e = cudaMalloc((void **) &ba.pairs, (size_t) inner->nrows * sizeof(gx_slot));
+        cudaError_t e = gx_tmp_alloc(ctx, (void **) &ba.cursor, (size_t) ba.nsub * sizeof(unsigned int) + sizeof(int));
+        if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &ba.pairs, (size_t) h->nslots * sizeof(gx_slot));
         if (e != cudaSuccess) {
-            if (ba.count) cudaFree(ba.count); if (ba.offs) cudaFree(ba.offs);
+            gx_tmp_free(ctx, ba.cursor);
             GX_SET_ERR(ctx, "hash_build: cudaMalloc of the bucketing buffers failed: %s", cudaGetErrorString(e));
             gx_hash_free(h);
             return GX_ERR_NOMEM;
         }
-        ba.cursor = ba.count + ba.nsub; ba.overflow = (int *) (ba.cursor + ba.nsub);
-        cudaMemsetAsync(ba.count, 0, (size_t) ba.nsub * 2 * sizeof(unsigned int) + sizeof(int), ctx->stream);
-        long long nb = (inner->nrows + 255) / 256, maxb = (long long) ctx->sm_count * 8;
-        unsigned grid = (unsigned) (nb < maxb ? nb : maxb);
-        {
-            gx_launch_scope ls(ctx, "build_bucket", 4);
-            gx_k_bbuild_count<<<grid, 256, 0, ctx->stream>>>(ba);
-            gx_k_bbuild_widen<<<(unsigned) ((ba.nsub + 255) / 256), 256, 0, ctx->stream>>>(ba.count, ba.offs, ba.nsub);
-            gx_k_scan_i64<<<1, 1024, 0, ctx->stream>>>(ba.offs, ba.nsub, ctx->d_scratch + 3);
-            gx_k_bbuild_scatter<<<grid, 256, 0, ctx->stream>>>(ba);
-        }
+        ba.overflow = (int *) (ba.cursor + ba.nsub);
+        cudaMemsetAsync(ba.cursor, 0, (size_t) ba.nsub * sizeof(unsigned int) + sizeof(int), ctx->stream);
+        cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
+        long long ntiles = (inner->nrows + 256 * BSCAT - 1) / (256 * BSCAT), maxb = (long long) ctx->sm_count * 8;
+        unsigned grid = (unsigned) (ntiles < maxb ? ntiles : maxb);
+        { gx_launch_scope ls(ctx, "build_scatter"); gx_k_bbuild_scatter<<<grid, 256, 0, ctx->stream>>>(ba); }
         {
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(gx_k_bbuild_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); attr = true; }
-            gx_launch_scope ls(ctx, "build");
-            gx_k_bbuild_fill<<<ctx->sm_count * 3, 256, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+            gx_launch_scope ls(ctx, "build", 2);
+            gx_k_bbuild_fill<<<ctx->sm_count * 3, 512, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+            gx_k_bbuild_total<<<ctx->sm_count, 256, 0, ctx->stream>>>(ba.cursor, ba.nsub, ctx->d_scratch + 3);
         }
         int h_over = 0;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&h_over, ba.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(ba.count); cudaFree(ba.offs); cudaFree(ba.pairs);
+        gx_tmp_free(ctx, ba.cursor); gx_tmp_free(ctx, ba.pairs);
         if (e != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e)); gx_hash_free(h); return GX_ERR_CUDA; }
         if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
         else nscattered = ctx->h_scratch[3];
@@ -285,8 +288,8 @@ extern "C" int64_t gx_hash_nslots(const gx_hash *h) { return h ? h->nslots : -1;
 extern "C" void gx_hash_free(gx_hash *h)
 {
     if (!h) return;
-    if (h->slots) cudaFree(h->slots);
-    if (h->special_payload) cudaFree(h->special_payload);
+    gx_tmp_free(h->ctx, h->slots);
+    gx_tmp_free(h->ctx, h->special_payload);
     free(h);
 }
 

@@ -66,7 +66,11 @@ def main():
                 emit(event="config2", sf=sf, strategy=s, error=str(e))
 
         # config 3: build orders, probe lineitem, GROUP BY o_orderdate
+        ctx.profile(True)
         bbest, bmed, ht = timed(ctx, lambda: ctx.hash_build(ot, 0, [1], unique=True), reps=3)
+        emit(event="build_breakdown", sf=sf, **{k: round(ctx.profile_get(k)[0] / max(ctx.profile_get(k)[1], 1), 3)
+                                                for k in ("build_count", "build_scan", "build_scatter", "build", "build_clear")})
+        ctx.profile(False)
         emit(event="build", sf=sf, ms_best=round(bbest, 3), ms_med=round(bmed, 3), nslots=ht.nslots,
              alg_GBps=round(no * 24 / bbest / 1e6, 1))
         for s in [int(x) for x in a.strategies.split(",")]:
