@@ -1,0 +1,39 @@
+"""The CustomScan provider (the reference-side binding of the C ABI) compiles
+against the reference's REAL headers and exports the module entry points.
+Skips where /root/reference is absent (e.g. on the GPU box)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROV = os.path.join(ROOT, "opentenbase_b200", "provider")
+HAVE_REF = os.path.isdir("/root/reference/src/include") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "include", "pg_config.h"))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference and oracle/_ref's generated headers")
+def test_provider_compiles_and_exports_module_entry_points():
+    so = os.path.join(PROV, "gpuexec_provider.so")
+    if os.path.exists(so):
+        os.unlink(so)
+    r = subprocess.run(["make", "-C", PROV], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "warning" not in r.stderr, r.stderr[-3000:]
+    assert os.path.exists(so)
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    assert " T _PG_init" in syms and " T Pg_magic_func" in syms
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True).stdout
+    # it talks to the GPU library only through the C ABI ...
+    used = sorted({l.split()[-1] for l in undefined.splitlines() if l.split()[-1].startswith("gx_")})
+    assert {"gx_init", "gx_table_append_heap_pages", "gx_hash_build", "gx_hash_agg", "gx_result_fetch"} <= set(used)
+    # ... and to the backend through the documented plug-in surface
+    for s in ("RegisterCustomScanMethods", "heapgetpage", "ExecStoreVirtualTuple", "create_upper_paths_hook", "add_path"):
+        assert s in undefined
+
+
+def test_provider_uses_only_declared_abi():
+    import re
+    import opentenbase_b200 as g
+    src = open(os.path.join(PROV, "gpuexec_provider.c")).read()
+    called = set(re.findall(r"\b(gx_[a-z0-9_]+)\s*\(", src))
+    assert called <= set(g.declared_symbols()), called - set(g.declared_symbols())
