@@ -485,21 +485,45 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
             longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
             long long k[4] = { ka.x, ka.y, kb.x, kb.y };
             gx_slot sl[4]; unsigned long long pos[4];
+            // A run of equal keys that started in the previous lane is not probed again:
+            // ncu showed such cross-lane repeats re-fetching their sector from DRAM
+            // (profiles/r01_ncu_fast_probe_and_bucket_build_sf100.csv).  The lane takes the
+            // neighbour's answer by shuffle once that lane has resolved it.
+            const unsigned int wmask = __activemask();
+            const int lane = threadIdx.x & 31;
+            long long prevk = __shfl_up_sync(wmask, k[3], 1);
+            bool lead_dup = lane > 0 && ((wmask >> (lane - 1)) & 1u) && k[0] == prevk;
             // issue the first probe of every distinct neighbour first: up to four loads in flight
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 pos[i] = gx_key_hash(k[i]) & A.mask;
-                if (i == 0 || k[i] != k[i - 1]) sl[i] = ld_slot(A.slots + pos[i]);
+                bool need = (i == 0) ? !lead_dup : (k[i] != k[i - 1]);
+                if (need) sl[i] = ld_slot(A.slots + pos[i]);
             }
+            bool valid0 = !lead_dup;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (i > 0 && k[i] == k[i - 1]) { g[i] = g[i - 1]; hit[i] = hit[i - 1]; continue; }
+                if (i == 0 && lead_dup) { g[0] = 0; hit[0] = false; continue; }       // filled in below
                 if (k[i] == GX_EMPTY_KEY) {                    // lives in the side list, never in the table
                     hit[i] = A.special_count > 0; g[i] = hit[i] ? (int) A.special[0] : 0; continue;
                 }
                 gx_slot c = sl[i]; unsigned long long p = pos[i];
                 while (c.key != k[i] && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
                 hit[i] = c.key == k[i]; g[i] = (int) (unsigned int) c.payload;
+            }
+            // hand results down the warp; a run can span several lanes, so iterate until every
+            // lane is settled (TPC-H orders have at most 7 lines: two rounds)
+            bool valid3 = valid0 || k[3] != k[0];
+            while (__any_sync(wmask, !valid0)) {
+                int pg = __shfl_up_sync(wmask, g[3], 1);
+                bool ph = __shfl_up_sync(wmask, hit[3], 1), pv = __shfl_up_sync(wmask, valid3, 1);
+                if (!valid0 && pv) {
+                    valid0 = true;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (k[i] == k[0]) { g[i] = pg; hit[i] = ph; }
+                    valid3 = true;
+                }
             }
         } else {
             int4 gg = ld_stream_i4(F.gcol + r);

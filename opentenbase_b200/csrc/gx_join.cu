@@ -99,6 +99,7 @@ struct gx_bbuild_args {
     unsigned int *cursor;       // [nsub] rows scattered to each sub-table so far
     gx_slot *pairs;             // nsub fixed-capacity buckets of GX_SUB pairs (a fuller bucket cannot be built anyway)
     int *overflow;
+    int dbg_mode;               // 0 normal; 1 atomics only; 2 stores only (development experiments)
 };
 
 __device__ __forceinline__ bool build_row_ok(const gx_build_args &a, long long r)
@@ -134,33 +135,178 @@ __global__ void __launch_bounds__(256) gx_k_bbuild_scatter(gx_bbuild_args a)
                 ok[u] = false;
             }
             sub[u] = (gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2;
-            if (ok[u]) pos[u] = atomicAdd(&a.cursor[sub[u]], 1u);
+            if (ok[u]) pos[u] = (a.dbg_mode == 2) ? (unsigned int) (gx_key_hash(key[u]) >> 52) : atomicAdd(&a.cursor[sub[u]], 1u);
         }
 #pragma unroll
         for (int u = 0; u < BSCAT; u++) {
             if (!ok[u]) continue;
             if (pos[u] >= GX_SUB) { *a.overflow = 1; continue; }
+            if (a.dbg_mode == 1) { if (pos[u] == 0xFFFFFFFFu) *a.overflow = 1; continue; }
             longlong2 v; v.x = key[u]; v.y = (long long) payload[u];
             ((longlong2 *) a.pairs)[sub[u] * GX_SUB + pos[u]] = v;
         }
     }
 }
+// ---------------------------------------------------------------------------
+// Two-level write-combined bucketing (replaces the one-pass scatter above for
+// big tables).  Measured: the one-pass scatter spends ~2.1 ms in per-row L2
+// atomics and ~2.1 ms in 16-byte scattered stores at SF100.  Here a CTA takes a
+// tile of 4096 rows, ranks them by bucket digit in shared memory (native 32-bit
+// shared atomics), stages them bucket by bucket and copies each bucket's run out
+// as one contiguous piece: one global atomic per (tile, bucket) instead of one
+// per row, and 256-byte runs instead of 16-byte stores.  Level 1 splits on the
+// high bits of the sub-table number, level 2 on the low bits.
+#define BP_TILE 4096
+#define BP_THREADS 512
+#define BP_PER (BP_TILE / BP_THREADS)
+struct gx_bpart_args {
+    gx_build_args b;
+    int bits_hi, bits_lo;
+    long long nsub;
+    gx_slot *l1; long long cap1; unsigned int *cur1;      // level-1 regions
+    gx_slot *pairs; unsigned int *cursor; int *overflow;  // final buckets
+    long long tiles_per_l1;
+};
+
+struct bp_smem {
+    longlong2 *stage; unsigned short *bid; unsigned int *hist, *base, *gbase;
+};
+__device__ __forceinline__ bp_smem bp_carve(unsigned char *raw, int nb)
+{
+    bp_smem m;
+    m.stage = (longlong2 *) raw;
+    m.hist = (unsigned int *) (raw + (size_t) BP_TILE * 16);
+    m.base = m.hist + nb; m.gbase = m.base + nb;
+    m.bid = (unsigned short *) (m.gbase + nb);
+    return m;
+}
+static size_t bp_smem_bytes(int nb) { return (size_t) BP_TILE * 16 + (size_t) nb * 12 + (size_t) BP_TILE * 2 + 64; }
+
+// rank + stage one tile; returns after the staging buffer is complete
+__device__ __forceinline__ void bp_stage_tile(const bp_smem &m, int nb, const long long *key, const unsigned long long *payload,
+                                              const bool *ok, const unsigned int *digit, long long *scan_smem)
+{
+    unsigned int rank[BP_PER];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) m.hist[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < BP_PER; u++) if (ok[u]) rank[u] = atomicAdd(&m.hist[digit[u]], 1u);
+    __syncthreads();
+    {   // exclusive scan of the histogram (nb <= blockDim.x)
+        long long tot;
+        long long h = (int) threadIdx.x < nb ? (long long) m.hist[threadIdx.x] : 0;
+        long long ex = gx_block_exscan(h, &tot, scan_smem);
+        if ((int) threadIdx.x < nb) m.base[threadIdx.x] = (unsigned int) ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < BP_PER; u++) {
+        if (!ok[u]) continue;
+        unsigned int p = m.base[digit[u]] + rank[u];
+        longlong2 v; v.x = key[u]; v.y = (long long) payload[u];
+        m.stage[p] = v; m.bid[p] = (unsigned short) digit[u];
+    }
+}
+
+__global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart1(gx_bpart_args a)
+{
+    extern __shared__ unsigned char bp_raw[];
+    __shared__ long long scan_smem[33];
+    const int nb = 1 << a.bits_hi;
+    bp_smem m = bp_carve(bp_raw, nb);
+    const long long ntiles = (a.b.nrows + BP_TILE - 1) / BP_TILE;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        long long key[BP_PER]; unsigned long long payload[BP_PER]; bool ok[BP_PER]; unsigned int digit[BP_PER];
+#pragma unroll
+        for (int u = 0; u < BP_PER; u++) {
+            long long r = t * BP_TILE + (long long) u * BP_THREADS + threadIdx.x;
+            ok[u] = r < a.b.nrows && build_row_ok(a.b, r);
+            key[u] = ok[u] ? gx_load_int(a.b.key, r) : 0;
+            payload[u] = ok[u] ? pack_payload(a.b, r) : 0;
+            if (ok[u] && key[u] == GX_EMPTY_KEY) {
+                int idx = (int) atomicAdd((unsigned long long *) &a.b.counters[1], 1ULL);
+                if (idx < a.b.special_cap) a.b.special[idx] = payload[u];
+                ok[u] = false;
+            }
+            digit[u] = (unsigned int) (((gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2) >> a.bits_lo);
+        }
+        bp_stage_tile(m, nb, key, payload, ok, digit, scan_smem);
+        if ((int) threadIdx.x < nb) m.gbase[threadIdx.x] = m.hist[threadIdx.x] ? atomicAdd(&a.cur1[threadIdx.x], m.hist[threadIdx.x]) : 0;
+        __syncthreads();
+        const unsigned int total = m.base[nb - 1] + m.hist[nb - 1];
+        for (unsigned int j = threadIdx.x; j < total; j += blockDim.x) {
+            unsigned int d = m.bid[j];
+            long long pos = (long long) m.gbase[d] + (j - m.base[d]);
+            if (pos >= a.cap1) { *a.overflow = 1; continue; }
+            ((longlong2 *) a.l1)[(long long) d * a.cap1 + pos] = m.stage[j];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart2(gx_bpart_args a)
+{
+    extern __shared__ unsigned char bp_raw[];
+    __shared__ long long scan_smem[33];
+    const int nb = 1 << a.bits_lo;
+    bp_smem m = bp_carve(bp_raw, nb);
+    const long long nwork = ((long long) 1 << a.bits_hi) * a.tiles_per_l1;
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const long long b1 = w / a.tiles_per_l1, t = w % a.tiles_per_l1;
+        long long n1 = a.cur1[b1]; if (n1 > a.cap1) n1 = a.cap1;
+        if (t * BP_TILE >= n1) continue;                       // uniform per CTA
+        const longlong2 *src = (const longlong2 *) a.l1 + b1 * a.cap1;
+        long long key[BP_PER]; unsigned long long payload[BP_PER]; bool ok[BP_PER]; unsigned int digit[BP_PER];
+#pragma unroll
+        for (int u = 0; u < BP_PER; u++) {
+            long long i = t * BP_TILE + (long long) u * BP_THREADS + threadIdx.x;
+            ok[u] = i < n1;
+            longlong2 v; v.x = 0; v.y = 0;
+            if (ok[u]) v = src[i];
+            key[u] = v.x; payload[u] = (unsigned long long) v.y;
+            digit[u] = (unsigned int) (((gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2) & (unsigned long long) (nb - 1));
+        }
+        bp_stage_tile(m, nb, key, payload, ok, digit, scan_smem);
+        if ((int) threadIdx.x < nb)
+            m.gbase[threadIdx.x] = m.hist[threadIdx.x] ? atomicAdd(&a.cursor[(b1 << a.bits_lo) | threadIdx.x], m.hist[threadIdx.x]) : 0;
+        __syncthreads();
+        const unsigned int total = m.base[nb - 1] + m.hist[nb - 1];
+        for (unsigned int j = threadIdx.x; j < total; j += blockDim.x) {
+            unsigned int d = m.bid[j];
+            unsigned int pos = m.gbase[d] + (j - m.base[d]);
+            if (pos >= GX_SUB) { *a.overflow = 1; continue; }
+            ((longlong2 *) a.pairs)[(((long long) b1 << a.bits_lo) | d) * GX_SUB + pos] = m.stage[j];
+        }
+        __syncthreads();
+    }
+}
+
 // one CTA per sub-table (grid-strided): build it in shared memory, stream it out
-__global__ void __launch_bounds__(512, 3) gx_k_bbuild_fill(gx_bbuild_args a)
+__global__ void __launch_bounds__(512, 2) gx_k_bbuild_fill(gx_bbuild_args a)
 {
     extern __shared__ gx_slot tab[];               // GX_SUB slots = 64 KB (dynamic: above the 48 KB static limit)
     for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
-        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
-        __syncthreads();
         unsigned int n = a.cursor[sub];
         if (n > GX_SUB) n = 0;                         // overflowed: the host rebuilds directly
         const longlong2 *src = (const longlong2 *) a.pairs + sub * GX_SUB;
-        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
-            longlong2 v = src[i];
-            unsigned int s = (unsigned int) (gx_key_hash(v.x) & (GX_SUB - 1));
+        // all of this thread's pairs are requested up front (GX_SUB / 512 = 8 loads in flight)
+        // and land while the sub-table is being cleared
+        longlong2 v[GX_SUB / 512];
+#pragma unroll
+        for (int u = 0; u < GX_SUB / 512; u++) {
+            unsigned int i = threadIdx.x + u * 512;
+            if (i < n) v[u] = src[i];
+        }
+        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < GX_SUB / 512; u++) {
+            unsigned int i = threadIdx.x + u * 512;
+            if (i >= n) continue;
+            unsigned int s = (unsigned int) (gx_key_hash(v[u].x) & (GX_SUB - 1));
             for (;;) {
-                long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v.x);
-                if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v.y; break; }
+                long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v[u].x);
+                if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v[u].y; break; }
                 s = (s + 1) & (GX_SUB - 1);
             }
         }
@@ -227,6 +373,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     if (inner->nrows > 0 && bucketed) {
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
         ba.b = a; ba.nsub = h->nslots / GX_SUB;
+        { const char *m = getenv("GX_SCATTER_MODE"); ba.dbg_mode = m ? atoi(m) : 0; }
         cudaError_t e = gx_tmp_alloc(ctx, (void **) &ba.cursor, (size_t) ba.nsub * sizeof(unsigned int) + sizeof(int));
         if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &ba.pairs, (size_t) h->nslots * sizeof(gx_slot));
         if (e != cudaSuccess) {
@@ -240,12 +387,39 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
         long long ntiles = (inner->nrows + 256 * BSCAT - 1) / (256 * BSCAT), maxb = (long long) ctx->sm_count * 8;
         unsigned grid = (unsigned) (ntiles < maxb ? ntiles : maxb);
-        { gx_launch_scope ls(ctx, "build_scatter"); gx_k_bbuild_scatter<<<grid, 256, 0, ctx->stream>>>(ba); }
+        int log2nsub = 0; while (((long long) 1 << log2nsub) < ba.nsub) log2nsub++;
+        const char *onepass = getenv("GX_BUILD_ONEPASS");
+        bool two_level = log2nsub >= 12 && log2nsub <= 18 && !(onepass && onepass[0] == '1');
+        if (two_level) {
+            gx_bpart_args pa; memset(&pa, 0, sizeof(pa));
+            pa.b = a; pa.nsub = ba.nsub; pa.bits_hi = (log2nsub + 1) / 2; pa.bits_lo = log2nsub - pa.bits_hi;
+            pa.pairs = ba.pairs; pa.cursor = ba.cursor; pa.overflow = ba.overflow;
+            const long long B1 = (long long) 1 << pa.bits_hi;
+            pa.cap1 = (inner->nrows / B1) + (inner->nrows / B1) / 4 + 2 * BP_TILE;
+            pa.tiles_per_l1 = (pa.cap1 + BP_TILE - 1) / BP_TILE;
+            e = gx_tmp_alloc(ctx, (void **) &pa.l1, (size_t) B1 * pa.cap1 * sizeof(gx_slot));
+            if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &pa.cur1, (size_t) B1 * sizeof(unsigned int));
+            if (e == cudaSuccess) {
+                cudaMemsetAsync(pa.cur1, 0, (size_t) B1 * sizeof(unsigned int), ctx->stream);
+                static bool attr = false;
+                if (!attr) {
+                    cudaFuncSetAttribute(gx_k_bpart1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bp_smem_bytes(512));
+                    cudaFuncSetAttribute(gx_k_bpart2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bp_smem_bytes(512));
+                    attr = true;
+                }
+                gx_launch_scope ls(ctx, "build_scatter", 2);
+                gx_k_bpart1<<<ctx->sm_count * 2, BP_THREADS, bp_smem_bytes(1 << pa.bits_hi), ctx->stream>>>(pa);
+                gx_k_bpart2<<<ctx->sm_count * 2, BP_THREADS, bp_smem_bytes(1 << pa.bits_lo), ctx->stream>>>(pa);
+            }
+            gx_tmp_free(ctx, pa.l1); gx_tmp_free(ctx, pa.cur1);
+            if (e != cudaSuccess) two_level = false;            // no room for the level-1 buffer: one-pass scatter
+        }
+        if (!two_level) { gx_launch_scope ls(ctx, "build_scatter"); gx_k_bbuild_scatter<<<grid, 256, 0, ctx->stream>>>(ba); }
         {
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(gx_k_bbuild_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); attr = true; }
             gx_launch_scope ls(ctx, "build", 2);
-            gx_k_bbuild_fill<<<ctx->sm_count * 3, 512, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+            gx_k_bbuild_fill<<<ctx->sm_count * 2, 512, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
             gx_k_bbuild_total<<<ctx->sm_count, 256, 0, ctx->stream>>>(ba.cursor, ba.nsub, ctx->d_scratch + 3);
         }
         int h_over = 0;
