@@ -140,6 +140,7 @@ def _declare(L):
         "gx_hash_build": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), C.c_int, C.POINTER(i32), C.c_int, pp]),
         "gx_hash_nentries": (i64, [vp]),
         "gx_hash_nslots": (i64, [vp]),
+        "gx_hash_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(dbl)]),
         "gx_hash_free": (None, [vp]),
         "gx_hash_probe": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), vp, C.c_int, C.POINTER(i32), pp]),
         "gx_hash_agg": (C.c_int, [vp, vp, vp, C.POINTER(GxAggPlan), pp]),
@@ -278,6 +279,11 @@ class HashTable:
     @property
     def nslots(self):
         return lib().gx_hash_nslots(self.h)
+
+    def info(self):
+        m, c = C.c_int(), C.c_double()
+        lib().gx_hash_info(self.h, C.byref(m), C.byref(c))
+        return {"slot_mode": m.value, "avg_chain": c.value}
 
     def free(self):
         if self.h:

@@ -33,7 +33,7 @@ struct gx_agg_dev {
     int wkind[GX_MAX_WORDS];
     // join table
     const gx_slot *slots; unsigned long long mask;
-    const unsigned long long *special; int special_count; int _pad0;
+    const unsigned long long *special; int special_count; int _pad0; gx_slotfn sf;
     long long row0, row1;
     // shared-memory table
     int s_slots;             // power of two; 0 = none
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_a
             for (int i = 0; i < A.special_count; i++) { consume_row<SINK>(A, T, r, A.special[i]); if (P.unique) break; }
             continue;
         }
-        unsigned long long s = gx_key_hash(key) & A.mask;
+        unsigned long long s = gx_slot_index(key, A.sf);
         for (;;) {
             gx_slot sl = A.slots[s];
             if (sl.key == GX_EMPTY_KEY) break;
@@ -454,11 +454,24 @@ __device__ __forceinline__ gx_slot ld_slot(const gx_slot *p)
     return s;
 }
 
+// Group-table update of the specialised kernel.  The key is one 4-byte value and the tag
+// word holds it whole, so the slot is taken from the key's low bits directly: dates, codes
+// and other dense domains then map without any collision (2406 consecutive dates into 4096
+// slots), anything else falls back on linear probing; a table that still overflows is
+// caught by the generic retry logic of gx_hash_agg.
 template <bool HAS_CNT, bool HAS_SUM>
 __device__ __forceinline__ void fast_flush(const SmemTable &T, const gx_agg_dev &A, int gkey, unsigned int cnt, double sum, int sum_word)
 {
-    int s = smem_upsert<false>(T, (unsigned long long) (unsigned int) gkey, 0ULL, 0u);
-    if (s < 0) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+    const unsigned long long tag = (1ULL << 63) | (unsigned long long) (unsigned int) gkey;
+    int s = (int) ((unsigned int) gkey & (unsigned int) (T.S - 1));
+    int n = 0;
+    for (;;) {
+        unsigned long long t = *(volatile unsigned long long *) &T.tag[s];
+        if (t == tag) break;
+        if (t == 0) { unsigned long long old = atomicCAS(&T.tag[s], 0ULL, tag); if (old == 0 || old == tag) break; }
+        s = (s + 1) & (T.S - 1);
+        if (++n >= 64) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+    }
     unsigned long long *w = T.w + (size_t) s * T.nwords;
     if (HAS_CNT) atomicAdd((unsigned int *) &w[0], cnt);
     if (HAS_SUM) atomicAdd((double *) &w[sum_word], sum);
@@ -496,7 +509,7 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
             // issue the first probe of every distinct neighbour first: up to four loads in flight
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                pos[i] = gx_key_hash(k[i]) & A.mask;
+                pos[i] = gx_slot_index(k[i], A.sf);
                 bool need = (i == 0) ? !lead_dup : (k[i] != k[i - 1]);
                 if (need) sl[i] = ld_slot(A.slots + pos[i]);
             }
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
                 long long key = F.okey[r];
                 if (key == GX_EMPTY_KEY) { h = A.special_count > 0; gk = h ? (int) A.special[0] : 0; }
                 else {
-                    unsigned long long p = gx_key_hash(key) & A.mask; gx_slot c = ld_slot(A.slots + p);
+                    unsigned long long p = gx_slot_index(key, A.sf); gx_slot c = ld_slot(A.slots + p);
                     while (c.key != key && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
                     h = c.key == key; gk = (int) (unsigned int) c.payload;
                 }
@@ -778,6 +791,7 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
         for (int i = 0; i < h->n_payload; i++) P.payload_types[i] = h->payload_types[i];
         cp->A.slots = h->slots; cp->A.mask = (unsigned long long) h->nslots - 1;
         cp->A.special = h->special_payload; cp->A.special_count = h->special_count;
+        cp->A.sf.mode = h->mode; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
     }
     // group columns: pack by byte width into k0 then k1
     int used[2] = { 0, 0 };

@@ -13,7 +13,7 @@
 
 #define GX_EMPTY_KEY   ((long long) 0x8000000000000000LL)   /* INT64_MIN marks an empty join slot */
 #define GX_MAX_NODES   64
-#define GX_SUB_LOG2    12                 /* join table: linear probing wraps inside 4096-slot (64 KB) sub-tables */
+#define GX_SUB_LOG2    11                 /* join table: linear probing wraps inside 2048-slot (32 KB) sub-tables */
 #define GX_SUB         (1 << GX_SUB_LOG2)
 
 // ---------------------------------------------------------------- host side
@@ -69,6 +69,9 @@ struct gx_hash {
     int n_payload;                  // 0: payload = build row number
     int32_t payload_types[GX_MAX_PAYLOAD];
     int unique;
+    int mode;                       // slot function: 0 mixing hash, 1 order-preserving interpolation (gx_slot_index)
+    long long kmin; unsigned long long scale;
+    double avg_chain;               // measured while the table was filled
     // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
     unsigned long long *special_payload; int special_cap; int special_count;
 };
@@ -315,6 +318,21 @@ __device__ __forceinline__ double gx_eval_expr(const gx_dexpr &e, long long r, b
 
 // join-table probe -------------------------------------------------------
 __device__ __forceinline__ unsigned long long gx_key_hash(long long key) { return gx_mix64((unsigned long long) key); }
+// Slot function.  A probe that misses L2 costs a whole 128-byte line of DRAM traffic
+// (profiles/r01_ncu_*: ~4 sectors per distinct key), i.e. eight 16-byte slots, so it pays
+// to keep keys that are probed together in the same line.
+//   mode 0: slot = fmix64(key) & mask                      (any keys)
+//   mode 1: slot = floor((key - kmin) * scale / 2^64)       order-preserving interpolation:
+//           keys spread near-uniformly over [kmin, kmax] (serial primary keys; TPC-H order
+//           keys) land in key order, so a probe side clustered on the key walks the table
+//           almost sequentially.  Picked from a key-density sample at build time and kept
+//           only if the chains measured while filling stay short (else rebuilt with mode 0).
+struct gx_slotfn { int mode; int _pad; long long kmin; unsigned long long scale; unsigned long long mask; };
+__device__ __forceinline__ unsigned long long gx_slot_index(long long key, const gx_slotfn &f)
+{
+    if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask;
+    return __umul64hi((unsigned long long) key - (unsigned long long) f.kmin, f.scale) & f.mask;
+}
 // next slot of a probe sequence: wraps inside the slot's sub-table (or the whole table when it is smaller)
 __device__ __forceinline__ unsigned long long gx_next_slot(unsigned long long s, unsigned long long mask)
 {

@@ -21,6 +21,7 @@ struct gx_build_args {
     long long nrows;
     gx_slot *slots; unsigned long long mask;
     unsigned long long *special; int special_cap;
+    gx_slotfn sf;                 // gx_slot_index
     long long *counters;          // [0] entries inserted, [1] special count
 };
 
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) gx_k_hash_build(gx_build_args a)
             if (idx < a.special_cap) a.special[idx] = payload;
             continue;
         }
-        unsigned long long s = gx_key_hash(key) & a.mask;
+        unsigned long long s = gx_slot_index(key, a.sf);
         for (;;) {
             long long old = (long long) atomicCAS((unsigned long long *) &a.slots[s].key,
                                                   (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key);
@@ -87,7 +88,7 @@ __global__ void gx_k_fill_slots(gx_slot *slots, long long n)
 // Bucketed build.  Random CAS into a table much larger than L2 tops out at
 // ~16-21 G inserts/s on B200 (profiles/r01_ubench_random_access.txt): every
 // insert is a DRAM read-modify-write of a sector that was just cleared.  So the
-// table is cut into sub-tables of GX_SUB slots (64 KB); linear probing wraps
+// table is cut into sub-tables of GX_SUB slots (32 KB); linear probing wraps
 // INSIDE a sub-table (all probe kernels use gx_next_slot()).  Build rows are
 // bucketed by sub-table (sequential read, 16-byte scattered stores that
 // write-combine in L2), then one CTA builds one sub-table entirely in shared
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) gx_k_bbuild_scatter(gx_bbuild_args a)
                 if (idx < a.b.special_cap) a.b.special[idx] = payload[u];
                 ok[u] = false;
             }
-            sub[u] = (gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2;
+            sub[u] = gx_slot_index(key[u], a.b.sf) >> GX_SUB_LOG2;
             if (ok[u]) pos[u] = (a.dbg_mode == 2) ? (unsigned int) (gx_key_hash(key[u]) >> 52) : atomicAdd(&a.cursor[sub[u]], 1u);
         }
 #pragma unroll
@@ -189,8 +190,19 @@ __device__ __forceinline__ void bp_stage_tile(const bp_smem &m, int nb, const lo
     unsigned int rank[BP_PER];
     for (int i = threadIdx.x; i < nb; i += blockDim.x) m.hist[i] = 0;
     __syncthreads();
+    // Sorted build input (serial keys + order-preserving slots) sends a whole warp to the same
+    // bucket: aggregate per warp first so the shared atomic is issued once per distinct bucket.
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int u = 0; u < BP_PER; u++) if (ok[u]) rank[u] = atomicAdd(&m.hist[digit[u]], 1u);
+    for (int u = 0; u < BP_PER; u++) {
+        unsigned int am = __ballot_sync(0xffffffffu, ok[u]);
+        if (!ok[u]) continue;
+        unsigned int peers = __match_any_sync(am, digit[u]);
+        int leader = __ffs(peers) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&m.hist[digit[u]], (unsigned int) __popc(peers));
+        rank[u] = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1));
+    }
     __syncthreads();
     {   // exclusive scan of the histogram (nb <= blockDim.x)
         long long tot;
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart1(gx_bpart_args a)
                 if (idx < a.b.special_cap) a.b.special[idx] = payload[u];
                 ok[u] = false;
             }
-            digit[u] = (unsigned int) (((gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2) >> a.bits_lo);
+            digit[u] = (unsigned int) ((gx_slot_index(key[u], a.b.sf) >> GX_SUB_LOG2) >> a.bits_lo);
         }
         bp_stage_tile(m, nb, key, payload, ok, digit, scan_smem);
         if ((int) threadIdx.x < nb) m.gbase[threadIdx.x] = m.hist[threadIdx.x] ? atomicAdd(&a.cur1[threadIdx.x], m.hist[threadIdx.x]) : 0;
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart2(gx_bpart_args a)
             longlong2 v; v.x = 0; v.y = 0;
             if (ok[u]) v = src[i];
             key[u] = v.x; payload[u] = (unsigned long long) v.y;
-            digit[u] = (unsigned int) (((gx_key_hash(key[u]) & a.b.mask) >> GX_SUB_LOG2) & (unsigned long long) (nb - 1));
+            digit[u] = (unsigned int) ((gx_slot_index(key[u], a.b.sf) >> GX_SUB_LOG2) & (unsigned long long) (nb - 1));
         }
         bp_stage_tile(m, nb, key, payload, ok, digit, scan_smem);
         if ((int) threadIdx.x < nb)
@@ -282,34 +294,41 @@ __global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart2(gx_bpart_args a)
 }
 
 // one CTA per sub-table (grid-strided): build it in shared memory, stream it out
-__global__ void __launch_bounds__(512, 2) gx_k_bbuild_fill(gx_bbuild_args a)
+#define FILL_THREADS 256
+__global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_bbuild_fill(gx_bbuild_args a)
 {
-    extern __shared__ gx_slot tab[];               // GX_SUB slots = 64 KB (dynamic: above the 48 KB static limit)
+    extern __shared__ gx_slot tab[];               // GX_SUB slots (dynamic shared memory)
     for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
         unsigned int n = a.cursor[sub];
         if (n > GX_SUB) n = 0;                         // overflowed: the host rebuilds directly
         const longlong2 *src = (const longlong2 *) a.pairs + sub * GX_SUB;
-        // all of this thread's pairs are requested up front (GX_SUB / 512 = 8 loads in flight)
+        unsigned int steps = 0;
+        // all of this thread's pairs are requested up front (GX_SUB / FILL_THREADS loads in flight)
         // and land while the sub-table is being cleared
-        longlong2 v[GX_SUB / 512];
+        longlong2 v[GX_SUB / FILL_THREADS];
 #pragma unroll
-        for (int u = 0; u < GX_SUB / 512; u++) {
-            unsigned int i = threadIdx.x + u * 512;
+        for (int u = 0; u < GX_SUB / FILL_THREADS; u++) {
+            unsigned int i = threadIdx.x + u * FILL_THREADS;
             if (i < n) v[u] = src[i];
         }
         for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
         __syncthreads();
 #pragma unroll
-        for (int u = 0; u < GX_SUB / 512; u++) {
-            unsigned int i = threadIdx.x + u * 512;
+        for (int u = 0; u < GX_SUB / FILL_THREADS; u++) {
+            unsigned int i = threadIdx.x + u * FILL_THREADS;
             if (i >= n) continue;
-            unsigned int s = (unsigned int) (gx_key_hash(v[u].x) & (GX_SUB - 1));
+            unsigned int s = (unsigned int) (gx_slot_index(v[u].x, a.b.sf) & (GX_SUB - 1));
             for (;;) {
                 long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v[u].x);
                 if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v[u].y; break; }
                 s = (s + 1) & (GX_SUB - 1);
+                steps++;
             }
         }
+        // chain statistics decide whether the interpolation slot function is kept
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if ((threadIdx.x & 31) == 0 && steps) atomicAdd((unsigned long long *) &a.b.counters[5], (unsigned long long) steps);
         __syncthreads();
         longlong2 *dst = (longlong2 *) (a.b.slots + sub * GX_SUB);
         for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { longlong2 v; v.x = tab[i].key; v.y = (long long) tab[i].payload; dst[i] = v; }
@@ -326,6 +345,20 @@ __global__ void gx_k_bbuild_total(const unsigned int *cursor, long long n, long 
     if ((threadIdx.x & 31) == 0 && sum) atomicAdd((unsigned long long *) total, (unsigned long long) sum);
 }
 __global__ void gx_k_scan_i64(long long *v, long long n, long long *total);   // gx_agg.cu
+
+// key-density estimate for the slot function: min / max over a strided sample
+__global__ void gx_k_key_range(gx_dcol key, long long nrows, long long stride, long long *minmax)
+{
+    long long i = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    long long lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL - 1;
+    if (i < nrows && !gx_is_null(key, i)) { lo = hi = gx_load_int(key, i); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long a = __shfl_down_sync(0xffffffffu, lo, o), b = __shfl_down_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], lo); atomicMax(&minmax[1], hi); }
+}
 
 extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, int n_preds, const gx_pred *preds,
                              int n_payload, const int32_t *payload_cols, int unique, gx_hash **out)
@@ -362,6 +395,38 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         gx_hash_free(h);
         return GX_ERR_NOMEM;
     }
+    // choose the slot function from a strided key sample (64 K keys): interpolation when the
+    // keys are spread near-uniformly over a range of at most 16 x their count
+    h->mode = 0; h->kmin = 0; h->scale = 0;
+    {
+        const char *fm = getenv("GX_SLOT_MODE");
+        int want = fm ? atoi(fm) : -1;
+        if (inner->nrows >= 4096 && h->nslots >= 64 * GX_SUB && want != 0) {
+            const long long nsample = 65536;
+            long long stride = inner->nrows / nsample; if (stride < 1) stride = 1;
+            long long nthreads = (inner->nrows + stride - 1) / stride;
+            long long init[2] = { 0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1 };
+            GX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch + 4, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+            { gx_launch_scope ls(ctx, "build_sample"); gx_k_key_range<<<(unsigned) ((nthreads + 255) / 256), 256, 0, ctx->stream>>>(a.key, inner->nrows, stride, ctx->d_scratch + 4); }
+            GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 4, ctx->d_scratch + 4, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            long long lo = ctx->h_scratch[4], hi = ctx->h_scratch[5];
+            if (hi > lo) {
+                double range = (double) hi - (double) lo + 1.0;
+                if (range <= 16.0 * (double) inner->nrows || want == 1) {
+                    // widen the sampled range a little: keys outside it still map (they just wrap)
+                    double pad = range / 1024.0 + 64.0;
+                    double lo_d = (double) lo - pad, range_d = range + 2 * pad;
+                    if (lo_d > -9.0e18 && lo_d + range_d < 9.0e18) {
+                        h->mode = 1; h->kmin = (long long) lo_d;
+                        long double sc = (long double) 18446744073709551616.0L * (long double) (h->nslots - GX_SUB) / (long double) range_d;
+                        h->scale = sc >= 18446744073709551615.0L ? ~0ULL : (unsigned long long) sc;
+                    }
+                }
+            }
+        }
+    }
+    a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_cap = h->special_cap;
     a.counters = ctx->d_scratch;
@@ -370,7 +435,10 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     const char *force = getenv("GX_BUILD_DIRECT");
     bool bucketed = h->nslots >= 64 * GX_SUB && !(force && force[0] == '1');
     long long nscattered = -1;
-    if (inner->nrows > 0 && bucketed) {
+    for (int pass = 0; pass < 2 && inner->nrows > 0 && bucketed && nscattered < 0; pass++) {
+        // second pass only when the interpolation slot function produced long chains / overflow
+        GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
+        a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
         ba.b = a; ba.nsub = h->nslots / GX_SUB;
         { const char *m = getenv("GX_SCATTER_MODE"); ba.dbg_mode = m ? atoi(m) : 0; }
@@ -385,6 +453,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         ba.overflow = (int *) (ba.cursor + ba.nsub);
         cudaMemsetAsync(ba.cursor, 0, (size_t) ba.nsub * sizeof(unsigned int) + sizeof(int), ctx->stream);
         cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
+        cudaMemsetAsync(ctx->d_scratch + 5, 0, sizeof(long long), ctx->stream);
         long long ntiles = (inner->nrows + 256 * BSCAT - 1) / (256 * BSCAT), maxb = (long long) ctx->sm_count * 8;
         unsigned grid = (unsigned) (ntiles < maxb ? ntiles : maxb);
         int log2nsub = 0; while (((long long) 1 << log2nsub) < ba.nsub) log2nsub++;
@@ -419,19 +488,22 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(gx_k_bbuild_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); attr = true; }
             gx_launch_scope ls(ctx, "build", 2);
-            gx_k_bbuild_fill<<<ctx->sm_count * 2, 512, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+            gx_k_bbuild_fill<<<ctx->sm_count * 8, FILL_THREADS, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
             gx_k_bbuild_total<<<ctx->sm_count, 256, 0, ctx->stream>>>(ba.cursor, ba.nsub, ctx->d_scratch + 3);
         }
         int h_over = 0;
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, 3 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&h_over, ba.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         gx_tmp_free(ctx, ba.cursor); gx_tmp_free(ctx, ba.pairs);
         if (e != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e)); gx_hash_free(h); return GX_ERR_CUDA; }
+        h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
+        if (h->mode == 1 && (h_over || h->avg_chain > 4.0)) { h->mode = 0; continue; }   // keys were not as uniform as the sample said
         if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
         else nscattered = ctx->h_scratch[3];
     }
+    a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
     if (inner->nrows > 0 && !bucketed) {
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
         { gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots); }
@@ -459,6 +531,13 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
 
 extern "C" int64_t gx_hash_nentries(const gx_hash *h) { return h ? h->nentries : -1; }
 extern "C" int64_t gx_hash_nslots(const gx_hash *h) { return h ? h->nslots : -1; }
+extern "C" int gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain)
+{
+    if (!h) return GX_ERR_ARG;
+    if (slot_mode) *slot_mode = h->mode;
+    if (avg_chain) *avg_chain = h->avg_chain;
+    return GX_OK;
+}
 extern "C" void gx_hash_free(gx_hash *h)
 {
     if (!h) return;
@@ -474,7 +553,7 @@ struct gx_probe_args {
     gx_dpred preds[GX_MAX_PREDS];
     long long nrows;
     const gx_slot *slots; unsigned long long mask;
-    const unsigned long long *special; int special_count;
+    const unsigned long long *special; int special_count; int _pad2; gx_slotfn sf;
     gx_dcol out_src[GX_MAX_COLS];
     void *out[GX_MAX_COLS];
     uint8_t *out_nulls[GX_MAX_COLS];
@@ -523,7 +602,7 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe(gx_probe_args a)
         }
         long long key = ok ? gx_load_int(a.key, r) : 0;
         // walk: the warp iterates until every lane has exhausted its chain
-        unsigned long long s = gx_key_hash(key) & a.mask;
+        unsigned long long s = gx_slot_index(key, a.sf);
         bool special = ok && key == GX_EMPTY_KEY;
         int sp_i = 0;
         bool active = ok;
@@ -570,6 +649,7 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
     a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique;
     a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_count = h->special_count;
+    a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     int rc = gx_fill_dpreds(ctx, outer, n_preds, preds, a.preds); if (rc) return rc;
     int32_t types[GX_MAX_COLS]; bool hn[GX_MAX_COLS];
     for (int c = 0; c < n_out_outer; c++) {

@@ -8,6 +8,6 @@ no = 1_500_000 * sf
 ot = ctx.table([g.GX_INT8, g.GX_DATE], no); ot.generate(g.T_ORDERS, sf, 0, no, colmap=[g.O_ORDERKEY, g.O_ORDERDATE])
 ctx.profile(True)
 for _ in range(4):
-    ht = ctx.hash_build(ot, 0, [1], unique=True); ht.free()
-print(json.dumps({"mode": os.environ.get("GX_SCATTER_MODE", "0"),
+    ht = ctx.hash_build(ot, 0, [1], unique=True); info = ht.info(); ht.free()
+print(json.dumps({"mode": os.environ.get("GX_SCATTER_MODE", "0"), **info,
                   **{k: round(ctx.profile_get(k)[0] / max(ctx.profile_get(k)[1], 1), 3) for k in ("build_scatter", "build")}}))
