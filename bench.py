@@ -249,6 +249,12 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
     probe_ms, probe_n = ctx.profile_get("probe_agg")
     build_ms, build_n = ctx.profile_get("build")
+    phases = {}
+    for name in ("build_sample", "build_bounds", "build_scatter", "build", "build_clear", "probe_agg", "agg", "agg_compact",
+                 "radix_partition", "radix_agg", "combine_partition", "alltoall"):
+        ms, n = ctx.profile_get(name)
+        if n:
+            phases[name] = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
     ctx.profile(False)
     dev_ms_max = allmax(dev_ms)
     wall_ms_max = allmax(wall_ms)
@@ -308,7 +314,8 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
             "config": workload_config(args, world), "rows_per_step": rows_all,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "checks": checks}
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "checks": checks,
+            "phases_ms": phases}
     print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

@@ -230,7 +230,7 @@ int  gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col,
 int64_t gx_hash_nentries(const gx_hash *h);
 int64_t gx_hash_nslots(const gx_hash *h);
 /* slot function in use (0 mixing hash, 1 order-preserving interpolation for near-uniform
- * keys) and the average probe-chain length measured while the table was filled */
+ * keys, 2 the same with the build side found in key order and built without bucketing) and the average probe-chain length measured while the table was filled */
 int  gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain);
 void gx_hash_free(gx_hash *h);
 

@@ -72,6 +72,7 @@ struct gx_hash {
     int mode;                       // slot function: 0 mixing hash, 1 order-preserving interpolation (gx_slot_index)
     long long kmin; unsigned long long scale;
     double avg_chain;               // measured while the table was filled
+    int sorted_build;               // built by the partition-free key-ordered path
     // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
     unsigned long long *special_payload; int special_cap; int special_count;
 };

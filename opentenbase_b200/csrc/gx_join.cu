@@ -101,6 +101,7 @@ struct gx_bbuild_args {
     gx_slot *pairs;             // nsub fixed-capacity buckets of GX_SUB pairs (a fuller bucket cannot be built anyway)
     int *overflow;
     int dbg_mode;               // 0 normal; 1 atomics only; 2 stores only (development experiments)
+    long long *start; int *unsorted;   // key-ordered build: first row of every sub-table
 };
 
 __device__ __forceinline__ bool build_row_ok(const gx_build_args &a, long long r)
@@ -335,6 +336,83 @@ __global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_bbuild_fill(gx_bbuild_ar
         __syncthreads();
     }
 }
+
+// ---------------------------------------------------------------------------
+// Partition-free build for a build side that is stored in key order (a table kept in
+// primary-key order, e.g. TPC-H orders) when the order-preserving slot function is in
+// use: the rows of one sub-table are then one CONTIGUOUS row range, found by binary
+// search, so no bucketing pass is needed at all — each CTA reads its rows straight from
+// the columns (coalesced), builds the sub-table in shared memory and streams it out.
+// one coalesced pass over the key column: verifies ascending order and records, for every
+// sub-table, the first row that maps to it (start[nsub] = nrows)
+__global__ void gx_k_sorted_bounds(gx_build_args a, long long nsub, long long *start, int *unsorted)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < a.nrows; i += stride) {
+        if (gx_is_null(a.key, i)) { *unsorted = 1; return; }
+        long long k = gx_load_int(a.key, i);
+        long long sb = (k == GX_EMPTY_KEY) ? -1 : (long long) (gx_slot_index(k, a.sf) >> GX_SUB_LOG2);
+        long long sp = -1;
+        if (i > 0) {
+            long long kp = gx_load_int(a.key, i - 1);
+            if (kp > k) { *unsorted = 1; return; }
+            sp = (kp == GX_EMPTY_KEY) ? -1 : (long long) (gx_slot_index(kp, a.sf) >> GX_SUB_LOG2);
+        }
+        for (long long s2 = sp + 1; s2 <= sb; s2++) start[s2] = i;
+        if (i == a.nrows - 1) for (long long s2 = sb + 1; s2 <= nsub; s2++) start[s2] = a.nrows;
+    }
+}
+
+__global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_sorted_fill(gx_bbuild_args a)
+{
+    extern __shared__ gx_slot tab[];
+    if (*a.unsorted) return;
+    for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
+        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
+        __syncthreads();
+        const long long lo = a.start[sub], hi = a.start[sub + 1];
+        unsigned int steps = 0, placed = 0;
+        if (hi - lo > GX_SUB) { if (threadIdx.x == 0) *a.overflow = 1; }
+        else {
+            for (long long r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+                if (!build_row_ok(a.b, r)) continue;
+                long long key = gx_load_int(a.b.key, r);
+                unsigned long long payload = pack_payload(a.b, r);
+                unsigned int s = (unsigned int) (gx_slot_index(key, a.b.sf) & (GX_SUB - 1));
+                for (;;) {
+                    long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key);
+                    if (old == GX_EMPTY_KEY) { tab[s].payload = payload; break; }
+                    s = (s + 1) & (GX_SUB - 1);
+                    steps++;
+                }
+                placed++;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { steps += __shfl_down_sync(0xffffffffu, steps, o); placed += __shfl_down_sync(0xffffffffu, placed, o); }
+        if ((threadIdx.x & 31) == 0) {
+            if (steps) atomicAdd((unsigned long long *) &a.b.counters[5], (unsigned long long) steps);
+            if (placed) atomicAdd((unsigned long long *) &a.b.counters[3], (unsigned long long) placed);
+        }
+        __syncthreads();
+        longlong2 *dst = (longlong2 *) (a.b.slots + sub * GX_SUB);
+        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { longlong2 v; v.x = tab[i].key; v.y = (long long) tab[i].payload; dst[i] = v; }
+        __syncthreads();
+    }
+}
+// rows with the reserved key INT64_MIN sort first: move them to the side list
+__global__ void gx_k_sorted_special(gx_build_args a, const long long *start, const int *unsorted)
+{
+    if (*unsorted) return;
+    const long long n = start[0];
+    for (long long r = threadIdx.x; r < n; r += blockDim.x) {
+        if (gx_is_null(a.key, r) || gx_load_int(a.key, r) != GX_EMPTY_KEY) continue;
+        if (!build_row_ok(a, r)) continue;
+        int idx = (int) atomicAdd((unsigned long long *) &a.counters[1], 1ULL);
+        if (idx < a.special_cap) a.special[idx] = pack_payload(a, r);
+    }
+}
+
 // entries actually placed = sum of the cursors
 __global__ void gx_k_bbuild_total(const unsigned int *cursor, long long n, long long *total)
 {
@@ -440,7 +518,57 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
         a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
-        ba.b = a; ba.nsub = h->nslots / GX_SUB;
+        ba.nsub = h->nslots / GX_SUB;
+        // ---- key-ordered build side + order-preserving slots: no bucketing needed
+        const char *nosort = getenv("GX_BUILD_NOSORTED");
+        if (h->mode == 1 && !(nosort && nosort[0] == '1')) {
+            int *d_flag = (int *) (ctx->d_scratch + 6);
+            long long ends[2] = { 0, 0 };
+            int ksz = gx_type_size(kt);
+            cudaMemsetAsync(d_flag, 0, 2 * sizeof(long long), ctx->stream);          // [6] unsorted flag, [7] overflow
+            cudaMemcpyAsync(&ends[0], (const char *) inner->cols[key_col], ksz, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(&ends[1], (const char *) inner->cols[key_col] + (size_t) (inner->nrows - 1) * ksz, ksz, cudaMemcpyDeviceToHost, ctx->stream);
+            GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            long long kmin = ksz == 4 ? (long long) (int) ends[0] : ends[0], kmax = ksz == 4 ? (long long) (int) ends[1] : ends[1];
+            if (kmin == GX_EMPTY_KEY) kmin = kmin + 1;                                  // the reserved key lives in the side list
+            double range_d = (double) kmax - (double) kmin + 1.0;
+            long long *d_start = nullptr;
+            if (range_d >= 1.0 && range_d < 9.0e18 && range_d <= 16.0 * (double) inner->nrows &&
+                gx_tmp_alloc(ctx, (void **) &d_start, (size_t) (ba.nsub + 1) * sizeof(long long)) == cudaSuccess) {
+                // exact bounds (if the column really is ordered): every key maps below nslots - GX_SUB, monotonically
+                long long save_kmin = h->kmin; unsigned long long save_scale = h->scale;
+                h->kmin = kmin;
+                long double sc = (long double) 18446744073709551616.0L * (long double) (h->nslots - GX_SUB) / (long double) range_d;
+                h->scale = sc >= 18446744073709551615.0L ? ~0ULL : (unsigned long long) sc;
+                a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+                ba.b = a; ba.overflow = (int *) (ctx->d_scratch + 7); ba.start = d_start; ba.unsorted = d_flag;
+                cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
+                cudaMemsetAsync(ctx->d_scratch + 5, 0, sizeof(long long), ctx->stream);
+                static bool sattr = false;
+                if (!sattr) { cudaFuncSetAttribute(gx_k_sorted_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); sattr = true; }
+                { gx_launch_scope ls(ctx, "build_bounds"); gx_k_sorted_bounds<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ba.nsub, d_start, d_flag); }
+                {
+                    gx_launch_scope ls(ctx, "build", 2);
+                    gx_k_sorted_special<<<1, 256, 0, ctx->stream>>>(a, d_start, d_flag);
+                    gx_k_sorted_fill<<<ctx->sm_count * 8, FILL_THREADS, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+                }
+                cudaError_t e2 = cudaGetLastError();
+                if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, 5 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+                gx_tmp_free(ctx, d_start);
+                if (e2 != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e2)); gx_hash_free(h); return GX_ERR_CUDA; }
+                if ((int) ctx->h_scratch[6] == 0) {
+                    h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
+                    if ((int) ctx->h_scratch[7] == 0 && h->avg_chain <= 4.0) { nscattered = ctx->h_scratch[3]; h->sorted_build = 1; break; }
+                    h->mode = 0; continue;                                               // clustered keys: rebuild with the mixing hash
+                }
+                // not in key order: back to the sampled slot function and the bucketing passes
+                h->kmin = save_kmin; h->scale = save_scale;
+                a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+                GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
+            }
+        }
+        ba.b = a;
         { const char *m = getenv("GX_SCATTER_MODE"); ba.dbg_mode = m ? atoi(m) : 0; }
         cudaError_t e = gx_tmp_alloc(ctx, (void **) &ba.cursor, (size_t) ba.nsub * sizeof(unsigned int) + sizeof(int));
         if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &ba.pairs, (size_t) h->nslots * sizeof(gx_slot));
@@ -534,7 +662,7 @@ extern "C" int64_t gx_hash_nslots(const gx_hash *h) { return h ? h->nslots : -1;
 extern "C" int gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain)
 {
     if (!h) return GX_ERR_ARG;
-    if (slot_mode) *slot_mode = h->mode;
+    if (slot_mode) *slot_mode = h->sorted_build ? 2 : h->mode;
     if (avg_chain) *avg_chain = h->avg_chain;
     return GX_OK;
 }

@@ -132,6 +132,42 @@ def test_config3_join_groupby(gx, data, strategy):
     assert got[1][:, 0].view(np.int64).sum() == data["lt"].nrows      # every line finds its order
 
 
+@pytest.mark.parametrize("layout", ["key_order", "shuffled", "key_order_filtered", "clustered"])
+def test_big_build_paths_agree_with_oracle(gx, layout):
+    """Build sides large enough for the sub-table builders (>= 64 sub-tables): the
+    partition-free path for a build side stored in key order, the two-level bucketing
+    path for an unordered one, and the fall-back to the mixing hash when the keys are
+    clustered — all three must give the oracle's join (nodeHash.c:1828, nodeHashjoin.c:446)."""
+    nord = 200_000
+    o, l = O.gen_orders(SF, 0, nord), O.gen_lineitem(SF, 0, nord)
+    o = [c.copy() for c in o]; l = [c.copy() for c in l]
+    inner_preds = []
+    if layout == "shuffled":
+        perm = np.random.default_rng(7).permutation(nord)
+        o = [c[perm] for c in o]
+    elif layout == "key_order_filtered":
+        inner_preds = [(g.O_ORDERDATE, g.GX_LT, -1752)]
+    elif layout == "clustered":                       # ascending but bunched: half the keys in a narrow band
+        k = o[g.O_ORDERKEY]
+        remap = np.where(k % 2 == 0, k // 64, k)
+        o[g.O_ORDERKEY] = np.sort(remap)
+        l[g.L_ORDERKEY] = np.where(l[g.L_ORDERKEY] % 2 == 0, l[g.L_ORDERKEY] // 64, l[g.L_ORDERKEY])
+    plan = O.make_plan(outer_key_col=g.L_ORDERKEY, group_cols=[(1, 0)],
+                       aggs=[(g.GX_AGG_COUNT_STAR, []), (g.GX_AGG_SUM_F8, [(g.GX_OP_COL, g.L_EXTENDEDPRICE, 0)])],
+                       est_groups=2500)
+    join = O.make_join(g.O_ORDERKEY, payload_cols=[g.O_ORDERDATE], inner_unique=0, inner_preds=inner_preds)
+    want = O.exec_agg(lineitem_rel(l), plan, orders_rel(o), join)
+    ot = gx.table_from(g.SCHEMAS[g.T_ORDERS], o); lt = gx.table_from(g.SCHEMAS[g.T_LINEITEM], l)
+    ht = gx.hash_build(ot, g.O_ORDERKEY, [g.O_ORDERDATE], unique=False, preds=inner_preds)
+    info = ht.info()
+    if layout in ("key_order", "key_order_filtered"):
+        assert info["slot_mode"] == 2, info          # partition-free key-ordered build
+    elif layout == "shuffled":
+        assert info["slot_mode"] == 1, info          # interpolation slots, bucketed build
+    got = gx.hash_agg(lt, to_gpu_plan(plan), ht).fetch()
+    assert_agg_equal(plan, got, want)
+
+
 def test_q3_shape_two_word_key(gx, data):
     """GROUP BY l_orderkey, o_orderdate, o_shippriority: 16-byte key, many groups -> radix."""
     C, K, S, M = g.GX_OP_COL, g.GX_OP_CONST, g.GX_OP_SUB, g.GX_OP_MUL
