@@ -791,7 +791,7 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
         for (int i = 0; i < h->n_payload; i++) P.payload_types[i] = h->payload_types[i];
         cp->A.slots = h->slots; cp->A.mask = (unsigned long long) h->nslots - 1;
         cp->A.special = h->special_payload; cp->A.special_count = h->special_count;
-        cp->A.sf.mode = h->mode; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
+        cp->A.sf.mode = h->mode; cp->A.sf.win = h->win; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
     }
     // group columns: pack by byte width into k0 then k1
     int used[2] = { 0, 0 };

@@ -70,7 +70,7 @@ struct gx_hash {
     int32_t payload_types[GX_MAX_PAYLOAD];
     int unique;
     int mode;                       // slot function: 0 mixing hash, 1 order-preserving interpolation (gx_slot_index)
-    long long kmin; unsigned long long scale;
+    long long kmin; unsigned long long scale; unsigned int win;
     double avg_chain;               // measured while the table was filled
     int sorted_build;               // built by the partition-free key-ordered path
     // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
@@ -328,11 +328,17 @@ __device__ __forceinline__ unsigned long long gx_key_hash(long long key) { retur
 //           keys) land in key order, so a probe side clustered on the key walks the table
 //           almost sequentially.  Picked from a key-density sample at build time and kept
 //           only if the chains measured while filling stay short (else rebuilt with mode 0).
-struct gx_slotfn { int mode; int _pad; long long kmin; unsigned long long scale; unsigned long long mask; };
+// mode 1 maps keys to slots in key order (probes of a key-ordered outer side then walk
+// the table front to back); `win` (0 or 2^w - 1) additionally scatters the low w slot bits
+// with a multiplicative hash, which breaks up the pile-ups that locally bunched keys
+// (TPC-H order keys: 8 used of every 32) cause under pure interpolation while keeping
+// every key inside the same few cache lines and the same sub-table.
+struct gx_slotfn { int mode; unsigned int win; long long kmin; unsigned long long scale; unsigned long long mask; };
 __device__ __forceinline__ unsigned long long gx_slot_index(long long key, const gx_slotfn &f)
 {
     if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask;
-    return __umul64hi((unsigned long long) key - (unsigned long long) f.kmin, f.scale) & f.mask;
+    unsigned long long s = __umul64hi((unsigned long long) key - (unsigned long long) f.kmin, f.scale) & f.mask;
+    return s ^ ((unsigned long long) (((unsigned long long) key * 0x9E3779B97F4A7C15ULL) >> 40) & f.win);
 }
 // next slot of a probe sequence: wraps inside the slot's sub-table (or the whole table when it is smaller)
 __device__ __forceinline__ unsigned long long gx_next_slot(unsigned long long s, unsigned long long mask)

@@ -294,47 +294,146 @@ __global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart2(gx_bpart_args a)
     }
 }
 
-// one CTA per sub-table (grid-strided): build it in shared memory, stream it out
+// ---------------------------------------------------------------------------
+// Building one sub-table (GX_SUB slots) in shared memory WITHOUT a compare-and-swap loop.
+// A linear-probing table filled in slot order has a closed form: with c[s] rows hashing to
+// slot s, the first of them lands at s + e[s], where e[s] = max(0, e[s-1] + c[s-1] - 1) is
+// the overflow carried in from the left.  With P[s] = sum_{t<s} (c[t] - 1) this is
+// e[s] = P[s] - min_{j<=s} P[j]: one histogram (native 32-bit shared atomics, which also
+// hand every row its rank among the rows of its slot), one block-wide scan of the pair
+// (sum, prefix-minimum), one conflict-free placement pass.  Rows pushed past the end of
+// the sub-table wrap to its start; they are rare and go through a CAS loop afterwards.
+// Any prober that walks from slot(key) to the right (gx_next_slot) finds every key before
+// it meets an empty slot, exactly as with CAS insertion.
 #define FILL_THREADS 256
+#define FILL_ROWS (GX_SUB / FILL_THREADS)          // rows (and slots) per thread
+struct gx_fill_smem {
+    gx_slot tab[GX_SUB];
+    unsigned int cnt[GX_SUB];                      // histogram, then e[s]
+    int wsum[FILL_THREADS / 32], wmin[FILL_THREADS / 32];
+};
+#define FILL_SMEM_BYTES ((int) sizeof(gx_fill_smem))
+#define FILL_INF (1 << 29)
+
+template <class LOAD>
+__device__ __forceinline__ void gx_subtable_build(gx_fill_smem &sm, unsigned int n, const gx_slotfn &sf, LOAD load, gx_slot *dst,
+                                                  unsigned int &steps, unsigned int &placed)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- clear: histogram and table
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 *c4 = (uint4 *) sm.cnt;
+        for (int i = tid; i < GX_SUB / 4; i += FILL_THREADS) c4[i] = z;
+        longlong2 e; e.x = GX_EMPTY_KEY; e.y = 0;
+        longlong2 *t2 = (longlong2 *) sm.tab;
+#pragma unroll
+        for (int u = 0; u < FILL_ROWS; u++) t2[tid + u * FILL_THREADS] = e;
+    }
+    __syncthreads();
+    // ---- histogram + rank
+    long long key[FILL_ROWS]; unsigned long long pay[FILL_ROWS]; unsigned int sr[FILL_ROWS];
+#pragma unroll
+    for (int u = 0; u < FILL_ROWS; u++) {
+        unsigned int i = tid + u * FILL_THREADS;
+        sr[u] = 0xffffffffu;
+        if (i < n && load(i, key[u], pay[u])) {
+            unsigned int sl = (unsigned int) (gx_slot_index(key[u], sf) & (GX_SUB - 1));
+            sr[u] = sl | (atomicAdd(&sm.cnt[sl], 1u) << GX_SUB_LOG2);
+        }
+    }
+    __syncthreads();
+    // ---- e[s] for the FILL_ROWS slots this thread owns
+    {
+        int c[FILL_ROWS];
+        const uint4 *c4 = (const uint4 *) (sm.cnt + tid * FILL_ROWS);
+#pragma unroll
+        for (int q = 0; q < FILL_ROWS / 4; q++) { uint4 v = c4[q]; c[4 * q] = (int) v.x; c[4 * q + 1] = (int) v.y; c[4 * q + 2] = (int) v.z; c[4 * q + 3] = (int) v.w; }
+        int p[FILL_ROWS], run = 0, lmin = 0;
+#pragma unroll
+        for (int j = 0; j < FILL_ROWS; j++) { p[j] = run; lmin = min(lmin, run); run += c[j] - 1; }
+        // inclusive warp scan of (sum, prefix-min) with combine(a, b) = (a.s + b.s, min(a.m, a.s + b.m))
+        int S = run, M = lmin;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int ps = __shfl_up_sync(0xffffffffu, S, o), pm = __shfl_up_sync(0xffffffffu, M, o);
+            if (lane >= o) { M = min(pm, ps + M); S = ps + S; }
+        }
+        if (lane == 31) { sm.wsum[warp] = S; sm.wmin[warp] = M; }
+        int xs = __shfl_up_sync(0xffffffffu, S, 1), xm = __shfl_up_sync(0xffffffffu, M, 1);
+        if (lane == 0) { xs = 0; xm = FILL_INF; }
+        __syncthreads();
+        int bs = 0, bm = FILL_INF;                    // everything in the warps before this one
+        for (int w = 0; w < warp; w++) { bm = min(bm, bs + sm.wmin[w]); bs += sm.wsum[w]; }
+        const int base = bs + xs, mprev = min(bm, bs + xm);   // P at this thread's first slot; min of P over all earlier slots
+        int rmin = mprev;
+        uint4 o4[FILL_ROWS / 4];
+        unsigned int *o = (unsigned int *) o4;
+#pragma unroll
+        for (int j = 0; j < FILL_ROWS; j++) { int P = base + p[j]; rmin = min(rmin, P); o[j] = (unsigned int) (P - rmin); }
+        uint4 *d4 = (uint4 *) (sm.cnt + tid * FILL_ROWS);
+#pragma unroll
+        for (int q = 0; q < FILL_ROWS / 4; q++) d4[q] = o4[q];
+    }
+    __syncthreads();
+    // ---- placement
+    int wrapped = 0;
+#pragma unroll
+    for (int u = 0; u < FILL_ROWS; u++) {
+        if (sr[u] == 0xffffffffu) continue;
+        unsigned int sl = sr[u] & (GX_SUB - 1), pos = sl + sm.cnt[sl] + (sr[u] >> GX_SUB_LOG2);
+        steps += pos - sl; placed++;
+        if (pos < GX_SUB) { longlong2 v; v.x = key[u]; v.y = (long long) pay[u]; ((longlong2 *) sm.tab)[pos] = v; sr[u] = 0xffffffffu; }
+        else wrapped = 1;
+    }
+    if (__syncthreads_or(wrapped)) {
+#pragma unroll
+        for (int u = 0; u < FILL_ROWS; u++) {
+            if (sr[u] == 0xffffffffu) continue;
+            unsigned int sl = 0;                      // everything from its slot to the end is full: continue from the start
+            for (;;) {
+                long long old = (long long) atomicCAS((unsigned long long *) &sm.tab[sl].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key[u]);
+                if (old == GX_EMPTY_KEY) { sm.tab[sl].payload = pay[u]; break; }
+                sl = (sl + 1) & (GX_SUB - 1); steps++;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- stream the finished sub-table out
+    {
+        const longlong2 *t2 = (const longlong2 *) sm.tab;
+        longlong2 *d2 = (longlong2 *) dst;
+#pragma unroll
+        for (int u = 0; u < FILL_ROWS; u++) d2[tid + u * FILL_THREADS] = t2[tid + u * FILL_THREADS];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void fill_report(const gx_build_args &b, unsigned int steps, unsigned int placed)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { steps += __shfl_down_sync(0xffffffffu, steps, o); placed += __shfl_down_sync(0xffffffffu, placed, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (steps) atomicAdd((unsigned long long *) &b.counters[5], (unsigned long long) steps);      // chain statistics decide whether
+        if (placed) atomicAdd((unsigned long long *) &b.counters[3], (unsigned long long) placed);    // the slot function is kept
+    }
+}
+
+// one CTA per sub-table (grid-strided) over the buckets the scatter passes produced
 __global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_bbuild_fill(gx_bbuild_args a)
 {
-    extern __shared__ gx_slot tab[];               // GX_SUB slots (dynamic shared memory)
+    extern __shared__ __align__(16) unsigned char fill_smem_raw[];
+    gx_fill_smem &sm = *(gx_fill_smem *) fill_smem_raw;
+    unsigned int steps = 0, placed = 0;
     for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
         unsigned int n = a.cursor[sub];
         if (n > GX_SUB) n = 0;                         // overflowed: the host rebuilds directly
         const longlong2 *src = (const longlong2 *) a.pairs + sub * GX_SUB;
-        unsigned int steps = 0;
-        // all of this thread's pairs are requested up front (GX_SUB / FILL_THREADS loads in flight)
-        // and land while the sub-table is being cleared
-        longlong2 v[GX_SUB / FILL_THREADS];
-#pragma unroll
-        for (int u = 0; u < GX_SUB / FILL_THREADS; u++) {
-            unsigned int i = threadIdx.x + u * FILL_THREADS;
-            if (i < n) v[u] = src[i];
-        }
-        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < GX_SUB / FILL_THREADS; u++) {
-            unsigned int i = threadIdx.x + u * FILL_THREADS;
-            if (i >= n) continue;
-            unsigned int s = (unsigned int) (gx_slot_index(v[u].x, a.b.sf) & (GX_SUB - 1));
-            for (;;) {
-                long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) v[u].x);
-                if (old == GX_EMPTY_KEY) { tab[s].payload = (unsigned long long) v[u].y; break; }
-                s = (s + 1) & (GX_SUB - 1);
-                steps++;
-            }
-        }
-        // chain statistics decide whether the interpolation slot function is kept
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
-        if ((threadIdx.x & 31) == 0 && steps) atomicAdd((unsigned long long *) &a.b.counters[5], (unsigned long long) steps);
-        __syncthreads();
-        longlong2 *dst = (longlong2 *) (a.b.slots + sub * GX_SUB);
-        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { longlong2 v; v.x = tab[i].key; v.y = (long long) tab[i].payload; dst[i] = v; }
-        __syncthreads();
+        gx_subtable_build(sm, n, a.b.sf,
+                          [&](unsigned int i, long long &k, unsigned long long &p) { longlong2 v = src[i]; k = v.x; p = (unsigned long long) v.y; return true; },
+                          a.b.slots + sub * GX_SUB, steps, placed);
     }
+    fill_report(a.b, steps, 0);                        // entries are counted from the cursors (gx_k_bbuild_total)
 }
 
 // ---------------------------------------------------------------------------
@@ -363,42 +462,65 @@ __global__ void gx_k_sorted_bounds(gx_build_args a, long long nsub, long long *s
     }
 }
 
-__global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_sorted_fill(gx_bbuild_args a)
+// the same for an int8 key column without NULLs: 4 consecutive keys per lane (two 16-byte
+// loads), the predecessor of a lane's first key comes from the lane below by shuffle
+__global__ void __launch_bounds__(256) gx_k_sorted_bounds_i8(const long long *__restrict__ keys, long long nrows, gx_slotfn sf,
+                                                             long long nsub, long long *start, int *unsorted)
 {
-    extern __shared__ gx_slot tab[];
-    if (*a.unsorted) return;
-    for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
-        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { tab[i].key = GX_EMPTY_KEY; tab[i].payload = 0; }
-        __syncthreads();
-        const long long lo = a.start[sub], hi = a.start[sub + 1];
-        unsigned int steps = 0, placed = 0;
-        if (hi - lo > GX_SUB) { if (threadIdx.x == 0) *a.overflow = 1; }
-        else {
-            for (long long r = lo + threadIdx.x; r < hi; r += blockDim.x) {
-                if (!build_row_ok(a.b, r)) continue;
-                long long key = gx_load_int(a.b.key, r);
-                unsigned long long payload = pack_payload(a.b, r);
-                unsigned int s = (unsigned int) (gx_slot_index(key, a.b.sf) & (GX_SUB - 1));
-                for (;;) {
-                    long long old = (long long) atomicCAS((unsigned long long *) &tab[s].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key);
-                    if (old == GX_EMPTY_KEY) { tab[s].payload = payload; break; }
-                    s = (s + 1) & (GX_SUB - 1);
-                    steps++;
-                }
-                placed++;
-            }
+    const int lane = threadIdx.x & 31;
+    const long long nwarp = ((long long) gridDim.x * blockDim.x) >> 5, wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long ngroups = (nrows + 127) >> 7;
+    bool bad = false;
+    for (long long gq = wid; gq < ngroups; gq += nwarp) {
+        const long long r0 = (gq << 7) + lane * 4;
+        long long k[4];
+        if (r0 + 3 < nrows) {
+            longlong2 a = __ldg((const longlong2 *) (keys + r0)), b = __ldg((const longlong2 *) (keys + r0 + 2));
+            k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) k[j] = r0 + j < nrows ? __ldg(keys + r0 + j) : 0x7fffffffffffffffLL;
+        }
+        long long sb[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) sb[j] = (k[j] == GX_EMPTY_KEY) ? -1 : (long long) (gx_slot_index(k[j], sf) >> GX_SUB_LOG2);
+        long long kp = __shfl_up_sync(0xffffffffu, k[3], 1), sp = __shfl_up_sync(0xffffffffu, sb[3], 1);
+        if (lane == 0) {
+            if (r0 == 0) { kp = k[0]; sp = -1; }
+            else { kp = __ldg(keys + r0 - 1); sp = (kp == GX_EMPTY_KEY) ? -1 : (long long) (gx_slot_index(kp, sf) >> GX_SUB_LOG2); }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { steps += __shfl_down_sync(0xffffffffu, steps, o); placed += __shfl_down_sync(0xffffffffu, placed, o); }
-        if ((threadIdx.x & 31) == 0) {
-            if (steps) atomicAdd((unsigned long long *) &a.b.counters[5], (unsigned long long) steps);
-            if (placed) atomicAdd((unsigned long long *) &a.b.counters[3], (unsigned long long) placed);
+        for (int j = 0; j < 4; j++) {
+            const long long r = r0 + j;
+            if (r < nrows) {
+                if (kp > k[j]) bad = true;
+                if (sb[j] != sp) for (long long s2 = sp + 1; s2 <= sb[j]; s2++) start[s2] = r;
+                if (r == nrows - 1) for (long long s2 = sb[j] + 1; s2 <= nsub; s2++) start[s2] = nrows;
+                kp = k[j]; sp = sb[j];
+            }
         }
-        __syncthreads();
-        longlong2 *dst = (longlong2 *) (a.b.slots + sub * GX_SUB);
-        for (int i = threadIdx.x; i < GX_SUB; i += blockDim.x) { longlong2 v; v.x = tab[i].key; v.y = (long long) tab[i].payload; dst[i] = v; }
-        __syncthreads();
     }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) *unsorted = 1;
+}
+
+__global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_sorted_fill(gx_bbuild_args a)
+{
+    extern __shared__ __align__(16) unsigned char fill_smem_raw[];
+    gx_fill_smem &sm = *(gx_fill_smem *) fill_smem_raw;
+    if (*a.unsorted) return;
+    unsigned int steps = 0, placed = 0;
+    for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
+        const long long lo = a.start[sub], hi = a.start[sub + 1];
+        unsigned int n = (unsigned int) (hi - lo);
+        if (hi - lo > GX_SUB) { n = 0; if (threadIdx.x == 0) *a.overflow = 1; }
+        gx_subtable_build(sm, n, a.b.sf,
+                          [&](unsigned int i, long long &k, unsigned long long &p) {
+                              long long r = lo + i;
+                              if (!build_row_ok(a.b, r)) return false;
+                              k = gx_load_int(a.b.key, r); p = pack_payload(a.b, r); return true; },
+                          a.b.slots + sub * GX_SUB, steps, placed);
+    }
+    fill_report(a.b, steps, placed);
 }
 // rows with the reserved key INT64_MIN sort first: move them to the side list
 __global__ void gx_k_sorted_special(gx_build_args a, const long long *start, const int *unsorted)
@@ -476,6 +598,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     // choose the slot function from a strided key sample (64 K keys): interpolation when the
     // keys are spread near-uniformly over a range of at most 16 x their count
     h->mode = 0; h->kmin = 0; h->scale = 0;
+    { const char *w = getenv("GX_SLOT_WIN"); h->win = w ? (unsigned int) atoi(w) : 31u; }
     {
         const char *fm = getenv("GX_SLOT_MODE");
         int want = fm ? atoi(fm) : -1;
@@ -504,7 +627,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             }
         }
     }
-    a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_cap = h->special_cap;
     a.counters = ctx->d_scratch;
@@ -516,7 +639,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     for (int pass = 0; pass < 2 && inner->nrows > 0 && bucketed && nscattered < 0; pass++) {
         // second pass only when the interpolation slot function produced long chains / overflow
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
-        a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+        a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
         ba.nsub = h->nslots / GX_SUB;
         // ---- key-ordered build side + order-preserving slots: no bucketing needed
@@ -545,12 +668,18 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch + 5, 0, sizeof(long long), ctx->stream);
                 static bool sattr = false;
-                if (!sattr) { cudaFuncSetAttribute(gx_k_sorted_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); sattr = true; }
-                { gx_launch_scope ls(ctx, "build_bounds"); gx_k_sorted_bounds<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ba.nsub, d_start, d_flag); }
+                if (!sattr) { cudaFuncSetAttribute(gx_k_sorted_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES); sattr = true; }
+                {
+                    gx_launch_scope ls(ctx, "build_bounds");
+                    if (kt == GX_INT8 && a.key.nulls == nullptr && ((uintptr_t) a.key.data & 15) == 0)
+                        gx_k_sorted_bounds_i8<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *) a.key.data, inner->nrows, a.sf, ba.nsub, d_start, d_flag);
+                    else
+                        gx_k_sorted_bounds<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ba.nsub, d_start, d_flag);
+                }
                 {
                     gx_launch_scope ls(ctx, "build", 2);
                     gx_k_sorted_special<<<1, 256, 0, ctx->stream>>>(a, d_start, d_flag);
-                    gx_k_sorted_fill<<<ctx->sm_count * 8, FILL_THREADS, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+                    gx_k_sorted_fill<<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
                 }
                 cudaError_t e2 = cudaGetLastError();
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, 5 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -614,9 +743,9 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         if (!two_level) { gx_launch_scope ls(ctx, "build_scatter"); gx_k_bbuild_scatter<<<grid, 256, 0, ctx->stream>>>(ba); }
         {
             static bool attr = false;
-            if (!attr) { cudaFuncSetAttribute(gx_k_bbuild_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GX_SUB * sizeof(gx_slot))); attr = true; }
+            if (!attr) { cudaFuncSetAttribute(gx_k_bbuild_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES); attr = true; }
             gx_launch_scope ls(ctx, "build", 2);
-            gx_k_bbuild_fill<<<ctx->sm_count * 8, FILL_THREADS, GX_SUB * sizeof(gx_slot), ctx->stream>>>(ba);
+            gx_k_bbuild_fill<<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
             gx_k_bbuild_total<<<ctx->sm_count, 256, 0, ctx->stream>>>(ba.cursor, ba.nsub, ctx->d_scratch + 3);
         }
         int h_over = 0;
@@ -631,7 +760,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
         else nscattered = ctx->h_scratch[3];
     }
-    a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
     if (inner->nrows > 0 && !bucketed) {
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
         { gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots); }
@@ -777,7 +906,7 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
     a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique;
     a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_count = h->special_count;
-    a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     int rc = gx_fill_dpreds(ctx, outer, n_preds, preds, a.preds); if (rc) return rc;
     int32_t types[GX_MAX_COLS]; bool hn[GX_MAX_COLS];
     for (int c = 0; c < n_out_outer; c++) {
