@@ -447,6 +447,14 @@ __device__ __forceinline__ int4 ld_stream_i4(const int *p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+// two neighbouring slots (one aligned 32-byte sector) with a single 256-bit load
+struct gx_slot2 { long long k0; unsigned long long p0; long long k1; unsigned long long p1; };
+__device__ __forceinline__ gx_slot2 ld_slot2(const gx_slot *p)
+{
+    gx_slot2 s;
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(s.k0), "=l"(s.p0), "=l"(s.k1), "=l"(s.p1) : "l"(p));
+    return s;
+}
 __device__ __forceinline__ gx_slot ld_slot(const gx_slot *p)
 {
     gx_slot s;
@@ -493,40 +501,55 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
     for (long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += stride) {
         const long long r = A.row0 + (q << 2);
         int g[4]; bool hit[4]; double v[4];
+        unsigned int rcnt = 0; double rsum = 0.0;                     // partial handed over by the lane above
         if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
         if (JOIN) {
             longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
             long long k[4] = { ka.x, ka.y, kb.x, kb.y };
-            gx_slot sl[4]; unsigned long long pos[4];
+            gx_slot2 sl[4];
             // A run of equal keys that started in the previous lane is not probed again:
             // ncu showed such cross-lane repeats re-fetching their sector from DRAM
-            // (profiles/r01_ncu_fast_probe_and_bucket_build_sf100.csv).  The lane takes the
-            // neighbour's answer by shuffle once that lane has resolved it.
+            // (profiles/r01_ncu_fast_probe_and_bucket_build_sf100.csv).
             const unsigned int wmask = __activemask();
             const int lane = threadIdx.x & 31;
             long long prevk = __shfl_up_sync(wmask, k[3], 1);
-            bool lead_dup = lane > 0 && ((wmask >> (lane - 1)) & 1u) && k[0] == prevk;
-            // issue the first probe of every distinct neighbour first: up to four loads in flight
+            const bool lead_dup = lane > 0 && ((wmask >> (lane - 1)) & 1u) && k[0] == prevk;
+            // a leading run that ends inside this lane is handed to the lane below as a partial
+            // (count, sum): that lane has probed the key and does the one group update
+            const bool give = lead_dup && k[3] != k[0];
+            // first probe of every distinct neighbour: one 32-byte load fetches the key's home
+            // pair of slots (gx_slot_index is even); up to four loads in flight
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                pos[i] = gx_slot_index(k[i], A.sf);
                 bool need = (i == 0) ? !lead_dup : (k[i] != k[i - 1]);
-                if (need) sl[i] = ld_slot(A.slots + pos[i]);
+                if (need) sl[i] = ld_slot2(A.slots + gx_slot_index(k[i], A.sf));
             }
-            bool valid0 = !lead_dup;
+            bool valid0 = !lead_dup || give;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (i > 0 && k[i] == k[i - 1]) { g[i] = g[i - 1]; hit[i] = hit[i - 1]; continue; }
-                if (i == 0 && lead_dup) { g[0] = 0; hit[0] = false; continue; }       // filled in below
+                if (i == 0 && lead_dup) { g[0] = 0; hit[0] = give; continue; }        // give: counted below; else filled in by the hand-down
                 if (k[i] == GX_EMPTY_KEY) {                    // lives in the side list, never in the table
                     hit[i] = A.special_count > 0; g[i] = hit[i] ? (int) A.special[0] : 0; continue;
                 }
-                gx_slot c = sl[i]; unsigned long long p = pos[i];
-                while (c.key != k[i] && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
-                hit[i] = c.key == k[i]; g[i] = (int) (unsigned int) c.payload;
+                gx_slot2 c = sl[i];
+                if (c.k0 == k[i]) { hit[i] = true; g[i] = (int) (unsigned int) c.p0; }
+                else if (c.k0 == GX_EMPTY_KEY) { hit[i] = false; g[i] = 0; }
+                else if (c.k1 == k[i]) { hit[i] = true; g[i] = (int) (unsigned int) c.p1; }
+                else if (c.k1 == GX_EMPTY_KEY) { hit[i] = false; g[i] = 0; }
+                else {                                         // both home slots taken by other keys: walk on, a pair at a time
+                    unsigned long long p = gx_slot_index(k[i], A.sf);
+                    for (;;) {
+                        p = gx_next_pair(p, A.mask); c = ld_slot2(A.slots + p);
+                        if (c.k0 == k[i]) { hit[i] = true; g[i] = (int) (unsigned int) c.p0; break; }
+                        if (c.k0 == GX_EMPTY_KEY) { hit[i] = false; g[i] = 0; break; }
+                        if (c.k1 == k[i]) { hit[i] = true; g[i] = (int) (unsigned int) c.p1; break; }
+                        if (c.k1 == GX_EMPTY_KEY) { hit[i] = false; g[i] = 0; break; }
+                    }
+                }
             }
-            // hand results down the warp; a run can span several lanes, so iterate until every
-            // lane is settled (TPC-H orders have at most 7 lines: two rounds)
+            // whole-lane runs (the lane's four rows all continue the previous lane's key) take the
+            // answer from below; such a run can span several lanes, so iterate until settled
             bool valid3 = valid0 || k[3] != k[0];
             while (__any_sync(wmask, !valid0)) {
                 int pg = __shfl_up_sync(wmask, g[3], 1);
@@ -538,6 +561,17 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
                     valid3 = true;
                 }
             }
+            // partial of a handed-over leading run
+            unsigned int gcnt = 0; double gsum = 0.0;
+            if (give) {
+#pragma unroll
+                bool in = true;
+#pragma unroll
+                for (int i = 0; i < 3; i++) { in = in && k[i] == k[0]; if (in) { gcnt++; if (HAS_SUM) gsum = __dadd_rn(gsum, v[i]); hit[i] = false; } }
+            }
+            rcnt = __shfl_down_sync(wmask, gcnt, 1);
+            if (HAS_SUM) rsum = __shfl_down_sync(wmask, gsum, 1);
+            if (lane == 31 || !((wmask >> (lane + 1)) & 1u)) { rcnt = 0; rsum = 0.0; }
         } else {
             int4 gg = ld_stream_i4(F.gcol + r);
             g[0] = gg.x; g[1] = gg.y; g[2] = gg.z; g[3] = gg.w;
@@ -552,7 +586,7 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
             if (open) fast_flush<HAS_CNT, HAS_SUM>(T, A, cur, cnt, sum, F.sum_word);
             open = true; cur = g[i]; cnt = 1; sum = HAS_SUM ? v[i] : 0.0;
         }
-        if (open) fast_flush<HAS_CNT, HAS_SUM>(T, A, cur, cnt, sum, F.sum_word);
+        if (open) { cnt += rcnt; if (HAS_SUM) sum = __dadd_rn(sum, rsum); fast_flush<HAS_CNT, HAS_SUM>(T, A, cur, cnt, sum, F.sum_word); }
     }
     // the (< 4) rows after the last full vector: one thread each
     {

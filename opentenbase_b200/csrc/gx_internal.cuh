@@ -336,9 +336,17 @@ __device__ __forceinline__ unsigned long long gx_key_hash(long long key) { retur
 struct gx_slotfn { int mode; unsigned int win; long long kmin; unsigned long long scale; unsigned long long mask; };
 __device__ __forceinline__ unsigned long long gx_slot_index(long long key, const gx_slotfn &f)
 {
-    if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask;
+    // Home slots are EVEN: a key's home is the aligned pair {s, s+1} (one 32-byte sector),
+    // which a prober can fetch with a single 256-bit load; linear probing is unchanged.
+    if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask & ~1ULL;
     unsigned long long s = __umul64hi((unsigned long long) key - (unsigned long long) f.kmin, f.scale) & f.mask;
-    return s ^ ((unsigned long long) (((unsigned long long) key * 0x9E3779B97F4A7C15ULL) >> 40) & f.win);
+    return (s ^ ((unsigned long long) (((unsigned long long) key * 0x9E3779B97F4A7C15ULL) >> 40) & f.win)) & ~1ULL;
+}
+// next aligned pair of a probe sequence (same wrapping rule as gx_next_slot)
+__device__ __forceinline__ unsigned long long gx_next_pair(unsigned long long s, unsigned long long mask)
+{
+    const unsigned long long w = mask < (GX_SUB - 1) ? mask : (unsigned long long) (GX_SUB - 1);
+    return (s & ~w) | ((s + 2) & w);
 }
 // next slot of a probe sequence: wraps inside the slot's sub-table (or the whole table when it is smaller)
 __device__ __forceinline__ unsigned long long gx_next_slot(unsigned long long s, unsigned long long mask)

@@ -503,22 +503,47 @@ __global__ void __launch_bounds__(256) gx_k_sorted_bounds_i8(const long long *__
     if (__any_sync(0xffffffffu, bad) && lane == 0) *unsorted = 1;
 }
 
+// PK selects the row loader: 0 generic (any key type, NULLs, build-side quals, packed payload),
+// 1 = int8 key without NULLs or quals + one 4-byte payload column, 2 = the same without payload
+template <int PK>
 __global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_sorted_fill(gx_bbuild_args a)
 {
     extern __shared__ __align__(16) unsigned char fill_smem_raw[];
     gx_fill_smem &sm = *(gx_fill_smem *) fill_smem_raw;
     if (*a.unsorted) return;
     unsigned int steps = 0, placed = 0;
+    const long long *keys = (const long long *) a.b.key.data;
+    const unsigned int *pay4 = (const unsigned int *) a.b.payload[0].data;
+    long long lo = 0, hi = 0;
+    if (blockIdx.x < a.nsub) { lo = a.start[blockIdx.x]; hi = a.start[blockIdx.x + 1]; }
     for (long long sub = blockIdx.x; sub < a.nsub; sub += gridDim.x) {
-        const long long lo = a.start[sub], hi = a.start[sub + 1];
+        // the next sub-table's row range: fetch its bounds now and pull its rows towards L2
+        // while this one is being built
+        long long nlo = 0, nhi = 0;
+        const long long nsubn = sub + gridDim.x;
+        if (nsubn < a.nsub) { nlo = a.start[nsubn]; nhi = a.start[nsubn + 1]; }
         unsigned int n = (unsigned int) (hi - lo);
         if (hi - lo > GX_SUB) { n = 0; if (threadIdx.x == 0) *a.overflow = 1; }
-        gx_subtable_build(sm, n, a.b.sf,
-                          [&](unsigned int i, long long &k, unsigned long long &p) {
-                              long long r = lo + i;
-                              if (!build_row_ok(a.b, r)) return false;
-                              k = gx_load_int(a.b.key, r); p = pack_payload(a.b, r); return true; },
-                          a.b.slots + sub * GX_SUB, steps, placed);
+        if (PK != 0 && nhi - nlo <= GX_SUB) {
+            const long long l = nlo + (long long) threadIdx.x * 16;          // 16 keys = one 128-byte line
+            if (l < nhi) asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + l));
+            if (PK == 1) { const long long l4 = nlo + (long long) threadIdx.x * 32; if (l4 < nhi) asm volatile("prefetch.global.L2 [%0];" :: "l"(pay4 + l4)); }
+        }
+        if (PK == 0)
+            gx_subtable_build(sm, n, a.b.sf,
+                              [&](unsigned int i, long long &k, unsigned long long &p) {
+                                  long long r = lo + i;
+                                  if (!build_row_ok(a.b, r)) return false;
+                                  k = gx_load_int(a.b.key, r); p = pack_payload(a.b, r); return true; },
+                              a.b.slots + sub * GX_SUB, steps, placed);
+        else
+            gx_subtable_build(sm, n, a.b.sf,
+                              [&](unsigned int i, long long &k, unsigned long long &p) {
+                                  k = __ldg(keys + lo + i);
+                                  p = PK == 1 ? (unsigned long long) __ldg(pay4 + lo + i) : (unsigned long long) (lo + i);
+                                  return true; },
+                              a.b.slots + sub * GX_SUB, steps, placed);
+        lo = nlo; hi = nhi;
     }
     fill_report(a.b, steps, placed);
 }
@@ -667,8 +692,18 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 ba.b = a; ba.overflow = (int *) (ctx->d_scratch + 7); ba.start = d_start; ba.unsorted = d_flag;
                 cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch + 5, 0, sizeof(long long), ctx->stream);
+                int pk = 0;
+                if (kt == GX_INT8 && a.key.nulls == nullptr && a.npreds == 0) {
+                    if (a.n_payload == 0) pk = 2;
+                    else if (a.n_payload == 1 && (a.payload[0].type == GX_INT4 || a.payload[0].type == GX_DATE)) pk = 1;
+                }
                 static bool sattr = false;
-                if (!sattr) { cudaFuncSetAttribute(gx_k_sorted_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES); sattr = true; }
+                if (!sattr) {
+                    cudaFuncSetAttribute(gx_k_sorted_fill<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    sattr = true;
+                }
                 {
                     gx_launch_scope ls(ctx, "build_bounds");
                     if (kt == GX_INT8 && a.key.nulls == nullptr && ((uintptr_t) a.key.data & 15) == 0)
@@ -679,7 +714,10 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 {
                     gx_launch_scope ls(ctx, "build", 2);
                     gx_k_sorted_special<<<1, 256, 0, ctx->stream>>>(a, d_start, d_flag);
-                    gx_k_sorted_fill<<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    const unsigned int fgrid = ctx->sm_count * 8;
+                    if (pk == 1) gx_k_sorted_fill<1><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else if (pk == 2) gx_k_sorted_fill<2><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else gx_k_sorted_fill<0><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
                 }
                 cudaError_t e2 = cudaGetLastError();
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, 5 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);

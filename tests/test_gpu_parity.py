@@ -132,7 +132,7 @@ def test_config3_join_groupby(gx, data, strategy):
     assert got[1][:, 0].view(np.int64).sum() == data["lt"].nrows      # every line finds its order
 
 
-@pytest.mark.parametrize("layout", ["key_order", "shuffled", "key_order_filtered", "clustered"])
+@pytest.mark.parametrize("layout", ["key_order", "shuffled", "key_order_filtered", "clustered", "key_order_no_payload"])
 def test_big_build_paths_agree_with_oracle(gx, layout):
     """Build sides large enough for the sub-table builders (>= 64 sub-tables): the
     partition-free path for a build side stored in key order, the two-level bucketing
@@ -152,15 +152,20 @@ def test_big_build_paths_agree_with_oracle(gx, layout):
         remap = np.where(k % 2 == 0, k // 64, k)
         o[g.O_ORDERKEY] = np.sort(remap)
         l[g.L_ORDERKEY] = np.where(l[g.L_ORDERKEY] % 2 == 0, l[g.L_ORDERKEY] // 64, l[g.L_ORDERKEY])
-    plan = O.make_plan(outer_key_col=g.L_ORDERKEY, group_cols=[(1, 0)],
+    payload = [g.O_ORDERDATE]
+    group_cols = [(1, 0)]
+    if layout == "key_order_no_payload":              # the join only filters: half the orders are kept out of the build side
+        payload, group_cols = [], [(0, g.L_SHIPDATE)]
+        o = [c[::2].copy() for c in o]
+    plan = O.make_plan(outer_key_col=g.L_ORDERKEY, group_cols=group_cols,
                        aggs=[(g.GX_AGG_COUNT_STAR, []), (g.GX_AGG_SUM_F8, [(g.GX_OP_COL, g.L_EXTENDEDPRICE, 0)])],
-                       est_groups=2500)
-    join = O.make_join(g.O_ORDERKEY, payload_cols=[g.O_ORDERDATE], inner_unique=0, inner_preds=inner_preds)
+                       est_groups=2600)
+    join = O.make_join(g.O_ORDERKEY, payload_cols=payload, inner_unique=0, inner_preds=inner_preds)
     want = O.exec_agg(lineitem_rel(l), plan, orders_rel(o), join)
     ot = gx.table_from(g.SCHEMAS[g.T_ORDERS], o); lt = gx.table_from(g.SCHEMAS[g.T_LINEITEM], l)
-    ht = gx.hash_build(ot, g.O_ORDERKEY, [g.O_ORDERDATE], unique=False, preds=inner_preds)
+    ht = gx.hash_build(ot, g.O_ORDERKEY, payload, unique=False, preds=inner_preds)
     info = ht.info()
-    if layout in ("key_order", "key_order_filtered"):
+    if layout in ("key_order", "key_order_filtered", "key_order_no_payload"):
         assert info["slot_mode"] == 2, info          # partition-free key-ordered build
     elif layout == "shuffled":
         assert info["slot_mode"] == 1, info          # interpolation slots, bucketed build
