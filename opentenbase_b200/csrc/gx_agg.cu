@@ -609,6 +609,120 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
     smem_dense_merge(T, A);
 }
 
+// ---------------------------------------------------------------------------
+// Join + aggregate for an outer side whose equal keys sit next to each other (lineitem in
+// order-key order: runs of 1..7 rows).  A warp takes 128 consecutive rows, four per lane,
+// finds the run heads, and folds every run to ONE (key, count, sum) entry of a per-warp
+// shared-memory list — the entries of a run that spans lanes are merged there.  Then the
+// list is processed densely, one run per lane: slot function, one 256-bit load of the key's
+// home pair, one group-table update.  Against the row-per-lane kernel above this removes
+// the repeated probes, the divergent per-row code and three of four group updates; ncu had
+// shown that kernel issue-bound at 13.8 of 32 threads per instruction
+// (profiles/r01_ncu_probe_pairs_sf100.csv).
+struct gx_runlist { long long key[128]; double sum[128]; unsigned int cnt[128]; };
+
+template <bool HAS_CNT, bool HAS_SUM>
+__global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
+{
+    extern __shared__ unsigned long long smem[];
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = 1; T.tagkey = 1; T.gmax = 0;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0; T.w = T.k0; T.gidx = nullptr; T.gcount = nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gx_runlist &Q = ((gx_runlist *) (smem + (size_t) T.S * (1 + T.nwords)))[warp];
+    for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+        T.tag[i] = 0;
+        for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+    }
+    __syncthreads();
+    const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    long long k[4]; double v[4];
+    bool act = q < nvec;
+    if (act) {
+        const long long r = A.row0 + (q << 2);
+        longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+        k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+        if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+    }
+    // the loop is warp-uniform: lanes past the end carry no rows
+    while (__any_sync(0xffffffffu, act)) {
+        // ---- run heads and their numbering inside the warp
+        const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+        bool hd[4];
+        hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+        const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
+        int inc = nh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int base = inc - nh, R = __shfl_sync(0xffffffffu, inc, 31);
+        // ---- fold: runs that start in this lane are stored, the rows that continue the previous
+        // lane's run are added to that run afterwards
+        unsigned int c0 = 0; double s0 = 0.0;
+        if (act) {
+            int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (hd[i]) {
+                    if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+                    rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
+                }
+                c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+            }
+            if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+        }
+        __syncwarp();
+        if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
+        __syncwarp();
+        // ---- next rows: requested now, they arrive while the runs are probed
+        q += stride; act = q < nvec;
+        if (act) {
+            const long long r = A.row0 + (q << 2);
+            longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+            k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+            if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+        }
+        // ---- one run per lane
+        for (int j = lane; j < R; j += 32) {
+            const long long key = Q.key[j];
+            const unsigned int rc = Q.cnt[j];
+            const double rs = HAS_SUM ? Q.sum[j] : 0.0;
+            bool hit; int g = 0;
+            if (key == GX_EMPTY_KEY) { hit = A.special_count > 0; if (hit) g = (int) A.special[0]; }    // side list, never in the table
+            else {
+                unsigned long long p = gx_slot_index(key, A.sf);
+                gx_slot2 c = ld_slot2(A.slots + p);
+                for (;;) {
+                    if (c.k0 == key) { hit = true; g = (int) (unsigned int) c.p0; break; }
+                    if (c.k0 == GX_EMPTY_KEY) { hit = false; break; }
+                    if (c.k1 == key) { hit = true; g = (int) (unsigned int) c.p1; break; }
+                    if (c.k1 == GX_EMPTY_KEY) { hit = false; break; }
+                    p = gx_next_pair(p, A.mask); c = ld_slot2(A.slots + p);
+                }
+            }
+            if (hit) fast_flush<HAS_CNT, HAS_SUM>(T, A, g, rc, rs, F.sum_word);
+        }
+        __syncwarp();
+    }
+    // the (< 4) rows after the last full vector: one thread each
+    {
+        long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < A.row1) {
+            bool h = true; int gk;
+            long long key = F.okey[r];
+            if (key == GX_EMPTY_KEY) { h = A.special_count > 0; gk = h ? (int) A.special[0] : 0; }
+            else {
+                unsigned long long p = gx_slot_index(key, A.sf); gx_slot c = ld_slot(A.slots + p);
+                while (c.key != key && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
+                h = c.key == key; gk = (int) (unsigned int) c.payload;
+            }
+            if (h) fast_flush<HAS_CNT, HAS_SUM>(T, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0, F.sum_word);
+        }
+    }
+    __syncthreads();
+    smem_dense_merge(T, A);
+}
+
 // global table -> dense records [meta][k0][k1][w..]
 __global__ void gx_k_compact_groups(const unsigned long long *g_tab, long long g_cap, int nwords,
                                     unsigned long long *recs, long long *cursor)
@@ -825,7 +939,7 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
         for (int i = 0; i < h->n_payload; i++) P.payload_types[i] = h->payload_types[i];
         cp->A.slots = h->slots; cp->A.mask = (unsigned long long) h->nslots - 1;
         cp->A.special = h->special_payload; cp->A.special_count = h->special_count;
-        cp->A.sf.mode = h->mode; cp->A.sf.win = h->win; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
+        cp->A.sf.mode = h->mode; cp->A.sf.win = h->win; cp->A.sf.shift = h->shift; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
     }
     // group columns: pack by byte width into k0 then k1
     int used[2] = { 0, 0 };
@@ -955,8 +1069,33 @@ static int launch_fast_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &F
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
+template <bool HAS_CNT, bool HAS_SUM>
+static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t smem, const char *name)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin<HAS_CNT, HAS_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set = true;
+    }
+    long long nvec = (A.row1 - A.row0 + 3) / 4;
+    long long nb = (nvec + 1023) / 1024, maxb = (long long) ctx->sm_count;
+    while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 32)) maxb *= 2;
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_k_runjoin<HAS_CNT, HAS_SUM><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
 static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name)
 {
+    // the run-folding join kernel needs a per-warp run list next to the group table
+    const size_t run_bytes = 32 * sizeof(gx_runlist);
+    const char *norun = getenv("GX_NO_RUNJOIN");
+    if (join && smem + run_bytes <= ctx->smem_optin - 1024 && !(norun && norun[0] == '1')) {
+        if (cnt && sum) return launch_runjoin_t<true, true>(ctx, A, FA, smem + run_bytes, name);
+        if (cnt) return launch_runjoin_t<true, false>(ctx, A, FA, smem + run_bytes, name);
+        return launch_runjoin_t<false, true>(ctx, A, FA, smem + run_bytes, name);
+    }
     if (join) {
         if (cnt && sum) return launch_fast_t<true, true, true>(ctx, A, FA, smem, name);
         if (cnt) return launch_fast_t<true, true, false>(ctx, A, FA, smem, name);

@@ -70,7 +70,7 @@ struct gx_hash {
     int32_t payload_types[GX_MAX_PAYLOAD];
     int unique;
     int mode;                       // slot function: 0 mixing hash, 1 order-preserving interpolation (gx_slot_index)
-    long long kmin; unsigned long long scale; unsigned int win;
+    long long kmin; unsigned long long scale; unsigned int win; unsigned int shift;
     double avg_chain;               // measured while the table was filled
     int sorted_build;               // built by the partition-free key-ordered path
     // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
@@ -333,12 +333,18 @@ __device__ __forceinline__ unsigned long long gx_key_hash(long long key) { retur
 // with a multiplicative hash, which breaks up the pile-ups that locally bunched keys
 // (TPC-H order keys: 8 used of every 32) cause under pure interpolation while keeping
 // every key inside the same few cache lines and the same sub-table.
-struct gx_slotfn { int mode; unsigned int win; long long kmin; unsigned long long scale; unsigned long long mask; };
+struct gx_slotfn { int mode; unsigned int win; long long kmin; unsigned long long scale; unsigned long long mask; unsigned int shift; unsigned int _pad; };
 __device__ __forceinline__ unsigned long long gx_slot_index(long long key, const gx_slotfn &f)
 {
     // Home slots are EVEN: a key's home is the aligned pair {s, s+1} (one 32-byte sector),
     // which a prober can fetch with a single 256-bit load; linear probing is unchanged.
     if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask & ~1ULL;
+    if (f.mode == 2) {
+        // key range below 2^32: the same interpolation in 32-bit arithmetic (one wide multiply)
+        const unsigned int d = (unsigned int) ((unsigned long long) key - (unsigned long long) f.kmin);
+        const unsigned long long s = (((unsigned long long) d * (unsigned int) f.scale) >> f.shift) & f.mask;
+        return (s ^ (unsigned long long) (((d * 0x9E3779B9u) >> 24) & f.win)) & ~1ULL;
+    }
     unsigned long long s = __umul64hi((unsigned long long) key - (unsigned long long) f.kmin, f.scale) & f.mask;
     return (s ^ ((unsigned long long) (((unsigned long long) key * 0x9E3779B97F4A7C15ULL) >> 40) & f.win)) & ~1ULL;
 }

@@ -585,6 +585,25 @@ __global__ void gx_k_key_range(gx_dcol key, long long nrows, long long stride, l
     if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], lo); atomicMax(&minmax[1], hi); }
 }
 
+// interpolation slot function over [kmin, kmin + range): slots [0, nslots - GX_SUB), monotone in the key.
+// Narrow ranges (< 2^32, the usual case: at most 16 keys of range per row) use 32-bit arithmetic.
+static void gx_set_interpolation(gx_hash *h, long long kmin, double range_d)
+{
+    const long double ratio = (long double) (h->nslots - GX_SUB) / (long double) range_d;
+    h->kmin = kmin;
+    const char *wide = getenv("GX_SLOT_WIDE");
+    if (range_d < 4294967295.0 && !(wide && wide[0] == '1')) {
+        int sh = 0;
+        while (sh < 62 && ratio * (long double) (1ULL << (sh + 1)) < 4294967295.0L) sh++;
+        h->mode = 2; h->shift = (unsigned int) sh;
+        h->scale = (unsigned long long) (ratio * (long double) (1ULL << sh));
+        return;
+    }
+    h->mode = 1; h->shift = 0;
+    const long double sc = (long double) 18446744073709551616.0L * ratio;
+    h->scale = sc >= 18446744073709551615.0L ? ~0ULL : (unsigned long long) sc;
+}
+
 extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, int n_preds, const gx_pred *preds,
                              int n_payload, const int32_t *payload_cols, int unique, gx_hash **out)
 {
@@ -622,7 +641,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     }
     // choose the slot function from a strided key sample (64 K keys): interpolation when the
     // keys are spread near-uniformly over a range of at most 16 x their count
-    h->mode = 0; h->kmin = 0; h->scale = 0;
+    h->mode = 0; h->kmin = 0; h->scale = 0; h->shift = 0;
     { const char *w = getenv("GX_SLOT_WIN"); h->win = w ? (unsigned int) atoi(w) : 31u; }
     {
         const char *fm = getenv("GX_SLOT_MODE");
@@ -644,15 +663,13 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     double pad = range / 1024.0 + 64.0;
                     double lo_d = (double) lo - pad, range_d = range + 2 * pad;
                     if (lo_d > -9.0e18 && lo_d + range_d < 9.0e18) {
-                        h->mode = 1; h->kmin = (long long) lo_d;
-                        long double sc = (long double) 18446744073709551616.0L * (long double) (h->nslots - GX_SUB) / (long double) range_d;
-                        h->scale = sc >= 18446744073709551615.0L ? ~0ULL : (unsigned long long) sc;
+                        gx_set_interpolation(h, (long long) lo_d, range_d);
                     }
                 }
             }
         }
     }
-    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_cap = h->special_cap;
     a.counters = ctx->d_scratch;
@@ -664,12 +681,12 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     for (int pass = 0; pass < 2 && inner->nrows > 0 && bucketed && nscattered < 0; pass++) {
         // second pass only when the interpolation slot function produced long chains / overflow
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
-        a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+        a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
         ba.nsub = h->nslots / GX_SUB;
         // ---- key-ordered build side + order-preserving slots: no bucketing needed
         const char *nosort = getenv("GX_BUILD_NOSORTED");
-        if (h->mode == 1 && !(nosort && nosort[0] == '1')) {
+        if (h->mode != 0 && !(nosort && nosort[0] == '1')) {
             int *d_flag = (int *) (ctx->d_scratch + 6);
             long long ends[2] = { 0, 0 };
             int ksz = gx_type_size(kt);
@@ -684,11 +701,10 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             if (range_d >= 1.0 && range_d < 9.0e18 && range_d <= 16.0 * (double) inner->nrows &&
                 gx_tmp_alloc(ctx, (void **) &d_start, (size_t) (ba.nsub + 1) * sizeof(long long)) == cudaSuccess) {
                 // exact bounds (if the column really is ordered): every key maps below nslots - GX_SUB, monotonically
-                long long save_kmin = h->kmin; unsigned long long save_scale = h->scale;
-                h->kmin = kmin;
-                long double sc = (long double) 18446744073709551616.0L * (long double) (h->nslots - GX_SUB) / (long double) range_d;
-                h->scale = sc >= 18446744073709551615.0L ? ~0ULL : (unsigned long long) sc;
-                a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+                const long long save_kmin = h->kmin; const unsigned long long save_scale = h->scale;
+                const int save_mode = h->mode; const unsigned int save_shift = h->shift;
+                gx_set_interpolation(h, kmin, range_d);
+                a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.shift = h->shift;
                 ba.b = a; ba.overflow = (int *) (ctx->d_scratch + 7); ba.start = d_start; ba.unsorted = d_flag;
                 cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch + 5, 0, sizeof(long long), ctx->stream);
@@ -730,8 +746,8 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     h->mode = 0; continue;                                               // clustered keys: rebuild with the mixing hash
                 }
                 // not in key order: back to the sampled slot function and the bucketing passes
-                h->kmin = save_kmin; h->scale = save_scale;
-                a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+                h->kmin = save_kmin; h->scale = save_scale; h->mode = save_mode; h->shift = save_shift;
+                a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.shift = h->shift;
                 GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
             }
         }
@@ -794,11 +810,11 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         gx_tmp_free(ctx, ba.cursor); gx_tmp_free(ctx, ba.pairs);
         if (e != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e)); gx_hash_free(h); return GX_ERR_CUDA; }
         h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
-        if (h->mode == 1 && (h_over || h->avg_chain > 4.0)) { h->mode = 0; continue; }   // keys were not as uniform as the sample said
+        if (h->mode != 0 && (h_over || h->avg_chain > 4.0)) { h->mode = 0; continue; }   // keys were not as uniform as the sample said
         if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
         else nscattered = ctx->h_scratch[3];
     }
-    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
     if (inner->nrows > 0 && !bucketed) {
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
         { gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots); }
@@ -829,7 +845,7 @@ extern "C" int64_t gx_hash_nslots(const gx_hash *h) { return h ? h->nslots : -1;
 extern "C" int gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain)
 {
     if (!h) return GX_ERR_ARG;
-    if (slot_mode) *slot_mode = h->sorted_build ? 2 : h->mode;
+    if (slot_mode) *slot_mode = h->sorted_build ? 2 : (h->mode != 0 ? 1 : 0);
     if (avg_chain) *avg_chain = h->avg_chain;
     return GX_OK;
 }
@@ -944,7 +960,7 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
     a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique;
     a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_count = h->special_count;
-    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     int rc = gx_fill_dpreds(ctx, outer, n_preds, preds, a.preds); if (rc) return rc;
     int32_t types[GX_MAX_COLS]; bool hn[GX_MAX_COLS];
     for (int c = 0; c < n_out_outer; c++) {

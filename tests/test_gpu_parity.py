@@ -145,6 +145,8 @@ def test_big_build_paths_agree_with_oracle(gx, layout):
     if layout == "shuffled":
         perm = np.random.default_rng(7).permutation(nord)
         o = [c[perm] for c in o]
+        lperm = np.random.default_rng(8).permutation(len(l[0]))      # outer side without key runs as well
+        l = [c[lperm] for c in l]
     elif layout == "key_order_filtered":
         inner_preds = [(g.O_ORDERDATE, g.GX_LT, -1752)]
     elif layout == "clustered":                       # ascending but bunched: half the keys in a narrow band
@@ -160,10 +162,11 @@ def test_big_build_paths_agree_with_oracle(gx, layout):
     plan = O.make_plan(outer_key_col=g.L_ORDERKEY, group_cols=group_cols,
                        aggs=[(g.GX_AGG_COUNT_STAR, []), (g.GX_AGG_SUM_F8, [(g.GX_OP_COL, g.L_EXTENDEDPRICE, 0)])],
                        est_groups=2600)
-    join = O.make_join(g.O_ORDERKEY, payload_cols=payload, inner_unique=0, inner_preds=inner_preds)
+    uniq = layout != "clustered"                     # unique build keys take the specialised probe kernels
+    join = O.make_join(g.O_ORDERKEY, payload_cols=payload, inner_unique=int(uniq), inner_preds=inner_preds)
     want = O.exec_agg(lineitem_rel(l), plan, orders_rel(o), join)
     ot = gx.table_from(g.SCHEMAS[g.T_ORDERS], o); lt = gx.table_from(g.SCHEMAS[g.T_LINEITEM], l)
-    ht = gx.hash_build(ot, g.O_ORDERKEY, payload, unique=False, preds=inner_preds)
+    ht = gx.hash_build(ot, g.O_ORDERKEY, payload, unique=uniq, preds=inner_preds)
     info = ht.info()
     if layout in ("key_order", "key_order_filtered", "key_order_no_payload"):
         assert info["slot_mode"] == 2, info          # partition-free key-ordered build
