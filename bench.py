@@ -296,7 +296,7 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "probe_agg_traffic.json"))).get("dram_bytes_per_launch_sf100")
     except (OSError, ValueError):
         pass
-    roofline = {"kernel": "gx_k_agg (fused hash probe + hash aggregate over lineitem)", "bound": "hbm",
+    roofline = {"kernel": "gx_k_runjoin (fused hash probe + hash aggregate over lineitem)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nl * ALG_BYTES_PER_PROBE_ROW, "avg_launch_ms": probe_avg_ms,
