@@ -642,6 +642,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     // choose the slot function from a strided key sample (64 K keys): interpolation when the
     // keys are spread near-uniformly over a range of at most 16 x their count
     h->mode = 0; h->kmin = 0; h->scale = 0; h->shift = 0;
+    bool have_ends = false, counts_read = false;
     { const char *w = getenv("GX_SLOT_WIN"); h->win = w ? (unsigned int) atoi(w) : 31u; }
     {
         const char *fm = getenv("GX_SLOT_MODE");
@@ -654,6 +655,14 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             GX_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch + 4, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
             { gx_launch_scope ls(ctx, "build_sample"); gx_k_key_range<<<(unsigned) ((nthreads + 255) / 256), 256, 0, ctx->stream>>>(a.key, inner->nrows, stride, ctx->d_scratch + 4); }
             GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 4, ctx->d_scratch + 4, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            // the column's first and last key ride along: the key-ordered build path below needs them
+            {
+                const int ksz0 = gx_type_size(kt);
+                ctx->h_scratch[20] = ctx->h_scratch[21] = 0;
+                GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 20, (const char *) inner->cols[key_col], ksz0, cudaMemcpyDeviceToHost, ctx->stream));
+                GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 21, (const char *) inner->cols[key_col] + (size_t) (inner->nrows - 1) * ksz0, ksz0, cudaMemcpyDeviceToHost, ctx->stream));
+                have_ends = true;
+            }
             GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             long long lo = ctx->h_scratch[4], hi = ctx->h_scratch[5];
             if (hi > lo) {
@@ -688,12 +697,17 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         const char *nosort = getenv("GX_BUILD_NOSORTED");
         if (h->mode != 0 && !(nosort && nosort[0] == '1')) {
             int *d_flag = (int *) (ctx->d_scratch + 6);
-            long long ends[2] = { 0, 0 };
+            long long ends[2];
             int ksz = gx_type_size(kt);
             cudaMemsetAsync(d_flag, 0, 2 * sizeof(long long), ctx->stream);          // [6] unsorted flag, [7] overflow
-            cudaMemcpyAsync(&ends[0], (const char *) inner->cols[key_col], ksz, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaMemcpyAsync(&ends[1], (const char *) inner->cols[key_col] + (size_t) (inner->nrows - 1) * ksz, ksz, cudaMemcpyDeviceToHost, ctx->stream);
-            GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (!have_ends) {
+                ctx->h_scratch[20] = ctx->h_scratch[21] = 0;
+                cudaMemcpyAsync(ctx->h_scratch + 20, (const char *) inner->cols[key_col], ksz, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(ctx->h_scratch + 21, (const char *) inner->cols[key_col] + (size_t) (inner->nrows - 1) * ksz, ksz, cudaMemcpyDeviceToHost, ctx->stream);
+                GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                have_ends = true;
+            }
+            ends[0] = ctx->h_scratch[20]; ends[1] = ctx->h_scratch[21];
             long long kmin = ksz == 4 ? (long long) (int) ends[0] : ends[0], kmax = ksz == 4 ? (long long) (int) ends[1] : ends[1];
             if (kmin == GX_EMPTY_KEY) kmin = kmin + 1;                                  // the reserved key lives in the side list
             double range_d = (double) kmax - (double) kmin + 1.0;
@@ -736,13 +750,13 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     else gx_k_sorted_fill<0><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
                 }
                 cudaError_t e2 = cudaGetLastError();
-                if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch + 3, ctx->d_scratch + 3, 5 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+                if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
                 if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
                 gx_tmp_free(ctx, d_start);
                 if (e2 != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e2)); gx_hash_free(h); return GX_ERR_CUDA; }
                 if ((int) ctx->h_scratch[6] == 0) {
                     h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
-                    if ((int) ctx->h_scratch[7] == 0 && h->avg_chain <= 4.0) { nscattered = ctx->h_scratch[3]; h->sorted_build = 1; break; }
+                    if ((int) ctx->h_scratch[7] == 0 && h->avg_chain <= 4.0) { nscattered = ctx->h_scratch[3]; h->sorted_build = 1; counts_read = true; break; }
                     h->mode = 0; continue;                                               // clustered keys: rebuild with the mixing hash
                 }
                 // not in key order: back to the sampled slot function and the bucketing passes
@@ -826,8 +840,10 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots);
     }
     GX_CUDA(ctx, cudaGetLastError());
-    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!counts_read) {
+        GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     if (nscattered >= 0) ctx->h_scratch[0] = nscattered;
     h->nentries = ctx->h_scratch[0] + ctx->h_scratch[1];
     h->special_count = (int) ctx->h_scratch[1];
