@@ -33,6 +33,7 @@ struct gx_agg_dev {
     int wkind[GX_MAX_WORDS];
     // join table
     const gx_slot *slots; unsigned long long mask;
+    const gx_cslot *cslots; unsigned long long cspan;      // compact form of the table (gx_k_runjoin reads it directly)
     const unsigned long long *special; int special_count; int _pad0; gx_slotfn sf;
     long long row0, row1;
     // shared-memory table
@@ -621,7 +622,42 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
 // (profiles/r01_ncu_probe_pairs_sf100.csv).
 struct gx_runlist { long long key[128]; double sum[128]; unsigned int cnt[128]; };
 
-template <bool HAS_CNT, bool HAS_SUM>
+// one key against the join table: the home group of slots arrives with a single 256-bit load
+template <bool COMPACT>
+__device__ __forceinline__ bool runjoin_probe(const gx_agg_dev &A, long long key, int &g)
+{
+    if (COMPACT) {
+        const unsigned long long dd = (unsigned long long) key - (unsigned long long) A.sf.kmin;
+        if (dd >= A.cspan) return false;                       // outside the build side's key span (also the reserved key)
+        const unsigned int d = (unsigned int) dd + 1u;
+        unsigned long long p = gx_slot_index(key, A.sf);
+        for (;;) {
+            gx_slot2 c = ld_slot2((const gx_slot *) (A.cslots + p));   // four 8-byte slots {d, payload}
+            if ((unsigned int) c.k0 == d) { g = (int) ((unsigned long long) c.k0 >> 32); return true; }
+            if ((unsigned int) c.k0 == 0u) return false;
+            if ((unsigned int) c.p0 == d) { g = (int) (c.p0 >> 32); return true; }
+            if ((unsigned int) c.p0 == 0u) return false;
+            if ((unsigned int) c.k1 == d) { g = (int) ((unsigned long long) c.k1 >> 32); return true; }
+            if ((unsigned int) c.k1 == 0u) return false;
+            if ((unsigned int) c.p1 == d) { g = (int) (c.p1 >> 32); return true; }
+            if ((unsigned int) c.p1 == 0u) return false;
+            p = gx_next_quad(p, A.mask);
+        }
+    } else {
+        if (key == GX_EMPTY_KEY) { if (A.special_count > 0) { g = (int) A.special[0]; return true; } return false; }   // side list
+        unsigned long long p = gx_slot_index(key, A.sf);
+        for (;;) {
+            gx_slot2 c = ld_slot2(A.slots + p);
+            if (c.k0 == key) { g = (int) (unsigned int) c.p0; return true; }
+            if (c.k0 == GX_EMPTY_KEY) return false;
+            if (c.k1 == key) { g = (int) (unsigned int) c.p1; return true; }
+            if (c.k1 == GX_EMPTY_KEY) return false;
+            p = gx_next_pair(p, A.mask);
+        }
+    }
+}
+
+template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
 __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
 {
     extern __shared__ unsigned long long smem[];
@@ -687,19 +723,8 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
             const long long key = Q.key[j];
             const unsigned int rc = Q.cnt[j];
             const double rs = HAS_SUM ? Q.sum[j] : 0.0;
-            bool hit; int g = 0;
-            if (key == GX_EMPTY_KEY) { hit = A.special_count > 0; if (hit) g = (int) A.special[0]; }    // side list, never in the table
-            else {
-                unsigned long long p = gx_slot_index(key, A.sf);
-                gx_slot2 c = ld_slot2(A.slots + p);
-                for (;;) {
-                    if (c.k0 == key) { hit = true; g = (int) (unsigned int) c.p0; break; }
-                    if (c.k0 == GX_EMPTY_KEY) { hit = false; break; }
-                    if (c.k1 == key) { hit = true; g = (int) (unsigned int) c.p1; break; }
-                    if (c.k1 == GX_EMPTY_KEY) { hit = false; break; }
-                    p = gx_next_pair(p, A.mask); c = ld_slot2(A.slots + p);
-                }
-            }
+            int g = 0;
+            const bool hit = runjoin_probe<COMPACT>(A, key, g);
             if (hit) fast_flush<HAS_CNT, HAS_SUM>(T, A, g, rc, rs, F.sum_word);
         }
         __syncwarp();
@@ -708,15 +733,8 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
     {
         long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
         if (r < A.row1) {
-            bool h = true; int gk;
-            long long key = F.okey[r];
-            if (key == GX_EMPTY_KEY) { h = A.special_count > 0; gk = h ? (int) A.special[0] : 0; }
-            else {
-                unsigned long long p = gx_slot_index(key, A.sf); gx_slot c = ld_slot(A.slots + p);
-                while (c.key != key && c.key != GX_EMPTY_KEY) { p = gx_next_slot(p, A.mask); c = ld_slot(A.slots + p); }
-                h = c.key == key; gk = (int) (unsigned int) c.payload;
-            }
-            if (h) fast_flush<HAS_CNT, HAS_SUM>(T, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0, F.sum_word);
+            int gk = 0;
+            if (runjoin_probe<COMPACT>(A, F.okey[r], gk)) fast_flush<HAS_CNT, HAS_SUM>(T, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0, F.sum_word);
         }
     }
     __syncthreads();
@@ -938,8 +956,9 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
         P.n_payload = h->n_payload;
         for (int i = 0; i < h->n_payload; i++) P.payload_types[i] = h->payload_types[i];
         cp->A.slots = h->slots; cp->A.mask = (unsigned long long) h->nslots - 1;
+        cp->A.cslots = h->cslots; cp->A.cspan = h->cspan;
         cp->A.special = h->special_payload; cp->A.special_count = h->special_count;
-        cp->A.sf.mode = h->mode; cp->A.sf.win = h->win; cp->A.sf.shift = h->shift; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
+        cp->A.sf.mode = h->mode; cp->A.sf.win = h->win; cp->A.sf.shift = h->shift; cp->A.sf.amask = h->amask; cp->A.sf.kmin = h->kmin; cp->A.sf.scale = h->scale; cp->A.sf.mask = (unsigned long long) h->nslots - 1;
     }
     // group columns: pack by byte width into k0 then k1
     int used[2] = { 0, 0 };
@@ -1069,12 +1088,12 @@ static int launch_fast_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &F
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
-template <bool HAS_CNT, bool HAS_SUM>
+template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
 static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t smem, const char *name)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin<HAS_CNT, HAS_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin<HAS_CNT, HAS_SUM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
         attr_set = true;
     }
     long long nvec = (A.row1 - A.row0 + 3) / 4;
@@ -1082,19 +1101,23 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 32)) maxb *= 2;
     unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
     gx_launch_scope ls(ctx, name);
-    gx_k_runjoin<HAS_CNT, HAS_SUM><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    gx_k_runjoin<HAS_CNT, HAS_SUM, COMPACT><<<grid, 1024, smem, ctx->stream>>>(A, FA);
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
-static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name)
+static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name, bool use_run)
 {
-    // the run-folding join kernel needs a per-warp run list next to the group table
+    // the run-folding join kernel keeps a per-warp run list next to the group table
     const size_t run_bytes = 32 * sizeof(gx_runlist);
-    const char *norun = getenv("GX_NO_RUNJOIN");
-    if (join && smem + run_bytes <= ctx->smem_optin - 1024 && !(norun && norun[0] == '1')) {
-        if (cnt && sum) return launch_runjoin_t<true, true>(ctx, A, FA, smem + run_bytes, name);
-        if (cnt) return launch_runjoin_t<true, false>(ctx, A, FA, smem + run_bytes, name);
-        return launch_runjoin_t<false, true>(ctx, A, FA, smem + run_bytes, name);
+    if (use_run) {
+        if (A.cslots) {
+            if (cnt && sum) return launch_runjoin_t<true, true, true>(ctx, A, FA, smem + run_bytes, name);
+            if (cnt) return launch_runjoin_t<true, false, true>(ctx, A, FA, smem + run_bytes, name);
+            return launch_runjoin_t<false, true, true>(ctx, A, FA, smem + run_bytes, name);
+        }
+        if (cnt && sum) return launch_runjoin_t<true, true, false>(ctx, A, FA, smem + run_bytes, name);
+        if (cnt) return launch_runjoin_t<true, false, false>(ctx, A, FA, smem + run_bytes, name);
+        return launch_runjoin_t<false, true, false>(ctx, A, FA, smem + run_bytes, name);
     }
     if (join) {
         if (cnt && sum) return launch_fast_t<true, true, true>(ctx, A, FA, smem, name);
@@ -1196,8 +1219,19 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         }
     }
 
+    // only gx_k_runjoin reads the compact table form; everything else needs the 16-byte slots
+    auto need_wide = [&]() -> int {
+        if (!h || A.slots) return GX_OK;
+        int wrc = gx_hash_wide(ctx, const_cast<gx_hash *>(h));
+        A.slots = h->slots;
+        return wrc;
+    };
+    const size_t run_bytes = 32 * sizeof(gx_runlist);
+    const char *norun = getenv("GX_NO_RUNJOIN");
+    const bool runjoin_env = !(norun && norun[0] == '1');
+
     for (int attempt = 0; attempt < 8; attempt++) {
-        if (strategy == 2) { rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
+        if (strategy == 2) { rc = need_wide(); if (rc) return rc; rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
         long long S = 16; while (S * 2 < est * 3 && S < smax) S *= 2;     // load factor <= 0.67
         // lane-private mode for a handful of groups: [warp][word][group][lane]
         int gmax = 0, lp_warps = 0; size_t lp_bytes = 0;
@@ -1218,7 +1252,10 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
         A.s_slots = strategy == 1 ? (int) S : 0; A.s_log2 = ilog2(S); A.s_tagkey = tagkey; A.s_gmax = gmax;
         const char *kname = h ? "probe_agg" : "agg";
-        if (strategy == 1 && !gmax && fast_ok) rc = launch_fast(ctx, A, FA, A.P.has_join != 0, cp.need_w0 != 0, FA.vcol != nullptr, dense_bytes(S), kname);
+        const bool use_fast = strategy == 1 && !gmax && fast_ok;
+        const bool use_run = use_fast && A.P.has_join && runjoin_env && dense_bytes(S) + run_bytes <= ctx->smem_optin - 1024;
+        if (!use_run) { rc = need_wide(); if (rc) { gx_tmp_free(ctx, g_tab); return rc; } }
+        if (use_fast) rc = launch_fast(ctx, A, FA, A.P.has_join != 0, cp.need_w0 != 0, FA.vcol != nullptr, dense_bytes(S), kname, use_run);
         else if (strategy == 1 && gmax) rc = launch_agg<SINK_SMEM_LP>(ctx, A, lp_bytes, kname, lp_warps * 32);
         else if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, dense_bytes(S), kname);
         else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, kname);

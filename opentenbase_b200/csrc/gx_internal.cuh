@@ -59,6 +59,9 @@ struct gx_table {
 };
 
 struct gx_slot { long long key; unsigned long long payload; };   // 16 B
+// Compact slot (8 B) of a table whose keys span less than 2^32 and whose payload fits 4
+// bytes: d = key - kmin + 1, 0 = empty.  Half the bytes to write, read and keep in L2.
+struct gx_cslot { unsigned int d; unsigned int payload; };
 
 struct gx_hash {
     gx_ctx *ctx;
@@ -73,9 +76,15 @@ struct gx_hash {
     long long kmin; unsigned long long scale; unsigned int win; unsigned int shift;
     double avg_chain;               // measured while the table was filled
     int sorted_build;               // built by the partition-free key-ordered path
+    // compact form (gx_cslot): produced by the key-ordered build when key range and payload allow;
+    // the 16-byte form is materialised from it on demand for consumers that only read that one
+    gx_cslot *cslots; unsigned long long cspan;   // cspan = kmax - kmin + 1
+    unsigned int amask;             // home slots are aligned to amask + 1 (2 for 16 B slots, 4 for compact ones)
     // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
     unsigned long long *special_payload; int special_cap; int special_count;
 };
+
+int gx_hash_wide(gx_ctx *ctx, gx_hash *h);   // materialise the 16-byte slot array of a compact table
 
 // A group-state record: [k0][k1][w0..w(nwords-1)], 8-byte words.
 // w0 is always the group's row count.
@@ -333,26 +342,31 @@ __device__ __forceinline__ unsigned long long gx_key_hash(long long key) { retur
 // with a multiplicative hash, which breaks up the pile-ups that locally bunched keys
 // (TPC-H order keys: 8 used of every 32) cause under pure interpolation while keeping
 // every key inside the same few cache lines and the same sub-table.
-struct gx_slotfn { int mode; unsigned int win; long long kmin; unsigned long long scale; unsigned long long mask; unsigned int shift; unsigned int _pad; };
+struct gx_slotfn { int mode; unsigned int win; long long kmin; unsigned long long scale; unsigned long long mask; unsigned int shift; unsigned int amask; };
 __device__ __forceinline__ unsigned long long gx_slot_index(long long key, const gx_slotfn &f)
 {
-    // Home slots are EVEN: a key's home is the aligned pair {s, s+1} (one 32-byte sector),
-    // which a prober can fetch with a single 256-bit load; linear probing is unchanged.
-    if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask & ~1ULL;
+    // Home slots are aligned to amask + 1 slots (2 x 16 B or 4 x 8 B = one 32-byte sector), which a
+    // prober can fetch with a single 256-bit load; linear probing is unchanged.
+    if (f.mode == 0) return gx_mix64((unsigned long long) key) & f.mask & ~(unsigned long long) f.amask;
     if (f.mode == 2) {
         // key range below 2^32: the same interpolation in 32-bit arithmetic (one wide multiply)
         const unsigned int d = (unsigned int) ((unsigned long long) key - (unsigned long long) f.kmin);
         const unsigned long long s = (((unsigned long long) d * (unsigned int) f.scale) >> f.shift) & f.mask;
-        return (s ^ (unsigned long long) (((d * 0x9E3779B9u) >> 24) & f.win)) & ~1ULL;
+        return (s ^ (unsigned long long) (((d * 0x9E3779B9u) >> 24) & f.win)) & ~(unsigned long long) f.amask;
     }
     unsigned long long s = __umul64hi((unsigned long long) key - (unsigned long long) f.kmin, f.scale) & f.mask;
-    return (s ^ ((unsigned long long) (((unsigned long long) key * 0x9E3779B97F4A7C15ULL) >> 40) & f.win)) & ~1ULL;
+    return (s ^ ((unsigned long long) (((unsigned long long) key * 0x9E3779B97F4A7C15ULL) >> 40) & f.win)) & ~(unsigned long long) f.amask;
 }
 // next aligned pair of a probe sequence (same wrapping rule as gx_next_slot)
 __device__ __forceinline__ unsigned long long gx_next_pair(unsigned long long s, unsigned long long mask)
 {
     const unsigned long long w = mask < (GX_SUB - 1) ? mask : (unsigned long long) (GX_SUB - 1);
     return (s & ~w) | ((s + 2) & w);
+}
+__device__ __forceinline__ unsigned long long gx_next_quad(unsigned long long s, unsigned long long mask)
+{
+    const unsigned long long w = mask < (GX_SUB - 1) ? mask : (unsigned long long) (GX_SUB - 1);
+    return (s & ~w) | ((s + 4) & w);
 }
 // next slot of a probe sequence: wraps inside the slot's sub-table (or the whole table when it is smaller)
 __device__ __forceinline__ unsigned long long gx_next_slot(unsigned long long s, unsigned long long mask)

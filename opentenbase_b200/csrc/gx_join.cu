@@ -10,6 +10,7 @@
 // chained buckets of MinimalTuple copies in 32 KB chunks) and
 // ExecScanHashBucket / ExecHashJoinImpl (nodeHash.c:2174, nodeHashjoin.c:186).
 #include "gx_internal.cuh"
+#include <type_traits>
 
 int gx_fill_dpreds(gx_ctx *ctx, const gx_table *t, int n_preds, const gx_pred *preds, gx_dpred *out);
 
@@ -102,6 +103,7 @@ struct gx_bbuild_args {
     int *overflow;
     int dbg_mode;               // 0 normal; 1 atomics only; 2 stores only (development experiments)
     long long *start; int *unsorted;   // key-ordered build: first row of every sub-table
+    gx_cslot *cslots;                  // compact output (gx_k_sorted_fill<.., true>)
 };
 
 __device__ __forceinline__ bool build_row_ok(const gx_build_args &a, long long r)
@@ -307,16 +309,19 @@ __global__ void __launch_bounds__(BP_THREADS, 2) gx_k_bpart2(gx_bpart_args a)
 // it meets an empty slot, exactly as with CAS insertion.
 #define FILL_THREADS 256
 #define FILL_ROWS (GX_SUB / FILL_THREADS)          // rows (and slots) per thread
-struct gx_fill_smem {
-    gx_slot tab[GX_SUB];
+template <bool C> struct gx_fill_smem_t {
+    typename std::conditional<C, gx_cslot, gx_slot>::type tab[GX_SUB];
     unsigned int cnt[GX_SUB];                      // histogram, then e[s]
     int wsum[FILL_THREADS / 32], wmin[FILL_THREADS / 32];
 };
+typedef gx_fill_smem_t<false> gx_fill_smem;
 #define FILL_SMEM_BYTES ((int) sizeof(gx_fill_smem))
+#define FILL_SMEM_BYTES_C ((int) sizeof(gx_fill_smem_t<true>))
 #define FILL_INF (1 << 29)
 
-template <class LOAD>
-__device__ __forceinline__ void gx_subtable_build(gx_fill_smem &sm, unsigned int n, const gx_slotfn &sf, LOAD load, gx_slot *dst,
+// C = compact 8-byte slots {key - kmin + 1, payload}; dst then points at gx_cslot
+template <bool C, class LOAD>
+__device__ __forceinline__ void gx_subtable_build(gx_fill_smem_t<C> &sm, unsigned int n, const gx_slotfn &sf, LOAD load, void *dst,
                                                   unsigned int &steps, unsigned int &placed)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -325,21 +330,33 @@ __device__ __forceinline__ void gx_subtable_build(gx_fill_smem &sm, unsigned int
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *c4 = (uint4 *) sm.cnt;
         for (int i = tid; i < GX_SUB / 4; i += FILL_THREADS) c4[i] = z;
-        longlong2 e; e.x = GX_EMPTY_KEY; e.y = 0;
-        longlong2 *t2 = (longlong2 *) sm.tab;
+        if (C) {
+            uint4 *t4 = (uint4 *) sm.tab;
 #pragma unroll
-        for (int u = 0; u < FILL_ROWS; u++) t2[tid + u * FILL_THREADS] = e;
+            for (int u = 0; u < FILL_ROWS / 2; u++) t4[tid + u * FILL_THREADS] = z;
+        } else {
+            longlong2 e; e.x = GX_EMPTY_KEY; e.y = 0;
+            longlong2 *t2 = (longlong2 *) sm.tab;
+#pragma unroll
+            for (int u = 0; u < FILL_ROWS; u++) t2[tid + u * FILL_THREADS] = e;
+        }
     }
     __syncthreads();
     // ---- histogram + rank
-    long long key[FILL_ROWS]; unsigned long long pay[FILL_ROWS]; unsigned int sr[FILL_ROWS];
+    // what is kept per row until placement: the slot's two words (compact: two 32-bit values)
+    typename std::conditional<C, unsigned int, long long>::type key[FILL_ROWS];
+    typename std::conditional<C, unsigned int, unsigned long long>::type pay[FILL_ROWS];
+    unsigned int sr[FILL_ROWS];
 #pragma unroll
     for (int u = 0; u < FILL_ROWS; u++) {
         unsigned int i = tid + u * FILL_THREADS;
         sr[u] = 0xffffffffu;
-        if (i < n && load(i, key[u], pay[u])) {
-            unsigned int sl = (unsigned int) (gx_slot_index(key[u], sf) & (GX_SUB - 1));
+        long long k64; unsigned long long p64;
+        if (i < n && load(i, k64, p64)) {
+            unsigned int sl = (unsigned int) (gx_slot_index(k64, sf) & (GX_SUB - 1));
             sr[u] = sl | (atomicAdd(&sm.cnt[sl], 1u) << GX_SUB_LOG2);
+            if (C) { key[u] = (unsigned int) ((unsigned long long) k64 - (unsigned long long) sf.kmin) + 1u; pay[u] = (unsigned int) p64; }
+            else { key[u] = k64; pay[u] = p64; }
         }
     }
     __syncthreads();
@@ -383,8 +400,11 @@ __device__ __forceinline__ void gx_subtable_build(gx_fill_smem &sm, unsigned int
         if (sr[u] == 0xffffffffu) continue;
         unsigned int sl = sr[u] & (GX_SUB - 1), pos = sl + sm.cnt[sl] + (sr[u] >> GX_SUB_LOG2);
         steps += pos - sl; placed++;
-        if (pos < GX_SUB) { longlong2 v; v.x = key[u]; v.y = (long long) pay[u]; ((longlong2 *) sm.tab)[pos] = v; sr[u] = 0xffffffffu; }
-        else wrapped = 1;
+        if (pos < GX_SUB) {
+            if (C) { uint2 v; v.x = (unsigned int) key[u]; v.y = (unsigned int) pay[u]; ((uint2 *) sm.tab)[pos] = v; }
+            else { longlong2 v; v.x = key[u]; v.y = (long long) pay[u]; ((longlong2 *) sm.tab)[pos] = v; }
+            sr[u] = 0xffffffffu;
+        } else wrapped = 1;
     }
     if (__syncthreads_or(wrapped)) {
 #pragma unroll
@@ -392,15 +412,29 @@ __device__ __forceinline__ void gx_subtable_build(gx_fill_smem &sm, unsigned int
             if (sr[u] == 0xffffffffu) continue;
             unsigned int sl = 0;                      // everything from its slot to the end is full: continue from the start
             for (;;) {
-                long long old = (long long) atomicCAS((unsigned long long *) &sm.tab[sl].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key[u]);
-                if (old == GX_EMPTY_KEY) { sm.tab[sl].payload = pay[u]; break; }
+                bool won;
+                if (C) {
+                    gx_cslot *t = (gx_cslot *) sm.tab;
+                    won = atomicCAS(&t[sl].d, 0u, (unsigned int) key[u]) == 0u;
+                    if (won) t[sl].payload = (unsigned int) pay[u];
+                } else {
+                    gx_slot *t = (gx_slot *) sm.tab;
+                    won = (long long) atomicCAS((unsigned long long *) &t[sl].key, (unsigned long long) GX_EMPTY_KEY, (unsigned long long) key[u]) == GX_EMPTY_KEY;
+                    if (won) t[sl].payload = pay[u];
+                }
+                if (won) break;
                 sl = (sl + 1) & (GX_SUB - 1); steps++;
             }
         }
         __syncthreads();
     }
     // ---- stream the finished sub-table out
-    {
+    if (C) {
+        const uint4 *t4 = (const uint4 *) sm.tab;
+        uint4 *d4 = (uint4 *) dst;
+#pragma unroll
+        for (int u = 0; u < FILL_ROWS / 2; u++) d4[tid + u * FILL_THREADS] = t4[tid + u * FILL_THREADS];
+    } else {
         const longlong2 *t2 = (const longlong2 *) sm.tab;
         longlong2 *d2 = (longlong2 *) dst;
 #pragma unroll
@@ -429,7 +463,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_bbuild_fill(gx_bbuild_ar
         unsigned int n = a.cursor[sub];
         if (n > GX_SUB) n = 0;                         // overflowed: the host rebuilds directly
         const longlong2 *src = (const longlong2 *) a.pairs + sub * GX_SUB;
-        gx_subtable_build(sm, n, a.b.sf,
+        gx_subtable_build<false>(sm, n, a.b.sf,
                           [&](unsigned int i, long long &k, unsigned long long &p) { longlong2 v = src[i]; k = v.x; p = (unsigned long long) v.y; return true; },
                           a.b.slots + sub * GX_SUB, steps, placed);
     }
@@ -505,11 +539,13 @@ __global__ void __launch_bounds__(256) gx_k_sorted_bounds_i8(const long long *__
 
 // PK selects the row loader: 0 generic (any key type, NULLs, build-side quals, packed payload),
 // 1 = int8 key without NULLs or quals + one 4-byte payload column, 2 = the same without payload
-template <int PK>
-__global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_sorted_fill(gx_bbuild_args a)
+template <int PK, bool C>
+__global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_bbuild_args a)
 {
     extern __shared__ __align__(16) unsigned char fill_smem_raw[];
-    gx_fill_smem &sm = *(gx_fill_smem *) fill_smem_raw;
+    gx_fill_smem_t<C> &sm = *(gx_fill_smem_t<C> *) fill_smem_raw;
+    void *const out = C ? (void *) a.cslots : (void *) a.b.slots;
+    const size_t slot_bytes = C ? sizeof(gx_cslot) : sizeof(gx_slot);
     if (*a.unsorted) return;
     unsigned int steps = 0, placed = 0;
     const long long *keys = (const long long *) a.b.key.data;
@@ -530,19 +566,19 @@ __global__ void __launch_bounds__(FILL_THREADS, 4) gx_k_sorted_fill(gx_bbuild_ar
             if (PK == 1) { const long long l4 = nlo + (long long) threadIdx.x * 32; if (l4 < nhi) asm volatile("prefetch.global.L2 [%0];" :: "l"(pay4 + l4)); }
         }
         if (PK == 0)
-            gx_subtable_build(sm, n, a.b.sf,
+            gx_subtable_build<C>(sm, n, a.b.sf,
                               [&](unsigned int i, long long &k, unsigned long long &p) {
                                   long long r = lo + i;
                                   if (!build_row_ok(a.b, r)) return false;
                                   k = gx_load_int(a.b.key, r); p = pack_payload(a.b, r); return true; },
-                              a.b.slots + sub * GX_SUB, steps, placed);
+                              (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed);
         else
-            gx_subtable_build(sm, n, a.b.sf,
+            gx_subtable_build<C>(sm, n, a.b.sf,
                               [&](unsigned int i, long long &k, unsigned long long &p) {
                                   k = __ldg(keys + lo + i);
                                   p = PK == 1 ? (unsigned long long) __ldg(pay4 + lo + i) : (unsigned long long) (lo + i);
                                   return true; },
-                              a.b.slots + sub * GX_SUB, steps, placed);
+                              (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed);
         lo = nlo; hi = nhi;
     }
     fill_report(a.b, steps, placed);
@@ -641,7 +677,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     }
     // choose the slot function from a strided key sample (64 K keys): interpolation when the
     // keys are spread near-uniformly over a range of at most 16 x their count
-    h->mode = 0; h->kmin = 0; h->scale = 0; h->shift = 0;
+    h->mode = 0; h->kmin = 0; h->scale = 0; h->shift = 0; h->amask = 1u;
     bool have_ends = false, counts_read = false;
     { const char *w = getenv("GX_SLOT_WIN"); h->win = w ? (unsigned int) atoi(w) : 31u; }
     {
@@ -678,7 +714,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             }
         }
     }
-    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.amask = h->amask; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_cap = h->special_cap;
     a.counters = ctx->d_scratch;
@@ -690,7 +726,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     for (int pass = 0; pass < 2 && inner->nrows > 0 && bucketed && nscattered < 0; pass++) {
         // second pass only when the interpolation slot function produced long chains / overflow
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
-        a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+        a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.amask = h->amask; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
         gx_bbuild_args ba; memset(&ba, 0, sizeof(ba));
         ba.nsub = h->nslots / GX_SUB;
         // ---- key-ordered build side + order-preserving slots: no bucketing needed
@@ -718,7 +754,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 const long long save_kmin = h->kmin; const unsigned long long save_scale = h->scale;
                 const int save_mode = h->mode; const unsigned int save_shift = h->shift;
                 gx_set_interpolation(h, kmin, range_d);
-                a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.shift = h->shift;
+                a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.shift = h->shift; a.sf.amask = h->amask;
                 ba.b = a; ba.overflow = (int *) (ctx->d_scratch + 7); ba.start = d_start; ba.unsorted = d_flag;
                 cudaMemsetAsync(ctx->d_scratch + 3, 0, sizeof(long long), ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch + 5, 0, sizeof(long long), ctx->stream);
@@ -727,11 +763,20 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     if (a.n_payload == 0) pk = 2;
                     else if (a.n_payload == 1 && (a.payload[0].type == GX_INT4 || a.payload[0].type == GX_DATE)) pk = 1;
                 }
+                // compact 8-byte slots when the exact key span and the payload fit 32 bits each
+                const char *nocompact = getenv("GX_NO_COMPACT");
+                bool compact = pk != 0 && h->mode == 2 && range_d < 4294967294.0 && inner->nrows < 0xffffffffLL &&
+                               !(nocompact && nocompact[0] == '1');
+                if (compact && gx_tmp_alloc(ctx, (void **) &h->cslots, (size_t) h->nslots * sizeof(gx_cslot)) != cudaSuccess) { h->cslots = nullptr; compact = false; }
+                h->amask = compact ? 3u : 1u; h->cspan = compact ? (unsigned long long) (kmax - kmin) + 1ULL : 0ULL;
+                a.sf.amask = h->amask; ba.b = a; ba.cslots = h->cslots;
                 static bool sattr = false;
                 if (!sattr) {
-                    cudaFuncSetAttribute(gx_k_sorted_fill<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
-                    cudaFuncSetAttribute(gx_k_sorted_fill<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
-                    cudaFuncSetAttribute(gx_k_sorted_fill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
                     sattr = true;
                 }
                 {
@@ -745,9 +790,11 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     gx_launch_scope ls(ctx, "build", 2);
                     gx_k_sorted_special<<<1, 256, 0, ctx->stream>>>(a, d_start, d_flag);
                     const unsigned int fgrid = ctx->sm_count * 8;
-                    if (pk == 1) gx_k_sorted_fill<1><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
-                    else if (pk == 2) gx_k_sorted_fill<2><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
-                    else gx_k_sorted_fill<0><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    if (compact && pk == 1) gx_k_sorted_fill<1, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                    else if (compact) gx_k_sorted_fill<2, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                    else if (pk == 1) gx_k_sorted_fill<1, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else if (pk == 2) gx_k_sorted_fill<2, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else gx_k_sorted_fill<0, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
                 }
                 cudaError_t e2 = cudaGetLastError();
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -756,12 +803,18 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 if (e2 != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e2)); gx_hash_free(h); return GX_ERR_CUDA; }
                 if ((int) ctx->h_scratch[6] == 0) {
                     h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
-                    if ((int) ctx->h_scratch[7] == 0 && h->avg_chain <= 4.0) { nscattered = ctx->h_scratch[3]; h->sorted_build = 1; counts_read = true; break; }
+                    if ((int) ctx->h_scratch[7] == 0 && h->avg_chain <= 4.0) {
+                        nscattered = ctx->h_scratch[3]; h->sorted_build = 1; counts_read = true;
+                        if (compact) { gx_tmp_free(ctx, h->slots); h->slots = nullptr; }      // the 16-byte form is made on demand (gx_hash_wide)
+                        break;
+                    }
+                    if (compact) { gx_tmp_free(ctx, h->cslots); h->cslots = nullptr; h->amask = 1u; h->cspan = 0; }
                     h->mode = 0; continue;                                               // clustered keys: rebuild with the mixing hash
                 }
+                if (compact) { gx_tmp_free(ctx, h->cslots); h->cslots = nullptr; h->amask = 1u; h->cspan = 0; }
                 // not in key order: back to the sampled slot function and the bucketing passes
                 h->kmin = save_kmin; h->scale = save_scale; h->mode = save_mode; h->shift = save_shift;
-                a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.shift = h->shift;
+                a.sf.mode = h->mode; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.shift = h->shift; a.sf.amask = h->amask;
                 GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
             }
         }
@@ -828,7 +881,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
         else nscattered = ctx->h_scratch[3];
     }
-    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.amask = h->amask; a.sf.kmin = h->kmin; a.sf.scale = h->scale;
     if (inner->nrows > 0 && !bucketed) {
         GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(long long), ctx->stream));
         { gx_launch_scope ls(ctx, "build_clear"); gx_k_fill_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->slots, h->nslots); }
@@ -856,6 +909,28 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     return GX_OK;
 }
 
+// compact table -> 16-byte slots, for the consumers that only read that form
+__global__ void gx_k_expand_slots(const gx_cslot *c, gx_slot *w, long long nslots, long long kmin)
+{
+    long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += stride) {
+        gx_cslot v = c[i];
+        longlong2 o;
+        o.x = v.d ? kmin + (long long) v.d - 1 : GX_EMPTY_KEY; o.y = (long long) (unsigned long long) v.payload;
+        ((longlong2 *) w)[i] = o;
+    }
+}
+int gx_hash_wide(gx_ctx *ctx, gx_hash *h)
+{
+    if (h->slots || !h->cslots) return GX_OK;
+    cudaError_t e = gx_tmp_alloc(ctx, (void **) &h->slots, (size_t) h->nslots * sizeof(gx_slot));
+    if (e != cudaSuccess) { h->slots = nullptr; GX_SET_ERR(ctx, "hash table: cudaMalloc of %lld slots failed: %s", (long long) h->nslots, cudaGetErrorString(e)); return GX_ERR_NOMEM; }
+    gx_launch_scope ls(ctx, "build_expand");
+    gx_k_expand_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->cslots, h->slots, h->nslots, h->kmin);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
+
 extern "C" int64_t gx_hash_nentries(const gx_hash *h) { return h ? h->nentries : -1; }
 extern "C" int64_t gx_hash_nslots(const gx_hash *h) { return h ? h->nslots : -1; }
 extern "C" int gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain)
@@ -869,6 +944,7 @@ extern "C" void gx_hash_free(gx_hash *h)
 {
     if (!h) return;
     gx_tmp_free(h->ctx, h->slots);
+    gx_tmp_free(h->ctx, h->cslots);
     gx_tmp_free(h->ctx, h->special_payload);
     free(h);
 }
@@ -974,9 +1050,10 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
     gx_probe_args a; memset(&a, 0, sizeof(a));
     a.key.data = outer->cols[key_col]; a.key.nulls = outer->nulls[key_col]; a.key.type = kt;
     a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique;
+    { int wrc = gx_hash_wide(ctx, const_cast<gx_hash *>(h)); if (wrc) return wrc; }
     a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_count = h->special_count;
-    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
+    a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.amask = h->amask; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     int rc = gx_fill_dpreds(ctx, outer, n_preds, preds, a.preds); if (rc) return rc;
     int32_t types[GX_MAX_COLS]; bool hn[GX_MAX_COLS];
     for (int c = 0; c < n_out_outer; c++) {
