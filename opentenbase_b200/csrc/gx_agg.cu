@@ -623,38 +623,41 @@ __global__ void __launch_bounds__(1024, 1) gx_k_fast(const __grid_constant__ gx_
 struct gx_runlist { long long key[128]; double sum[128]; unsigned int cnt[128]; };
 
 // one key against the join table: the home group of slots arrives with a single 256-bit load
+// Branch-free inside the group: a table that is only ever filled (never deleted from) has no
+// match behind an empty slot, so "any slot matches" / "any slot empty" decide the step, and the
+// function has ONE exit (several exits made the compiler clone the group update per exit).
 template <bool COMPACT>
 __device__ __forceinline__ bool runjoin_probe(const gx_agg_dev &A, long long key, int &g)
 {
+    bool found = false;
     if (COMPACT) {
         const unsigned long long dd = (unsigned long long) key - (unsigned long long) A.sf.kmin;
-        if (dd >= A.cspan) return false;                       // outside the build side's key span (also the reserved key)
-        const unsigned int d = (unsigned int) dd + 1u;
-        unsigned long long p = gx_slot_index(key, A.sf);
-        for (;;) {
-            gx_slot2 c = ld_slot2((const gx_slot *) (A.cslots + p));   // four 8-byte slots {d, payload}
-            if ((unsigned int) c.k0 == d) { g = (int) ((unsigned long long) c.k0 >> 32); return true; }
-            if ((unsigned int) c.k0 == 0u) return false;
-            if ((unsigned int) c.p0 == d) { g = (int) (c.p0 >> 32); return true; }
-            if ((unsigned int) c.p0 == 0u) return false;
-            if ((unsigned int) c.k1 == d) { g = (int) ((unsigned long long) c.k1 >> 32); return true; }
-            if ((unsigned int) c.k1 == 0u) return false;
-            if ((unsigned int) c.p1 == d) { g = (int) (c.p1 >> 32); return true; }
-            if ((unsigned int) c.p1 == 0u) return false;
-            p = gx_next_quad(p, A.mask);
+        if (dd < A.cspan) {                                    // else outside the build side's key span (also the reserved key)
+            const unsigned int d = (unsigned int) dd + 1u;
+            unsigned long long p = gx_slot_index(key, A.sf);
+            for (;;) {
+                const gx_slot2 c = ld_slot2((const gx_slot *) (A.cslots + p));   // four 8-byte slots {d, payload}
+                const unsigned int d0 = (unsigned int) c.k0, d1 = (unsigned int) c.p0, d2 = (unsigned int) c.k1, d3 = (unsigned int) c.p1;
+                const unsigned long long m = d0 == d ? (unsigned long long) c.k0 : d1 == d ? c.p0 : d2 == d ? (unsigned long long) c.k1 : c.p1;
+                found = (d0 == d) | (d1 == d) | (d2 == d) | (d3 == d);
+                g = (int) (m >> 32);
+                if (found | (d0 == 0u) | (d1 == 0u) | (d2 == 0u) | (d3 == 0u)) break;
+                p = gx_next_quad(p, A.mask);
+            }
         }
+    } else if (key == GX_EMPTY_KEY) {                          // side list, never in the table
+        found = A.special_count > 0; if (found) g = (int) A.special[0];
     } else {
-        if (key == GX_EMPTY_KEY) { if (A.special_count > 0) { g = (int) A.special[0]; return true; } return false; }   // side list
         unsigned long long p = gx_slot_index(key, A.sf);
         for (;;) {
-            gx_slot2 c = ld_slot2(A.slots + p);
-            if (c.k0 == key) { g = (int) (unsigned int) c.p0; return true; }
-            if (c.k0 == GX_EMPTY_KEY) return false;
-            if (c.k1 == key) { g = (int) (unsigned int) c.p1; return true; }
-            if (c.k1 == GX_EMPTY_KEY) return false;
+            const gx_slot2 c = ld_slot2(A.slots + p);
+            found = (c.k0 == key) | (c.k1 == key);
+            g = (int) (unsigned int) (c.k0 == key ? c.p0 : c.p1);
+            if (found | (c.k0 == GX_EMPTY_KEY) | (c.k1 == GX_EMPTY_KEY)) break;
             p = gx_next_pair(p, A.mask);
         }
     }
+    return found;
 }
 
 template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
