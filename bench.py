@@ -48,21 +48,28 @@ def env_int(name, default):
 
 
 # ------------------------------------------------------------------ clocks
+REAL_STDOUT = sys.stdout
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons.  The sampler needs a few hundred ms to come up
+    and the timed region is short, so it is started before the warm-up steps (the GPU is under
+    the same load there); stop(t0, t1) reports the samples that fall inside the timed region
+    and, when the region was too short to catch any, the ones taken under load since start."""
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.p:
             return out
@@ -71,24 +78,33 @@ class ClockSampler:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for r in rows if t1 is None or r[0] <= t1]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+        if inside:
+            reasons = set()
+            for r in inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out = {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": max(r[2] for r in inside),
+                   "reasons": sorted(reasons), "samples": len(inside), "window": window}
         return out
 
 
@@ -157,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": r["rows_per_sec"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
     return 0
 
 
@@ -229,24 +245,24 @@ def run_ours(args):
         r.free(); ht.free()
         return out
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     # ---- timed region: exactly K steps, device events on the library's stream
     ctx.profile(True)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launches
     barrier()
-    t0 = time.perf_counter()
+    t0 = time.perf_counter(); wall0 = time.time()
     ctx.timer_start()
     last = None
     for _ in range(args.steps):
         last = step()
     dev_ms = ctx.timer_stop()
     ctx.sync()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    wall_ms = (time.perf_counter() - t0) * 1e3; wall1 = time.time()
     barrier()
     launches = ctx.launches - launches0
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(wall0, wall1) if clocks else None
     probe_ms, probe_n = ctx.profile_get("probe_agg")
     build_ms, build_n = ctx.profile_get("build")
     phases = {}
@@ -316,7 +332,7 @@ def run_ours(args):
             "config": workload_config(args, world), "rows_per_step": rows_all,
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "checks": checks,
             "phases_ms": phases}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -362,7 +378,7 @@ def run_e2e(ctx, g, ot, lt, no, nl, plan, args, barrier, allmax, rows_all):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sf", type=int, default=100, help="scale factor per GPU")
@@ -371,6 +387,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 meanwhile (NCCL's
+    # version banner, for one) is sent to stderr instead
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

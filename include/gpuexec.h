@@ -139,7 +139,8 @@ typedef struct gx_agg_plan {
  * CUDA init is illegal; the provider calls this from BeginCustomScan). */
 int  gx_abi_version(void);
 int  gx_init(int device, gx_ctx **out);
-void gx_shutdown(gx_ctx *ctx);
+void gx_shutdown(gx_ctx *ctx);                /* free every table/hash/result handle first: their
+                                               * device memory is returned on the context's stream */
 const char *gx_last_error(gx_ctx *ctx);      /* ctx may be NULL: global msg   */
 int  gx_device_info(gx_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                     int64_t *hbm_bytes);

@@ -257,7 +257,7 @@ class Table:
         return (out, nl) if with_nulls else out
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:          # handles die with their context (stream-ordered frees need its stream)
             lib().gx_table_free(self.h)
             self.h = None
 
@@ -286,7 +286,7 @@ class HashTable:
         return {"slot_mode": m.value, "avg_chain": c.value}
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:          # handles die with their context (stream-ordered frees need its stream)
             lib().gx_hash_free(self.h)
             self.h = None
 
@@ -319,7 +319,7 @@ class Result:
         return keys, aggs, nulls
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:          # handles die with their context (stream-ordered frees need its stream)
             lib().gx_result_free(self.h)
             self.h = None
 

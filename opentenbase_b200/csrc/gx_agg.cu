@@ -1311,10 +1311,10 @@ int gx_aggregate_records(gx_ctx *ctx, gx_agg_dev A, unsigned long long *d_recs, 
     unsigned nblk = (unsigned) (ctx->sm_count * 2);
     if ((long long) nblk * 512 > nrec) nblk = (unsigned) ((nrec + 511) / 512);
     long long *d_hist; unsigned long long *d_part, *d_groups; int *d_over;
-    GX_CUDA(ctx, cudaMalloc((void **) &d_hist, (size_t) P * nblk * sizeof(long long)));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_part, (size_t) nrec * RW * 8));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_groups, (size_t) nrec * RW * 8));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_over, (size_t) P * sizeof(int)));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_hist, (size_t) P * nblk * sizeof(long long)));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_part, (size_t) nrec * RW * 8));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_groups, (size_t) nrec * RW * 8));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_over, (size_t) P * sizeof(int)));
     GX_CUDA(ctx, cudaMemsetAsync(d_over, 0, (size_t) P * sizeof(int), ctx->stream));
     GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 12, 0, sizeof(long long), ctx->stream));
     static bool attr = false;
@@ -1347,7 +1347,7 @@ int gx_aggregate_records(gx_ctx *ctx, gx_agg_dev A, unsigned long long *d_recs, 
     if (nover) {
         long long g_cap = gx_pow2_ceil(over_recs * 2 + 1024);
         unsigned long long *g_tab;
-        GX_CUDA(ctx, cudaMalloc((void **) &g_tab, (size_t) g_cap * RW * 8));
+        GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &g_tab, (size_t) g_cap * RW * 8));
         GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
         GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
         A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
@@ -1361,10 +1361,10 @@ int gx_aggregate_records(gx_ctx *ctx, gx_agg_dev A, unsigned long long *d_recs, 
         rc = read_counters(ctx, c);
         if (rc == GX_OK && c[1]) { GX_SET_ERR(ctx, "radix overflow table overflowed"); rc = GX_ERR_STATE; }
         if (rc == GX_OK) ngroups += c[0];
-        cudaFree(g_tab);
+        gx_tmp_free(ctx, g_tab);
     }
-    cudaFree(d_hist); cudaFree(d_part); cudaFree(d_over);
-    if (rc != GX_OK) { cudaFree(d_groups); return rc; }
+    gx_tmp_free(ctx, d_hist); gx_tmp_free(ctx, d_part); gx_tmp_free(ctx, d_over);
+    if (rc != GX_OK) { gx_tmp_free(ctx, d_groups); return rc; }
     *d_out = d_groups; *ngroups_out = ngroups;
     return GX_OK;
 }
@@ -1389,27 +1389,27 @@ static int run_radix(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *plan, lo
     long long cap = nrows_in;
     unsigned long long *d_recs = nullptr;
     for (int pass = 0; pass < 2; pass++) {
-        GX_CUDA(ctx, cudaMalloc((void **) &d_recs, (size_t) (cap > 0 ? cap : 1) * RW * 8));
+        GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_recs, (size_t) (cap > 0 ? cap : 1) * RW * 8));
         GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 4 * sizeof(long long), ctx->stream));
         A.recs = d_recs; A.rec_cap = cap; A.s_slots = 0;
         int rc = launch_agg<SINK_RECORD>(ctx, A, 0, A.P.has_join ? "probe_records" : "scan_records");
         long long c[4];
         if (rc == GX_OK) rc = read_counters(ctx, c);
-        if (rc != GX_OK) { cudaFree(d_recs); return rc; }
+        if (rc != GX_OK) { gx_tmp_free(ctx, d_recs); return rc; }
         if (!(c[1] & 4)) { cap = c[2]; break; }
-        cudaFree(d_recs); d_recs = nullptr;
+        gx_tmp_free(ctx, d_recs); d_recs = nullptr;
         cap = c[2];                                   // exact need (N:M join fan-out)
         if (pass == 1) { GX_SET_ERR(ctx, "radix: record buffer overflow"); return GX_ERR_STATE; }
     }
     unsigned long long *d_groups; long long ngroups;
     int rc = gx_aggregate_records(ctx, A, d_recs, cap, &d_groups, &ngroups);
-    cudaFree(d_recs);
+    gx_tmp_free(ctx, d_recs);
     if (rc) return rc;
     gx_result *r; gx_result_alloc(ctx, plan, cp->group_types, ngroups, &r);
     r->nkw = A.P.nkw; r->nwords = nwords; r->rec_words = RW; r->need_w0 = cp->need_w0;
     for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp->agg_word[a]; r->agg_cnt_word[a] = cp->agg_cnt_word[a]; }
     r->d_recs = (long long *) d_groups; r->ngroups = ngroups; r->cap = ngroups;
-    if (!d_groups) { GX_CUDA(ctx, cudaMalloc((void **) &r->d_recs, 64)); }
+    if (!d_groups) { GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &r->d_recs, 64)); }
     *out = r;
     return GX_OK;
 }

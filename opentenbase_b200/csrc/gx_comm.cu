@@ -180,8 +180,8 @@ static int route_setup(gx_ctx *ctx, const gx_table *in, int key_col, gx_route_ar
     if ((long long) nblk * 256 > in->nrows) nblk = (unsigned) ((in->nrows + 255) / 256);
     if (nblk == 0) nblk = 1;
     *nblk_out = nblk;
-    GX_CUDA(ctx, cudaMalloc((void **) &a->dest, (size_t) (in->nrows > 0 ? in->nrows : 1)));
-    GX_CUDA(ctx, cudaMalloc((void **) &a->hist, (size_t) ctx->nnodes * nblk * sizeof(long long)));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &a->dest, (size_t) (in->nrows > 0 ? in->nrows : 1)));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &a->hist, (size_t) ctx->nnodes * nblk * sizeof(long long)));
     return GX_OK;
 }
 
@@ -195,7 +195,7 @@ extern "C" int gx_route(gx_ctx *ctx, const gx_table *in, int key_col, int32_t *h
     cudaError_t e = cudaMemcpyAsync(h, a.dest, (size_t) in->nrows, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     for (int64_t i = 0; i < in->nrows; i++) host_dest_out[i] = h[i];
-    free(h); cudaFree(a.dest); cudaFree(a.hist);
+    free(h); gx_tmp_free(ctx, a.dest); gx_tmp_free(ctx, a.hist);
     if (e != cudaSuccess) { GX_SET_ERR(ctx, "route: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
     return GX_OK;
 }
@@ -209,7 +209,7 @@ static int partition_impl(gx_ctx *ctx, const gx_table *in, int key_col, gx_table
     for (int c = 0; c < in->ncols; c++) hn[c] = in->nulls[c] != nullptr;
     gx_table *t;
     rc = gx_table_alloc_like(ctx, in->ncols, in->types, hn, in->nrows, &t);
-    if (rc) { cudaFree(a.dest); cudaFree(a.hist); return rc; }
+    if (rc) { gx_tmp_free(ctx, a.dest); gx_tmp_free(ctx, a.hist); return rc; }
     gx_scatter_args s; memset(&s, 0, sizeof(s));
     s.nrows = in->nrows; s.ncols = in->ncols; s.nnodes = ctx->nnodes; s.dest = a.dest; s.offs = a.hist;
     for (int c = 0; c < in->ncols; c++) {
@@ -227,7 +227,7 @@ static int partition_impl(gx_ctx *ctx, const gx_table *in, int key_col, gx_table
         gx_k_route_scatter<<<nblk, 256, 0, ctx->stream>>>(s);
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(a.dest); cudaFree(a.hist);
+    gx_tmp_free(ctx, a.dest); gx_tmp_free(ctx, a.hist);
     if (e != cudaSuccess) { free(h_offs); gx_table_free(t); GX_SET_ERR(ctx, "partition: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
     for (int n = 0; n < ctx->nnodes; n++)
         host_counts[n] = ((n + 1 < ctx->nnodes) ? h_offs[n + 1] : in->nrows) - h_offs[n];
@@ -260,13 +260,13 @@ static int alltoallv_bytes(gx_ctx *ctx, const char *sendbuf, const int64_t *send
 static int allgather_i64(gx_ctx *ctx, const int64_t *mine, int n, int64_t *all /* nranks*n */)
 {
     long long *d_in, *d_out;
-    GX_CUDA(ctx, cudaMalloc((void **) &d_in, (size_t) n * 8));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_out, (size_t) n * 8 * ctx->nranks));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_in, (size_t) n * 8));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_out, (size_t) n * 8 * ctx->nranks));
     GX_CUDA(ctx, cudaMemcpyAsync(d_in, mine, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
     GX_NCCL(ctx, g_nccl.AllGather(d_in, d_out, (size_t) n, GX_NCCL_INT64, ctx->comm, ctx->stream));
     GX_CUDA(ctx, cudaMemcpyAsync(all, d_out, (size_t) n * 8 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
     GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_in); cudaFree(d_out);
+    gx_tmp_free(ctx, d_in); gx_tmp_free(ctx, d_out);
     return GX_OK;
 }
 
@@ -310,9 +310,9 @@ extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_
                 // a rank without a NULL array for this column sends zeros
                 uint8_t *src = part->nulls[c];
                 uint8_t *tmp = nullptr;
-                if (!src) { cudaMalloc((void **) &tmp, (size_t) (in->nrows > 0 ? in->nrows : 1)); cudaMemsetAsync(tmp, 0, (size_t) in->nrows, ctx->stream); src = tmp; }
+                if (!src) { gx_tmp_alloc(ctx, (void **) &tmp, (size_t) (in->nrows > 0 ? in->nrows : 1)); cudaMemsetAsync(tmp, 0, (size_t) in->nrows, ctx->stream); src = tmp; }
                 rc = alltoallv_bytes(ctx, (const char *) src, sendoff, counts, (char *) t->nulls[c], recvoff, recvcnt);
-                if (tmp) { cudaStreamSynchronize(ctx->stream); cudaFree(tmp); }
+                if (tmp) { cudaStreamSynchronize(ctx->stream); gx_tmp_free(ctx, tmp); }
             }
         }
     }
@@ -375,9 +375,9 @@ extern "C" int gx_result_combine(gx_ctx *ctx, gx_result *r)
     if ((long long) nblk * 256 > nrec) nblk = (unsigned) ((nrec + 255) / 256);
     if (nblk == 0) nblk = 1;
     unsigned char *d_dest; long long *d_hist; unsigned long long *d_send;
-    GX_CUDA(ctx, cudaMalloc((void **) &d_dest, (size_t) (nrec > 0 ? nrec : 1)));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_hist, (size_t) N * nblk * 8));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_send, (size_t) (nrec > 0 ? nrec : 1) * RW * 8));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_dest, (size_t) (nrec > 0 ? nrec : 1)));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_hist, (size_t) N * nblk * 8));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_send, (size_t) (nrec > 0 ? nrec : 1) * RW * 8));
     long long h_offs[GX_MAX_NODES];
     {
         gx_launch_scope ls(ctx, "combine_partition", 3);
@@ -397,21 +397,21 @@ extern "C" int gx_result_combine(gx_ctx *ctx, gx_result *r)
     free(all);
     unsigned long long *d_recv = nullptr;
     if (rc == GX_OK) {
-        GX_CUDA(ctx, cudaMalloc((void **) &d_recv, (size_t) (total > 0 ? total : 1) * RW * 8));
+        GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_recv, (size_t) (total > 0 ? total : 1) * RW * 8));
         int64_t so[GX_MAX_NODES], sc[GX_MAX_NODES], ro[GX_MAX_NODES], rcn[GX_MAX_NODES];
         for (int p = 0; p < N; p++) { so[p] = sendoff[p] * RW * 8; sc[p] = counts[p] * RW * 8; ro[p] = recvoff[p] * RW * 8; rcn[p] = recvcnt[p] * RW * 8; }
         gx_launch_scope ls(ctx, "alltoall");
         rc = alltoallv_bytes(ctx, (const char *) d_send, so, sc, (char *) d_recv, ro, rcn);
     }
     if (rc == GX_OK) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) { GX_SET_ERR(ctx, "combine: %s", cudaGetErrorString(e)); rc = GX_ERR_CUDA; } }
-    cudaFree(d_dest); cudaFree(d_hist); cudaFree(d_send);
-    if (rc) { if (d_recv) cudaFree(d_recv); return rc; }
+    gx_tmp_free(ctx, d_dest); gx_tmp_free(ctx, d_hist); gx_tmp_free(ctx, d_send);
+    if (rc) { if (d_recv) gx_tmp_free(ctx, d_recv); return rc; }
     unsigned long long *d_groups; long long ngroups;
     rc = gx_combine_records(ctx, r, d_recv, total, &d_groups, &ngroups);
-    cudaFree(d_recv);
+    gx_tmp_free(ctx, d_recv);
     if (rc) return rc;
-    cudaFree(r->d_recs);
-    if (!d_groups) { GX_CUDA(ctx, cudaMalloc((void **) &d_groups, 64)); }
+    gx_tmp_free(ctx, r->d_recs);
+    if (!d_groups) { GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_groups, 64)); }
     r->d_recs = (long long *) d_groups; r->ngroups = ngroups; r->cap = ngroups; r->finalized_across = 1;
     return GX_OK;
 }
@@ -437,12 +437,12 @@ extern "C" int gx_debug_hash(gx_ctx *ctx, int which, const int64_t *host_in, int
     if (!ctx || !host_in || !host_out || n < 0) return GX_ERR_ARG;
     if (n == 0) return GX_OK;
     long long *d_in; unsigned int *d_out;
-    GX_CUDA(ctx, cudaMalloc((void **) &d_in, (size_t) n * 8));
-    GX_CUDA(ctx, cudaMalloc((void **) &d_out, (size_t) n * 4));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_in, (size_t) n * 8));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_out, (size_t) n * 4));
     GX_CUDA(ctx, cudaMemcpyAsync(d_in, host_in, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->stream));
     { gx_launch_scope ls(ctx, "debug_hash"); gx_k_debug_hash<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(which, d_in, n, d_out); }
     GX_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_in); cudaFree(d_out);
+    gx_tmp_free(ctx, d_in); gx_tmp_free(ctx, d_out);
     return GX_OK;
 }

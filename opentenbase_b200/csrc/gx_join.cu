@@ -621,6 +621,12 @@ __global__ void gx_k_key_range(gx_dcol key, long long nrows, long long stride, l
     if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], lo); atomicMax(&minmax[1], hi); }
 }
 
+// Interpolation is tried when the key span is at most this many times the row count: TPC-H order
+// keys use 8 of every 32 values (spread 4), and each of N datanodes holds a pseudo-random 1/N of
+// them (spread 4 N).  Uniformity itself is not sampled: a build whose sub-tables overflow or whose
+// average chain exceeds 4 is redone with the mixing hash.
+#define GX_INTERP_MAX_SPREAD 256.0
+
 // interpolation slot function over [kmin, kmin + range): slots [0, nslots - GX_SUB), monotone in the key.
 // Narrow ranges (< 2^32, the usual case: at most 16 keys of range per row) use 32-bit arithmetic.
 static void gx_set_interpolation(gx_hash *h, long long kmin, double range_d)
@@ -676,7 +682,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         return GX_ERR_NOMEM;
     }
     // choose the slot function from a strided key sample (64 K keys): interpolation when the
-    // keys are spread near-uniformly over a range of at most 16 x their count
+    // keys span at most GX_INTERP_MAX_SPREAD x their count
     h->mode = 0; h->kmin = 0; h->scale = 0; h->shift = 0; h->amask = 1u;
     bool have_ends = false, counts_read = false;
     { const char *w = getenv("GX_SLOT_WIN"); h->win = w ? (unsigned int) atoi(w) : 31u; }
@@ -703,7 +709,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             long long lo = ctx->h_scratch[4], hi = ctx->h_scratch[5];
             if (hi > lo) {
                 double range = (double) hi - (double) lo + 1.0;
-                if (range <= 16.0 * (double) inner->nrows || want == 1) {
+                if (range <= GX_INTERP_MAX_SPREAD * (double) inner->nrows || want == 1) {
                     // widen the sampled range a little: keys outside it still map (they just wrap)
                     double pad = range / 1024.0 + 64.0;
                     double lo_d = (double) lo - pad, range_d = range + 2 * pad;
@@ -748,7 +754,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             if (kmin == GX_EMPTY_KEY) kmin = kmin + 1;                                  // the reserved key lives in the side list
             double range_d = (double) kmax - (double) kmin + 1.0;
             long long *d_start = nullptr;
-            if (range_d >= 1.0 && range_d < 9.0e18 && range_d <= 16.0 * (double) inner->nrows &&
+            if (range_d >= 1.0 && range_d < 9.0e18 && range_d <= GX_INTERP_MAX_SPREAD * (double) inner->nrows &&
                 gx_tmp_alloc(ctx, (void **) &d_start, (size_t) (ba.nsub + 1) * sizeof(long long)) == cudaSuccess) {
                 // exact bounds (if the column really is ordered): every key maps below nslots - GX_SUB, monotonically
                 const long long save_kmin = h->kmin; const unsigned long long save_scale = h->scale;

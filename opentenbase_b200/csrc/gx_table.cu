@@ -14,9 +14,9 @@ int gx_table_alloc_like(gx_ctx *ctx, int ncols, const int32_t *types, const bool
         int sz = gx_type_size(types[c]);
         if (!sz) { free(t); GX_SET_ERR(ctx, "table: column %d has unknown type %d", c, types[c]); return GX_ERR_ARG; }
         t->types[c] = types[c];
-        cudaError_t e = cudaMalloc(&t->cols[c], (size_t) t->capacity * sz + 32);
+        cudaError_t e = gx_tmp_alloc(ctx, &t->cols[c], (size_t) t->capacity * sz + 32);
         if (e == cudaSuccess && has_nulls && has_nulls[c]) {
-            e = cudaMalloc((void **) &t->nulls[c], (size_t) t->capacity + 32);
+            e = gx_tmp_alloc(ctx, (void **) &t->nulls[c], (size_t) t->capacity + 32);
             if (e == cudaSuccess) e = cudaMemsetAsync(t->nulls[c], 0, (size_t) t->capacity, ctx->stream);
         }
         if (e != cudaSuccess) {
@@ -38,7 +38,7 @@ extern "C" int gx_table_create(gx_ctx *ctx, int ncols, const int32_t *types, int
 extern "C" void gx_table_free(gx_table *t)
 {
     if (!t) return;
-    for (int c = 0; c < t->ncols; c++) { if (t->cols[c]) cudaFree(t->cols[c]); if (t->nulls[c]) cudaFree(t->nulls[c]); }
+    for (int c = 0; c < t->ncols; c++) { if (t->cols[c]) gx_tmp_free(t->ctx, t->cols[c]); if (t->nulls[c]) gx_tmp_free(t->ctx, t->nulls[c]); }
     free(t);
 }
 extern "C" int64_t gx_table_nrows(const gx_table *t) { return t ? t->nrows : -1; }
@@ -54,7 +54,7 @@ extern "C" int gx_table_column_devptr(gx_table *t, int col, void **dptr)
 static int ensure_null_array(gx_table *t, int c)
 {
     if (t->nulls[c]) return GX_OK;
-    GX_CUDA(t->ctx, cudaMalloc((void **) &t->nulls[c], (size_t) t->capacity + 32));
+    GX_CUDA(t->ctx, gx_tmp_alloc(t->ctx, (void **) &t->nulls[c], (size_t) t->capacity + 32));
     GX_CUDA(t->ctx, cudaMemsetAsync(t->nulls[c], 0, (size_t) t->capacity, t->ctx->stream));
     return GX_OK;
 }
@@ -212,7 +212,7 @@ static int generate_impl(gx_table *t, int table_id, int sf, int64_t o0, int64_t 
     const int BS = 256;
     long long nblocks = (n + BS - 1) / BS;
     long long *d_sums;
-    GX_CUDA(ctx, cudaMalloc(&d_sums, (size_t) nblocks * sizeof(long long)));
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_sums, (size_t) nblocks * sizeof(long long)));
     {
         gx_launch_scope ls(ctx, "generate", 3);
         gx_k_gen_count<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
@@ -220,16 +220,16 @@ static int generate_impl(gx_table *t, int table_id, int sf, int64_t o0, int64_t 
     }
     cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cudaFree(d_sums); GX_SET_ERR(ctx, "generate: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    if (e != cudaSuccess) { gx_tmp_free(ctx, d_sums); GX_SET_ERR(ctx, "generate: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
     long long total = ctx->h_scratch[0];
     if (t->nrows + total > t->capacity) {
-        cudaFree(d_sums);
+        gx_tmp_free(ctx, d_sums);
         GX_SET_ERR(ctx, "generate: %lld + %lld rows exceed capacity %lld", (long long) t->nrows, total, (long long) t->capacity);
         return GX_ERR_ARG;
     }
     gx_k_gen_write<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
     e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_sums);
+    gx_tmp_free(ctx, d_sums);
     if (e != cudaSuccess) { GX_SET_ERR(ctx, "generate: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
     t->nrows += total;
     return GX_OK;
@@ -335,7 +335,7 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
     long long total = 0;
     long long *d_sums = nullptr;
     if (nblocks > 0) {
-        GX_CUDA(ctx, cudaMalloc(&d_sums, (size_t) nblocks * sizeof(long long)));
+        GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_sums, (size_t) nblocks * sizeof(long long)));
         {
             gx_launch_scope ls(ctx, "filter", 2);
             gx_k_filter_count<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
@@ -343,12 +343,12 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
         }
         cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { cudaFree(d_sums); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+        if (e != cudaSuccess) { gx_tmp_free(ctx, d_sums); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
         total = ctx->h_scratch[0];
     }
     gx_table *t;
     rc = gx_table_alloc_like(ctx, n_out_cols, types, hn, total, &t);
-    if (rc) { if (d_sums) cudaFree(d_sums); return rc; }
+    if (rc) { if (d_sums) gx_tmp_free(ctx, d_sums); return rc; }
     if (nblocks > 0) {
         for (int c = 0; c < n_out_cols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
         {
@@ -356,7 +356,7 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
             gx_k_filter_write<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
         }
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_sums);
+        gx_tmp_free(ctx, d_sums);
         if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
     }
     t->nrows = total;
@@ -503,12 +503,12 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
     }
     // stage the raw pages (and visibility lists) in HBM
     uint8_t *d_pages = nullptr; uint16_t *d_vis = nullptr; int32_t *d_cnt = nullptr; long long *d_offs = nullptr;
-    cudaError_t e = cudaMalloc((void **) &d_pages, (size_t) npages * PG_BLCKSZ);
-    if (e == cudaSuccess) e = cudaMalloc((void **) &d_offs, (size_t) npages * sizeof(long long));
+    cudaError_t e = gx_tmp_alloc(ctx, (void **) &d_pages, (size_t) npages * PG_BLCKSZ);
+    if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &d_offs, (size_t) npages * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_pages, pages, (size_t) npages * PG_BLCKSZ, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && vis_offsets) {
-        e = cudaMalloc((void **) &d_vis, (size_t) npages * vis_stride * sizeof(uint16_t));
-        if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, (size_t) npages * sizeof(int32_t));
+        e = gx_tmp_alloc(ctx, (void **) &d_vis, (size_t) npages * vis_stride * sizeof(uint16_t));
+        if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &d_cnt, (size_t) npages * sizeof(int32_t));
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_vis, vis_offsets, (size_t) npages * vis_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, vis_counts, (size_t) npages * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
     }
@@ -538,7 +538,7 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
             }
         }
     }
-    cudaFree(d_pages); cudaFree(d_offs); if (d_vis) cudaFree(d_vis); if (d_cnt) cudaFree(d_cnt);
+    gx_tmp_free(ctx, d_pages); gx_tmp_free(ctx, d_offs); if (d_vis) gx_tmp_free(ctx, d_vis); if (d_cnt) gx_tmp_free(ctx, d_cnt);
     if (e != cudaSuccess) { GX_SET_ERR(ctx, "append_heap_pages: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GX_ERR_NOMEM : GX_ERR_CUDA; }
     return rc;
 }
