@@ -258,17 +258,23 @@ __device__ __forceinline__ void apply_aggs(const gx_dplan &P, bool need_w0, long
 }
 
 template <int SINK>
-__device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable &T, long long r, unsigned long long payload)
+__device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable &T, long long r, unsigned long long payload, unsigned int cm = 0)
 {
     unsigned long long k0, k1; unsigned int nullmask;
     pack_group_key(A.P, r, payload, k0, k1, nullmask);
     Sink<SINK> sink; sink.wstride = 1;
+    // The table lookups below leave their probe loops at different iterations; without an explicit
+    // reconvergence point the lanes then run the whole aggregate section in separate passes
+    // (ncu, Q1 shape: 15 of 32 threads active per instruction).  cm = the lanes the caller KNOWS to be
+    // in this call together (a ballot taken in warp-uniform code), 0 = unknown: no barrier.
     if (SINK == SINK_SMEM) {
         int s = smem_upsert<false>(T, k0, k1, nullmask);
+        if (cm) __syncwarp(cm);
         if (s < 0) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
         sink.w = T.w + (size_t) s * T.nwords;
     } else if (SINK == SINK_SMEM_LP) {
         int s = smem_upsert<true>(T, k0, k1, nullmask);
+        if (cm) __syncwarp(cm);
         unsigned int gi = s < 0 ? 0xFFFFFFFFu : T.gidx[s];
         if (gi >= (unsigned) T.gmax) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
         // [warp][word][group][lane]
@@ -276,6 +282,7 @@ __device__ __forceinline__ void consume_row(const gx_agg_dev &A, const SmemTable
         sink.w = T.w + ((size_t) (threadIdx.x >> 5) * T.nwords * T.gmax + gi) * 32 + (threadIdx.x & 31);
     } else if (SINK == SINK_GLOBAL) {
         unsigned long long *rec = global_upsert(A, k0, k1, nullmask);
+        if (cm) __syncwarp(cm);
         if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); return; }
         sink.w = rec + 3;
     } else {
@@ -367,12 +374,20 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_a
     }
     const gx_dplan &P = A.P;
     long long stride = (long long) gridDim.x * blockDim.x;
-    for (long long r = A.row0 + (long long) blockIdx.x * blockDim.x + threadIdx.x; r < A.row1; r += stride) {
-        bool ok = true;
+    // warp-uniform loop: every lane of a warp makes the same number of trips (lanes past the end idle)
+    const int lane = threadIdx.x & 31;
+    for (long long r = A.row0 + (long long) blockIdx.x * blockDim.x + threadIdx.x; r - lane < A.row1; r += stride) {
+        bool ok = r < A.row1;
 #pragma unroll
-        for (int p = 0; p < GX_MAX_PREDS; p++) if (p < P.npreds) ok = ok && gx_eval_pred(P.preds[p], r);
+        for (int p = 0; p < GX_MAX_PREDS; p++) if (p < P.npreds) ok = ok && gx_eval_pred(P.preds[p], ok ? r : A.row0);
+        if (!P.has_join) {
+            // exactly the lanes that consume a row now; the barrier only pays when a row has several
+            // state words to update (with one counter it cost 20 % on the config-1 shape)
+            const unsigned int m = P.nwords >= 3 ? __ballot_sync(0xffffffffu, ok) : 0u;
+            if (ok) consume_row<SINK>(A, T, r, 0ULL, m);
+            continue;
+        }
         if (!ok) continue;
-        if (!P.has_join) { consume_row<SINK>(A, T, r, 0ULL); continue; }
         if (gx_is_null(P.okey, r)) continue;                  // NULL outer key never joins
         long long key = gx_load_int(P.okey, r);
         if (key == GX_EMPTY_KEY) {
@@ -1239,12 +1254,16 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         // lane-private mode for a handful of groups: [warp][word][group][lane]
         int gmax = 0, lp_warps = 0; size_t lp_bytes = 0;
         if (strategy == 1 && est <= 16) {
-            gmax = 8; while (gmax < est * 2) gmax *= 2;              // 8, 16 or 32 groups per CTA
+            // 8, 16 or 32 groups per CTA.  Sized to the estimate, not twice it: the accumulators are
+            // words x groups x 8 B PER LANE, and a wrong estimate only costs the retry below — while
+            // falling back to the CTA-shared table with a handful of groups serialises every atomic
+            // (Q1 shape, 11 words: 212 ms instead of single-digit ms).
+            gmax = 8; while (gmax < est) gmax *= 2;
             S = 4 * gmax;
             size_t dir = (size_t) S * 8 * (1 + (tagkey ? 0 : A.P.nkw)) + ((S + 2) / 2 + 1) * 8;
             size_t per_warp = (size_t) nwords * gmax * 32 * 8;
             lp_warps = (int) ((budget - dir) / per_warp); if (lp_warps > 32) lp_warps = 32;
-            if (lp_warps < 8) { gmax = 0; S = 16; while (S < est * 2 && S < smax) S *= 2; }   // too many words: use the dense table
+            if (lp_warps < 4) { gmax = 0; S = 16; while (S < est * 2 && S < smax) S *= 2; }   // too many words: use the dense table
             else lp_bytes = dir + per_warp * lp_warps;
         }
         long long g_cap = gx_pow2_ceil((strategy == 1 ? S : est) * 4 + 1024);
@@ -1273,7 +1292,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         }
         gx_tmp_free(ctx, g_tab);
         // the planner's estimate was too low: grow, then fall over to radix
-        est = est < 16 ? 17 : est * 8;
+        est = est < 8 ? 9 : est < 16 ? 17 : est * 8;
         if (strategy == 1 && est * 3 / 2 > smax) strategy = (plan->strategy == 1) ? 3 : 2;
     }
     GX_SET_ERR(ctx, "hash_agg: group table kept overflowing");

@@ -391,6 +391,40 @@ def test_heap_page_deform_matches_oracle(gx):
     assert t2.nrows == n
 
 
+def test_heap_page_deform_throughput(gx, capsys):
+    """K0 at a size where the kernel time is visible: ~25 k pages (200 MB) of lineitem-shaped
+    tuples.  Checks the columns again and reports GB/s of page bytes (kernel only and from host
+    pages); the floor is deliberately loose — the number itself goes to DESIGN.md."""
+    n_orders = 300_000
+    cols = list(O.gen_lineitem(1, 0, n_orders))
+    use = [g.L_ORDERKEY, g.L_QUANTITY, g.L_EXTENDEDPRICE, g.L_DISCOUNT, g.L_TAX, g.L_RETURNFLAG, g.L_LINESTATUS, g.L_SHIPDATE]
+    cols = [cols[c] for c in use]
+    types = [g.SCHEMAS[g.T_LINEITEM][c] for c in use]
+    rel = O.Rel(types, cols)
+    pages = rel.pages()
+    n = len(cols[0])
+    att_len = [8, 8, 8, 8, 8, 1, 1, 4]; att_align = [8, 8, 8, 8, 8, 1, 1, 4]
+    t = gx.table(types, n); t.append_heap_pages(pages, att_len, att_align, list(range(8)))
+    assert t.nrows == n
+    np.testing.assert_array_equal(t.read(0), cols[0])
+    np.testing.assert_array_equal(t.read(7), cols[7])
+    np.testing.assert_array_equal(t.read(2).view(np.int64), cols[2].view(np.int64))
+    t.free()
+    iters = 5
+    gx.profile(True)
+    gx.sync(); gx.timer_start()
+    for _ in range(iters):
+        t = gx.table(types, n); t.append_heap_pages(pages, att_len, att_align, list(range(8))); t.free()
+    ms = gx.timer_stop() / iters
+    kms, kn = gx.profile_get("deform")
+    gx.profile(False)
+    page_gb = rel.npages * 8192 / 1e9
+    with capsys.disabled():
+        print(f"\nK0: {rel.npages} pages, {n} tuples: {ms:.2f} ms from host pages ({page_gb / ms * 1e3:.1f} GB/s of pages); "
+              f"deform kernels {kms / iters:.3f} ms per call ({page_gb / (kms / iters) * 1e3:.0f} GB/s of pages, {kn // iters} launches)")
+    assert page_gb / (kms / iters) * 1e3 > 200.0           # the kernels stream pages well above PCIe speed
+
+
 # ----------------------------------------------------- host-buffer entry
 def test_exec_host_matches_resident_path(gx, data):
     plan = O.make_plan(outer_key_col=g.L_ORDERKEY, group_cols=[(1, 0)],
