@@ -322,7 +322,7 @@ typedef gx_fill_smem_t<false> gx_fill_smem;
 // C = compact 8-byte slots {key - kmin + 1, payload}; dst then points at gx_cslot
 template <bool C, class LOAD>
 __device__ __forceinline__ void gx_subtable_build(gx_fill_smem_t<C> &sm, unsigned int n, const gx_slotfn &sf, LOAD load, void *dst,
-                                                  unsigned int &steps, unsigned int &placed)
+                                                  unsigned int &steps, unsigned int &placed, long long want_sub = -1, int *misplaced = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- clear: histogram and table
@@ -353,7 +353,9 @@ __device__ __forceinline__ void gx_subtable_build(gx_fill_smem_t<C> &sm, unsigne
         sr[u] = 0xffffffffu;
         long long k64; unsigned long long p64;
         if (i < n && load(i, k64, p64)) {
-            unsigned int sl = (unsigned int) (gx_slot_index(k64, sf) & (GX_SUB - 1));
+            const unsigned long long fs = gx_slot_index(k64, sf);
+            if (want_sub >= 0 && (long long) (fs >> GX_SUB_LOG2) != want_sub) *misplaced = 1;   // caller's row range was wrong
+            unsigned int sl = (unsigned int) (fs & (GX_SUB - 1));
             sr[u] = sl | (atomicAdd(&sm.cnt[sl], 1u) << GX_SUB_LOG2);
             if (C) { key[u] = (unsigned int) ((unsigned long long) k64 - (unsigned long long) sf.kmin) + 1u; pay[u] = (unsigned int) p64; }
             else { key[u] = k64; pay[u] = p64; }
@@ -539,15 +541,16 @@ __global__ void __launch_bounds__(256) gx_k_sorted_bounds_i8(const long long *__
 
 // PK selects the row loader: 0 generic (any key type, NULLs, build-side quals, packed payload),
 // 1 = int8 key without NULLs or quals + one 4-byte payload column, 2 = the same without payload
-template <int PK, bool C>
+template <int PK, bool C, bool VERIFY>
 __global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_bbuild_args a)
 {
     extern __shared__ __align__(16) unsigned char fill_smem_raw[];
     gx_fill_smem_t<C> &sm = *(gx_fill_smem_t<C> *) fill_smem_raw;
     void *const out = C ? (void *) a.cslots : (void *) a.b.slots;
     const size_t slot_bytes = C ? sizeof(gx_cslot) : sizeof(gx_slot);
-    if (*a.unsorted) return;
+    if (!VERIFY && *a.unsorted) return;
     unsigned int steps = 0, placed = 0;
+    int bad = 0;
     const long long *keys = (const long long *) a.b.key.data;
     const unsigned int *pay4 = (const unsigned int *) a.b.payload[0].data;
     long long lo = 0, hi = 0;
@@ -560,6 +563,7 @@ __global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_b
         if (nsubn < a.nsub) { nlo = a.start[nsubn]; nhi = a.start[nsubn + 1]; }
         unsigned int n = (unsigned int) (hi - lo);
         if (hi - lo > GX_SUB) { n = 0; if (threadIdx.x == 0) *a.overflow = 1; }
+        if (VERIFY && hi < lo) { n = 0; bad = 1; }
         if (PK != 0 && nhi - nlo <= GX_SUB) {
             const long long l = nlo + (long long) threadIdx.x * 16;          // 16 keys = one 128-byte line
             if (l < nhi) asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + l));
@@ -572,17 +576,101 @@ __global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_b
                                   if (!build_row_ok(a.b, r)) return false;
                                   k = gx_load_int(a.b.key, r); p = pack_payload(a.b, r); return true; },
                               (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed);
-        else
+        else if (!VERIFY)
             gx_subtable_build<C>(sm, n, a.b.sf,
                               [&](unsigned int i, long long &k, unsigned long long &p) {
                                   k = __ldg(keys + lo + i);
                                   p = PK == 1 ? (unsigned long long) __ldg(pay4 + lo + i) : (unsigned long long) (lo + i);
                                   return true; },
                               (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed);
+        else
+            gx_subtable_build<C>(sm, n, a.b.sf,
+                              [&](unsigned int i, long long &k, unsigned long long &p) {
+                                  const long long r = lo + i;
+                                  k = __ldg(keys + r);
+                                  const long long kp = r > 0 ? __ldg(keys + r - 1) : k;    // the neighbour's load: an L1 hit
+                                  if (kp > k || k == GX_EMPTY_KEY) bad = 1;
+                                  p = PK == 1 ? (unsigned long long) __ldg(pay4 + r) : (unsigned long long) r;
+                                  return true; },
+                              (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed, sub, &bad);
         lo = nlo; hi = nhi;
     }
+    if (VERIFY && bad) *a.unsorted = 1;
     fill_report(a.b, steps, placed);
 }
+// ---------------------------------------------------------------------------
+// Bounds by SEARCH instead of by a pass over the key column (int8 key, no NULLs, no quals).
+//  * lower_bound(s) = first row whose key maps to sub-table >= s.  One warp: the 32 rows around
+//    the interpolated position s * rows-per-sub-table decide it in one round when the keys are
+//    as uniform as the slot function assumes; otherwise a bracket is grown (x16 per round) and
+//    narrowed 32-ary.  All nsub + 1 bounds cost microseconds (gx_k_sorted_bounds_search).
+//  * what the pass over the column used to establish is then VERIFIED by the fill itself
+//    (gx_k_sorted_fill<.., VERIFY>): every CTA checks that its rows map to its sub-table and
+//    ascend (each row against its predecessor, including the one before its range).
+//    start[0] = 0 and start[nsub] = nrows are fixed and the ranges [start[s], start[s+1]) tile
+//    [0, nrows), so if no CTA raises the flag every adjacent pair of rows has been compared and
+//    every row sits in the right sub-table — whatever the search returned.  A raised flag sends
+//    the host down the bucketing path.  (Doing the search inside the fill kernel, one sub-table
+//    ahead, was measured slower: 1.91 ms against 0.41 + 1.07 ms.)
+__device__ __forceinline__ long long sorted_lower_bound(const long long *__restrict__ keys, long long nrows, const gx_slotfn &sf,
+                                                        long long s, long long nsub, double rows_per_sub, int lane)
+{
+    if (s <= 0) return 0;
+    if (s >= nsub) return nrows;
+    auto pred = [&](long long r) -> bool {                      // true from the bound onwards
+        if (r >= nrows) return true;
+        if (r < 0) return false;
+        return (long long) (gx_slot_index(__ldg(keys + r), sf) >> GX_SUB_LOG2) >= s;
+    };
+    long long g = (long long) ((double) s * rows_per_sub);
+    if (g > nrows) g = nrows;
+    // one round when the guess is within 16 rows
+    {
+        const long long pos = g - 16;
+        const unsigned int b = __ballot_sync(0xffffffffu, pred(pos + lane));
+        if (b != 0u && b != 0xffffffffu) return pos + (__ffs((int) b) - 1);
+    }
+    // grow a bracket [lo, hi]: pred(lo - 1) false (or lo == 0), pred(hi) true (or hi == nrows)
+    long long lo = 0, hi = nrows;
+    for (long long e = 256; ; e *= 16) {
+        const long long cl = g - e > 0 ? g - e : 0, ch = g + e < nrows ? g + e : nrows;
+        const bool p = lane == 0 ? pred(cl - 1) : (lane == 1 ? pred(ch) : false);
+        const unsigned int b = __ballot_sync(0xffffffffu, p);
+        const bool lo_ok = cl == 0 || !(b & 1u), hi_ok = ch == nrows || (b & 2u);
+        if (lo_ok) lo = cl;
+        if (hi_ok) hi = ch;
+        if ((lo_ok && hi_ok) || (cl == 0 && ch == nrows)) break;
+    }
+    // 32-ary narrowing
+    for (int round = 0; round < 16 && hi - lo > 32; round++) {
+        const long long step = (hi - lo + 31) / 32;
+        const long long r = lo + (long long) lane * step;
+        const unsigned int b = __ballot_sync(0xffffffffu, r >= hi ? true : pred(r));
+        if (b == 0u) { lo = lo + 31 * step + 1; continue; }
+        const int f = __ffs((int) b) - 1;
+        hi = lo + (long long) f * step < hi ? lo + (long long) f * step : hi;
+        if (f > 0) lo = lo + (long long) (f - 1) * step + 1;
+    }
+    {
+        const long long r = lo + lane;
+        const unsigned int b = __ballot_sync(0xffffffffu, r >= hi ? true : pred(r));
+        return b ? lo + (__ffs((int) b) - 1) : hi;
+    }
+}
+
+// start[s] for every sub-table by search: one warp per bound, ~one 256-byte read each
+__global__ void __launch_bounds__(256) gx_k_sorted_bounds_search(const long long *__restrict__ keys, long long nrows, gx_slotfn sf,
+                                                                 long long nsub, long long nslots, long long *start)
+{
+    const int lane = threadIdx.x & 31;
+    const long long nwarp = ((long long) gridDim.x * blockDim.x) >> 5, wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const double rows_per_sub = (double) nrows * (double) GX_SUB / (double) (nslots - GX_SUB);
+    for (long long s = wid; s <= nsub; s += nwarp) {
+        const long long v = sorted_lower_bound(keys, nrows, sf, s, nsub, rows_per_sub, lane);
+        if (lane == 0) start[s] = v;
+    }
+}
+
 // rows with the reserved key INT64_MIN sort first: move them to the side list
 __global__ void gx_k_sorted_special(gx_build_args a, const long long *start, const int *unsorted)
 {
@@ -778,29 +866,50 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 a.sf.amask = h->amask; ba.b = a; ba.cslots = h->cslots;
                 static bool sattr = false;
                 if (!sattr) {
-                    cudaFuncSetAttribute(gx_k_sorted_fill<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
-                    cudaFuncSetAttribute(gx_k_sorted_fill<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
-                    cudaFuncSetAttribute(gx_k_sorted_fill<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
-                    cudaFuncSetAttribute(gx_k_sorted_fill<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
-                    cudaFuncSetAttribute(gx_k_sorted_fill<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
+                    cudaFuncSetAttribute(gx_k_sorted_fill<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
                     sattr = true;
                 }
-                {
-                    gx_launch_scope ls(ctx, "build_bounds");
-                    if (kt == GX_INT8 && a.key.nulls == nullptr && ((uintptr_t) a.key.data & 15) == 0)
-                        gx_k_sorted_bounds_i8<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *) a.key.data, inner->nrows, a.sf, ba.nsub, d_start, d_flag);
-                    else
-                        gx_k_sorted_bounds<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ba.nsub, d_start, d_flag);
-                }
-                {
-                    gx_launch_scope ls(ctx, "build", 2);
-                    gx_k_sorted_special<<<1, 256, 0, ctx->stream>>>(a, d_start, d_flag);
-                    const unsigned int fgrid = ctx->sm_count * 8;
-                    if (compact && pk == 1) gx_k_sorted_fill<1, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
-                    else if (compact) gx_k_sorted_fill<2, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
-                    else if (pk == 1) gx_k_sorted_fill<1, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
-                    else if (pk == 2) gx_k_sorted_fill<2, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
-                    else gx_k_sorted_fill<0, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                // int8 key without NULLs or quals whose first key is an ordinary key: bounds by search, order
+                // and placement verified by the fill (see sorted_lower_bound)
+                const char *nosearch = getenv("GX_NO_BOUNDS_SEARCH");
+                const bool searched = pk != 0 && ends[0] != GX_EMPTY_KEY && ((uintptr_t) a.key.data & 15) == 0 && !(nosearch && nosearch[0] == '1');
+                if (searched) {
+                    static bool fattr = false;
+                    if (!fattr) {
+                        cudaFuncSetAttribute(gx_k_sorted_fill<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                        cudaFuncSetAttribute(gx_k_sorted_fill<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                        cudaFuncSetAttribute(gx_k_sorted_fill<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
+                        cudaFuncSetAttribute(gx_k_sorted_fill<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
+                        fattr = true;
+                    }
+                    { gx_launch_scope ls(ctx, "build_bounds"); gx_k_sorted_bounds_search<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *) a.key.data, inner->nrows, a.sf, ba.nsub, h->nslots, d_start); }
+                    gx_launch_scope ls(ctx, "build");
+                    if (compact && pk == 1) gx_k_sorted_fill<1, true, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                    else if (compact) gx_k_sorted_fill<2, true, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                    else if (pk == 1) gx_k_sorted_fill<1, false, true><<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else gx_k_sorted_fill<2, false, true><<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                } else {
+                    {
+                        gx_launch_scope ls(ctx, "build_bounds");
+                        if (kt == GX_INT8 && a.key.nulls == nullptr && ((uintptr_t) a.key.data & 15) == 0)
+                            gx_k_sorted_bounds_i8<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *) a.key.data, inner->nrows, a.sf, ba.nsub, d_start, d_flag);
+                        else
+                            gx_k_sorted_bounds<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ba.nsub, d_start, d_flag);
+                    }
+                    {
+                        gx_launch_scope ls(ctx, "build", 2);
+                        gx_k_sorted_special<<<1, 256, 0, ctx->stream>>>(a, d_start, d_flag);
+                        const unsigned int fgrid = ctx->sm_count * 8;
+                        if (compact && pk == 1) gx_k_sorted_fill<1, true, false><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                        else if (compact) gx_k_sorted_fill<2, true, false><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                        else if (pk == 1) gx_k_sorted_fill<1, false, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                        else if (pk == 2) gx_k_sorted_fill<2, false, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                        else gx_k_sorted_fill<0, false, false><<<fgrid, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    }
                 }
                 cudaError_t e2 = cudaGetLastError();
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
