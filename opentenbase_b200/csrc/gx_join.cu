@@ -101,7 +101,6 @@ struct gx_bbuild_args {
     unsigned int *cursor;       // [nsub] rows scattered to each sub-table so far
     gx_slot *pairs;             // nsub fixed-capacity buckets of GX_SUB pairs (a fuller bucket cannot be built anyway)
     int *overflow;
-    int dbg_mode;               // 0 normal; 1 atomics only; 2 stores only (development experiments)
     long long *start; int *unsorted;   // key-ordered build: first row of every sub-table
     gx_cslot *cslots;                  // compact output (gx_k_sorted_fill<.., true>)
 };
@@ -139,13 +138,12 @@ __global__ void __launch_bounds__(256) gx_k_bbuild_scatter(gx_bbuild_args a)
                 ok[u] = false;
             }
             sub[u] = gx_slot_index(key[u], a.b.sf) >> GX_SUB_LOG2;
-            if (ok[u]) pos[u] = (a.dbg_mode == 2) ? (unsigned int) (gx_key_hash(key[u]) >> 52) : atomicAdd(&a.cursor[sub[u]], 1u);
+            if (ok[u]) pos[u] = atomicAdd(&a.cursor[sub[u]], 1u);
         }
 #pragma unroll
         for (int u = 0; u < BSCAT; u++) {
             if (!ok[u]) continue;
             if (pos[u] >= GX_SUB) { *a.overflow = 1; continue; }
-            if (a.dbg_mode == 1) { if (pos[u] == 0xFFFFFFFFu) *a.overflow = 1; continue; }
             longlong2 v; v.x = key[u]; v.y = (long long) payload[u];
             ((longlong2 *) a.pairs)[sub[u] * GX_SUB + pos[u]] = v;
         }
@@ -934,7 +932,6 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
             }
         }
         ba.b = a;
-        { const char *m = getenv("GX_SCATTER_MODE"); ba.dbg_mode = m ? atoi(m) : 0; }
         cudaError_t e = gx_tmp_alloc(ctx, (void **) &ba.cursor, (size_t) ba.nsub * sizeof(unsigned int) + sizeof(int));
         if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &ba.pairs, (size_t) h->nslots * sizeof(gx_slot));
         if (e != cudaSuccess) {

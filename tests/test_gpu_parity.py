@@ -132,13 +132,19 @@ def test_config3_join_groupby(gx, data, strategy):
     assert got[1][:, 0].view(np.int64).sum() == data["lt"].nrows      # every line finds its order
 
 
-@pytest.mark.parametrize("layout", ["key_order", "shuffled", "key_order_filtered", "clustered", "key_order_no_payload"])
-def test_big_build_paths_agree_with_oracle(gx, layout):
+@pytest.mark.parametrize("layout", ["key_order", "shuffled", "key_order_filtered", "clustered", "key_order_no_payload",
+                                    "key_order_wide_span", "shuffled_wide_span"])
+def test_big_build_paths_agree_with_oracle(gx, layout, monkeypatch):
     """Build sides large enough for the sub-table builders (>= 64 sub-tables): the
     partition-free path for a build side stored in key order, the two-level bucketing
     path for an unordered one, and the fall-back to the mixing hash when the keys are
     clustered — all three must give the oracle's join (nodeHash.c:1828, nodeHashjoin.c:446)."""
     nord = 200_000
+    if layout.endswith("_wide_span"):
+        # what a key span above 2^32 selects (8 datanodes at SF100 each): 64-bit interpolation
+        # arithmetic and 16-byte slots instead of the 32-bit / compact forms
+        monkeypatch.setenv("GX_SLOT_WIDE", "1")
+        layout = layout[:-len("_wide_span")]
     o, l = O.gen_orders(SF, 0, nord), O.gen_lineitem(SF, 0, nord)
     o = [c.copy() for c in o]; l = [c.copy() for c in l]
     inner_preds = []
