@@ -1035,6 +1035,25 @@ static int compile_plan(gx_ctx *ctx, const gx_table *outer, const gx_hash *h, co
             }
             case GX_AGG_SUM_F8: case GX_AGG_AVG_F8: case GX_AGG_MIN_F8: case GX_AGG_MAX_F8: {
                 GX_CHECK_ARG(ctx, src.arg.nops >= 1 && src.arg.nops <= GX_MAX_EXPR_OPS, "agg %d: missing argument expression", a);
+                // sum(x) and avg(x) over the same argument keep ONE running sum (float8pl and float8_accum
+                // add the same values in the same order: float.c:970, :2823) — Q1 has two such pairs
+                if (src.fn == GX_AGG_SUM_F8 || src.fn == GX_AGG_AVG_F8) {
+                    int twin = -1;
+                    for (int b = 0; b < a && twin < 0; b++) {
+                        const gx_agg &o = plan->aggs[b];
+                        if ((o.fn != GX_AGG_SUM_F8 && o.fn != GX_AGG_AVG_F8) || o.arg.nops != src.arg.nops) continue;
+                        bool same = true;
+                        for (int k = 0; k < src.arg.nops && same; k++)
+                            same = o.arg.ops[k].op == src.arg.ops[k].op && o.arg.ops[k].col == src.arg.ops[k].col &&
+                                   memcmp(&o.arg.ops[k].k, &src.arg.ops[k].k, sizeof(double)) == 0;
+                        if (same) twin = b;
+                    }
+                    if (twin >= 0) {
+                        g.kind = GXU_NONE; cp->agg_word[a] = cp->agg_word[twin]; cp->agg_cnt_word[a] = cp->agg_cnt_word[twin];
+                        if (cp->agg_cnt_word[a] == 0 && src.fn == GX_AGG_AVG_F8) cp->need_w0 = 1;
+                        break;
+                    }
+                }
                 if (!compile_expr(ctx, outer, &src.arg, &g.expr, &nullable)) return GX_ERR_ARG;
                 if (src.fn == GX_AGG_MIN_F8) {        // identity of float8smaller under float8_cmp: NaN
                     double nan = __builtin_nan(""); long long bits; memcpy(&bits, &nan, 8);
