@@ -567,13 +567,23 @@ __global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_b
             if (l < nhi) asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + l));
             if (PK == 1) { const long long l4 = nlo + (long long) threadIdx.x * 32; if (l4 < nhi) asm volatile("prefetch.global.L2 [%0];" :: "l"(pay4 + l4)); }
         }
-        if (PK == 0)
+        if (PK == 0 && !VERIFY)
             gx_subtable_build<C>(sm, n, a.b.sf,
                               [&](unsigned int i, long long &k, unsigned long long &p) {
                                   long long r = lo + i;
                                   if (!build_row_ok(a.b, r)) return false;
                                   k = gx_load_int(a.b.key, r); p = pack_payload(a.b, r); return true; },
                               (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed);
+        else if (PK == 0)                                      // int8 key without NULLs; quals and any payload
+            gx_subtable_build<C>(sm, n, a.b.sf,
+                              [&](unsigned int i, long long &k, unsigned long long &p) {
+                                  const long long r = lo + i;
+                                  k = __ldg(keys + r);
+                                  const long long kp = r > 0 ? __ldg(keys + r - 1) : k;
+                                  if (kp > k || k == GX_EMPTY_KEY) bad = 1;          // order is checked on every row, kept or not
+                                  if (!build_row_ok(a.b, r)) return false;
+                                  p = pack_payload(a.b, r); return true; },
+                              (char *) out + (size_t) sub * GX_SUB * slot_bytes, steps, placed, sub, &bad);
         else if (!VERIFY)
             gx_subtable_build<C>(sm, n, a.b.sf,
                               [&](unsigned int i, long long &k, unsigned long long &p) {
@@ -597,7 +607,7 @@ __global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_b
     fill_report(a.b, steps, placed);
 }
 // ---------------------------------------------------------------------------
-// Bounds by SEARCH instead of by a pass over the key column (int8 key, no NULLs, no quals).
+// Bounds by SEARCH instead of by a pass over the key column (int8 key without NULLs).
 //  * lower_bound(s) = first row whose key maps to sub-table >= s.  One warp: the 32 rows around
 //    the interpolated position s * rows-per-sub-table decide it in one round when the keys are
 //    as uniform as the slot function assumes; otherwise a bracket is grown (x16 per round) and
@@ -747,15 +757,16 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     int bytes = 0;
     gx_hash *h = (gx_hash *) calloc(1, sizeof(gx_hash));
     h->ctx = ctx; h->key_type = kt; h->n_payload = n_payload; h->unique = unique;
+    struct hash_guard { gx_hash *h; ~hash_guard() { if (h) gx_hash_free(h); } } guard{h};     // every early return frees the table
     for (int i = 0; i < n_payload; i++) {
         int c = payload_cols[i];
-        if (c < 0 || c >= inner->ncols) { free(h); GX_SET_ERR(ctx, "hash_build: payload column %d out of range", c); return GX_ERR_ARG; }
-        if (inner->nulls[c]) { free(h); GX_SET_ERR(ctx, "hash_build: nullable payload column %d not supported in-slot", c); return GX_ERR_ARG; }
+        if (c < 0 || c >= inner->ncols) { GX_SET_ERR(ctx, "hash_build: payload column %d out of range", c); return GX_ERR_ARG; }
+        if (inner->nulls[c]) { GX_SET_ERR(ctx, "hash_build: nullable payload column %d not supported in-slot", c); return GX_ERR_ARG; }
         a.payload[i].data = inner->cols[c]; a.payload[i].nulls = nullptr; a.payload[i].type = inner->types[c];
         h->payload_types[i] = inner->types[c];
         bytes += gx_type_size(inner->types[c]);
     }
-    if (bytes > 8) { free(h); GX_SET_ERR(ctx, "hash_build: payload columns total %d bytes > 8", bytes); return GX_ERR_ARG; }
+    if (bytes > 8) { GX_SET_ERR(ctx, "hash_build: payload columns total %d bytes > 8", bytes); return GX_ERR_ARG; }
 
     int64_t want = inner->nrows + inner->nrows / 2 + 16;       // load factor <= 0.67
     h->nslots = gx_pow2_ceil(want);
@@ -764,7 +775,6 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     if (e == cudaSuccess) e = gx_tmp_alloc(ctx, (void **) &h->special_payload, (size_t) h->special_cap * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         GX_SET_ERR(ctx, "hash_build: cudaMalloc of %lld slots failed: %s", (long long) h->nslots, cudaGetErrorString(e));
-        gx_hash_free(h);
         return GX_ERR_NOMEM;
     }
     // choose the slot function from a strided key sample (64 K keys): interpolation when the
@@ -855,9 +865,15 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     if (a.n_payload == 0) pk = 2;
                     else if (a.n_payload == 1 && (a.payload[0].type == GX_INT4 || a.payload[0].type == GX_DATE)) pk = 1;
                 }
+                // int8 key without NULLs whose first key is an ordinary key: bounds by search, order and
+                // placement verified by the fill (see sorted_lower_bound)
+                const char *nosearch = getenv("GX_NO_BOUNDS_SEARCH");
+                const bool searched = kt == GX_INT8 && a.key.nulls == nullptr && ends[0] != GX_EMPTY_KEY && ((uintptr_t) a.key.data & 15) == 0 &&
+                                      !(nosearch && nosearch[0] == '1');
                 // compact 8-byte slots when the exact key span and the payload fit 32 bits each
                 const char *nocompact = getenv("GX_NO_COMPACT");
-                bool compact = pk != 0 && h->mode == 2 && range_d < 4294967294.0 && inner->nrows < 0xffffffffLL &&
+                const bool small_payload = a.n_payload == 0 ? inner->nrows < 0xffffffffLL : bytes <= 4;
+                bool compact = (pk != 0 || searched) && small_payload && h->mode == 2 && range_d < 4294967294.0 &&
                                !(nocompact && nocompact[0] == '1');
                 if (compact && gx_tmp_alloc(ctx, (void **) &h->cslots, (size_t) h->nslots * sizeof(gx_cslot)) != cudaSuccess) { h->cslots = nullptr; compact = false; }
                 h->amask = compact ? 3u : 1u; h->cspan = compact ? (unsigned long long) (kmax - kmin) + 1ULL : 0ULL;
@@ -871,13 +887,11 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     cudaFuncSetAttribute(gx_k_sorted_fill<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
                     sattr = true;
                 }
-                // int8 key without NULLs or quals whose first key is an ordinary key: bounds by search, order
-                // and placement verified by the fill (see sorted_lower_bound)
-                const char *nosearch = getenv("GX_NO_BOUNDS_SEARCH");
-                const bool searched = pk != 0 && ends[0] != GX_EMPTY_KEY && ((uintptr_t) a.key.data & 15) == 0 && !(nosearch && nosearch[0] == '1');
                 if (searched) {
                     static bool fattr = false;
                     if (!fattr) {
+                        cudaFuncSetAttribute(gx_k_sorted_fill<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
+                        cudaFuncSetAttribute(gx_k_sorted_fill<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
                         cudaFuncSetAttribute(gx_k_sorted_fill<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
                         cudaFuncSetAttribute(gx_k_sorted_fill<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES);
                         cudaFuncSetAttribute(gx_k_sorted_fill<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILL_SMEM_BYTES_C);
@@ -887,9 +901,11 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                     { gx_launch_scope ls(ctx, "build_bounds"); gx_k_sorted_bounds_search<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *) a.key.data, inner->nrows, a.sf, ba.nsub, h->nslots, d_start); }
                     gx_launch_scope ls(ctx, "build");
                     if (compact && pk == 1) gx_k_sorted_fill<1, true, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
-                    else if (compact) gx_k_sorted_fill<2, true, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                    else if (compact && pk == 2) gx_k_sorted_fill<2, true, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
+                    else if (compact) gx_k_sorted_fill<0, true, true><<<ctx->sm_count * 10, FILL_THREADS, FILL_SMEM_BYTES_C, ctx->stream>>>(ba);
                     else if (pk == 1) gx_k_sorted_fill<1, false, true><<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
-                    else gx_k_sorted_fill<2, false, true><<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else if (pk == 2) gx_k_sorted_fill<2, false, true><<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
+                    else gx_k_sorted_fill<0, false, true><<<ctx->sm_count * 8, FILL_THREADS, FILL_SMEM_BYTES, ctx->stream>>>(ba);
                 } else {
                     {
                         gx_launch_scope ls(ctx, "build_bounds");
@@ -913,7 +929,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
                 if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
                 gx_tmp_free(ctx, d_start);
-                if (e2 != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e2)); gx_hash_free(h); return GX_ERR_CUDA; }
+                if (e2 != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e2)); return GX_ERR_CUDA; }
                 if ((int) ctx->h_scratch[6] == 0) {
                     h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
                     if ((int) ctx->h_scratch[7] == 0 && h->avg_chain <= 4.0) {
@@ -937,7 +953,6 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         if (e != cudaSuccess) {
             gx_tmp_free(ctx, ba.cursor);
             GX_SET_ERR(ctx, "hash_build: cudaMalloc of the bucketing buffers failed: %s", cudaGetErrorString(e));
-            gx_hash_free(h);
             return GX_ERR_NOMEM;
         }
         ba.overflow = (int *) (ba.cursor + ba.nsub);
@@ -987,7 +1002,7 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
         if (e == cudaSuccess) e = cudaMemcpyAsync(&h_over, ba.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         gx_tmp_free(ctx, ba.cursor); gx_tmp_free(ctx, ba.pairs);
-        if (e != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e)); gx_hash_free(h); return GX_ERR_CUDA; }
+        if (e != cudaSuccess) { GX_SET_ERR(ctx, "hash_build: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
         h->avg_chain = ctx->h_scratch[3] > 0 ? (double) ctx->h_scratch[5] / (double) ctx->h_scratch[3] : 0.0;
         if (h->mode != 0 && (h_over || h->avg_chain > 4.0)) { h->mode = 0; continue; }   // keys were not as uniform as the sample said
         if (h_over) bucketed = false;                 // a sub-table overflowed (heavy key skew): build it the direct way
@@ -1014,9 +1029,9 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     h->special_count = (int) ctx->h_scratch[1];
     if (h->special_count > h->special_cap) {
         GX_SET_ERR(ctx, "hash_build: %d rows carry key INT64_MIN (side list holds %d)", h->special_count, h->special_cap);
-        gx_hash_free(h);
         return GX_ERR_ARG;
     }
+    guard.h = nullptr;
     *out = h;
     return GX_OK;
 }
