@@ -648,7 +648,7 @@ __device__ __forceinline__ bool runjoin_probe(const gx_agg_dev &A, long long key
     if (COMPACT) {
         const unsigned long long dd = (unsigned long long) key - (unsigned long long) A.sf.kmin;
         if (dd < A.cspan) {                                    // else outside the build side's key span (also the reserved key)
-            const unsigned int d = (unsigned int) dd + 1u;
+            const unsigned int d = GX_CSLOT_D(key, A.sf.kmin);
             unsigned long long p = gx_slot_index(key, A.sf);
             for (;;) {
                 const gx_slot2 c = ld_slot2((const gx_slot *) (A.cslots + p));   // four 8-byte slots {d, payload}

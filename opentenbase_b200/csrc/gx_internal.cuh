@@ -59,8 +59,14 @@ struct gx_table {
 };
 
 struct gx_slot { long long key; unsigned long long payload; };   // 16 B
-// Compact slot (8 B) of a table whose keys span less than 2^32 and whose payload fits 4
-// bytes: d = key - kmin + 1, 0 = empty.  Half the bytes to write, read and keep in L2.
+// Compact slot (8 B).  With an order-preserving slot function the keys that can land in one
+// 2048-slot sub-table lie within a few thousand key units of each other, so 31 bits of
+// (key - kmin) identify a key inside its sub-table whatever the total key span is:
+// d = ((key - kmin) << 1) | 1 truncated to 32 bits; d is never 0, which marks an empty slot.
+// Half the bytes to write, read and keep in L2.  Needs a payload of at most 4 bytes and the
+// exact kmin/kmax of the build side (probe keys outside [kmin, kmax] are rejected before the
+// 31-bit compare).
+#define GX_CSLOT_D(key, kmin) ((unsigned int) (((((unsigned long long) (key)) - ((unsigned long long) (kmin))) << 1) | 1ULL))
 struct gx_cslot { unsigned int d; unsigned int payload; };
 
 struct gx_hash {
@@ -79,6 +85,7 @@ struct gx_hash {
     // compact form (gx_cslot): produced by the key-ordered build when key range and payload allow;
     // the 16-byte form is materialised from it on demand for consumers that only read that one
     gx_cslot *cslots; unsigned long long cspan;   // cspan = kmax - kmin + 1
+    double keys_per_slot;           // key range / slot range of the interpolation (compact -> wide reconstruction)
     unsigned int amask;             // home slots are aligned to amask + 1 (2 for 16 B slots, 4 for compact ones)
     // rows whose key equals GX_EMPTY_KEY cannot live in the table: side list
     unsigned long long *special_payload; int special_cap; int special_count;

@@ -355,7 +355,7 @@ __device__ __forceinline__ void gx_subtable_build(gx_fill_smem_t<C> &sm, unsigne
             if (want_sub >= 0 && (long long) (fs >> GX_SUB_LOG2) != want_sub) *misplaced = 1;   // caller's row range was wrong
             unsigned int sl = (unsigned int) (fs & (GX_SUB - 1));
             sr[u] = sl | (atomicAdd(&sm.cnt[sl], 1u) << GX_SUB_LOG2);
-            if (C) { key[u] = (unsigned int) ((unsigned long long) k64 - (unsigned long long) sf.kmin) + 1u; pay[u] = (unsigned int) p64; }
+            if (C) { key[u] = GX_CSLOT_D(k64, sf.kmin); pay[u] = (unsigned int) p64; }
             else { key[u] = k64; pay[u] = p64; }
         }
     }
@@ -873,8 +873,11 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
                 // compact 8-byte slots when the exact key span and the payload fit 32 bits each
                 const char *nocompact = getenv("GX_NO_COMPACT");
                 const bool small_payload = a.n_payload == 0 ? inner->nrows < 0xffffffffLL : bytes <= 4;
-                bool compact = (pk != 0 || searched) && small_payload && h->mode == 2 && range_d < 4294967294.0 &&
+                // (a sub-table's keys must be told apart by 31 bits: its key span is range / #sub-tables)
+                const double keys_per_slot = range_d / (double) (h->nslots - GX_SUB);
+                bool compact = (pk != 0 || searched) && small_payload && h->mode != 0 && keys_per_slot * GX_SUB < 268435456.0 &&
                                !(nocompact && nocompact[0] == '1');
+                h->keys_per_slot = keys_per_slot;
                 if (compact && gx_tmp_alloc(ctx, (void **) &h->cslots, (size_t) h->nslots * sizeof(gx_cslot)) != cudaSuccess) { h->cslots = nullptr; compact = false; }
                 h->amask = compact ? 3u : 1u; h->cspan = compact ? (unsigned long long) (kmax - kmin) + 1ULL : 0ULL;
                 a.sf.amask = h->amask; ba.b = a; ba.cslots = h->cslots;
@@ -1036,14 +1039,24 @@ extern "C" int gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col, in
     return GX_OK;
 }
 
-// compact table -> 16-byte slots, for the consumers that only read that form
-__global__ void gx_k_expand_slots(const gx_cslot *c, gx_slot *w, long long nslots, long long kmin)
+// compact table -> 16-byte slots, for the consumers that only read that form.  The full key is
+// rebuilt from its 31 stored bits and the slot's position: the interpolation maps slot i back to
+// key offset ~ i * keys_per_slot (the entry sits within a chain length and a 32-slot window of its
+// home), and the offset congruent to the stored bits nearest to that estimate is the key's.
+__global__ void gx_k_expand_slots(const gx_cslot *c, gx_slot *w, long long nslots, long long kmin, double keys_per_slot)
 {
     long long stride = (long long) gridDim.x * blockDim.x;
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += stride) {
         gx_cslot v = c[i];
         longlong2 o;
-        o.x = v.d ? kmin + (long long) v.d - 1 : GX_EMPTY_KEY; o.y = (long long) (unsigned long long) v.payload;
+        o.x = GX_EMPTY_KEY; o.y = 0;
+        if (v.d) {
+            const long long est = (long long) ((double) i * keys_per_slot);
+            long long off = (est & ~0x7FFFFFFFLL) | (long long) (v.d >> 1);
+            if (off - est > 0x40000000LL) off -= 0x80000000LL;
+            else if (est - off > 0x40000000LL) off += 0x80000000LL;
+            o.x = kmin + off; o.y = (long long) (unsigned long long) v.payload;
+        }
         ((longlong2 *) w)[i] = o;
     }
 }
@@ -1053,7 +1066,7 @@ int gx_hash_wide(gx_ctx *ctx, gx_hash *h)
     cudaError_t e = gx_tmp_alloc(ctx, (void **) &h->slots, (size_t) h->nslots * sizeof(gx_slot));
     if (e != cudaSuccess) { h->slots = nullptr; GX_SET_ERR(ctx, "hash table: cudaMalloc of %lld slots failed: %s", (long long) h->nslots, cudaGetErrorString(e)); return GX_ERR_NOMEM; }
     gx_launch_scope ls(ctx, "build_expand");
-    gx_k_expand_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->cslots, h->slots, h->nslots, h->kmin);
+    gx_k_expand_slots<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(h->cslots, h->slots, h->nslots, h->kmin, h->keys_per_slot);
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }

@@ -133,7 +133,7 @@ def test_config3_join_groupby(gx, data, strategy):
 
 
 @pytest.mark.parametrize("layout", ["key_order", "shuffled", "key_order_filtered", "clustered", "key_order_no_payload",
-                                    "key_order_wide_span", "shuffled_wide_span"])
+                                    "key_order_wide_span", "shuffled_wide_span", "key_order_no_payload_wide_span"])
 def test_big_build_paths_agree_with_oracle(gx, layout, monkeypatch):
     """Build sides large enough for the sub-table builders (>= 64 sub-tables): the
     partition-free path for a build side stored in key order, the two-level bucketing
