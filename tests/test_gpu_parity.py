@@ -350,6 +350,58 @@ def test_route_bit_exact_with_reference_rule(gx, data, nnodes):
     np.testing.assert_array_equal(np.sort(r.read(0)), np.sort(data["o"][0]))
 
 
+def test_sf100_full_size_properties(gx):
+    """BASELINE config 3 at its full size (150 M orders, ~600 M lineitem rows, the tables bench.py
+    runs on).  The oracle cannot follow here; size-independent properties must hold instead:
+    every lineitem row finds exactly one order (count(*) sums to the row count), the groups are the
+    2406 order dates, the per-group sums add up to the plain sum of the column (1e-9), and three
+    independent paths agree group by group: the run-folding kernel on the compact table, the
+    row-per-lane kernel on 16-byte slots with the mixing hash, and the radix strategy."""
+    import os
+    sf = 100
+    no = 1_500_000 * sf
+    free_b = gx.device_info()["hbm_bytes"]
+    if free_b < 60e9:
+        pytest.skip("needs a GPU with room for the SF100 columns")
+    ot = gx.table([g.GX_INT8, g.GX_DATE], no); ot.generate(g.T_ORDERS, sf, 0, no, colmap=[g.O_ORDERKEY, g.O_ORDERDATE])
+    lt = gx.table([g.GX_INT8, g.GX_FLOAT8], no * 4 + no // 8); lt.generate(g.T_LINEITEM, sf, 0, no, colmap=[g.L_ORDERKEY, g.L_EXTENDEDPRICE])
+    nl = lt.nrows
+    assert 3.99 * no < nl < 4.01 * no
+    aggs = [(g.GX_AGG_COUNT_STAR, []), (g.GX_AGG_SUM_F8, [(g.GX_OP_COL, 1, 0)])]
+    total = gx.hash_agg(lt, g.make_plan(aggs=aggs)).fetch()[1]
+    assert total[0, 0].view(np.int64) == nl
+    results = {}
+    for name, env, strategy in (("runjoin_compact", {}, 1),
+                                ("row_per_lane_mixhash", {"GX_NO_RUNJOIN": "1", "GX_SLOT_MODE": "0"}, 1),
+                                ("radix", {}, 2)):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            ht = gx.hash_build(ot, 0, [1], unique=True)
+            assert ht.nentries == no
+            if name == "runjoin_compact":
+                assert ht.info()["slot_mode"] == 2
+            k, a, _ = gx.hash_agg(lt, g.make_plan(outer_key_col=0, group_cols=[(1, 0)], aggs=aggs, est_groups=2500, strategy=strategy), ht).fetch()
+            ht.free()
+        finally:
+            for kk, v in old.items():
+                if v is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = v
+        assert len(k) == 2406
+        assert a[:, 0].view(np.int64).sum() == nl
+        np.testing.assert_allclose(a[:, 1].sum(), total[0, 1], rtol=1e-9)
+        o = np.argsort(k[:, 0])
+        results[name] = (k[o, 0], a[o, 0].view(np.int64).copy(), a[o, 1].copy())
+    ref = results["runjoin_compact"]
+    for name in ("row_per_lane_mixhash", "radix"):
+        np.testing.assert_array_equal(results[name][0], ref[0])
+        np.testing.assert_array_equal(results[name][1], ref[1], err_msg=f"{name}: counts differ from the run-folding kernel")
+        np.testing.assert_allclose(results[name][2], ref[2], rtol=1e-9, atol=0)
+    ot.free(); lt.free()
+
+
 # ----------------------------------------------------- heap pages (K0)
 def test_heap_page_deform_matches_oracle(gx):
     """Raw 8 KB OpenTenBase heap pages -> columns on the device, against the
