@@ -427,6 +427,139 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_a
 }
 
 // ---------------------------------------------------------------------------
+// Few groups, many float8 aggregates, no join (the Q1 shape): lane-private accumulators as in
+// gx_k_agg<SINK_SMEM_LP>, but the plan is walked once per TILE of LPT_K x 32 rows instead of
+// once per row.  A lane holds LPT_K rows; for every aggregate the expression descriptor is
+// decoded once and its terms are evaluated for the lane's LPT_K rows back to back (LPT_K
+// independent loads in flight per term), then added to the rows' accumulators.  ncu on the
+// row-at-a-time interpreter: 1000 warp instructions per 32 rows and 14 warps per SM with
+// nothing to overlap the column loads (profiles/r01_bench_configs_sf100.json).
+// Plan shape (checked by the host): no join, every aggregate is count(*) or a sum/avg over a
+// chain expression of NOT-NULL float8 columns and constants.
+#define LPT_K 4
+__device__ __forceinline__ void lpt_term(const gx_dterm &t, const long long (&r)[LPT_K], const bool (&ok)[LPT_K], double (&out)[LPT_K])
+{
+    const double *c = (const double *) t.col.data;
+    const double k = t.k;
+    if (t.kind == GXT_CONST) {
+#pragma unroll
+        for (int j = 0; j < LPT_K; j++) out[j] = k;
+        return;
+    }
+    double x[LPT_K];
+#pragma unroll
+    for (int j = 0; j < LPT_K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0.0;
+    switch (t.kind) {
+        case GXT_COL:
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) out[j] = x[j];
+            break;
+        case GXT_K_SUB_COL:
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) out[j] = __dsub_rn(k, x[j]);
+            break;
+        case GXT_K_ADD_COL:
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) out[j] = __dadd_rn(k, x[j]);
+            break;
+        case GXT_K_MUL_COL:
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) out[j] = __dmul_rn(k, x[j]);
+            break;
+        default:                                               // GXT_COL_SUB_K
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) out[j] = __dsub_rn(x[j], k);
+            break;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) gx_k_agg_lptile(const __grid_constant__ gx_agg_dev A)
+{
+    extern __shared__ unsigned long long smem[];
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = A.P.nkw; T.tagkey = A.s_tagkey; T.gmax = A.s_gmax;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0 + (T.tagkey ? 0 : T.S);
+    unsigned long long *after_keys = T.k1 + ((!T.tagkey && A.P.nkw > 1) ? T.S : 0);
+    T.gidx = (unsigned int *) after_keys;                       // same layout as gx_k_agg<SINK_SMEM_LP>
+    T.gcount = T.gidx + T.S;
+    T.w = after_keys + (T.S + 2) / 2 + 1;
+    const int nwarps = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < T.S; i += blockDim.x) T.tag[i] = 0;
+    if (threadIdx.x == 0) *T.gcount = 0;
+    {
+        const int per_warp = T.nwords * T.gmax * 32;
+        for (int i = threadIdx.x; i < per_warp * nwarps; i += blockDim.x) T.w[i] = (unsigned long long) A.winit[(i % per_warp) / (T.gmax * 32)];
+    }
+    __syncthreads();
+    const gx_dplan &P = A.P;
+    const int wstride = T.gmax * 32;
+    unsigned long long *const wbase = T.w + (size_t) warp * T.nwords * T.gmax * 32 + lane;    // + gi * 32 + word * wstride
+    const long long tile = 32LL * LPT_K, step = (long long) gridDim.x * nwarps * tile;
+    for (long long base = A.row0 + ((long long) blockIdx.x * nwarps + warp) * tile; base < A.row1; base += step) {
+        long long r[LPT_K]; bool ok[LPT_K]; unsigned long long *acc[LPT_K];
+#pragma unroll
+        for (int j = 0; j < LPT_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < A.row1; acc[j] = wbase; }
+        for (int p = 0; p < P.npreds; p++) {
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) if (ok[j]) ok[j] = gx_eval_pred(P.preds[p], r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < LPT_K; j++) {
+            if (!ok[j]) continue;
+            unsigned long long k0, k1; unsigned int nullmask;
+            pack_group_key(P, r[j], 0ULL, k0, k1, nullmask);
+            const int s = smem_upsert<true>(T, k0, k1, nullmask);
+            const unsigned int gi = s < 0 ? 0xFFFFFFFFu : T.gidx[s];
+            if (gi >= (unsigned) T.gmax) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); ok[j] = false; }
+            else acc[j] = wbase + (size_t) gi * 32;
+        }
+        __syncwarp();                                          // the lookups leave their probe loops at different times
+        if (A.need_w0) {
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) if (ok[j]) acc[j][0] += 1ULL;
+        }
+        for (int a = 0; a < P.nagg; a++) {
+            const gx_dagg &g = P.aggs[a];
+            if (g.kind == GXU_NONE) continue;
+            double v[LPT_K];
+            lpt_term(g.expr.t[0], r, ok, v);
+            for (int i = 1; i < g.expr.nterms; i++) {
+                double x[LPT_K];
+                lpt_term(g.expr.t[i], r, ok, x);
+                const int op = g.expr.t[i].op;
+                if (op == GX_OP_ADD) {
+#pragma unroll
+                    for (int j = 0; j < LPT_K; j++) v[j] = __dadd_rn(v[j], x[j]);
+                } else if (op == GX_OP_SUB) {
+#pragma unroll
+                    for (int j = 0; j < LPT_K; j++) v[j] = __dsub_rn(v[j], x[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < LPT_K; j++) v[j] = __dmul_rn(v[j], x[j]);
+                }
+            }
+            const int wo = g.word * wstride;
+#pragma unroll
+            for (int j = 0; j < LPT_K; j++) if (ok[j]) { double *pp = (double *) (acc[j] + wo); *pp = __dadd_rn(*pp, v[j]); }
+        }
+    }
+    __syncthreads();
+    for (int i = warp; i < T.S; i += nwarps) {                 // one warp per directory slot, as in gx_k_agg
+        unsigned long long t = T.tag[i];
+        if (t == 0) continue;
+        unsigned int gi = T.gidx[i];
+        if (gi >= (unsigned) T.gmax) continue;
+        unsigned int nullmask = (unsigned int) (t >> 59) & 0xF;
+        unsigned long long k0 = T.tagkey ? (t & 0x00FFFFFFFFFFFFFFULL) : T.k0[i];
+        unsigned long long *rec = nullptr;
+        if (lane == 0) rec = global_upsert(A, k0, (!T.tagkey && T.nkw > 1) ? T.k1[i] : 0ULL, nullmask);
+        for (int j = 0; j < T.nwords; j++) {
+            unsigned long long v = lp_reduce_word(T, nwarps, j, gi, A.wkind[j], lane);
+            if (lane == 0) { if (rec) merge_word(&rec[3 + j], A.wkind[j], v); else atomicOr((unsigned long long *) &A.counters[1], 2ULL); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Specialised kernel for the dominant plan shape (BASELINE configs 2 and 3):
 //   [probe a unique-key join table with an int8 key ->] GROUP BY one 4-byte
 //   column (a scanned int4/date column, or the 4-byte join payload), aggregates
@@ -1108,6 +1241,22 @@ static int launch_agg(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char 
     return GX_OK;
 }
 
+static int launch_lptile(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name, int threads)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_agg_lptile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set = true;
+    }
+    long long nrows = A.row1 - A.row0, per_block = (long long) (threads / 32) * 32 * LPT_K;
+    long long nb = (nrows + per_block - 1) / per_block, maxb = (long long) ctx->sm_count;
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_k_agg_lptile<<<grid, threads, smem, ctx->stream>>>(A);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
+
 template <bool JOIN, bool HAS_CNT, bool HAS_SUM>
 static int launch_fast_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t smem, const char *name)
 {
@@ -1267,6 +1416,17 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
     const char *norun = getenv("GX_NO_RUNJOIN");
     const bool runjoin_env = !(norun && norun[0] == '1');
 
+    // the tile-at-a-time lane-private kernel: no join, count(*) and float8 sums over NOT-NULL float8 columns
+    bool lptile_ok = !A.P.has_join;
+    for (int a = 0; a < A.P.nagg && lptile_ok; a++) {
+        const gx_dagg &ga = A.P.aggs[a];
+        if (ga.kind == GXU_NONE) continue;
+        lptile_ok = ga.kind == GXU_ADD_F64 && !ga.is_int && ga.cnt_word == 0 && ga.expr.nterms >= 1;
+        for (int t = 0; t < ga.expr.nterms && lptile_ok; t++)
+            lptile_ok = ga.expr.t[t].kind == GXT_CONST || (ga.expr.t[t].col.type == GX_FLOAT8 && ga.expr.t[t].col.nulls == nullptr);
+    }
+    { const char *e = getenv("GX_NO_LPTILE"); if (e && e[0] == '1') lptile_ok = false; }
+
     for (int attempt = 0; attempt < 8; attempt++) {
         if (strategy == 2) { rc = need_wide(); if (rc) return rc; rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
         long long S = 16; while (S * 2 < est * 3 && S < smax) S *= 2;     // load factor <= 0.67
@@ -1297,6 +1457,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         const bool use_run = use_fast && A.P.has_join && runjoin_env && dense_bytes(S) + run_bytes <= ctx->smem_optin - 1024;
         if (!use_run) { rc = need_wide(); if (rc) { gx_tmp_free(ctx, g_tab); return rc; } }
         if (use_fast) rc = launch_fast(ctx, A, FA, A.P.has_join != 0, cp.need_w0 != 0, FA.vcol != nullptr, dense_bytes(S), kname, use_run);
+        else if (strategy == 1 && gmax && lptile_ok) rc = launch_lptile(ctx, A, lp_bytes, kname, lp_warps * 32);
         else if (strategy == 1 && gmax) rc = launch_agg<SINK_SMEM_LP>(ctx, A, lp_bytes, kname, lp_warps * 32);
         else if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, dense_bytes(S), kname);
         else rc = launch_agg<SINK_GLOBAL>(ctx, A, 0, kname);
