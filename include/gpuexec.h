@@ -230,8 +230,12 @@ int  gx_hash_build(gx_ctx *ctx, const gx_table *inner, int key_col,
                    gx_hash **out);
 int64_t gx_hash_nentries(const gx_hash *h);
 int64_t gx_hash_nslots(const gx_hash *h);
-/* slot function in use (0 mixing hash, 1 order-preserving interpolation for near-uniform
- * keys, 2 the same with the build side found in key order and built without bucketing) and the average probe-chain length measured while the table was filled */
+/* How the table was built — chosen per build from the data, never from hints:
+ * slot_mode 0 = mixing hash; 1 = order-preserving interpolation (near-uniform keys,
+ * two-level bucketing build); 2 = the same with the build side found stored in key
+ * order and built without any bucketing pass.  avg_chain = average displacement of an
+ * entry from its home slot, measured while the table was filled (a build whose chains
+ * exceed 4 is redone with the mixing hash before this call returns). */
 int  gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain);
 void gx_hash_free(gx_hash *h);
 
