@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg(const __grid_constant__ gx_a
 // nothing to overlap the column loads (profiles/r01_bench_configs_sf100.json).
 // Plan shape (checked by the host): no join, every aggregate is count(*) or a sum/avg over a
 // chain expression of NOT-NULL float8 columns and constants.
-#define LPT_K 4
+// LPT_K = rows per lane and tile: 8 when the CTA is small enough for the registers (<= 640 threads), else 4
+template <int LPT_K>
 __device__ __forceinline__ void lpt_term(const gx_dterm &t, const long long (&r)[LPT_K], const bool (&ok)[LPT_K], double (&out)[LPT_K])
 {
     const double *c = (const double *) t.col.data;
@@ -473,7 +474,8 @@ __device__ __forceinline__ void lpt_term(const gx_dterm &t, const long long (&r)
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) gx_k_agg_lptile(const __grid_constant__ gx_agg_dev A)
+template <int LPT_K>
+__global__ void __launch_bounds__(LPT_K == 8 ? 640 : 1024, 1) gx_k_agg_lptile(const __grid_constant__ gx_agg_dev A)
 {
     extern __shared__ unsigned long long smem[];
     SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = A.P.nkw; T.tagkey = A.s_tagkey; T.gmax = A.s_gmax;
@@ -521,10 +523,10 @@ __global__ void __launch_bounds__(1024, 1) gx_k_agg_lptile(const __grid_constant
             const gx_dagg &g = P.aggs[a];
             if (g.kind == GXU_NONE) continue;
             double v[LPT_K];
-            lpt_term(g.expr.t[0], r, ok, v);
+            lpt_term<LPT_K>(g.expr.t[0], r, ok, v);
             for (int i = 1; i < g.expr.nterms; i++) {
                 double x[LPT_K];
-                lpt_term(g.expr.t[i], r, ok, x);
+                lpt_term<LPT_K>(g.expr.t[i], r, ok, x);
                 const int op = g.expr.t[i].op;
                 if (op == GX_OP_ADD) {
 #pragma unroll
@@ -1241,20 +1243,27 @@ static int launch_agg(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char 
     return GX_OK;
 }
 
-static int launch_lptile(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name, int threads)
+template <int K>
+static int launch_lptile_k(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name, int threads)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_agg_lptile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_agg_lptile<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
         attr_set = true;
     }
-    long long nrows = A.row1 - A.row0, per_block = (long long) (threads / 32) * 32 * LPT_K;
+    long long nrows = A.row1 - A.row0, per_block = (long long) (threads / 32) * 32 * K;
     long long nb = (nrows + per_block - 1) / per_block, maxb = (long long) ctx->sm_count;
     unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
     gx_launch_scope ls(ctx, name);
-    gx_k_agg_lptile<<<grid, threads, smem, ctx->stream>>>(A);
+    gx_k_agg_lptile<K><<<grid, threads, smem, ctx->stream>>>(A);
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
+}
+static int launch_lptile(gx_ctx *ctx, const gx_agg_dev &A, size_t smem, const char *name, int threads)
+{
+    const char *k4 = getenv("GX_LPTILE_K4");
+    if (threads <= 640 && !(k4 && k4[0] == '1')) return launch_lptile_k<8>(ctx, A, smem, name, threads);
+    return launch_lptile_k<4>(ctx, A, smem, name, threads);
 }
 
 template <bool JOIN, bool HAS_CNT, bool HAS_SUM>
