@@ -1,0 +1,186 @@
+"""Executable statements of three arguments the CUDA build path relies on (csrc/gx_join.cu,
+DESIGN.md §3.1).  They restate the device algorithms in numpy/Python and check them against the
+obvious sequential definition, so the reasoning is tested where no GPU is available; the kernels
+themselves are tested against the oracle by tests/test_gpu_parity.py.
+
+1. A linear-probing table filled in slot order has the closed form the fill kernel uses.
+2. The warp-wide lower-bound search returns the first row of every sub-table on key-ordered data.
+3. 31 stored bits identify a key inside its sub-table, and the 16-byte slot can be rebuilt from
+   the compact one and its position.
+"""
+import numpy as np
+import pytest
+
+SUB = 2048
+LOG = 11
+
+
+# ------------------------------------------------------------------ 1. closed-form fill
+def sequential_fill(home_slots, nslots):
+    """Insert rows in (home slot, arrival) order with linear probing, no wrap handling needed
+    as long as nothing runs past the end."""
+    tab = -np.ones(nslots, np.int64)
+    for row in np.argsort(home_slots, kind="stable"):
+        s = home_slots[row]
+        while tab[s] >= 0:
+            s += 1
+        tab[s] = row
+    return tab
+
+
+def closed_form_positions(home_slots, nslots):
+    """position = home + e[home] + rank among the rows of that home slot, with
+    e[s] = P[s] - min_{j<=s} P[j],  P[s] = sum_{t<s} (c[t] - 1)   (gx_subtable_build)."""
+    c = np.bincount(home_slots, minlength=nslots)
+    P = np.concatenate([[0], np.cumsum(c - 1)[:-1]])
+    e = P - np.minimum.accumulate(P)
+    rank = np.zeros(len(home_slots), np.int64)
+    seen = {}
+    for i in np.argsort(home_slots, kind="stable"):
+        s = home_slots[i]
+        rank[i] = seen.get(s, 0)
+        seen[s] = rank[i] + 1
+    return home_slots + e[home_slots] + rank
+
+
+@pytest.mark.parametrize("load,seed", [(0.3, 1), (0.56, 2), (0.75, 3), (0.56, 4)])
+def test_closed_form_equals_sequential_linear_probing(load, seed):
+    rng = np.random.default_rng(seed)
+    nslots = 4096
+    n = int(load * nslots)
+    # homes are even (pair buckets) and kept away from the end so the sequential reference needs no wrap
+    home = (rng.integers(0, nslots - 600, n) & ~1).astype(np.int64)
+    if seed == 4:                                   # a pile-up: 200 rows on one slot
+        home[:200] = 1000
+    pos = closed_form_positions(home, nslots)
+    assert len(np.unique(pos)) == n                  # conflict-free
+    tab = sequential_fill(home, nslots)
+    for row in range(n):
+        # the same SET of slots is occupied, and every key is reachable: no hole between home and position
+        assert tab[pos[row]] >= 0
+        assert (tab[home[row]:pos[row] + 1] >= 0).all()
+    assert set(np.flatnonzero(tab >= 0)) == set(pos)
+
+
+# ------------------------------------------------------------------ 2. lower-bound search
+def make_slot_fn(kmin, krange, nslots):
+    ratio = (nslots - SUB) / krange
+    sh = 0
+    while sh < 62 and ratio * (1 << (sh + 1)) < 4294967295.0:
+        sh += 1
+    M = int(ratio * (1 << sh))
+
+    def slot(k):
+        d = (k - kmin) & 0xFFFFFFFF
+        s = ((d * M) >> sh) & (nslots - 1)
+        h = ((d * 0x9E3779B9) & 0xFFFFFFFF) >> 24
+        return (s ^ (h & 31)) & ~3
+    return slot
+
+
+def warp_lower_bound(keys, slot, s, nsub, rows_per_sub):
+    """sorted_lower_bound() with the 32 lanes written out as a loop."""
+    nrows = len(keys)
+    if s <= 0:
+        return 0
+    if s >= nsub:
+        return nrows
+
+    def pred(r):
+        if r >= nrows:
+            return True
+        if r < 0:
+            return False
+        return (slot(int(keys[r])) >> LOG) >= s
+
+    def ballot(f):
+        return sum(1 << lane for lane in range(32) if f(lane))
+
+    def ffs(b):
+        return (b & -b).bit_length()
+
+    g = min(int(s * rows_per_sub), nrows)
+    pos = g - 16
+    b = ballot(lambda lane: pred(pos + lane))
+    if b not in (0, 0xFFFFFFFF):
+        return pos + ffs(b) - 1
+    lo, hi, e = 0, nrows, 256
+    while True:
+        cl, ch = max(g - e, 0), min(g + e, nrows)
+        b = ballot(lambda lane: pred(cl - 1) if lane == 0 else (pred(ch) if lane == 1 else False))
+        lo_ok, hi_ok = cl == 0 or not b & 1, ch == nrows or bool(b & 2)
+        if lo_ok:
+            lo = cl
+        if hi_ok:
+            hi = ch
+        if (lo_ok and hi_ok) or (cl == 0 and ch == nrows):
+            break
+        e *= 16
+    for _ in range(16):
+        if hi - lo <= 32:
+            break
+        step = (hi - lo + 31) // 32
+        b = ballot(lambda lane: True if lo + lane * step >= hi else pred(lo + lane * step))
+        if b == 0:
+            lo = lo + 31 * step + 1
+            continue
+        f = ffs(b) - 1
+        hi = min(lo + f * step, hi)
+        if f > 0:
+            lo = lo + (f - 1) * step + 1
+    b = ballot(lambda lane: True if lo + lane >= hi else pred(lo + lane))
+    return lo + ffs(b) - 1 if b else hi
+
+
+def key_sets():
+    n = 120_000
+    i = np.arange(n, dtype=np.int64)
+    rng = np.random.default_rng(11)
+    yield "tpch order keys (8 of every 32)", ((i >> 3) << 5 | (i & 7)) + 1
+    yield "pseudo-random quarter of a key space (one of four datanodes)", np.sort(rng.choice(np.arange(1, 4 * n), n, replace=False)).astype(np.int64)
+    yield "dense", np.arange(5, 5 + n, dtype=np.int64)
+    yield "two clusters (the guess is far off)", np.sort(np.concatenate([rng.integers(0, 10**6, n // 2), rng.integers(3 * 10**6, 31 * 10**5, n // 2)])).astype(np.int64)
+
+
+@pytest.mark.parametrize("name,keys", list(key_sets()), ids=[k[0].split(" (")[0] for k in key_sets()])
+def test_lower_bound_search_finds_every_sub_table_start(name, keys):
+    nrows = len(keys)
+    nslots = 1
+    while nslots < nrows + nrows // 2 + 16:
+        nslots *= 2
+    nsub = nslots // SUB
+    slot = make_slot_fn(int(keys[0]), float(int(keys[-1]) - int(keys[0]) + 1), nslots)
+    subs = np.array([slot(int(k)) >> LOG for k in keys])
+    assert (np.diff(subs) >= 0).all()                # the slot function keeps key order at sub-table granularity
+    rows_per_sub = nrows * SUB / (nslots - SUB)
+    for s in range(nsub + 1):
+        assert warp_lower_bound(keys, slot, s, nsub, rows_per_sub) == int(np.searchsorted(subs, s, side="left")), (name, s)
+
+
+# ------------------------------------------------------------------ 3. compact slots
+def test_31_bits_identify_a_key_inside_its_sub_table_and_rebuild_it():
+    rng = np.random.default_rng(5)
+    n = 100_000
+    # a span above 2^32: what 8 datanodes at SF100 each see
+    keys = np.sort(rng.choice(np.arange(1, 40 * n, dtype=np.int64) * 1200, n, replace=False))
+    kmin, kmax = int(keys[0]), int(keys[-1])
+    assert kmax - kmin > 2**32
+    nslots = 1
+    while nslots < n + n // 2 + 16:
+        nslots *= 2
+    keys_per_slot = (kmax - kmin + 1) / (nslots - SUB)
+    assert keys_per_slot * SUB < 2**28               # the host's eligibility test
+    home = ((keys - kmin) / keys_per_slot).astype(np.int64)          # order-preserving interpolation
+    d = (((keys - kmin) << 1) | 1) & 0xFFFFFFFF                     # GX_CSLOT_D
+    assert (d != 0).all()
+    sub = home >> LOG
+    for s in np.unique(sub)[:200]:
+        ds = d[sub == s]
+        assert len(np.unique(ds)) == len(ds)         # no two keys of a sub-table share their 31 bits
+    # gx_k_expand_slots: the entry sits within a sub-table of its home; rebuild the key from d and the position
+    displaced = np.clip(home + rng.integers(-SUB + 1, SUB, n), 0, nslots - 1)
+    est = (displaced * keys_per_slot).astype(np.int64)
+    off = (est & ~0x7FFFFFFF) | (d >> 1)
+    off = np.where(off - est > 0x40000000, off - 0x80000000, off)
+    off = np.where(est - off > 0x40000000, off + 0x80000000, off)
+    np.testing.assert_array_equal(kmin + off, keys)
