@@ -368,11 +368,39 @@ def run_e2e(ctx, g, ot, lt, no, nl, plan, args, barrier, allmax, rows_all):
     barrier()
     dt = allmax(dt)
     d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes)
+    placement = staging_placement(bufs)
     for p in bufs:
         ctx.host_free(p)
     return {"value": rows_all / (dt / steps), "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "steps": steps, "ms_per_step": dt / steps * 1e3, "h2d_gb_per_s": h2d / (dt / steps) / 1e9, "staging": placement,
             "note": "gx_exec_host: pinned host columns -> HBM -> build -> probe+agg -> result on the host, every step"}
+
+
+def staging_placement(bufs):
+    """Where the pinned staging buffers ended up (pages per NUMA node, from /proc/self/numa_maps) and the
+    node the GPU hangs off: the e2e figure halves when the two differ."""
+    info = {}
+    try:
+        want = {int(p) for p in bufs}
+        pages = {}
+        for line in open("/proc/self/numa_maps"):
+            f = line.split()
+            if int(f[0], 16) in want:
+                for tok in f[1:]:
+                    if tok[0] == "N" and "=" in tok:
+                        node, n = tok[1:].split("=")
+                        pages[node] = pages.get(node, 0) + int(n)
+        info["pages_by_node"] = pages
+    except (OSError, ValueError, IndexError):
+        pass
+    try:
+        bus = subprocess.check_output(["nvidia-smi", f"--id={env_int('LOCAL_RANK', 0)}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True, stderr=subprocess.DEVNULL).strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                     # 00000000:1B:00.0 -> 0000:1b:00.0
+        info["gpu_numa_node"] = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return info
 
 
 def main():

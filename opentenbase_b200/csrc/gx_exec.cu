@@ -11,7 +11,7 @@
 // PCIe rate (measured through gx_exec_host on B200 hosts: 15-18 GB/s instead of 48 GB/s), and
 // which socket a backend's first touch lands on is a coin toss.  The node comes from sysfs
 // (/sys/bus/pci/devices/<bus id>/numa_node); the allocation runs under a temporary
-// MPOL_PREFERRED policy (raw syscall, no libnuma).  Anything that fails leaves the default policy.
+// MPOL_BIND policy (raw syscall, no libnuma), retried unbound if the node cannot hold it.  Anything that fails leaves the default policy.
 static int gpu_numa_node(int device)
 {
     char bus[32] = { 0 }, path[128];
@@ -34,10 +34,12 @@ extern "C" int gx_host_alloc(gx_ctx *ctx, size_t bytes, void **out)
     if (node >= 0 && node < 1024) {
         unsigned long mask[16] = { 0 };
         mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
-        bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long) (8 * sizeof(mask))) == 0;
+        // MPOL_BIND: "preferred" silently spills to the other node when the local one is full of page cache
+        bound = syscall(SYS_set_mempolicy, 2 /* MPOL_BIND */, mask, (unsigned long) (8 * sizeof(mask))) == 0;
     }
     cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
     if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, (unsigned long *) nullptr, 0UL);
+    if (e != cudaSuccess && bound) { cudaGetLastError(); e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault); }   // node full: anywhere
     GX_CUDA(ctx, e);
     return GX_OK;
 }
