@@ -216,3 +216,48 @@ def test_bloom_filter_restatement():
     assert fp < 0.02 * 10000
     L.orc_bloom_free(b)
     assert not L.orc_bloom_create(10**9)             # logNumBuckets > 20: "give up using bloom filter"
+
+
+def test_oracle_matches_committed_reference_object_vectors():
+    """tests/golden/reference_object_vectors.json holds values computed by the reference's own
+    object code (generator: tests/golden/make_reference_object_vectors.py).  Unlike
+    tests/test_oracle_vs_ref.py this needs neither /root/reference nor oracle/_ref."""
+    import ctypes as C
+    import json
+    import os
+    import struct
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_object_vectors.json")))
+    L = O.lib()
+    for v, h in g["hashint4"]:
+        assert L.orc_hashint4(v) == h
+    for v, h in g["hashint4new"]:
+        assert L.orc_hashint4new(v) == h
+    for v, h in g["hashint8"]:
+        assert L.orc_hashint8(v) == h
+    for v, h in g["hashint8new"]:
+        assert L.orc_hashint8new(v) == h
+    for v, h in g["murmurhash32"]:
+        assert L.orc_murmurhash32(v) == h
+    for v, h in g["hashchar"]:
+        assert L.orc_hashchar(v) == h
+    for bits, h in g["hashfloat8_bits"]:
+        assert L.orc_hashfloat8(struct.unpack("<d", struct.pack("<q", bits))[0]) == h
+    for a, b, h in g["hash_combine"]:
+        assert L.orc_hash_combine(a, b) == h
+    for hx, h_old, h_new in g["hash_any"]:
+        b = bytes.fromhex(hx)
+        assert L.orc_hash_any(b, len(b)) == h_old and L.orc_hash_any_new(b, len(b)) == h_new
+    for v, h in g["evaluate_hashkey_int4"]:
+        assert L.orc_evaluate_hashkey((C.c_int * 1)(O.GX_INT4), None, (C.c_int64 * 1)(v), 1) == h
+    for v, h in g["evaluate_hashkey_int8"]:
+        assert L.orc_evaluate_hashkey((C.c_int * 1)(O.GX_INT8), None, (C.c_int64 * 1)(v), 1) == h
+    for a, b, h in g["evaluate_hashkey_int8_int4"]:
+        assert L.orc_evaluate_hashkey((C.c_int * 2)(O.GX_INT8, O.GX_INT4), None, (C.c_int64 * 2)(a, b), 2) == h
+    # float8_accum / float8pl: the oracle's aggregate states over the same inputs in the same order
+    import opentenbase_b200 as gpu
+    acc = g["float8_accum"]
+    vals = np.array(acc["inputs_bits"], np.int64).view(np.float64)
+    plan = O.make_plan(aggs=[(gpu.GX_AGG_AVG_F8, [(gpu.GX_OP_COL, 0, 0)]), (gpu.GX_AGG_SUM_F8, [(gpu.GX_OP_COL, 0, 0)])])
+    r, _ = O.exec_agg(O.Rel([O.GX_FLOAT8], [vals]), plan, keep_raw=True)
+    np.testing.assert_array_equal(r.states[0, 0].view(np.int64), np.array(acc["state_bits"], np.int64))
+    assert np.float64(r.aggs[0, 1]).view(np.int64) == acc["float8pl_sum_bits"]
