@@ -155,11 +155,30 @@ def cpu_reference_run(sample_orders: int, threads: int, steps: int, warmup: int)
             "count_star_total": total_count, "groups": final.ngroups}
 
 
+def effective_cpus() -> int:
+    """Host threads this process can really run at once: the affinity mask, capped by a cgroup
+    CPU quota if there is one (a container may show 128 CPUs and be allowed 16 of them)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]              # cgroup v2
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())            # cgroup v1
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = effective_cpus()
     sample_orders = (args.cpu_sample_orders // 2) * threads          # ~0.75 M orders (3.75 M rows) per thread
     r = cpu_reference_run(sample_orders, threads, args.steps, args.warmup)
     line = {
