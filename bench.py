@@ -36,6 +36,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "rows/sec lineitem JOIN orders hashjoin+groupby SF100"
+try:                                   # BASELINE.json names the metric; use its wording when it is there
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"] or METRIC
+except (OSError, ValueError, KeyError):
+    pass
 ALG_BYTES_PER_PROBE_ROW = 24     # 8 B key + 8 B payload on hit + 8 B l_extendedprice
 ALG_BYTES_PER_BUILD_ROW = 24     # 8 B key read + 16 B slot write
 
