@@ -159,6 +159,9 @@ int  gx_l2_flush(gx_ctx *ctx);              /* writes a >L2-sized buffer      */
 /* pinned host memory for the staging buffers the loader DMA-copies from */
 int  gx_host_alloc(gx_ctx *ctx, size_t bytes, void **out);
 int  gx_host_free(gx_ctx *ctx, void *p);
+/* host -> device copy rate (GB/s, best of 3) of `bytes` from `host` over
+ * nstreams (1..4) copy streams: the same-run PCIe ceiling bench.py reports */
+int  gx_h2d_probe(gx_ctx *ctx, const void *host, size_t bytes, int nstreams, double *gb_per_s);
 
 /* ---- K0: columnar loader ------------------------------------------------
  * Replaces heap_getnext/heapgetpage + slot_deform_tuple + SeqNext
@@ -194,6 +197,9 @@ int  gx_table_ncols(const gx_table *t);
 int  gx_table_read_column(gx_table *t, int col, int64_t row0, int64_t nrows,
                           void *host_out, uint8_t *host_nulls_out);
 int  gx_table_truncate(gx_table *t);         /* keep capacity, nrows = 0      */
+/* projection in place: forget column `col` (ExecProject of a narrower target
+ * list, execScan.c:237); later columns move down by one */
+int  gx_table_drop_column(gx_table *t, int col);
 void gx_table_free(gx_table *t);
 /* raw device pointer of a column (bench/test plumbing; not used by the provider) */
 int  gx_table_column_devptr(gx_table *t, int col, void **dptr);
@@ -271,8 +277,10 @@ int  gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_out,
 void gx_result_free(gx_result *r);
 
 /* One-call form used by the provider and by bench.py's e2e leg: HOST column
- * buffers in, finalized HOST result out; H2D staging is pipelined with the
- * kernels inside. inner_* may be NULL/0 when there is no join. */
+ * buffers in, partial-state result handle out.  The columns are copied in 64 MB
+ * chunks over several copy streams, inner table first, so the join-table build
+ * overlaps the upload of the outer columns; the probe+aggregate kernel starts
+ * when the outer table has landed.  inner_* may be NULL/0 when there is no join. */
 typedef struct gx_host_table {
     int32_t ncols;
     int32_t _pad;

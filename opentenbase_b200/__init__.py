@@ -125,6 +125,7 @@ def _declare(L):
         "gx_l2_flush": (C.c_int, [vp]),
         "gx_host_alloc": (C.c_int, [vp, sz, pp]),
         "gx_host_free": (C.c_int, [vp, vp]),
+        "gx_h2d_probe": (C.c_int, [vp, vp, sz, C.c_int, C.POINTER(dbl)]),
         "gx_table_create": (C.c_int, [vp, C.c_int, C.POINTER(i32), i64, pp]),
         "gx_table_append_columns": (C.c_int, [vp, pp, pp, i64]),
         "gx_table_append_heap_pages": (C.c_int, [vp, vp, i64, C.POINTER(GxHeapDesc), vp, vp, i32]),
@@ -132,6 +133,7 @@ def _declare(L):
         "gx_table_ncols": (C.c_int, [vp]),
         "gx_table_read_column": (C.c_int, [vp, C.c_int, i64, i64, vp, vp]),
         "gx_table_truncate": (C.c_int, [vp]),
+        "gx_table_drop_column": (C.c_int, [vp, C.c_int]),
         "gx_table_free": (None, [vp]),
         "gx_table_column_devptr": (C.c_int, [vp, C.c_int, pp]),
         "gx_table_generate": (C.c_int, [vp, C.c_int, C.c_int, i64, i64, C.c_int, C.c_int]),
@@ -255,6 +257,11 @@ class Table:
         nl = np.zeros(n, np.uint8) if with_nulls else None
         self.ctx._chk(lib().gx_table_read_column(self.h, col, 0, n, out.ctypes.data, None if nl is None else nl.ctypes.data))
         return (out, nl) if with_nulls else out
+
+    def drop_column(self, col):
+        self.ctx._chk(lib().gx_table_drop_column(self.h, col))
+        del self.types[col]
+        return self
 
     def free(self):
         if self.h and self.ctx.h:          # handles die with their context (stream-ordered frees need its stream)
@@ -387,6 +394,11 @@ class Context:
 
     def host_free(self, p):
         self._chk(lib().gx_host_free(self.h, p))
+
+    def h2d_probe(self, host_ptr, nbytes, nstreams=1) -> float:
+        r = C.c_double()
+        self._chk(lib().gx_h2d_probe(self.h, host_ptr, nbytes, nstreams, C.byref(r)))
+        return r.value
 
     # ---- tables
     def table(self, types, capacity) -> Table:

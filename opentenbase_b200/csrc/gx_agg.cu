@@ -1023,6 +1023,39 @@ __global__ void gx_k_merge_records(const gx_agg_dev A, const unsigned long long 
     }
 }
 
+// Finalize over an all-gathered buffer of partial states (gx_result_combine's small-result
+// path): segment p = [ngroups_p][flags_p][cap records of RW words].  Every rank sees every
+// partial record and keeps the groups it OWNS (the same key hash the redistribute path
+// uses), so the union over ranks holds each group exactly once — the contract of
+// "Distribute results by S -> Finalize HashAggregate" (xc_groupby.out:193-205) without a
+// partition step, a count exchange or a host round trip.
+__global__ void gx_k_merge_gathered(const gx_agg_dev A, const unsigned long long *gathered, int nseg, long long cap, int rank, int nranks)
+{
+    const int RW = 3 + A.P.nwords;
+    const long long seg_words = 2 + cap * RW, total = (long long) nseg * cap;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int p = (int) (i / cap); const long long j = i - (long long) p * cap;
+        const unsigned long long *seg = gathered + (long long) p * seg_words;
+        if (seg[1]) { if (j == 0) atomicOr((unsigned long long *) &A.counters[3], 1ULL); continue; }   // that rank had more than cap groups
+        if (j >= (long long) seg[0]) continue;
+        const unsigned long long *rec = seg + 2 + j * RW;
+        const unsigned long long h = gx_mix64(rec[1] ^ (rec[2] * 0x9E3779B97F4A7C15ULL) ^ (rec[0] << 56));
+        if ((int) (h % (unsigned long long) nranks) != rank) continue;
+        unsigned long long *g = global_upsert(A, rec[1], rec[2], (unsigned int) rec[0]);
+        if (!g) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+        for (int w = 0; w < A.P.nwords; w++) merge_word(&g[3 + w], A.wkind[w], rec[3 + w]);
+    }
+}
+__global__ void gx_k_pack_partial(const unsigned long long *recs, long long n, long long cap, int RW, unsigned long long *out)
+{
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    const bool big = n > cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = big ? 0ULL : (unsigned long long) n; out[1] = big ? 1ULL : 0ULL; }
+    if (big) return;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n * RW; i += stride) out[2 + i] = recs[i];
+}
+
 __global__ void gx_k_scan_i64(long long *v, long long n, long long *total);   // below
 
 // ============================================================ host side
@@ -1586,6 +1619,52 @@ int gx_combine_records(gx_ctx *ctx, gx_result *r, unsigned long long *d_recs, lo
     int rc = gx_result_layout_words(r, A.wkind, A.winit); if (rc) { GX_SET_ERR(ctx, "combine: unknown result"); return rc; }
     A.counters = ctx->d_scratch + 8;
     return gx_aggregate_records(ctx, A, d_recs, nrec, d_out, ngroups_out);
+}
+
+// small-result Finalize: pack this rank's partial records into a fixed-capacity segment
+int gx_pack_partial(gx_ctx *ctx, gx_result *r, long long cap, unsigned long long *d_seg)
+{
+    gx_launch_scope ls(ctx, "combine_pack");
+    long long words = r->ngroups * r->rec_words;
+    unsigned grid = (unsigned) ((words + 255) / 256); if (grid < 1) grid = 1; if (grid > (unsigned) ctx->sm_count * 4) grid = (unsigned) ctx->sm_count * 4;
+    gx_k_pack_partial<<<grid, 256, 0, ctx->stream>>>((const unsigned long long *) r->d_recs, r->ngroups, cap, r->rec_words, d_seg);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
+// ... and merge the all-gathered segments; *anybig = some rank did not fit (caller takes the general path)
+int gx_combine_gathered(gx_ctx *ctx, gx_result *r, const unsigned long long *d_gather, int nseg, long long cap,
+                        unsigned long long **d_out, long long *ngroups_out, int *anybig)
+{
+    gx_agg_dev A; memset(&A, 0, sizeof(A));
+    A.P.nwords = r->nwords; A.P.nkw = 2;
+    int rc = gx_result_layout_words(r, A.wkind, A.winit); if (rc) { GX_SET_ERR(ctx, "combine: unknown result"); return rc; }
+    A.counters = ctx->d_scratch + 8;
+    const int RW = 3 + r->nwords;
+    long long g_cap = gx_pow2_ceil(2 * (long long) nseg * cap + 1024);
+    unsigned long long *g_tab, *d_groups;
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &g_tab, (size_t) g_cap * RW * 8));
+    GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
+    GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 5 * sizeof(long long), ctx->stream));     // [4] = compact cursor
+    A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
+    // every group of the gathered set may be owned by this rank in the worst case
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_groups, (size_t) nseg * cap * RW * 8 + 64));
+    {
+        gx_launch_scope ls(ctx, "combine_merge", 2);
+        long long total = (long long) nseg * cap;
+        unsigned grid = (unsigned) ((total + 255) / 256); if (grid > (unsigned) ctx->sm_count * 8) grid = (unsigned) ctx->sm_count * 8;
+        gx_k_merge_gathered<<<grid, 256, 0, ctx->stream>>>(A, d_gather, nseg, cap, ctx->rank, ctx->nranks);
+        gx_k_compact_groups<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g_tab, g_cap, r->nwords, d_groups, ctx->d_scratch + 12);
+    }
+    GX_CUDA(ctx, cudaGetLastError());
+    long long c[4];
+    rc = read_counters(ctx, c);
+    gx_tmp_free(ctx, g_tab);
+    if (rc == GX_OK && c[1]) { GX_SET_ERR(ctx, "combine: merge table overflowed"); rc = GX_ERR_STATE; }
+    if (rc != GX_OK) { gx_tmp_free(ctx, d_groups); return rc; }
+    *anybig = c[3] != 0;
+    if (*anybig) { gx_tmp_free(ctx, d_groups); *d_out = nullptr; *ngroups_out = 0; return GX_OK; }
+    *d_out = d_groups; *ngroups_out = c[0];
+    return GX_OK;
 }
 
 static int run_radix(gx_ctx *ctx, compiled_plan *cp, const gx_agg_plan *plan, long long nrows_in, gx_result **out)

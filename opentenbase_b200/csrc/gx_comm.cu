@@ -330,6 +330,9 @@ struct gx_agg_dev;
 int gx_result_layout_words(gx_result *r, int *wkind, long long *winit);
 int gx_combine_records(gx_ctx *ctx, gx_result *r, unsigned long long *d_recs, long long nrec,
                        unsigned long long **d_out, long long *ngroups_out);   // gx_agg.cu
+int gx_pack_partial(gx_ctx *ctx, gx_result *r, long long cap, unsigned long long *d_seg);
+int gx_combine_gathered(gx_ctx *ctx, gx_result *r, const unsigned long long *d_gather, int nseg, long long cap,
+                        unsigned long long **d_out, long long *ngroups_out, int *anybig);
 
 __global__ void gx_k_rec_dest_hist(const unsigned long long *recs, long long nrec, int RW, int nranks,
                                    unsigned char *dest, long long *hist)
@@ -371,6 +374,37 @@ extern "C" int gx_result_combine(gx_ctx *ctx, gx_result *r)
     if (N == 1 || !ctx->comm || r->finalized_across) return GX_OK;
     const int RW = r->rec_words;
     long long nrec = r->ngroups;
+    // ---- few groups (Q1, GROUP BY date): one ncclAllGather of fixed-capacity segments and a
+    // device-side merge; no partition, no count exchange, one host synchronisation (the group
+    // count).  The capacity comes from the planner's estimate, which every datanode shares
+    // (same plan), so all ranks issue the same collective; a rank whose partial result does
+    // not fit says so in its segment header and everybody falls through to the general path.
+    {
+        const char *off = getenv("GX_NO_GATHER_COMBINE");
+        long long est = r->plan.n_group_cols == 0 ? 1 : (r->plan.est_groups > 0 ? r->plan.est_groups : 1024);
+        long long cap = gx_pow2_ceil(est * 2 < 1024 ? 1024 : est * 2);
+        if (cap <= 65536 && !(off && off[0] == '1')) {
+            const size_t seg_bytes = (size_t) (2 + cap * RW) * 8;
+            unsigned long long *d_seg, *d_all;
+            GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_seg, seg_bytes));
+            GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_all, seg_bytes * N));
+            int rc = gx_pack_partial(ctx, r, cap, d_seg);
+            if (rc == GX_OK) {
+                gx_launch_scope ls(ctx, "allgather");
+                int nr = g_nccl.AllGather(d_seg, d_all, seg_bytes, GX_NCCL_INT8, ctx->comm, ctx->stream);
+                if (nr != 0) { GX_SET_ERR(ctx, "NCCL error %d in ncclAllGather: %s", nr, g_nccl.GetErrorString(nr)); rc = GX_ERR_NCCL; }
+            }
+            unsigned long long *d_groups = nullptr; long long ngroups = 0; int anybig = 0;
+            if (rc == GX_OK) rc = gx_combine_gathered(ctx, r, d_all, N, cap, &d_groups, &ngroups, &anybig);
+            gx_tmp_free(ctx, d_seg); gx_tmp_free(ctx, d_all);
+            if (rc) return rc;
+            if (!anybig) {
+                gx_tmp_free(ctx, r->d_recs);
+                r->d_recs = (long long *) d_groups; r->ngroups = ngroups; r->cap = ngroups > 0 ? ngroups : 1; r->finalized_across = 1;
+                return GX_OK;
+            }
+        }
+    }
     unsigned nblk = (unsigned) ctx->sm_count;
     if ((long long) nblk * 256 > nrec) nblk = (unsigned) ((nrec + 255) / 256);
     if (nblk == 0) nblk = 1;

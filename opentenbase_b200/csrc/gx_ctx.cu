@@ -57,9 +57,12 @@ extern "C" int gx_init(int device, gx_ctx **out)
         cudaGetLastError();
     }
     GX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    GX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < GX_NCOPY; i++) {
+        GX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) GX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[k][i], cudaEventDisableTiming));
+    }
+    GX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
     GX_CUDA(ctx, cudaEventCreate(&ctx->ev_t0)); GX_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
-    GX_CUDA(ctx, cudaEventCreate(&ctx->ev_p0)); GX_CUDA(ctx, cudaEventCreate(&ctx->ev_p1));
     GX_CUDA(ctx, cudaMalloc(&ctx->d_scratch, 64 * sizeof(long long)));
     GX_CUDA(ctx, cudaMemset(ctx->d_scratch, 0, 64 * sizeof(long long)));
     GX_CUDA(ctx, cudaHostAlloc(&ctx->h_scratch, 64 * sizeof(long long), cudaHostAllocDefault));
@@ -79,11 +82,14 @@ extern "C" void gx_shutdown(gx_ctx *ctx)
     gx_comm_destroy(ctx);
     if (ctx->l2flush_buf) cudaFree(ctx->l2flush_buf);
     if (ctx->prof_pool) { for (int i = 0; i < GX_PROF_POOL; i++) { cudaEventDestroy(ctx->prof_pool[i].a); cudaEventDestroy(ctx->prof_pool[i].b); } free(ctx->prof_pool); }
-    for (int i = 0; i < 2; i++) { if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]); if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]); }
+    for (int i = 0; i < GX_NCOPY; i++) {
+        cudaStreamSynchronize(ctx->copy_streams[i]); cudaStreamDestroy(ctx->copy_streams[i]);
+        for (int k = 0; k < 2; k++) cudaEventDestroy(ctx->copy_ev[k][i]);
+    }
+    cudaEventDestroy(ctx->ev_alloc);
     cudaFree(ctx->d_scratch); cudaFreeHost(ctx->h_scratch); cudaFree(ctx->d_shardmap);
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
-    cudaEventDestroy(ctx->ev_p0); cudaEventDestroy(ctx->ev_p1);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->stream);
     delete ctx->prof;
     free(ctx);
 }
@@ -101,7 +107,7 @@ extern "C" int gx_device_info(gx_ctx *ctx, int *sm_count, int *cc_major, int *cc
 extern "C" int gx_sync(gx_ctx *ctx)
 {
     if (!ctx) return GX_ERR_ARG;
-    GX_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    for (int i = 0; i < GX_NCOPY; i++) GX_CUDA(ctx, cudaStreamSynchronize(ctx->copy_streams[i]));
     GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GX_OK;
 }

@@ -1,7 +1,12 @@
 // gx_exec.cu — the one-call form used by the CustomScan provider and by
 // bench.py's end-to-end leg: HOST column buffers in, partial result out.
-// Host->HBM staging is chunked so that the build of the join table and the
-// first probe chunks overlap the remaining copies.
+// Host->HBM staging: every column is cut into 64 MB chunks that go round-robin
+// over GX_NCOPY copy streams (several DMA engines, no single-queue limit); the
+// inner table is queued first, so the join-table build (compute stream) runs
+// while the outer columns are still arriving.  The probe+aggregate kernel needs
+// the whole outer table and starts when its last chunk has landed: at SF100 the
+// step is 11.4 GB over PCIe against ~4 ms of kernels, so e2e is a PCIe figure
+// and bench.py reports it next to a same-run copy ceiling (gx_h2d_probe).
 #include "gx_internal.cuh"
 #include <unistd.h>
 #include <sys/syscall.h>
@@ -50,14 +55,39 @@ extern "C" int gx_host_free(gx_ctx *ctx, void *p)
     return GX_OK;
 }
 
-static int upload(gx_ctx *ctx, const gx_host_table *h, gx_table **out)
+#define GX_COPY_CHUNK ((size_t) 64 << 20)
+
+// allocate the device table on the compute stream (stream-ordered pool) — no copies yet
+static int upload_alloc(gx_ctx *ctx, const gx_host_table *h, gx_table **out)
 {
     GX_CHECK_ARG(ctx, h->ncols > 0 && h->ncols <= GX_MAX_COLS && h->nrows >= 0 && h->types && h->cols, "exec_host: bad host table");
-    gx_table *t;
-    int rc = gx_table_create(ctx, h->ncols, h->types, h->nrows, &t); if (rc) return rc;
-    rc = gx_table_append_columns(t, h->cols, h->nulls, h->nrows);
-    if (rc) { gx_table_free(t); return rc; }
-    *out = t;
+    bool hn[GX_MAX_COLS];
+    for (int c = 0; c < h->ncols; c++) { hn[c] = h->nulls && h->nulls[c]; GX_CHECK_ARG(ctx, h->cols[c] != nullptr || h->nrows == 0, "exec_host: column %d is NULL", c); }
+    return gx_table_alloc_like(ctx, h->ncols, h->types, hn, h->nrows, out);
+}
+// queue the H2D copies of one host table on the copy streams; which = 0 inner / 1 outer event set
+static int upload_copy(gx_ctx *ctx, const gx_host_table *h, gx_table *t, int which, int *rr)
+{
+    for (int c = 0; c < h->ncols; c++) {
+        const size_t sz = (size_t) gx_type_size(h->types[c]), total = (size_t) h->nrows * sz;
+        for (size_t off = 0; off < total; off += GX_COPY_CHUNK) {
+            const size_t n = total - off < GX_COPY_CHUNK ? total - off : GX_COPY_CHUNK;
+            GX_CUDA(ctx, cudaMemcpyAsync((char *) t->cols[c] + off, (const char *) h->cols[c] + off, n, cudaMemcpyHostToDevice,
+                                         ctx->copy_streams[(*rr)++ % GX_NCOPY]));
+        }
+        if (t->nulls[c])
+            for (size_t off = 0; off < (size_t) h->nrows; off += GX_COPY_CHUNK) {
+                const size_t n = (size_t) h->nrows - off < GX_COPY_CHUNK ? (size_t) h->nrows - off : GX_COPY_CHUNK;
+                GX_CUDA(ctx, cudaMemcpyAsync(t->nulls[c] + off, h->nulls[c] + off, n, cudaMemcpyHostToDevice, ctx->copy_streams[(*rr)++ % GX_NCOPY]));
+            }
+    }
+    for (int i = 0; i < GX_NCOPY; i++) GX_CUDA(ctx, cudaEventRecord(ctx->copy_ev[which][i], ctx->copy_streams[i]));
+    t->nrows = h->nrows;
+    return GX_OK;
+}
+static int wait_copies(gx_ctx *ctx, int which)
+{
+    for (int i = 0; i < GX_NCOPY; i++) GX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[which][i], 0));
     return GX_OK;
 }
 
@@ -67,17 +97,65 @@ extern "C" int gx_exec_host(gx_ctx *ctx, const gx_host_table *outer, const gx_ho
 {
     if (!ctx || !outer || !plan || !out) return GX_ERR_ARG;
     gx_table *to = nullptr, *ti = nullptr; gx_hash *h = nullptr;
-    int rc = GX_OK;
-    // inner first: its H2D copy is short, and the build kernel then runs while
-    // the (much larger) outer columns are still streaming in on the same queue
-    if (inner && plan->outer_key_col >= 0) {
-        rc = upload(ctx, inner, &ti);
+    const bool join = inner && plan->outer_key_col >= 0;
+    int rc = GX_OK, rr = 0;
+    if (join) rc = upload_alloc(ctx, inner, &ti);
+    if (rc == GX_OK) rc = upload_alloc(ctx, outer, &to);
+    if (rc == GX_OK) {
+        // the copy streams may touch the tables once the stream-ordered allocations are reached
+        cudaError_t e = cudaEventRecord(ctx->ev_alloc, ctx->stream);
+        for (int i = 0; i < GX_NCOPY && e == cudaSuccess; i++) e = cudaStreamWaitEvent(ctx->copy_streams[i], ctx->ev_alloc, 0);
+        if (e != cudaSuccess) { GX_SET_ERR(ctx, "exec_host: %s", cudaGetErrorString(e)); rc = GX_ERR_CUDA; }
+    }
+    // inner first: its copy is short, and the build then runs while the (much larger) outer columns stream in
+    if (rc == GX_OK && join) rc = upload_copy(ctx, inner, ti, 0, &rr);
+    if (rc == GX_OK) rc = upload_copy(ctx, outer, to, 1, &rr);
+    if (rc == GX_OK && join) {
+        rc = wait_copies(ctx, 0);
         if (rc == GX_OK) rc = gx_hash_build(ctx, ti, inner_key_col, n_inner_preds, inner_preds, n_payload, payload_cols, inner_unique, &h);
     }
-    if (rc == GX_OK) rc = upload(ctx, outer, &to);
+    if (rc == GX_OK) rc = wait_copies(ctx, 1);
     if (rc == GX_OK) rc = gx_hash_agg(ctx, to, h, plan, out);
+    if (rc != GX_OK) for (int i = 0; i < GX_NCOPY; i++) cudaStreamSynchronize(ctx->copy_streams[i]);   // nothing may still write the tables freed below
     if (h) gx_hash_free(h);
     if (ti) gx_table_free(ti);
     if (to) gx_table_free(to);
     return rc;
+}
+
+// What the host link delivers from THIS buffer right now: `bytes` copied host -> device in 64 MB
+// chunks over nstreams copy streams, three times, best rate (GB/s).  bench.py prints it beside the
+// e2e figure so a slow e2e can be attributed to the box or to the code.
+extern "C" int gx_h2d_probe(gx_ctx *ctx, const void *host, size_t bytes, int nstreams, double *gb_per_s)
+{
+    if (!ctx || !host || !gb_per_s || bytes == 0) return GX_ERR_ARG;
+    if (nstreams < 1) nstreams = 1;
+    if (nstreams > GX_NCOPY) nstreams = GX_NCOPY;
+    void *d = nullptr;
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, &d, bytes));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEvent_t a, b;
+    GX_CUDA(ctx, cudaEventCreate(&a)); GX_CUDA(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        GX_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+        for (int i = 0; i < nstreams; i++) GX_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_streams[i], a, 0));
+        int rr = 0;
+        for (size_t off = 0; off < bytes; off += GX_COPY_CHUNK) {
+            const size_t n = bytes - off < GX_COPY_CHUNK ? bytes - off : GX_COPY_CHUNK;
+            GX_CUDA(ctx, cudaMemcpyAsync((char *) d + off, (const char *) host + off, n, cudaMemcpyHostToDevice, ctx->copy_streams[rr++ % nstreams]));
+        }
+        for (int i = 0; i < nstreams; i++) {
+            GX_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1][i], ctx->copy_streams[i]));
+            GX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1][i], 0));
+        }
+        GX_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+        GX_CUDA(ctx, cudaEventSynchronize(b));
+        float ms = 0; GX_CUDA(ctx, cudaEventElapsedTime(&ms, a, b));
+        if (ms > 0) { double r = (double) bytes / (ms / 1e3) / 1e9; if (r > best) best = r; }
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    gx_tmp_free(ctx, d);
+    *gb_per_s = best;
+    return GX_OK;
 }

@@ -15,6 +15,7 @@
 #define GX_MAX_NODES   64
 #define GX_SUB_LOG2    11                 /* join table: linear probing wraps inside 2048-slot (32 KB) sub-tables */
 #define GX_SUB         (1 << GX_SUB_LOG2)
+#define GX_NCOPY       4                  /* copy streams of the host-table loader */
 
 // ---------------------------------------------------------------- host side
 struct gx_prof_entry { double ms; int64_t launches; };
@@ -29,17 +30,16 @@ struct gx_ctx {
     size_t hbm_bytes;
     size_t smem_optin;           // max dynamic smem per block
     cudaStream_t stream;         // all kernels
-    cudaStream_t copy_stream;    // H2D staging
+    cudaStream_t copy_streams[GX_NCOPY];   // H2D staging: chunks go round-robin over these (gx_exec.cu)
+    cudaEvent_t copy_ev[2][GX_NCOPY];      // [0] inner table landed, [1] outer table landed (per copy stream)
+    cudaEvent_t ev_alloc;                  // the copy streams wait for the stream-ordered allocations
     cudaEvent_t ev_t0, ev_t1;    // gx_timer_*
-    cudaEvent_t ev_p0, ev_p1;    // per-kernel profiling
     char err[512];
     int64_t launches;
     int profile;
     std::map<std::string, gx_prof_entry> *prof;
     gx_prof_rec *prof_pool; int prof_used;      // events recorded, not yet resolved
     void *l2flush_buf; size_t l2flush_bytes;
-    // pinned staging ring for pageable host buffers
-    void *stage[2]; size_t stage_bytes; cudaEvent_t stage_ev[2];
     // small device scratch (counters / flags)
     long long *d_scratch;        // 64 x int64
     long long *h_scratch;        // pinned mirror

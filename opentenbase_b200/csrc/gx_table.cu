@@ -44,6 +44,15 @@ extern "C" void gx_table_free(gx_table *t)
 extern "C" int64_t gx_table_nrows(const gx_table *t) { return t ? t->nrows : -1; }
 extern "C" int gx_table_ncols(const gx_table *t) { return t ? t->ncols : -1; }
 extern "C" int gx_table_truncate(gx_table *t) { if (!t) return GX_ERR_ARG; t->nrows = 0; return GX_OK; }
+extern "C" int gx_table_drop_column(gx_table *t, int col)
+{
+    if (!t || col < 0 || col >= t->ncols || t->ncols < 2) return GX_ERR_ARG;
+    gx_tmp_free(t->ctx, t->cols[col]); gx_tmp_free(t->ctx, t->nulls[col]);
+    for (int c = col; c + 1 < t->ncols; c++) { t->cols[c] = t->cols[c + 1]; t->nulls[c] = t->nulls[c + 1]; t->types[c] = t->types[c + 1]; }
+    t->ncols--;
+    t->cols[t->ncols] = nullptr; t->nulls[t->ncols] = nullptr; t->types[t->ncols] = 0;
+    return GX_OK;
+}
 extern "C" int gx_table_column_devptr(gx_table *t, int col, void **dptr)
 {
     if (!t || col < 0 || col >= t->ncols || !dptr) return GX_ERR_ARG;
@@ -370,6 +379,7 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
 #define PG_BLCKSZ       8192
 #define PG_PAGE_HDR     44      // offsetof(PageHeaderData, pd_linp); LocationIndex is uint32 (__OPENTENBASE_C__)
 #define PG_PD_LOWER     16
+#define PG_HTH_INFOMASK2 38     // low 11 bits: number of attributes in THIS tuple (HEAP_NATTS_MASK)
 #define PG_HTH_INFOMASK 40
 #define PG_HTH_HOFF     46
 #define PG_HTH_BITS     47
@@ -434,9 +444,13 @@ __global__ void gx_k_deform(gx_deform_args a, const long long *pageoffs)
         const uint8_t *tp = tup + tup[PG_HTH_HOFF];
         unsigned int off = 0;
         long long row = row0 + myrow;
+        // a tuple written before ALTER TABLE ADD COLUMN carries fewer attributes than the descriptor:
+        // natts = Min(HeapTupleHeaderGetNatts(tup), natts), the rest reads as NULL (heaptuple.c:1424,1497-1502;
+        // relations with missing-value defaults are declined by the provider)
+        const int tnatts = (int) (*(const uint16_t *) (tup + PG_HTH_INFOMASK2) & 0x07FF);
         for (int att = 0; att < a.maxatt; att++) {
             int c = a.col_of_att[att];
-            if (hasnulls && !(bp[att >> 3] & (1 << (att & 7)))) {
+            if (att >= tnatts || (hasnulls && !(bp[att >> 3] & (1 << (att & 7))))) {
                 if (c >= 0) {
                     if (a.out_nulls[c]) a.out_nulls[c][row] = 1;
                     switch (a.out_type[c]) { case GX_INT4: case GX_DATE: ((int *) a.out[c])[row] = 0; break;

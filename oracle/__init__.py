@@ -108,6 +108,7 @@ def _declare(L: C.CDLL) -> None:
         ("orc_gen_lineitem", i64, [C.c_int, i64, i64, C.c_int, C.c_int] + [vp] * 8),
         ("orc_gen_customer", i64, [C.c_int, i64, i64, C.c_int, C.c_int, vp, vp]),
         ("orc_rel_create", vp, [C.c_int, vp]), ("orc_rel_free", None, [vp]),
+        ("orc_rel_add_column", C.c_int, [vp, i32]),
         ("orc_rel_insert_columns", C.c_int, [vp, vp, vp, i64]),
         ("orc_rel_ntuples", i64, [vp]), ("orc_rel_npages", i64, [vp]),
         ("orc_rel_page", vp, [vp, i64]), ("orc_rel_copy_pages", None, [vp, vp]),
@@ -198,6 +199,11 @@ class Rel:
             npp = (C.c_void_p * len(kn))(*[None if x is None else x.ctypes.data for x in kn])
         rc = lib().orc_rel_insert_columns(self.h, cp, npp, n)
         assert rc == 0
+
+    def add_column(self, gx_type):
+        """ALTER TABLE ADD COLUMN without a rewrite: old tuples read the new attribute as NULL"""
+        assert lib().orc_rel_add_column(self.h, gx_type) == 0
+        self.types.append(gx_type)
 
     @property
     def ntuples(self):
@@ -357,3 +363,23 @@ def exec_join(outer: Rel, outer_key_col, inner: Rel, join: OrcJoinSpec, out_oute
 
 def last_exec_seconds() -> float:
     return lib().orc_last_exec_seconds()
+
+
+# ---- whole-query references for the multi-datanode plan shapes ---------------
+def q3_reference(sf, n_orders, n_cust, date, segment, orders_cols=None):
+    """TPC-H Q3 shape on ONE node, tuple at a time: the customer semi-join is restated with
+    numpy (c_custkey is unique), the orders JOIN lineitem + GROUP BY runs through the
+    tuple-at-a-time executor.  Returns the sorted AggResult over
+    (l_orderkey, o_orderdate, o_shippriority): sum(l_extendedprice * (1 - l_discount))."""
+    GX_OP_COL, GX_OP_CONST, GX_OP_SUB, GX_OP_MUL, GX_AGG_SUM_F8, GX_GT = 1, 2, 4, 5, 3, 5
+    c = gen_customer(sf, 0, n_cust)
+    o = gen_orders(sf, 0, n_orders)
+    l = gen_lineitem(sf, 0, n_orders)
+    good = np.isin(o[1], c[0][c[1] == segment]) & (o[2] < date)
+    oj = [x[good] for x in o]
+    rev = [(GX_OP_COL, 2, 0), (GX_OP_CONST, 0, 1.0), (GX_OP_COL, 3, 0), (GX_OP_SUB, 0, 0), (GX_OP_MUL, 0, 0)]
+    plan = make_plan(preds=[(5, GX_GT, date)], outer_key_col=0, group_cols=[(0, 0), (1, 0), (1, 1)],
+                     aggs=[(GX_AGG_SUM_F8, rev)])
+    ltypes = [GX_INT8, GX_FLOAT8, GX_FLOAT8, GX_FLOAT8, GX_FLOAT8, GX_DATE, GX_CHAR, GX_CHAR]
+    otypes = [GX_INT8, GX_INT4, GX_DATE, GX_INT4]
+    return exec_agg(Rel(ltypes, l), plan, Rel(otypes, oj), make_join(0, payload_cols=[2, 3], inner_unique=1)).sorted()

@@ -41,6 +41,22 @@ orc_rel *orc_rel_create(int natts, const int32_t *types)
     return r;
 }
 
+/* ALTER TABLE ADD COLUMN without a rewrite: the descriptor grows, tuples already on the
+ * pages keep their old attribute count in t_infomask2 and read the new attribute as NULL
+ * (no missing-value default is modelled: heap_deform_tuple, heaptuple.c:1424,1497-1502 with
+ * atthasmissing = false). */
+int orc_rel_add_column(orc_rel *r, int32_t type)
+{
+    if (r->natts >= 64) return -1;
+    r->attrs = (orc_attr *) realloc(r->attrs, (size_t) (r->natts + 1) * sizeof(orc_attr));
+    memset(&r->attrs[r->natts], 0, sizeof(orc_attr));
+    r->attrs[r->natts].type = type;
+    orc_type_layout(type, &r->attrs[r->natts].attlen, &r->attrs[r->natts].attalign);
+    r->attrs[r->natts].attcacheoff = -1;
+    r->natts++;
+    return 0;
+}
+
 void orc_rel_free(orc_rel *r)
 {
     if (!r) return;
@@ -290,6 +306,13 @@ void orc_slot_deform(orc_slot *slot, int natts)
 
     if (attnum == 0) { off = 0; slow = 0; }
     else { off = slot->off; slow = slot->slow; }
+
+    /* natts = Min(HeapTupleHeaderGetNatts(tup), natts) (heaptuple.c:1424, :1555): attributes the
+     * tuple was written without read as NULL (getmissingattr without a missing value) */
+    const int want = natts;
+    const int tnatts = (int) (rd16(tup + HTH_INFOMASK2) & HEAP_NATTS_MASK);
+    if (natts > tnatts) natts = tnatts;
+    for (int a = natts > attnum ? natts : attnum; a < want; a++) { slot->values[a] = 0; slot->isnull[a] = 1; }
 
     for (; attnum < natts; attnum++) {
         orc_attr *att = &slot->attrs[attnum];

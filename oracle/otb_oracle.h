@@ -77,6 +77,7 @@ typedef struct orc_rel orc_rel;
 /* A relation of by-value attributes stored as OpenTenBase heap pages
  * (bufpage.h:153-175, htup_details.h:126-201, itemid.h). */
 orc_rel *orc_rel_create(int natts, const int32_t *types);
+int      orc_rel_add_column(orc_rel *r, int32_t type);   /* ALTER TABLE ADD COLUMN, no rewrite */
 void     orc_rel_free(orc_rel *r);
 /* heap_form_tuple + PageAddItem (heaptuple.c:1012, bufpage.c:218) */
 int      orc_rel_insert_columns(orc_rel *r, const void *const *cols,

@@ -20,7 +20,6 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opentenbase_b200 as g  # noqa: E402
 
-DATE = -1752            # 1995-03-15 as days since 2000-01-01
 
 
 def main():
@@ -43,40 +42,30 @@ def main():
     ctx.comm_init(rank, world, box[0])
     ctx.set_shardmap(world)
 
+    from opentenbase_b200 import plans as P
     nord = a.orders or 1_500_000 * a.sf
     ncust = 150_000 * a.sf
     cust = ctx.table(g.SCHEMAS[g.T_CUSTOMER], ncust // world * 2 + 1024).generate(g.T_CUSTOMER, a.sf, 0, ncust, rank, world)
     orders = ctx.table(g.SCHEMAS[g.T_ORDERS], nord // world * 2 + 1024).generate(g.T_ORDERS, a.sf, 0, nord, rank, world)
     line = ctx.table(g.SCHEMAS[g.T_LINEITEM], nord * 7 // world * 2 + 1024).generate(g.T_LINEITEM, a.sf, 0, nord, rank, world)
-
-    C, K, S, M = g.GX_OP_COL, g.GX_OP_CONST, g.GX_OP_SUB, g.GX_OP_MUL
-    rev = [(C, g.L_EXTENDEDPRICE, 0), (K, 0, 1.0), (C, g.L_DISCOUNT, 0), (S, 0, 0), (M, 0, 0)]
-    plan = g.make_plan(preds=[(g.L_SHIPDATE, g.GX_GT, DATE)], outer_key_col=g.L_ORDERKEY,
-                       group_cols=[(0, g.L_ORDERKEY), (1, 0), (1, 1)], aggs=[(g.GX_AGG_SUM_F8, rev)],
-                       est_groups=max(nord // world // 4, 1024))
+    ccols = {"custkey": g.C_CUSTKEY, "mktsegment": g.C_MKTSEGMENT}
+    ocols = {"orderkey": g.O_ORDERKEY, "custkey": g.O_CUSTKEY, "orderdate": g.O_ORDERDATE, "shippriority": g.O_SHIPPRIORITY}
+    lcols = {"orderkey": g.L_ORDERKEY, "extendedprice": g.L_EXTENDEDPRICE, "discount": g.L_DISCOUNT, "shipdate": g.L_SHIPDATE}
+    stats = {}
     for it in range(a.iters):
         ctx.sync(); dist.barrier()
         t0 = time.perf_counter()
-        t1 = ctx.scan_filter(cust, [(g.C_MKTSEGMENT, g.GX_EQ, ord("B"))], [g.C_CUSTKEY])
-        t2 = ctx.scan_filter(orders, [(g.O_ORDERDATE, g.GX_LT, DATE)], [g.O_ORDERKEY, g.O_CUSTKEY, g.O_ORDERDATE, g.O_SHIPPRIORITY])
-        t2r = ctx.redistribute(t2, 1)                                   # all-to-all on o_custkey
-        h1 = ctx.hash_build(t1, 0, [], unique=True)
-        j1 = ctx.hash_probe(t2r, 1, h1, [0, 2, 3])                      # o_orderkey, o_orderdate, o_shippriority (+ build row)
-        j1r = ctx.redistribute(j1, 0)                                   # all-to-all back on o_orderkey
-        h2 = ctx.hash_build(j1r, 0, [1, 2], unique=True)
-        res = ctx.hash_agg(line, plan, h2)
+        res = P.q3_datanode(ctx, cust, orders, line, ccols, ocols, lcols, stats)
         keys, aggs, nulls = res.fetch()
+        res.free()
         ctx.sync(); dist.barrier()
         dt = time.perf_counter() - t0
         if rank == 0 and a.iters > 1:
             print(f"q3 iteration {it}: {dt * 1e3:.2f} ms")
-        if it + 1 < a.iters:
-            for x in (res, h2, h1): x.free()
-            for x in (j1r, j1, t2r, t2, t1): x.free()
     rows_in = cust.nrows + orders.nrows + line.nrows
 
     gathered = [None] * world
-    dist.all_gather_object(gathered, (keys, aggs, rows_in, t2.nrows, j1.nrows))
+    dist.all_gather_object(gathered, (keys, aggs, rows_in, stats["redistributed_custkey"], stats["redistributed_orderkey"]))
     if rank == 0:
         allk = np.concatenate([x[0] for x in gathered]); alla = np.concatenate([x[1] for x in gathered])
         total_rows = sum(x[2] for x in gathered)
@@ -84,14 +73,7 @@ def main():
               f"{total_rows / dt / 1e9:.2f} G rows/s; redistributed {sum(x[3] for x in gathered)} + {sum(x[4] for x in gathered)} rows")
         if a.check:
             import oracle as O
-            from oracle import make_join, make_plan
-            c, o, l = O.gen_customer(a.sf, 0, ncust), O.gen_orders(a.sf, 0, nord), O.gen_lineitem(a.sf, 0, nord)
-            good = np.isin(o[1], c[0][c[1] == ord("B")]) & (o[2] < DATE)     # the customer join, restated with numpy
-            oj = [x[good] for x in o]
-            oplan = make_plan(preds=[(g.L_SHIPDATE, g.GX_GT, DATE)], outer_key_col=g.L_ORDERKEY,
-                              group_cols=[(0, g.L_ORDERKEY), (1, 0), (1, 1)], aggs=[(g.GX_AGG_SUM_F8, rev)])
-            want = O.exec_agg(O.Rel(g.SCHEMAS[g.T_LINEITEM], l), oplan, O.Rel(g.SCHEMAS[g.T_ORDERS], oj),
-                              make_join(g.O_ORDERKEY, payload_cols=[g.O_ORDERDATE, g.O_SHIPPRIORITY], inner_unique=1)).sorted()
+            want = O.q3_reference(a.sf, nord, ncust, P.DATE_Q3, P.SEGMENT_Q3)
             order = np.lexsort([allk[:, 2], allk[:, 1], allk[:, 0]])
             np.testing.assert_array_equal(allk[order], want.keys)
             np.testing.assert_allclose(alla[order, 0], want.aggs[:, 0], rtol=1e-9, atol=0)

@@ -66,3 +66,21 @@ def test_staging_placement_never_raises():
 def test_effective_cpus_is_sane():
     n = bench.effective_cpus()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_same_result_is_strict_about_integers_and_tolerant_about_floats():
+    import numpy as np
+    import bench
+    import oracle as O
+    keys = np.array([[3], [1], [2]], np.int64)
+    aggs = np.zeros((3, 2)); aggs[:, 0] = np.array([30, 10, 20], np.int64).view(np.float64); aggs[:, 1] = [3.0, 1.0, 2.0]
+    want = O.AggResult(np.array([[1], [2], [3]], np.int64),
+                       np.stack([np.array([10, 20, 30], np.int64).view(np.float64), np.array([1.0, 2.0, 3.0 * (1 + 1e-12)])], 1),
+                       np.zeros((3, 3), np.uint8))
+    ok, _ = bench.same_result((keys, aggs, None), want, int_aggs=(0,))
+    assert ok
+    bad = aggs.copy(); bad[0, 0] = np.array([31], np.int64).view(np.float64)[0]
+    assert not bench.same_result((keys, bad, None), want, int_aggs=(0,))[0]
+    bad = aggs.copy(); bad[1, 1] = 1.0 + 1e-6
+    assert not bench.same_result((keys, bad, None), want, int_aggs=(0,))[0]
+    assert not bench.same_result((keys[:2], aggs[:2], None), want, int_aggs=(0,))[0]

@@ -261,3 +261,32 @@ def test_oracle_matches_committed_reference_object_vectors():
     r, _ = O.exec_agg(O.Rel([O.GX_FLOAT8], [vals]), plan, keep_raw=True)
     np.testing.assert_array_equal(r.states[0, 0].view(np.int64), np.array(acc["state_bits"], np.int64))
     assert np.float64(r.aggs[0, 1]).view(np.int64) == acc["float8pl_sum_bits"]
+
+
+def test_short_tuples_read_added_columns_as_null():
+    """heap_deform_tuple / slot_deform_tuple stop at the tuple's own attribute count
+    (heaptuple.c:1424, :1555); the rest is NULL when the column has no missing value (:1497-1502)."""
+    rel = O.Rel([O.GX_INT8, O.GX_INT4], [np.arange(10), np.arange(10, dtype=np.int32)])
+    rel.add_column(O.GX_FLOAT8)
+    rel.insert([np.arange(3), np.arange(3, dtype=np.int32), np.full(3, 2.5)])
+    cols, nulls = rel.scan([0, 2])
+    np.testing.assert_array_equal(nulls[1], [1] * 10 + [0] * 3)
+    np.testing.assert_array_equal(cols[1][10:], [2.5] * 3)
+    np.testing.assert_array_equal(cols[0], list(range(10)) + [0, 1, 2])
+
+
+def test_q3_reference_agrees_with_a_numpy_restatement():
+    """The whole-query Q3 reference used by bench.py and the multi-datanode tests, against plain numpy."""
+    sf, nord, ncust, date, seg = 1, 20000, 150000, -1752, ord("B")
+    want = O.q3_reference(sf, nord, ncust, date, seg)
+    c, o, l = O.gen_customer(sf, 0, ncust), O.gen_orders(sf, 0, nord), O.gen_lineitem(sf, 0, nord)
+    good = np.isin(o[1], c[0][c[1] == seg]) & (o[2] < date)
+    okeys = dict(zip(o[0][good].tolist(), zip(o[2][good].tolist(), o[3][good].tolist())))
+    sums = {}
+    for k, p, d, sd in zip(l[0].tolist(), l[2].tolist(), l[3].tolist(), l[5].tolist()):
+        if sd > date and k in okeys:
+            sums[k] = sums.get(k, 0.0) + p * (1.0 - d)
+    assert want.ngroups == len(sums) > 50
+    for (k, od, sp), s in zip(want.keys.tolist(), want.aggs[:, 0].tolist()):
+        assert okeys[k] == (od, sp)
+        assert abs(sums[k] - s) <= 1e-9 * abs(s)
