@@ -404,7 +404,8 @@ def run_ours(args):
                         "nvlink_gb_s_per_gpu": (sent / world * (world - 1) / world / (a2a_ms / 1e3) / 1e9) if (a2a_ms and world > 1) else None,
                         "nvlink_peak_gb_s": 900.0,
                         "algorithmic_bytes": alg, "hbm_gb_s_per_gpu": alg / world / (ms / 1e3) / 1e9,
-                        "frac_hbm": alg / world / (ms / 1e3) / 1e9 / peak, "phases_ms": ph}
+                        "frac_hbm": alg / world / (ms / 1e3) / 1e9 / peak, "phases_ms": ph,
+                        "host_ms_per_call_last_step": {k: round(v, 3) for k, v in q3stats.get("host_ms_per_call", {}).items()}}
 
         # Q1 shape (configs[4]): Partial HashAggregate -> all-gather of partial states -> Finalize
         def q1():

@@ -562,6 +562,235 @@ __global__ void __launch_bounds__(LPT_K == 8 ? 640 : 1024, 1) gx_k_agg_lptile(co
 }
 
 // ---------------------------------------------------------------------------
+// A handful of groups (<= FG_G), no join: the Q1 shape and config 1.  The accumulators live in
+// REGISTERS: a thread keeps (row count, FG_NV float8 sums) for each of the FG_G groups the CTA
+// has discovered, every row adds to the accumulators of its group through predicated adds
+// (adding nothing to the other groups), and the threads' accumulators meet once, at the end
+// (warp shuffles -> one shared-memory table per CTA -> the global table).  Against the
+// lane-private shared-memory accumulators of gx_k_agg_lptile this needs no shared memory per
+// lane (full occupancy instead of 18 warps/SM) and no load-add-store per word and row.
+// The group directory is a FG_G-entry list in shared memory, claimed with a CAS on first
+// sight of a key; a (FG_G+1)-th key raises the overflow flag and the host retries with the
+// general kernels — the result never depends on the estimate.
+// Plan shape (checked by the host): no join; group key <= 8 bytes without NULLs; aggregates are
+// count(*) or sum/avg over chain expressions of NOT-NULL float8 columns and constants.
+#define FG_G  4
+#define FG_NV 5
+#define FG_K  4                         /* rows per lane and tile: independent loads in flight */
+struct gx_fewgroups_args { int nv; int _pad; int vagg[FG_NV], vword[FG_NV]; };
+
+__device__ __forceinline__ int fg_insert(unsigned long long *s_keys, unsigned int *s_state, unsigned long long key)
+{
+    for (int gI = 0; gI < FG_G; gI++) {
+        for (;;) {
+            const unsigned int st = *(volatile unsigned int *) &s_state[gI];
+            if (st == 2u) { if (*(volatile unsigned long long *) &s_keys[gI] == key) return gI; break; }
+            if (st == 0u && atomicCAS(&s_state[gI], 0u, 1u) == 0u) {
+                *(volatile unsigned long long *) &s_keys[gI] = key;
+                __threadfence_block();
+                *(volatile unsigned int *) &s_state[gI] = 2u;
+                return gI;
+            }
+        }
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_fewgroups_args F)
+{
+    __shared__ unsigned long long s_keys[FG_G];
+    __shared__ unsigned int s_state[FG_G];
+    __shared__ unsigned long long s_acc[FG_G][1 + FG_NV];
+    __shared__ int s_over;
+    const int lane = threadIdx.x & 31, nv = F.nv;
+    if (threadIdx.x < FG_G) { s_state[threadIdx.x] = 0u; s_keys[threadIdx.x] = 0ULL; }
+    if (threadIdx.x < FG_G * (1 + FG_NV)) ((unsigned long long *) s_acc)[threadIdx.x] = 0ULL;
+    if (threadIdx.x == 0) s_over = 0;
+    __syncthreads();
+    const gx_dplan &P = A.P;
+    double acc[FG_G][FG_NV]; unsigned int cnt[FG_G];
+#pragma unroll
+    for (int gI = 0; gI < FG_G; gI++) { cnt[gI] = 0u;
+#pragma unroll
+        for (int w = 0; w < FG_NV; w++) acc[gI][w] = 0.0; }
+    unsigned long long gk[FG_G]; unsigned int gvalid = 0u;
+#pragma unroll
+    for (int gI = 0; gI < FG_G; gI++) gk[gI] = 0ULL;
+    const long long tile = 32LL * FG_K, nwarp_total = (long long) gridDim.x * (blockDim.x >> 5);
+    const long long wid = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long base = A.row0 + wid * tile; base < A.row1; base += nwarp_total * tile) {
+        if (*(volatile int *) &s_over) break;
+        long long r[FG_K]; bool ok[FG_K]; int gi[FG_K];
+#pragma unroll
+        for (int j = 0; j < FG_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < A.row1; }
+        for (int p = 0; p < P.npreds; p++) {
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) if (ok[j]) ok[j] = gx_eval_pred(P.preds[p], r[j]);
+        }
+        // group of every row: compare with the keys this CTA knows
+        unsigned long long key[FG_K];
+        bool miss = false;
+#pragma unroll
+        for (int j = 0; j < FG_K; j++) {
+            unsigned long long k0 = 0, k1; unsigned int nm;
+            if (ok[j]) pack_group_key(P, r[j], 0ULL, k0, k1, nm);
+            key[j] = k0; gi[j] = -1;
+#pragma unroll
+            for (int gI = 0; gI < FG_G; gI++) if (((gvalid >> gI) & 1u) && k0 == gk[gI]) gi[j] = gI;
+            miss |= ok[j] && gi[j] < 0;
+        }
+        if (__any_sync(0xffffffffu, miss)) {                       // first sight of a key (a handful of times per CTA)
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) if (ok[j] && gi[j] < 0) { gi[j] = fg_insert(s_keys, s_state, key[j]); if (gi[j] < 0) { s_over = 1; ok[j] = false; } }
+            __syncwarp();
+#pragma unroll
+            for (int gI = 0; gI < FG_G; gI++) if (*(volatile unsigned int *) &s_state[gI] == 2u) { gk[gI] = *(volatile unsigned long long *) &s_keys[gI]; gvalid |= 1u << gI; }
+            if (*(volatile int *) &s_over) break;                  // more groups than accumulators: the host takes the general path
+        }
+#pragma unroll
+        for (int j = 0; j < FG_K; j++) {
+#pragma unroll
+            for (int gI = 0; gI < FG_G; gI++) cnt[gI] += (ok[j] && gi[j] == gI) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int w = 0; w < FG_NV; w++) {
+            if (w >= nv) break;
+            const gx_dexpr &e = P.aggs[F.vagg[w]].expr;
+            double v[FG_K];
+            lpt_term<FG_K>(e.t[0], r, ok, v);
+            for (int i = 1; i < e.nterms; i++) {
+                double x[FG_K];
+                lpt_term<FG_K>(e.t[i], r, ok, x);
+                const int op = e.t[i].op;
+                if (op == GX_OP_ADD) {
+#pragma unroll
+                    for (int j = 0; j < FG_K; j++) v[j] = __dadd_rn(v[j], x[j]);
+                } else if (op == GX_OP_SUB) {
+#pragma unroll
+                    for (int j = 0; j < FG_K; j++) v[j] = __dsub_rn(v[j], x[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < FG_K; j++) v[j] = __dmul_rn(v[j], x[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) {
+#pragma unroll
+                for (int gI = 0; gI < FG_G; gI++) if (ok[j] && gi[j] == gI) acc[gI][w] = __dadd_rn(acc[gI][w], v[j]);
+            }
+        }
+    }
+    // ---- threads -> warp -> CTA -> global table
+#pragma unroll
+    for (int gI = 0; gI < FG_G; gI++) {
+        unsigned long long c = cnt[gI];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(&s_acc[gI][0], c);
+#pragma unroll
+        for (int w = 0; w < FG_NV; w++) {
+            if (w >= nv) break;
+            double x = acc[gI][w];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_down_sync(0xffffffffu, x, o));
+            if (lane == 0) atomicAdd((double *) &s_acc[gI][1 + w], x);
+        }
+    }
+    __syncthreads();
+    if (s_over) { if (threadIdx.x == 0) atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+    if (threadIdx.x < FG_G && s_state[threadIdx.x] == 2u && s_acc[threadIdx.x][0] != 0ULL) {
+        unsigned long long *rec = global_upsert(A, s_keys[threadIdx.x], 0ULL, 0u);
+        if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); return; }
+        atomicAdd(&rec[3], s_acc[threadIdx.x][0]);
+        for (int w = 0; w < nv; w++) atomicAdd((double *) &rec[3 + F.vword[w]], __longlong_as_double((long long) s_acc[threadIdx.x][1 + w]));
+    }
+}
+
+// config 1's shape exactly: count(*) GROUP BY one 1-byte column, no quals.  16 rows per 128-bit
+// load; every byte is compared with the (<= 8) keys the CTA knows, four bytes per instruction
+// (__vcmpeq4), matches are counted with a population count.  1 B/row of traffic.
+#define CC_G 8
+__global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant__ gx_agg_dev A, const signed char *__restrict__ col)
+{
+    __shared__ unsigned long long s_keys[CC_G];
+    __shared__ unsigned int s_state[CC_G];
+    __shared__ unsigned long long s_cnt[CC_G];
+    __shared__ int s_over;
+    if (threadIdx.x < CC_G) { s_state[threadIdx.x] = 0u; s_keys[threadIdx.x] = 0ULL; s_cnt[threadIdx.x] = 0ULL; }
+    if (threadIdx.x == 0) s_over = 0;
+    __syncthreads();
+    unsigned int cnt[CC_G], rep[CC_G]; unsigned int gvalid = 0u;
+#pragma unroll
+    for (int gI = 0; gI < CC_G; gI++) { cnt[gI] = 0u; rep[gI] = 0u; }
+    auto insert = [&](unsigned int byte) -> bool {
+        for (int gI = 0; gI < CC_G; gI++) {
+            for (;;) {
+                const unsigned int st = *(volatile unsigned int *) &s_state[gI];
+                if (st == 2u) { if (*(volatile unsigned long long *) &s_keys[gI] == (unsigned long long) byte) return true; break; }
+                if (st == 0u && atomicCAS(&s_state[gI], 0u, 1u) == 0u) {
+                    *(volatile unsigned long long *) &s_keys[gI] = (unsigned long long) byte; __threadfence_block();
+                    *(volatile unsigned int *) &s_state[gI] = 2u; return true;
+                }
+            }
+        }
+        return false;
+    };
+    auto reload = [&]() {
+#pragma unroll
+        for (int gI = 0; gI < CC_G; gI++) if (*(volatile unsigned int *) &s_state[gI] == 2u) {
+            rep[gI] = (unsigned int) *(volatile unsigned long long *) &s_keys[gI] * 0x01010101u; gvalid |= 1u << gI; }
+    };
+    auto count_word = [&](unsigned int w, unsigned int keep /* 0xff per byte that is a row */) {
+        unsigned int seen = 0u;
+#pragma unroll
+        for (int gI = 0; gI < CC_G; gI++) {
+            const unsigned int m = ((gvalid >> gI) & 1u) ? (__vcmpeq4(w, rep[gI]) & keep) : 0u;
+            cnt[gI] += (unsigned int) __popc(m) >> 3; seen |= m;
+        }
+        if (seen != keep) {                                        // a byte value this thread has not seen yet
+            for (int b = 0; b < 4; b++) if (((keep & ~seen) >> (8 * b)) & 0xffu) { if (!insert((w >> (8 * b)) & 0xffu)) s_over = 1; }
+            reload();
+            const unsigned int todo = keep & ~seen;
+#pragma unroll
+            for (int gI = 0; gI < CC_G; gI++) { const unsigned int m = ((gvalid >> gI) & 1u) ? (__vcmpeq4(w, rep[gI]) & todo) : 0u; cnt[gI] += (unsigned int) __popc(m) >> 3; }
+        }
+    };
+    const long long n = A.row1 - A.row0;
+    const signed char *p0 = col + A.row0;
+    // head: bytes up to the first 16-byte boundary; body: vectors; tail: the rest
+    long long head = (long long) ((16 - ((unsigned long long) p0 & 15ULL)) & 15ULL); if (head > n) head = n;
+    const long long nvec = (n - head) >> 4, tail0 = head + (nvec << 4);
+    const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long) gridDim.x * blockDim.x;
+    if (tid < head) count_word((unsigned int) (unsigned char) p0[tid], 0xffu);
+    if (tid < n - tail0) count_word((unsigned int) (unsigned char) p0[tail0 + tid], 0xffu);
+    const uint4 *pv = (const uint4 *) (p0 + head);
+    for (long long i = tid; i < nvec; i += 2 * nthr) {             // two vectors in flight per thread
+        uint4 v, u = make_uint4(0, 0, 0, 0);
+        const bool two = i + nthr < nvec;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pv + i));
+        if (two) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(pv + i + nthr));
+        count_word(v.x, 0xffffffffu); count_word(v.y, 0xffffffffu); count_word(v.z, 0xffffffffu); count_word(v.w, 0xffffffffu);
+        if (two) { count_word(u.x, 0xffffffffu); count_word(u.y, 0xffffffffu); count_word(u.z, 0xffffffffu); count_word(u.w, 0xffffffffu); }
+    }
+    const int lane = threadIdx.x & 31;                             // list positions are the CTA's: every thread counts key g in cnt[g]
+#pragma unroll
+    for (int gI = 0; gI < CC_G; gI++) {
+        unsigned long long c = cnt[gI];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(&s_cnt[gI], c);
+    }
+    __syncthreads();
+    if (s_over) { if (threadIdx.x == 0) atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+    if (threadIdx.x < CC_G && s_state[threadIdx.x] == 2u && s_cnt[threadIdx.x]) {
+        // group key = the byte sign-extended the way pack_group_key packs a 1-byte column
+        unsigned long long *rec = global_upsert(A, s_keys[threadIdx.x] & 0xffULL, 0ULL, 0u);
+        if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); return; }
+        atomicAdd(&rec[3], s_cnt[threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Specialised kernel for the dominant plan shape (BASELINE configs 2 and 3):
 //   [probe a unique-key join table with an int8 key ->] GROUP BY one 4-byte
 //   column (a scanned int4/date column, or the 4-byte join payload), aggregates
@@ -892,6 +1121,251 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
     }
     __syncthreads();
     smem_dense_merge(T, A);
+}
+
+// ---------------------------------------------------------------------------
+// GROUP BY keys that CONTAIN the join key of a unique build side (the Q3 shape: GROUP BY
+// l_orderkey, o_orderdate, o_shippriority) over an outer side stored in key order: all rows of
+// a group are one run of consecutive rows, so a run IS a group.  Each warp owns a contiguous
+// chunk of rows; per slab of 32 rows it evaluates quals and aggregate arguments, finds the run
+// heads, reduces (count, sums) per run with a segmented warp scan, and appends every finished
+// run to a per-warp shared-memory list; the list is then processed densely, one run per lane:
+// one probe of the join table, one FINAL record written.  No per-row records, no radix passes,
+// no group table — except for the (at most two) runs per chunk that touch a chunk boundary and
+// may continue in a neighbour's chunk: their pieces meet in a small global table through the
+// ordinary merge operator.  The kernel verifies on every adjacent pair of rows (across slabs,
+// tiles and chunks) that the keys do not descend; any violation raises a flag and the host
+// takes the general path (records + radix), so the result never depends on the layout.
+// Replaces ExecHashJoinImpl's probe loop + agg_fill_hash_table for this shape
+// (nodeHashjoin.c:446-666, nodeAgg.c:2609-2648).
+#define RA_NV   4                        /* float8 sum words per group (beyond the row count) */
+#define RA_LIST 136
+#define RA_BND  0x80000000u
+struct gx_runagg_args {
+    int nv, need_cnt, nthreads_unused, _pad;
+    int vagg[RA_NV], vword[RA_NV];
+    unsigned long long *out; long long out_cap; long long *cursor;   // dense final records + cursor
+    long long rows_per_warp;
+    // group-key packing: the join key and/or payload bit fields
+    int ngk; int gk_from_key[GX_MAX_GROUP_COLS]; int gk_word[GX_MAX_GROUP_COLS], gk_shift[GX_MAX_GROUP_COLS], gk_bytes[GX_MAX_GROUP_COLS], gk_pbit[GX_MAX_GROUP_COLS];
+};
+
+__device__ __forceinline__ bool runagg_probe(const gx_agg_dev &A, long long key, unsigned long long &payload)
+{
+    bool found = false;
+    if (key == GX_EMPTY_KEY) { found = A.special_count > 0; if (found) payload = A.special[0]; return found; }
+    unsigned long long p = gx_slot_index(key, A.sf);
+    for (;;) {
+        const gx_slot2 c = ld_slot2(A.slots + p);
+        found = (c.k0 == key) | (c.k1 == key);
+        payload = c.k0 == key ? c.p0 : c.p1;
+        if (found | (c.k0 == GX_EMPTY_KEY) | (c.k1 == GX_EMPTY_KEY)) break;
+        p = gx_next_pair(p, A.mask);
+    }
+    return found;
+}
+
+// quals of a tile of K rows per lane: the predicate descriptor is decoded once, the K column loads are independent
+template <int K>
+__device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K])
+{
+    if (p.col.nulls == nullptr && (p.col.type == GX_INT4 || p.col.type == GX_DATE)) {
+        const int *c = (const int *) p.col.data; int x[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) ok[j] = ok[j] && gx_op_holds(p.op, (long long) x[j] > p.ival ? 1 : ((long long) x[j] < p.ival ? -1 : 0));
+    } else if (p.col.nulls == nullptr && p.col.type == GX_FLOAT8) {
+        const double *c = (const double *) p.col.data; double x[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < K; j++) ok[j] = ok[j] && gx_op_holds(p.op, gx_f8cmp(x[j], p.fval));
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; j++) if (ok[j]) ok[j] = gx_eval_pred(p, r[j]);
+    }
+}
+
+#define RA_K 4                           /* slabs (of 32 rows) per tile: their loads are issued together */
+template <int NV>
+__global__ void __launch_bounds__(512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_runagg_args R)
+{
+    extern __shared__ unsigned long long smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nv = R.nv;
+    // per-warp list: key[RA_LIST], sum[nv][RA_LIST], cnt[RA_LIST]
+    const size_t per_warp = (size_t) RA_LIST * (1 + nv) + RA_LIST / 2;
+    unsigned long long *base = smem + (size_t) warp * per_warp;
+    long long *Qkey = (long long *) base;
+    double *Qsum = (double *) (base + RA_LIST);
+    unsigned int *Qcnt = (unsigned int *) (base + (size_t) RA_LIST * (1 + nv));
+    const gx_dplan &P = A.P;
+    const long long *okey = (const long long *) P.okey.data;
+    const int RW = 3 + P.nwords;
+    const long long gw = (long long) blockIdx.x * nwarps + warp;
+    const long long c0 = A.row0 + gw * R.rows_per_warp;
+    long long c1 = c0 + R.rows_per_warp; if (c1 > A.row1) c1 = A.row1;
+    if (c0 >= c1) return;
+    const unsigned int le = 0xffffffffu >> (31 - lane), lt = le >> 1;
+    bool bad = false;
+    // carry = the (unfinished) last run seen so far
+    bool carry_valid = false, first_pending = true;
+    long long carry_key = 0; unsigned int carry_c = 0; double carry_v[NV];
+#pragma unroll
+    for (int q = 0; q < NV; q++) carry_v[q] = 0.0;
+    long long prev_last = c0 > A.row0 ? __ldg(okey + c0 - 1) : __ldg(okey + c0);
+    int n_list = 0;
+
+    auto flush = [&]() {
+        __syncwarp();
+        for (int b = 0; b < n_list; b += 32) {
+            const int i = b + lane;
+            const bool valid = i < n_list;
+            const long long key = valid ? Qkey[i] : 0;
+            const unsigned int craw = valid ? Qcnt[i] : 0u, cnt = craw & ~RA_BND;
+            const bool bnd = (craw & RA_BND) != 0;
+            unsigned long long payload = 0;
+            const bool hit = valid && cnt > 0 && runagg_probe(A, key, payload);
+            __syncwarp();
+            unsigned long long k0 = 0, k1 = 0;
+            if (hit) {
+#pragma unroll
+                for (int c = 0; c < GX_MAX_GROUP_COLS; c++) {
+                    if (c >= R.ngk) break;
+                    unsigned long long v = R.gk_from_key[c] ? (unsigned long long) key : (payload >> R.gk_pbit[c]);
+                    if (R.gk_bytes[c] < 8) v &= (1ULL << (8 * R.gk_bytes[c])) - 1;
+                    if (R.gk_word[c] == 0) k0 |= v << R.gk_shift[c]; else k1 |= v << R.gk_shift[c];
+                }
+            }
+            const unsigned int dm = __ballot_sync(0xffffffffu, hit && !bnd);
+            if (dm) {
+                long long pos = 0;
+                if (lane == 0) pos = (long long) atomicAdd((unsigned long long *) R.cursor, (unsigned long long) __popc(dm));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(dm & lt);
+                if (hit && !bnd) {
+                    if (pos < R.out_cap) {
+                        unsigned long long *rec = R.out + (size_t) pos * RW;
+                        rec[0] = 0; rec[1] = k0; rec[2] = k1;
+                        for (int w = 0; w < P.nwords; w++) rec[3 + w] = (unsigned long long) A.winit[w];
+                        rec[3] = (unsigned long long) cnt;
+#pragma unroll
+                        for (int q = 0; q < NV; q++) if (q < nv) rec[3 + R.vword[q]] = (unsigned long long) __double_as_longlong(Qsum[(size_t) q * RA_LIST + i]);
+                    } else atomicOr((unsigned long long *) &A.counters[1], 4ULL);
+                }
+            }
+            if (hit && bnd) {                                   // a run that may continue in the neighbouring chunk
+                unsigned long long *rec = global_upsert(A, k0, k1, 0u);
+                if (!rec) atomicOr((unsigned long long *) &A.counters[1], 2ULL);
+                else {
+                    atomicAdd(&rec[3], (unsigned long long) cnt);
+#pragma unroll
+                    for (int q = 0; q < NV; q++) if (q < nv) atomicAdd((double *) &rec[3 + R.vword[q]], Qsum[(size_t) q * RA_LIST + i]);
+                }
+            }
+        }
+        n_list = 0;
+        __syncwarp();
+    };
+
+    for (long long tb = c0; tb < c1; tb += 32 * RA_K) {
+        // ---- the tile's loads: keys, qual columns, aggregate arguments of RA_K slabs, issued together
+        long long r[RA_K], kk[RA_K]; bool ok[RA_K]; double vv[NV][RA_K];
+#pragma unroll
+        for (int j = 0; j < RA_K; j++) { r[j] = tb + j * 32 + lane; ok[j] = r[j] < c1; }
+#pragma unroll
+        for (int j = 0; j < RA_K; j++) kk[j] = ok[j] ? __ldg(okey + r[j]) : 0;
+        for (int p = 0; p < P.npreds; p++) pred_tile<RA_K>(P.preds[p], r, ok);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+#pragma unroll
+            for (int j = 0; j < RA_K; j++) vv[q][j] = 0.0;
+            if (q < nv) {
+                const gx_dexpr &e = P.aggs[R.vagg[q]].expr;
+                lpt_term<RA_K>(e.t[0], r, ok, vv[q]);
+                for (int i = 1; i < e.nterms; i++) {
+                    double x[RA_K];
+                    lpt_term<RA_K>(e.t[i], r, ok, x);
+                    const int op = e.t[i].op;
+#pragma unroll
+                    for (int j = 0; j < RA_K; j++) vv[q][j] = op == GX_OP_ADD ? __dadd_rn(vv[q][j], x[j]) : (op == GX_OP_SUB ? __dsub_rn(vv[q][j], x[j]) : __dmul_rn(vv[q][j], x[j]));
+                }
+#pragma unroll
+                for (int j = 0; j < RA_K; j++) vv[q][j] = ok[j] ? vv[q][j] : 0.0;
+            }
+        }
+        // ---- slab by slab: run heads, segmented reduction, list
+#pragma unroll
+        for (int j = 0; j < RA_K; j++) {
+            const long long sb = tb + j * 32;
+            if (sb >= c1) break;
+            const int nvalid = (int) (c1 - sb < 32 ? c1 - sb : 32);
+            const bool in = lane < nvalid;
+            const long long klast = __shfl_sync(0xffffffffu, kk[j], nvalid - 1);
+            const long long k = in ? kk[j] : klast;                        // lanes past the end extend the last run with nothing
+            unsigned int c = (in && ok[j]) ? 1u : 0u;
+            double v[NV];
+#pragma unroll
+            for (int q = 0; q < NV; q++) v[q] = vv[q][j];
+            long long prevk = __shfl_up_sync(0xffffffffu, k, 1);
+            if (lane == 0) prevk = prev_last;
+            bad |= k < prevk;
+            const bool head = lane == 0 ? (!carry_valid || k != carry_key) : (k != prevk);
+            const unsigned int heads = __ballot_sync(0xffffffffu, head);
+            const int seg = 31 - __clz((heads | 1u) & le);                 // first lane of this lane's run inside the slab
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int tc = __shfl_up_sync(0xffffffffu, c, d);
+                const bool take = lane - d >= seg;
+                if (take) c += tc;
+#pragma unroll
+                for (int q = 0; q < NV; q++) if (q < nv) { const double tv = __shfl_up_sync(0xffffffffu, v[q], d); if (take) v[q] = __dadd_rn(v[q], tv); }
+            }
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            const bool cont = !(heads & 1u);                               // lane 0 continues the carried run
+            if (cont && seg == 0 && tail) {
+                c += carry_c;
+#pragma unroll
+                for (int q = 0; q < NV; q++) if (q < nv) v[q] = __dadd_rn(v[q], carry_v[q]);
+            }
+            // the carried run is finished when lane 0 starts a new one
+            const int carry_done = (carry_valid && !cont) ? 1 : 0;
+            if (carry_done && lane == 0) {
+                Qkey[n_list] = carry_key; Qcnt[n_list] = carry_c | (first_pending ? RA_BND : 0u);
+#pragma unroll
+                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + n_list] = carry_v[q];
+            }
+            const unsigned int emit = (heads >> 1) & 0x7fffffffu;         // tails except lane 31's run, which becomes the carry
+            if (tail && lane != 31) {
+                const int rank = __popc(emit & lt);
+                const int pos = n_list + carry_done + rank;
+                // the chunk's first run (the one holding row c0) may have started in the previous chunk
+                const bool is_first = first_pending && !carry_done && rank == 0;
+                Qkey[pos] = k; Qcnt[pos] = c | (is_first ? RA_BND : 0u);
+#pragma unroll
+                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + pos] = v[q];
+            }
+            const int nemit = carry_done + __popc(emit);
+            if (nemit) first_pending = false;
+            n_list += nemit;
+            // new carry = lane 31's run
+            carry_key = __shfl_sync(0xffffffffu, k, 31); carry_c = __shfl_sync(0xffffffffu, c, 31);
+#pragma unroll
+            for (int q = 0; q < NV; q++) if (q < nv) carry_v[q] = __shfl_sync(0xffffffffu, v[q], 31);
+            carry_valid = true;
+            prev_last = carry_key;
+        }
+        flush();                                                           // <= RA_K * 32 + 1 entries per tile
+    }
+    // the last run of the chunk may continue in the next chunk
+    if (lane == 0) {
+        Qkey[0] = carry_key; Qcnt[0] = carry_c | RA_BND;
+#pragma unroll
+        for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST] = carry_v[q];
+    }
+    n_list = 1;
+    flush();
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr((unsigned long long *) &A.counters[1], 8ULL);
 }
 
 // global table -> dense records [meta][k0][k1][w..]
@@ -1357,11 +1831,12 @@ static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA,
     return launch_fast_t<false, false, true>(ctx, A, FA, smem, name);
 }
 
-static int read_counters(gx_ctx *ctx, long long *c /* 4 */)
+static int read_counters(gx_ctx *ctx, long long *c /* 4 */, long long *cursor = nullptr)
 {
-    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 4 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 5 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 4; i++) c[i] = ctx->h_scratch[8 + i];
+    if (cursor) *cursor = ctx->h_scratch[12];                     // d_scratch[12]: the dense-output cursor
     return GX_OK;
 }
 
@@ -1468,6 +1943,102 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             lptile_ok = ga.expr.t[t].kind == GXT_CONST || (ga.expr.t[t].col.type == GX_FLOAT8 && ga.expr.t[t].col.nulls == nullptr);
     }
     { const char *e = getenv("GX_NO_LPTILE"); if (e && e[0] == '1') lptile_ok = false; }
+    // register-accumulator kernels for <= FG_G groups (Q1, config 1): same plan shape as the tiled kernel,
+    // key in one word without NULLs
+    gx_fewgroups_args FG; memset(&FG, 0, sizeof(FG));
+    bool fewgroups_ok = lptile_ok && A.P.nkw == 1 && plan->n_group_cols >= 1 && outer->nrows > 0;
+    for (int c = 0; c < plan->n_group_cols && fewgroups_ok; c++) fewgroups_ok = A.P.gcols[c].side == 0 && A.P.gcols[c].col.nulls == nullptr;
+    for (int a = 0; a < A.P.nagg && fewgroups_ok; a++) {
+        if (A.P.aggs[a].kind == GXU_NONE) continue;
+        if (FG.nv >= FG_NV) { fewgroups_ok = false; break; }
+        FG.vagg[FG.nv] = a; FG.vword[FG.nv] = A.P.aggs[a].word; FG.nv++;
+    }
+    { const char *e = getenv("GX_NO_FEWGROUPS"); if (e && e[0] == '1') fewgroups_ok = false; }
+    bool countchar_ok = fewgroups_ok && FG.nv == 0 && plan->n_preds == 0 && plan->n_group_cols == 1 && A.P.gcols[0].type == GX_CHAR;
+
+    // ---- GROUP BY contains the join key of a unique build side and the outer side is in key order:
+    // a run of equal keys is a group (gx_k_runagg).  Tried first; a raised "keys descend" flag sends the
+    // plan down the general path below.
+    {
+        gx_runagg_args RA; memset(&RA, 0, sizeof(RA));
+        const char *e = getenv("GX_NO_RUNAGG");
+        bool ok = !(e && e[0] == '1') && plan->strategy == 0 && A.P.has_join && h->unique && A.P.key_type == GX_INT8 && A.P.okey.nulls == nullptr &&
+                  outer->nrows > 0 && plan->n_group_cols >= 1;
+        bool has_key = false;
+        for (int c = 0; c < plan->n_group_cols && ok; c++) {
+            const gx_dgroupcol &gc = A.P.gcols[c];
+            if (gc.side == 0) { ok = plan->group_cols[c].col == plan->outer_key_col; RA.gk_from_key[c] = 1; has_key = true; }
+            else RA.gk_pbit[c] = gc.payload_idx;
+            RA.gk_word[c] = gc.word; RA.gk_shift[c] = gc.shift; RA.gk_bytes[c] = gc.bytes;
+        }
+        RA.ngk = plan->n_group_cols;
+        ok = ok && has_key;
+        for (int a = 0; a < A.P.nagg && ok; a++) {
+            const gx_dagg &ga = A.P.aggs[a];
+            if (ga.kind == GXU_NONE) continue;
+            ok = ga.kind == GXU_ADD_F64 && !ga.is_int && ga.cnt_word == 0 && RA.nv < RA_NV && ga.expr.nterms >= 1;
+            for (int t = 0; t < ga.expr.nterms && ok; t++)
+                ok = ga.expr.t[t].kind == GXT_CONST || (ga.expr.t[t].col.type == GX_FLOAT8 && ga.expr.t[t].col.nulls == nullptr);
+            if (ok) { RA.vagg[RA.nv] = a; RA.vword[RA.nv] = ga.word; RA.nv++; }
+        }
+        if (ok) {
+            rc = need_wide(); if (rc) return rc;
+            static bool attr = false;
+            const int threads = 512, nwarps = threads / 32;
+            const size_t smem = (size_t) nwarps * ((size_t) RA_LIST * (1 + RA.nv) + RA_LIST / 2) * 8;
+            if (!attr) {
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<RA_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                attr = true;
+            }
+            const long long nrows = outer->nrows, total_warps = (long long) ctx->sm_count * (RA.nv <= 2 ? 2 : 1) * nwarps;
+            long long rpw = (nrows + total_warps - 1) / total_warps; rpw = (rpw + 31) / 32 * 32; if (rpw < 128) rpw = 128;
+            const long long nchunks = (nrows + rpw - 1) / rpw;
+            const unsigned grid = (unsigned) ((nchunks + nwarps - 1) / nwarps);
+            RA.rows_per_warp = rpw;
+            const long long out_cap = (h->nentries < nrows ? h->nentries : nrows) + 64;
+            const long long g_cap = gx_pow2_ceil(8 * nchunks + 1024);
+            unsigned long long *g_tab, *d_out;
+            GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &g_tab, (size_t) g_cap * RW * 8));
+            cudaError_t ae = gx_tmp_alloc(ctx, (void **) &d_out, (size_t) out_cap * RW * 8);
+            if (ae != cudaSuccess) { gx_tmp_free(ctx, g_tab); GX_SET_ERR(ctx, "hash_agg: %s", cudaGetErrorString(ae)); return GX_ERR_NOMEM; }
+            GX_CUDA(ctx, cudaMemsetAsync(g_tab, 0, (size_t) g_cap * RW * 8, ctx->stream));
+            GX_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 5 * sizeof(long long), ctx->stream));
+            A.g_tab = g_tab; A.g_mask = (unsigned long long) g_cap - 1;
+            RA.out = d_out; RA.out_cap = out_cap; RA.cursor = ctx->d_scratch + 12;
+            {
+                gx_launch_scope ls(ctx, "runagg");
+                if (RA.nv <= 1) gx_k_runagg<1><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                else if (RA.nv == 2) gx_k_runagg<2><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                else gx_k_runagg<RA_NV><<<grid, threads, smem, ctx->stream>>>(A, RA);
+            }
+            GX_CUDA(ctx, cudaGetLastError());
+            long long c[4], direct = 0;
+            rc = read_counters(ctx, c, &direct);
+            // an out-of-order outer side (flag 8) may also overrun the output: the general path answers either way
+            if (rc == GX_OK && !(c[1] & 8) && (c[1] & 6)) { GX_SET_ERR(ctx, "hash_agg: run-aggregate output overflowed (flags %lld)", c[1]); rc = GX_ERR_STATE; }
+            if (rc != GX_OK) { gx_tmp_free(ctx, g_tab); gx_tmp_free(ctx, d_out); return rc; }
+            if (!(c[1] & 8)) {
+                if (c[0] > 0) {
+                    gx_launch_scope ls(ctx, "runagg_merge");
+                    gx_k_compact_groups<<<(unsigned) ((g_cap + 255) / 256 < (long long) ctx->sm_count * 4 ? (g_cap + 255) / 256 : (long long) ctx->sm_count * 4), 256, 0, ctx->stream>>>(
+                        g_tab, g_cap, nwords, d_out, ctx->d_scratch + 12);
+                    GX_CUDA(ctx, cudaGetLastError());
+                }
+                gx_tmp_free(ctx, g_tab);
+                gx_result *r; gx_result_alloc(ctx, plan, cp.group_types, direct + c[0], &r);
+                r->nkw = A.P.nkw; r->nwords = nwords; r->rec_words = RW; r->need_w0 = 1;
+                for (int a = 0; a < plan->n_aggs; a++) { r->agg_word[a] = cp.agg_word[a]; r->agg_cnt_word[a] = cp.agg_cnt_word[a]; }
+                r->d_recs = (long long *) d_out; r->ngroups = direct + c[0]; r->cap = out_cap;
+                remember_layout(r, &cp);
+                *out = r;
+                return GX_OK;
+            }
+            gx_tmp_free(ctx, g_tab); gx_tmp_free(ctx, d_out);      // keys descend somewhere: general path
+            A.g_tab = nullptr;
+        }
+    }
 
     for (int attempt = 0; attempt < 8; attempt++) {
         if (strategy == 2) { rc = need_wide(); if (rc) return rc; rc = run_radix(ctx, &cp, plan, outer->nrows, out); if (rc == GX_OK) remember_layout(*out, &cp); return rc; }
@@ -1498,7 +2069,18 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         const bool use_fast = strategy == 1 && !gmax && fast_ok;
         const bool use_run = use_fast && A.P.has_join && runjoin_env && dense_bytes(S) + run_bytes <= ctx->smem_optin - 1024;
         if (!use_run) { rc = need_wide(); if (rc) { gx_tmp_free(ctx, g_tab); return rc; } }
+        const bool use_few = strategy == 1 && gmax && fewgroups_ok && est <= 2 * FG_G;
         if (use_fast) rc = launch_fast(ctx, A, FA, A.P.has_join != 0, cp.need_w0 != 0, FA.vcol != nullptr, dense_bytes(S), kname, use_run);
+        else if (use_few && countchar_ok) {
+            gx_launch_scope ls(ctx, kname);
+            gx_k_count_char<<<ctx->sm_count * 2, 512, 0, ctx->stream>>>(A, (const signed char *) A.P.gcols[0].col.data);
+            rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
+        } else if (use_few) {
+            long long nb = (outer->nrows + 16 * 32 * FG_K - 1) / (16 * 32 * FG_K);
+            gx_launch_scope ls(ctx, kname);
+            gx_k_fewgroups<<<(unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count), 512, 0, ctx->stream>>>(A, FG);
+            rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
+        }
         else if (strategy == 1 && gmax && lptile_ok) rc = launch_lptile(ctx, A, lp_bytes, kname, lp_warps * 32);
         else if (strategy == 1 && gmax) rc = launch_agg<SINK_SMEM_LP>(ctx, A, lp_bytes, kname, lp_warps * 32);
         else if (strategy == 1) rc = launch_agg<SINK_SMEM>(ctx, A, dense_bytes(S), kname);
@@ -1513,6 +2095,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             return rc;
         }
         gx_tmp_free(ctx, g_tab);
+        if (use_few) { fewgroups_ok = false; continue; }          // more than FG_G groups: same estimate, general kernels
         // the planner's estimate was too low: grow, then fall over to radix
         est = est < 8 ? 9 : est < 16 ? 17 : est * 8;
         if (strategy == 1 && est * 3 / 2 > smax) strategy = (plan->strategy == 1) ? 3 : 2;
@@ -1728,8 +2311,83 @@ int gx_result_layout_words(gx_result *r, int *wkind, long long *winit)
     return GX_OK;
 }
 
-// finalize_aggregates (nodeAgg.c:1363) on the host: the result is tiny next to
-// the input.  float8_avg = Sx / N, NULL when N == 0 (float.c:2991-3008).
+// finalize_aggregates (nodeAgg.c:1363).  float8_avg = Sx / N, NULL when N == 0 (float.c:2991-3008).
+// Small results are finalized on the host from the raw records; large ones (Q3: millions of
+// groups) on the device, straight into the caller's column layout, so the host only copies.
+struct gx_final_args {
+    const unsigned long long *recs; long long ngroups; int RW, ng, na, need_w0;
+    int gword[GX_MAX_GROUP_COLS], gshift[GX_MAX_GROUP_COLS], gtype[GX_MAX_GROUP_COLS];
+    int fn[GX_MAX_AGGS], word[GX_MAX_AGGS], cw[GX_MAX_AGGS];
+    long long *key_out; double *agg_out; unsigned char *null_out; int *overflow;
+};
+__global__ void gx_k_finalize(const gx_final_args F)
+{
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long gI = (long long) blockIdx.x * blockDim.x + threadIdx.x; gI < F.ngroups; gI += stride) {
+        const unsigned long long *rec = F.recs + (size_t) gI * F.RW, *w = rec + 3;
+        const unsigned int nullmask = (unsigned int) rec[0];
+        for (int c = 0; c < F.ng; c++) {
+            const bool isnull = (nullmask >> c) & 1;
+            const unsigned long long v = (F.gword[c] == 0 ? rec[1] : rec[2]) >> F.gshift[c];
+            long long sv;
+            switch (F.gtype[c]) {
+                case GX_INT4: case GX_DATE: sv = (long long) (int) (unsigned int) v; break;
+                case GX_CHAR: sv = (long long) (signed char) (unsigned char) v; break;
+                default: sv = (long long) v; break;
+            }
+            F.key_out[gI * F.ng + c] = isnull ? 0 : sv;
+            if (F.null_out) F.null_out[gI * (F.ng + F.na) + c] = isnull;
+        }
+        for (int a = 0; a < F.na; a++) {
+            const int fn = F.fn[a], word = F.word[a], cw = F.cw[a];
+            const long long cnt = cw ? (long long) w[cw] : (F.need_w0 ? (long long) w[0] : 1);
+            bool isnull = false, is_int = false; double res = 0.0; long long ires = 0;
+            switch (fn) {
+                case GX_AGG_COUNT_STAR: ires = (long long) w[0]; is_int = true; break;
+                case GX_AGG_COUNT: ires = (long long) w[word]; is_int = true; break;
+                case GX_AGG_SUM_I4: case GX_AGG_SUM_I8: ires = (long long) w[word]; is_int = true; isnull = cnt == 0; break;
+                case GX_AGG_AVG_F8: { const double sx = __longlong_as_double((long long) w[word]); if (cnt == 0) isnull = true; else res = sx / (double) cnt; break; }
+                default: res = __longlong_as_double((long long) w[word]); isnull = cnt == 0; break;
+            }
+            if (isnull) { res = 0.0; ires = 0; }
+            F.agg_out[gI * F.na + a] = is_int ? __longlong_as_double(ires) : res;
+            if (F.null_out) F.null_out[gI * (F.ng + F.na) + F.ng + a] = isnull;
+            if (!is_int && !isnull && (fn == GX_AGG_SUM_F8 || fn == GX_AGG_AVG_F8) && isinf(res)) *F.overflow = 1;
+        }
+    }
+}
+
+static int fetch_on_device(gx_result *r, const result_layout &L, int64_t *key_out, double *agg_out, uint8_t *null_out)
+{
+    gx_ctx *ctx = r->ctx;
+    const int ng = r->plan.n_group_cols, na = r->plan.n_aggs;
+    const size_t n = (size_t) r->ngroups;
+    gx_final_args F; memset(&F, 0, sizeof(F));
+    F.recs = (const unsigned long long *) r->d_recs; F.ngroups = r->ngroups; F.RW = r->rec_words; F.ng = ng; F.na = na; F.need_w0 = r->need_w0;
+    for (int c = 0; c < ng; c++) { F.gword[c] = L.gword[c]; F.gshift[c] = L.gshift[c]; F.gtype[c] = r->group_types[c]; }
+    for (int a = 0; a < na; a++) { F.fn[a] = r->plan.aggs[a].fn; F.word[a] = r->agg_word[a]; F.cw[a] = r->agg_cnt_word[a]; }
+    char *d = nullptr;
+    const size_t kb = n * (ng > 0 ? ng : 1) * 8, ab = n * (na > 0 ? na : 1) * 8, nb = (n * (ng + na) + 15) & ~(size_t) 15;
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d, kb + ab + nb + 16));
+    F.key_out = (long long *) d; F.agg_out = (double *) (d + kb); F.null_out = null_out ? (unsigned char *) (d + kb + ab) : nullptr;
+    F.overflow = (int *) (d + kb + ab + nb);
+    GX_CUDA(ctx, cudaMemsetAsync(F.overflow, 0, sizeof(int), ctx->stream));
+    {
+        gx_launch_scope ls(ctx, "finalize");
+        gx_k_finalize<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(F);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && ng) e = cudaMemcpyAsync(key_out, F.key_out, n * ng * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && na) e = cudaMemcpyAsync(agg_out, F.agg_out, n * na * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && null_out) e = cudaMemcpyAsync(null_out, F.null_out, n * (ng + na), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch + 16, F.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    gx_tmp_free(ctx, d);
+    if (e != cudaSuccess) { GX_SET_ERR(ctx, "result_fetch: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    if (*(int *) (ctx->h_scratch + 16)) { GX_SET_ERR(ctx, "value out of range: overflow"); return GX_ERR_OVERFLOW; }
+    return GX_OK;
+}
+
 extern "C" int gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_out, double *agg_out, uint8_t *null_out)
 {
     if (!r) return GX_ERR_ARG;
@@ -1749,6 +2407,7 @@ extern "C" int gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_ou
     if (r->ngroups == 0) return GX_OK;
     GX_CHECK_ARG(ctx, g_layouts && g_layouts->count(r), "result_fetch: unknown result");
     const result_layout &L = (*g_layouts)[r];
+    if (r->ngroups > 8192) return fetch_on_device(r, L, key_out, agg_out, null_out);
     unsigned long long *h = (unsigned long long *) malloc((size_t) r->ngroups * RW * 8);
     cudaError_t e = cudaMemcpyAsync(h, r->d_recs, (size_t) r->ngroups * RW * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

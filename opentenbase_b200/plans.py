@@ -68,19 +68,35 @@ def q3_datanode(ctx, cust, orders, line, ccols, ocols, lcols, stats=None):
     to column numbers of those tables.  Returns the Result (partial == final: the group key
     contains the distribution key, so every group lives on one datanode —
     grouping_distribution_match, planner.c:10026).  `stats` (dict) receives row counts."""
+    import time
+    clock = [time.perf_counter()]
+    host_ms = {}
+
+    def lap(name):
+        now = time.perf_counter()
+        host_ms[name] = host_ms.get(name, 0.0) + (now - clock[0]) * 1e3
+        clock[0] = now
     t1 = ctx.scan_filter(cust, [(ccols["mktsegment"], GX_EQ, SEGMENT_Q3)], [ccols["custkey"]])
     t2 = ctx.scan_filter(orders, [(ocols["orderdate"], GX_LT, DATE_Q3)],
                          [ocols["orderkey"], ocols["custkey"], ocols["orderdate"], ocols["shippriority"]])
+    lap("scan_filter")
     t2r = ctx.redistribute(t2, 1)                                   # Distribute by o_custkey
+    lap("redistribute_custkey")
     h1 = ctx.hash_build(t1, 0, [], unique=True)
+    lap("build_customer")
     j1 = ctx.hash_probe(t2r, 1, h1, [0, 2, 3])                      # o_orderkey, o_orderdate, o_shippriority, build row
     j1.drop_column(3)                                               # the customer row number is not part of the target list
+    lap("probe_customer")
     j1r = ctx.redistribute(j1, 0)                                   # Distribute by o_orderkey
+    lap("redistribute_orderkey")
     h2 = ctx.hash_build(j1r, 0, [1, 2], unique=True)
+    lap("build_orders")
     plan = q3_agg_plan(lcols["orderkey"], lcols["extendedprice"], lcols["discount"], lcols["shipdate"],
                        est_groups=max(j1r.nrows // 2, 1024))
     res = ctx.hash_agg(line, plan, h2)
+    lap("probe_agg_lineitem")
     if stats is not None:
+        stats["host_ms_per_call"] = host_ms
         stats.update(cust_kept=t1.nrows, orders_kept=t2.nrows, redistributed_custkey=t2.nrows, joined=j1.nrows,
                      redistributed_orderkey=j1.nrows, build_rows=j1r.nrows,
                      bytes_sent=t2.nrows * 20 + j1.nrows * 16)

@@ -125,3 +125,95 @@ def test_sf10_slice_config2_config3_q3(gx):
     assert_agg_equal(res.plan, res.fetch(), O.q3_reference(sf, nord, ncust, P.DATE_Q3, P.SEGMENT_Q3))
     for t in (ot, lt, ct):
         t.free()
+
+
+def _runagg_case(gx, okeys, odate, oprio, lkeys, lprice, ldisc, lship, aggs, group_cols, preds=()):
+    """orders(key, date, prio) JOIN lineitem(key, price, disc, ship) with the group key containing the join key"""
+    otypes = [g.GX_INT8, g.GX_DATE, g.GX_INT4]
+    ltypes = [g.GX_INT8, g.GX_FLOAT8, g.GX_FLOAT8, g.GX_DATE]
+    ocols, lcols = [okeys, odate, oprio], [lkeys, lprice, ldisc, lship]
+    plan = O.make_plan(preds=list(preds), outer_key_col=0, group_cols=group_cols, aggs=aggs, est_groups=max(len(okeys), 16))
+    want = O.exec_agg(O.Rel(ltypes, lcols), plan, O.Rel(otypes, ocols), O.make_join(0, payload_cols=[1, 2], inner_unique=1))
+    ot, lt = gx.table_from(otypes, ocols), gx.table_from(ltypes, lcols)
+    ht = gx.hash_build(ot, 0, [1, 2], unique=True)
+    gx.profile(True)
+    got = gx.hash_agg(lt, to_gpu_plan(plan), ht).fetch()
+    used = gx.profile_get("runagg")[1] > 0
+    fell_back = gx.profile_get("probe_records")[1] > 0
+    gx.profile(False)
+    assert_agg_equal(plan, got, want)
+    for t in (ot, lt):
+        t.free()
+    return used, fell_back
+
+
+def test_runagg_group_key_contains_join_key(gx):
+    """gx_k_runagg: runs of equal keys are groups.  Long runs that span warp chunks and slabs, runs of one,
+    rows that fail the qual, keys without a partner, several aggregates; then the layouts that must NOT
+    take the kernel's answer: keys that descend somewhere (shuffled, or clustered but unordered)."""
+    rng = np.random.default_rng(3)
+    C, K, S, M = g.GX_OP_COL, g.GX_OP_CONST, g.GX_OP_SUB, g.GX_OP_MUL
+    rev = [(C, 1, 0), (K, 0, 1.0), (C, 2, 0), (S, 0, 0), (M, 0, 0)]
+    nkeys = 40000
+    okeys = np.sort(rng.choice(np.arange(1, 10 * nkeys), nkeys, replace=False)).astype(np.int64)
+    odate = rng.integers(-3000, -1000, nkeys).astype(np.int32); oprio = rng.integers(0, 3, nkeys).astype(np.int32)
+    # run lengths: mostly 1..7, a few of thousands (span several 32-row slabs and whole warp chunks), keys missing from orders
+    reps = rng.integers(1, 8, nkeys); reps[rng.choice(nkeys, 12, replace=False)] = rng.integers(2000, 9000, 12)
+    lk = np.repeat(okeys + (rng.random(nkeys) < 0.1), reps).astype(np.int64)      # 10 % of the keys shifted off their partner
+    lk.sort()
+    n = len(lk)
+    lprice, ldisc = np.round(rng.random(n) * 1e5, 2), np.round(rng.random(n) * 0.1, 2)
+    lship = rng.integers(-3000, -1000, n).astype(np.int32)
+    aggs3 = [(g.GX_AGG_SUM_F8, rev), (g.GX_AGG_COUNT_STAR, []), (g.GX_AGG_AVG_F8, [(C, 1, 0)]), (g.GX_AGG_SUM_F8, [(C, 2, 0)])]
+    full_key = [(0, 0), (1, 0), (1, 1)]
+    used, fb = _runagg_case(gx, okeys, odate, oprio, lk, lprice, ldisc, lship, [(g.GX_AGG_SUM_F8, rev)], full_key, preds=[(3, g.GX_GT, -1752)])
+    assert used and not fb
+    used, fb = _runagg_case(gx, okeys, odate, oprio, lk, lprice, ldisc, lship, aggs3, full_key)
+    assert used and not fb
+    used, fb = _runagg_case(gx, okeys, odate, oprio, lk, lprice, ldisc, lship, aggs3, [(0, 0)], preds=[(3, g.GX_GT, -2500), (1, g.GX_LT, 9e4, True)])
+    assert used and not fb
+    # clustered but not ordered: the runs are intact, their order is not -> the flag must fire and the general path answers
+    order = np.argsort(rng.permutation(len(okeys))[np.searchsorted(okeys, lk - (~np.isin(lk, okeys)))], kind="stable")
+    used, fb = _runagg_case(gx, okeys, odate, oprio, lk[order], lprice[order], ldisc[order], lship[order], aggs3, full_key)
+    assert used and fb
+    perm = rng.permutation(n)
+    used, fb = _runagg_case(gx, okeys, odate, oprio, lk[perm], lprice[perm], ldisc[perm], lship[perm], aggs3, full_key)
+    assert used and fb
+    # tiny inputs: fewer rows than one slab, a single row
+    for m in (1, 5, 33):
+        used, fb = _runagg_case(gx, okeys, odate, oprio, lk[:m], lprice[:m], ldisc[:m], lship[:m], aggs3, full_key)
+        assert used and not fb
+
+
+@pytest.mark.parametrize("ndistinct", [1, 3, 4, 5, 8, 9, 40])
+def test_few_groups_register_kernels(gx, ndistinct):
+    """gx_k_fewgroups / gx_k_count_char (<= 4 resp. 8 groups in registers) and their fall-back when the data
+    holds more groups than the planner promised; 1-byte keys with the sign bit set; int4 keys; row counts that
+    are not a multiple of the vector width."""
+    rng = np.random.default_rng(ndistinct)
+    n = 100003
+    vals = rng.choice(np.arange(-128, 128), ndistinct, replace=False).astype(np.int8)
+    flag = rng.choice(vals, n)
+    k4 = rng.choice(rng.integers(-2**31, 2**31, ndistinct), n).astype(np.int32)
+    x, y = np.round(rng.random(n) * 1e4, 2), np.round(rng.random(n), 2)
+    types = [g.GX_CHAR, g.GX_INT4, g.GX_FLOAT8, g.GX_FLOAT8]
+    cols = [flag, k4, x, y]
+    rel = O.Rel(types, cols)
+    t = gx.table_from(types, cols)
+    C, K, S, M = g.GX_OP_COL, g.GX_OP_CONST, g.GX_OP_SUB, g.GX_OP_MUL
+    expr = [(C, 2, 0), (K, 0, 1.0), (C, 3, 0), (S, 0, 0), (M, 0, 0)]
+    plans = [
+        O.make_plan(group_cols=[(0, 0)], aggs=[(g.GX_AGG_COUNT_STAR, [])], est_groups=3),                       # config 1 shape
+        O.make_plan(group_cols=[(0, 0)], aggs=[(g.GX_AGG_SUM_F8, expr), (g.GX_AGG_COUNT_STAR, []), (g.GX_AGG_AVG_F8, [(C, 3, 0)])],
+                    preds=[(2, g.GX_LT, 9000.0, True)], est_groups=4),
+        O.make_plan(group_cols=[(0, 1)], aggs=[(g.GX_AGG_SUM_F8, [(C, 2, 0)]), (g.GX_AGG_COUNT_STAR, [])], est_groups=2),
+        O.make_plan(group_cols=[(0, 0), (0, 1)], aggs=[(g.GX_AGG_AVG_F8, [(C, 2, 0)])], est_groups=6),
+    ]
+    for plan in plans:
+        assert_agg_equal(plan, gx.hash_agg(t, to_gpu_plan(plan)).fetch(), O.exec_agg(rel, plan))
+    # short and unaligned inputs through the byte-vector kernel
+    for m in (0, 1, 15, 16, 17, 33):
+        sub = gx.table_from(types, [c[:m] for c in cols]) if m else gx.table(types, 1)
+        assert_agg_equal(plans[0], gx.hash_agg(sub, to_gpu_plan(plans[0])).fetch(), O.exec_agg(O.Rel(types, [c[:m] for c in cols]), plans[0]))
+        sub.free()
+    t.free()
