@@ -188,10 +188,19 @@ typedef struct gx_heap_desc {
     int8_t  att_align[64];
     int32_t attnums[GX_MAX_COLS];
 } gx_heap_desc;
+/* With vis_offsets the call only ENQUEUES (copies + the deform kernel; row offsets are
+ * scanned on the host from vis_counts) and grows the table if needed; `pages`, if it came
+ * from gx_stage_acquire(), may be refilled after the NEXT gx_stage_acquire() returns it. */
 int  gx_table_append_heap_pages(gx_table *t, const void *pages, int64_t npages,
                                 const gx_heap_desc *desc,
                                 const uint16_t *vis_offsets, const int32_t *vis_counts,
                                 int32_t vis_stride);
+/* Pinned staging for the loader above: one of two library-owned buffers; the call waits
+ * until the previous copy out of that buffer has completed.  Filling one buffer while the
+ * other one's DMA and deform run is how the provider overlaps heapgetpage() with the GPU. */
+int  gx_stage_acquire(gx_ctx *ctx, size_t bytes, void **out);
+/* grow a table's capacity (the loader doubles it when a relation holds more rows than estimated) */
+int  gx_table_reserve(gx_table *t, int64_t capacity_rows);
 int64_t gx_table_nrows(const gx_table *t);
 int  gx_table_ncols(const gx_table *t);
 int  gx_table_read_column(gx_table *t, int col, int64_t row0, int64_t nrows,
@@ -274,6 +283,12 @@ int64_t gx_result_ngroups(const gx_result *r);
  * [g*(n_group_cols+n_aggs) + i] = 1 for SQL NULL. */
 int  gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_out,
                      double *agg_out, uint8_t *null_out);
+/* Partial (transition) states instead of finalized values, for a two-phase plan whose
+ * Finalize Agg runs in the reference above a RemoteSubplan (aggsplit INITIAL_SERIAL,
+ * planner.c:8743-8749): per aggregate cnt_out = N, val_out = Sx / min / max (float8) or the
+ * int8 sum bit-cast; null_out = 1 while the transition value is NULL. */
+int  gx_result_fetch_states(gx_result *r, int64_t max_groups, int64_t *key_out,
+                            double *val_out, int64_t *cnt_out, uint8_t *null_out);
 void gx_result_free(gx_result *r);
 
 /* One-call form used by the provider and by bench.py's e2e leg: HOST column

@@ -129,6 +129,8 @@ def _declare(L):
         "gx_table_create": (C.c_int, [vp, C.c_int, C.POINTER(i32), i64, pp]),
         "gx_table_append_columns": (C.c_int, [vp, pp, pp, i64]),
         "gx_table_append_heap_pages": (C.c_int, [vp, vp, i64, C.POINTER(GxHeapDesc), vp, vp, i32]),
+        "gx_stage_acquire": (C.c_int, [vp, sz, pp]),
+        "gx_table_reserve": (C.c_int, [vp, i64]),
         "gx_table_nrows": (i64, [vp]),
         "gx_table_ncols": (C.c_int, [vp]),
         "gx_table_read_column": (C.c_int, [vp, C.c_int, i64, i64, vp, vp]),
@@ -149,6 +151,7 @@ def _declare(L):
         "gx_result_combine": (C.c_int, [vp, vp]),
         "gx_result_ngroups": (i64, [vp]),
         "gx_result_fetch": (C.c_int, [vp, i64, vp, vp, vp]),
+        "gx_result_fetch_states": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "gx_result_free": (None, [vp]),
         "gx_exec_host": (C.c_int, [vp, C.POINTER(GxHostTable), C.POINTER(GxHostTable), C.c_int, C.c_int,
                                    C.POINTER(GxPred), C.c_int, C.POINTER(i32), C.c_int, C.POINTER(GxAggPlan), pp]),
@@ -324,6 +327,14 @@ class Result:
         nulls = np.zeros((n, ng + na), np.uint8)
         self.ctx._chk(lib().gx_result_fetch(self.h, n, keys.ctypes.data, aggs.ctypes.data, nulls.ctypes.data))
         return keys, aggs, nulls
+
+    def fetch_states(self):
+        """partial states: keys int64[n, ng], vals float64[n, na], cnts int64[n, na], nulls uint8[n, ng+na]"""
+        n, ng, na = self.ngroups, self.plan.n_group_cols, self.plan.n_aggs
+        keys = np.zeros((n, ng), np.int64); vals = np.zeros((n, na), np.float64)
+        cnts = np.zeros((n, na), np.int64); nulls = np.zeros((n, ng + na), np.uint8)
+        self.ctx._chk(lib().gx_result_fetch_states(self.h, n, keys.ctypes.data, vals.ctypes.data, cnts.ctypes.data, nulls.ctypes.data))
+        return keys, vals, cnts, nulls
 
     def free(self):
         if self.h and self.ctx.h:          # handles die with their context (stream-ordered frees need its stream)

@@ -2452,3 +2452,69 @@ extern "C" int gx_result_fetch(gx_result *r, int64_t max_groups, int64_t *key_ou
     free(h);
     return GX_OK;
 }
+
+// Partial (transition) states for a two-phase plan: the reference's Finalize Agg above a
+// RemoteSubplan combines them with int8pl / float8pl / float8_combine / float8smaller ...
+// (AGGSPLIT_INITIAL_SERIAL on this side, planner.c:8743-8749; combine functions
+// pg_aggregate.h:178-252).  Per aggregate: cnt_out = N (rows for count(*), non-NULL inputs
+// otherwise), val_out = Sx / min / max as float8 or the int8 sum bit-cast; null_out = 1 when the
+// transition value is still NULL (no non-NULL input seen; count states are never NULL).
+extern "C" int gx_result_fetch_states(gx_result *r, int64_t max_groups, int64_t *key_out, double *val_out, int64_t *cnt_out, uint8_t *null_out)
+{
+    if (!r || !key_out || !val_out || !cnt_out) return GX_ERR_ARG;
+    gx_ctx *ctx = r->ctx;
+    const int ng = r->plan.n_group_cols, na = r->plan.n_aggs, RW = r->rec_words;
+    if (ng == 0 && r->ngroups == 0) {                           // plain aggregate over zero rows: initial states
+        GX_CHECK_ARG(ctx, max_groups >= 1, "result_fetch_states: buffer too small");
+        for (int a = 0; a < na; a++) {
+            const int fn = r->plan.aggs[a].fn;
+            val_out[a] = 0.0; cnt_out[a] = 0;
+            if (null_out) null_out[a] = (fn == GX_AGG_COUNT_STAR || fn == GX_AGG_COUNT || fn == GX_AGG_AVG_F8) ? 0 : 1;
+        }
+        return GX_OK;
+    }
+    GX_CHECK_ARG(ctx, max_groups >= r->ngroups, "result_fetch_states: buffer holds %lld groups, result has %lld", (long long) max_groups, (long long) r->ngroups);
+    if (r->ngroups == 0) return GX_OK;
+    GX_CHECK_ARG(ctx, g_layouts && g_layouts->count(r), "result_fetch_states: unknown result");
+    const result_layout &L = (*g_layouts)[r];
+    unsigned long long *h = (unsigned long long *) malloc((size_t) r->ngroups * RW * 8);
+    cudaError_t e = cudaMemcpyAsync(h, r->d_recs, (size_t) r->ngroups * RW * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); GX_SET_ERR(ctx, "result_fetch_states: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    for (int64_t gI = 0; gI < r->ngroups; gI++) {
+        const unsigned long long *rec = h + (size_t) gI * RW, *w = rec + 3;
+        const unsigned int nullmask = (unsigned int) rec[0];
+        for (int c = 0; c < ng; c++) {
+            const bool isnull = (nullmask >> c) & 1;
+            const unsigned long long v = (L.gword[c] == 0 ? rec[1] : rec[2]) >> L.gshift[c];
+            long long sv;
+            switch (r->group_types[c]) {
+                case GX_INT4: case GX_DATE: sv = (long long) (int32_t) (uint32_t) v; break;
+                case GX_CHAR: sv = (long long) (int8_t) (uint8_t) v; break;
+                default: sv = (long long) v; break;
+            }
+            key_out[gI * ng + c] = isnull ? 0 : sv;
+            if (null_out) null_out[gI * (ng + na) + c] = isnull;
+        }
+        for (int a = 0; a < na; a++) {
+            const int fn = r->plan.aggs[a].fn, word = r->agg_word[a], cw = r->agg_cnt_word[a];
+            const long long rows = (long long) w[0];
+            const long long cnt = cw ? (long long) w[cw] : (r->need_w0 ? rows : 1);
+            double v = 0.0; long long n = cnt; uint8_t isnull = 0;
+            switch (fn) {
+                case GX_AGG_COUNT_STAR: n = rows; break;
+                case GX_AGG_COUNT: n = (long long) w[word]; break;
+                case GX_AGG_SUM_I4: case GX_AGG_SUM_I8: memcpy(&v, &w[word], 8); isnull = cnt == 0; break;
+                case GX_AGG_AVG_F8: memcpy(&v, &w[word], 8); break;              // {N, Sx}: never NULL (initial state '{0,0,0}')
+                default: memcpy(&v, &w[word], 8); isnull = cnt == 0; break;      // sum / min / max: strict, NULL until the first input
+            }
+            if ((fn == GX_AGG_SUM_F8 || fn == GX_AGG_AVG_F8) && !isnull && __builtin_isinf(v)) {
+                free(h); GX_SET_ERR(ctx, "value out of range: overflow"); return GX_ERR_OVERFLOW;
+            }
+            val_out[gI * na + a] = isnull ? 0.0 : v; cnt_out[gI * na + a] = n;
+            if (null_out) null_out[gI * (ng + na) + ng + a] = isnull;
+        }
+    }
+    free(h);
+    return GX_OK;
+}

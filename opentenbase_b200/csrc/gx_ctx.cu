@@ -87,6 +87,7 @@ extern "C" void gx_shutdown(gx_ctx *ctx)
         for (int k = 0; k < 2; k++) cudaEventDestroy(ctx->copy_ev[k][i]);
     }
     cudaEventDestroy(ctx->ev_alloc);
+    for (int i = 0; i < 2; i++) { if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]); if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]); }
     cudaFree(ctx->d_scratch); cudaFreeHost(ctx->h_scratch); cudaFree(ctx->d_shardmap);
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
     cudaStreamDestroy(ctx->stream);

@@ -58,6 +58,36 @@ extern "C" int gx_host_free(gx_ctx *ctx, void *p)
 #define GX_COPY_CHUNK ((size_t) 64 << 20)
 
 // allocate the device table on the compute stream (stream-ordered pool) — no copies yet
+// ---- pinned staging ring for the page loader ---------------------------------------------
+// gx_stage_acquire() hands out one of two pinned buffers (NUMA-bound like gx_host_alloc); a slot
+// that still has a copy in flight is waited for first.  gx_table_append_heap_pages() on such a
+// buffer records the slot's event after enqueueing its copies (gx_stage_mark), so the caller can
+// fill the other slot meanwhile: heapgetpage/memcpy on the host overlap DMA + deform on the device.
+extern "C" int gx_stage_acquire(gx_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out || bytes == 0) return GX_ERR_ARG;
+    const int s = ctx->stage_next; ctx->stage_next ^= 1;
+    if (ctx->stage_busy[s]) { GX_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[s])); ctx->stage_busy[s] = 0; }
+    if (ctx->stage_bytes[s] < bytes) {
+        if (ctx->stage[s]) { GX_CUDA(ctx, cudaFreeHost(ctx->stage[s])); ctx->stage[s] = nullptr; ctx->stage_bytes[s] = 0; }
+        int rc = gx_host_alloc(ctx, bytes, &ctx->stage[s]); if (rc) return rc;
+        ctx->stage_bytes[s] = bytes;
+        if (!ctx->stage_ev[s]) GX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[s], cudaEventDisableTiming));
+    }
+    *out = ctx->stage[s];
+    return GX_OK;
+}
+cudaError_t gx_stage_mark(gx_ctx *ctx, const void *host)
+{
+    for (int s = 0; s < 2; s++)
+        if (ctx->stage[s] && host >= ctx->stage[s] && (const char *) host < (const char *) ctx->stage[s] + ctx->stage_bytes[s]) {
+            cudaError_t e = cudaEventRecord(ctx->stage_ev[s], ctx->stream);
+            if (e == cudaSuccess) ctx->stage_busy[s] = 1;
+            return e;
+        }
+    return cudaSuccess;      // not a ring buffer: pageable or caller-owned pinned memory
+}
+
 static int upload_alloc(gx_ctx *ctx, const gx_host_table *h, gx_table **out)
 {
     GX_CHECK_ARG(ctx, h->ncols > 0 && h->ncols <= GX_MAX_COLS && h->nrows >= 0 && h->types && h->cols, "exec_host: bad host table");

@@ -40,6 +40,9 @@ struct gx_ctx {
     std::map<std::string, gx_prof_entry> *prof;
     gx_prof_rec *prof_pool; int prof_used;      // events recorded, not yet resolved
     void *l2flush_buf; size_t l2flush_bytes;
+    // pinned staging ring of the heap-page loader (gx_stage_acquire): the host fills one slot while the
+    // DMA of the other is in flight
+    void *stage[2]; size_t stage_bytes[2]; cudaEvent_t stage_ev[2]; int stage_busy[2]; int stage_next;
     // small device scratch (counters / flags)
     long long *d_scratch;        // 64 x int64
     long long *h_scratch;        // pinned mirror
@@ -91,7 +94,8 @@ struct gx_hash {
     unsigned long long *special_payload; int special_cap; int special_count;
 };
 
-int gx_hash_wide(gx_ctx *ctx, gx_hash *h);   // materialise the 16-byte slot array of a compact table
+int gx_hash_wide(gx_ctx *ctx, gx_hash *h);
+cudaError_t gx_stage_mark(gx_ctx *ctx, const void *host);   // gx_exec.cu: record "copy of this staging slot enqueued"   // materialise the 16-byte slot array of a compact table
 
 // A group-state record: [k0][k1][w0..w(nwords-1)], 8-byte words.
 // w0 is always the group's row count.

@@ -60,6 +60,30 @@ extern "C" int gx_table_column_devptr(gx_table *t, int col, void **dptr)
     return GX_OK;
 }
 
+// grow the column arrays (stream-ordered): the loader does not know a heap relation's row count up front
+extern "C" int gx_table_reserve(gx_table *t, int64_t capacity_rows)
+{
+    if (!t || capacity_rows < 0) return GX_ERR_ARG;
+    if (capacity_rows <= t->capacity) return GX_OK;
+    gx_ctx *ctx = t->ctx;
+    for (int c = 0; c < t->ncols; c++) {
+        const int sz = gx_type_size(t->types[c]);
+        void *nc = nullptr; uint8_t *nn = nullptr;
+        cudaError_t e = gx_tmp_alloc(ctx, &nc, (size_t) capacity_rows * sz + 32);
+        if (e == cudaSuccess && t->nulls[c]) e = gx_tmp_alloc(ctx, (void **) &nn, (size_t) capacity_rows + 32);
+        if (e != cudaSuccess) { gx_tmp_free(ctx, nc); GX_SET_ERR(ctx, "table_reserve: %lld rows: %s", (long long) capacity_rows, cudaGetErrorString(e)); cudaGetLastError(); return GX_ERR_NOMEM; }
+        if (t->nrows) GX_CUDA(ctx, cudaMemcpyAsync(nc, t->cols[c], (size_t) t->nrows * sz, cudaMemcpyDeviceToDevice, ctx->stream));
+        gx_tmp_free(ctx, t->cols[c]); t->cols[c] = nc;
+        if (nn) {
+            GX_CUDA(ctx, cudaMemsetAsync(nn, 0, (size_t) capacity_rows, ctx->stream));
+            if (t->nrows) GX_CUDA(ctx, cudaMemcpyAsync(nn, t->nulls[c], (size_t) t->nrows, cudaMemcpyDeviceToDevice, ctx->stream));
+            gx_tmp_free(ctx, t->nulls[c]); t->nulls[c] = nn;
+        }
+    }
+    t->capacity = capacity_rows;
+    return GX_OK;
+}
+
 static int ensure_null_array(gx_table *t, int c)
 {
     if (t->nulls[c]) return GX_OK;
@@ -515,6 +539,24 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
         int rc = ensure_null_array(t, c); if (rc) return rc;
         a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; a.out_type[c] = t->types[c];
     }
+    // With visibility lists the host knows every page's row count: the row offsets are scanned here and
+    // travel with the batch, so the call only ENQUEUES work (copies + one kernel) — no device round
+    // trip per batch.  Without them the LP_NORMAL items are counted on the device (one synchronisation).
+    const bool host_counts = vis_counts != nullptr;
+    long long total = 0;
+    long long *h_offs = nullptr;
+    if (host_counts) {
+        h_offs = (long long *) malloc((size_t) npages * sizeof(long long));
+        for (int64_t p = 0; p < npages; p++) {
+            GX_CHECK_ARG(ctx, vis_counts[p] >= 0 && vis_counts[p] <= vis_stride, "heap pages: page %lld has %d visible items (stride %d)", (long long) p, vis_counts[p], vis_stride);
+            h_offs[p] = total; total += vis_counts[p];
+        }
+        if (t->nrows + total > t->capacity) {
+            int64_t want = t->capacity * 2 > t->nrows + total ? t->capacity * 2 : t->nrows + total;
+            int grc = gx_table_reserve(t, want); if (grc) { free(h_offs); return grc; }
+            for (int c = 0; c < desc->ncols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
+        }
+    }
     // stage the raw pages (and visibility lists) in HBM
     uint8_t *d_pages = nullptr; uint16_t *d_vis = nullptr; int32_t *d_cnt = nullptr; long long *d_offs = nullptr;
     cudaError_t e = gx_tmp_alloc(ctx, (void **) &d_pages, (size_t) npages * PG_BLCKSZ);
@@ -527,7 +569,18 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, vis_counts, (size_t) npages * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
     }
     int rc = GX_OK;
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && host_counts) {
+        a.pages = d_pages; a.vis = d_vis; a.vis_counts = d_cnt;
+        // h_offs is pageable: the copy is staged by the driver before the call returns
+        e = cudaMemcpyAsync(d_offs, h_offs, (size_t) npages * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            gx_launch_scope ls(ctx, "deform", 1);
+            long long nthreads = npages * 32;
+            gx_k_deform<<<(unsigned) ((nthreads + 255) / 256), 256, 0, ctx->stream>>>(a, d_offs);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) { t->nrows += total; e = gx_stage_mark(ctx, pages); }
+    } else if (e == cudaSuccess) {
         a.pages = d_pages; a.vis = d_vis; a.vis_counts = d_cnt;
         {
             gx_launch_scope ls(ctx, "deform", 2);
@@ -537,11 +590,13 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
         e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e == cudaSuccess) {
-            long long total = ctx->h_scratch[0];
+            total = ctx->h_scratch[0];
             if (t->nrows + total > t->capacity) {
-                GX_SET_ERR(ctx, "append_heap_pages: %lld + %lld rows exceed capacity %lld", (long long) t->nrows, total, (long long) t->capacity);
-                rc = GX_ERR_ARG;
-            } else {
+                int64_t want = t->capacity * 2 > t->nrows + total ? t->capacity * 2 : t->nrows + total;
+                rc = gx_table_reserve(t, want);
+                for (int c = 0; c < desc->ncols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
+            }
+            if (rc == GX_OK) {
                 {
                     gx_launch_scope ls(ctx, "deform", 1);
                     long long nthreads = npages * 32;
@@ -552,6 +607,7 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
             }
         }
     }
+    free(h_offs);
     gx_tmp_free(ctx, d_pages); gx_tmp_free(ctx, d_offs); if (d_vis) gx_tmp_free(ctx, d_vis); if (d_cnt) gx_tmp_free(ctx, d_cnt);
     if (e != cudaSuccess) { GX_SET_ERR(ctx, "append_heap_pages: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GX_ERR_NOMEM : GX_ERR_CUDA; }
     return rc;

@@ -24,18 +24,27 @@
  * pg_config.h of oracle/ref (compile check only; `make -C opentenbase_b200/provider`).
  *
  * Status: the executor side (Begin/Exec/End/ReScan/Explain), the plan
- * (de)serialisation into custom_private and the heap-page loader are complete;
- * the planner hook recognises the plan shapes of BASELINE configs 1-3
- * (single-relation or two-relation inner equi-join on one int4/int8 key, Var
- * group keys, count(*) / sum / avg / min / max over float8 Var/Const
- * arithmetic).  It has been compiled against the reference headers but never
- * run inside a live backend (none can be built here: SURVEY.md §8c).
+ * (de)serialisation into custom_private and the heap-page loader are complete
+ * and are EXECUTED by provider/harness (a stub-linked fake backend: fake EState,
+ * heapgetpage() fed from heap-page images, real libgpuexec.so; see
+ * tests/test_provider_harness.py).  The planner hook recognises the plan shapes
+ * of BASELINE configs 1-3 and Q1 (single-relation or two-relation inner equi-join
+ * on one int4/int8 key, "Var op Const" quals, Var group keys, count(*) / count /
+ * sum / avg / min / max over float8 Var/Const arithmetic) and offers
+ *   - the whole aggregation pushed down when the GROUP BY covers the input's
+ *     distribution key (grouping_distribution_match, planner.c:8588-8668), or
+ *   - PARTIAL states (AGGSPLIT_INITIAL_SERIAL) under the reference's own
+ *     redistribute + Finalize Agg (create_redistribute_grouping_path,
+ *     pathnode.c:6091; planner.c:9045-9075) otherwise.
+ * The planner side compiles against the reference headers but has never run
+ * inside a live backend (none can be built here: SURVEY.md §8c).
  */
 #include "postgres.h"
 
 #include "access/heapam.h"
 #include "access/htup_details.h"
 #include "access/relscan.h"
+#include "audit/audit_fga.h"
 #include "catalog/pg_type.h"
 #include "commands/explain.h"
 #include "executor/executor.h"
@@ -44,11 +53,20 @@
 #include "nodes/extensible.h"
 #include "nodes/makefuncs.h"
 #include "nodes/nodeFuncs.h"
+#include "optimizer/clauses.h"
+#include "optimizer/distribution.h"
 #include "optimizer/pathnode.h"
 #include "optimizer/paths.h"
 #include "optimizer/planner.h"
 #include "optimizer/tlist.h"
+#include "parser/parsetree.h"
+#include "pgxc/locator.h"
+#include "utils/array.h"
+#include "utils/builtins.h"
+#include "utils/cls.h"
+#include "utils/datamask.h"
 #include "utils/fmgroids.h"
+#include "utils/mls.h"
 #include "storage/bufmgr.h"
 #include "utils/guc.h"
 #include "utils/memutils.h"
@@ -64,6 +82,7 @@ void		_PG_init(void);
 
 static bool gpuexec_enabled = true;
 static int	gpuexec_device = 0;
+static int	gpuexec_hbm_limit_mb = 150 * 1024;	/* decline plans whose staged columns + join table would not fit */
 static create_upper_paths_hook_type prev_upper_paths_hook = NULL;
 
 /* one CUDA context per backend process, created lazily (never in the postmaster:
@@ -92,6 +111,9 @@ typedef struct GpuExecState
 	int			n_payload;
 	int32		payload_cols[GX_MAX_PAYLOAD];
 	bool		inner_unique;
+	int			n_inner_preds;
+	gx_pred		inner_preds[GX_MAX_PREDS];
+	bool		partial;		/* emit transition states (AGGSPLIT_INITIAL_SERIAL), not final values */
 	gx_agg_plan plan;
 	/* run time */
 	Relation	outer_rel,
@@ -104,6 +126,7 @@ typedef struct GpuExecState
 				next;
 	int64	   *keys;
 	double	   *aggs;
+	int64	   *cnts;			/* partial mode: N of every transition state */
 	uint8	   *nulls;
 	double		load_ms,
 				exec_ms;
@@ -206,7 +229,11 @@ gpuexec_type_of(Oid typid)
 /* ------------------------------------------------ K0: heap page loader
  * One heapgetpage() per block (pins the buffer, runs HeapTupleSatisfiesMVCC once
  * per tuple, fills rs_vistuples[]); the raw page bytes and the visible line
- * pointers go to the device in batches, the deform runs there. */
+ * pointers go to the device in batches, the deform runs there.  A batch lives in
+ * one slot of the library's pinned staging ring (gx_stage_acquire): while the DMA
+ * and the deform of batch i run, the host fills batch i+1 — the append call only
+ * enqueues.  The ring belongs to the library, so an ereport() out of
+ * heapgetpage() leaks nothing. */
 #define LOAD_BATCH_PAGES 4096	/* 32 MB of pages per gx_table_append_heap_pages() */
 
 static void
@@ -216,10 +243,15 @@ gpuexec_load_relation(Relation rel, EState *estate, GpuRelInfo *info, gx_table *
 	HeapScanDesc scan = heap_beginscan(rel, estate->es_snapshot, 0, NULL);
 	BlockNumber nblocks = scan->rs_nblocks;
 	gx_heap_desc hd;
-	char	   *pages;
-	uint16	   *vis;
-	int32	   *cnt;
-	int64		est_rows = (int64) nblocks * MaxHeapTuplesPerPage;
+	const size_t pages_bytes = (size_t) LOAD_BATCH_PAGES * BLCKSZ;
+	const size_t vis_bytes = sizeof(uint16) * (size_t) LOAD_BATCH_PAGES * MaxHeapTuplesPerPage;
+	const size_t slot_bytes = pages_bytes + vis_bytes + sizeof(int32) * LOAD_BATCH_PAGES;
+	char	   *slot = NULL;
+	char	   *pages = NULL;
+	uint16	   *vis = NULL;
+	int32	   *cnt = NULL;
+	double		reltuples = rel->rd_rel ? rel->rd_rel->reltuples : 0;
+	int64		est_rows;
 	BlockNumber blk;
 	int			nbatch = 0;
 	int			i;
@@ -237,17 +269,32 @@ gpuexec_load_relation(Relation rel, EState *estate, GpuRelInfo *info, gx_table *
 		hd.att_align[i] = att->attalign == 'd' ? 8 : att->attalign == 'i' ? 4 : att->attalign == 's' ? 2 : 1;
 	}
 	for (i = 0; i < info->ncols; i++)
+	{
 		hd.attnums[i] = info->attnums[i];
+		/* the device deform reads attributes a tuple was written without as NULL; a
+		 * fast default (atthasmissing, heaptuple.c:109-135) would need the value */
+		if (TupleDescAttr(desc, info->attnums[i])->atthasmissing)
+			ereport(ERROR, (errcode(ERRCODE_FEATURE_NOT_SUPPORTED),
+							errmsg("gpuexec: column \"%s\" has a missing-value default", NameStr(TupleDescAttr(desc, info->attnums[i])->attname))));
+	}
 
-	GX_CHECK(gx_table_create(backend_ctx, info->ncols, info->types, est_rows > 0 ? est_rows : 1, out));
-	/* staging lives in pinned memory so the copy is one DMA */
-	GX_CHECK(gx_host_alloc(backend_ctx, (size_t) LOAD_BATCH_PAGES * BLCKSZ, (void **) &pages));
-	vis = (uint16 *) palloc(sizeof(uint16) * LOAD_BATCH_PAGES * MaxHeapTuplesPerPage);
-	cnt = (int32 *) palloc(sizeof(int32) * LOAD_BATCH_PAGES);
+	/* sized from the statistics, never from MaxHeapTuplesPerPage (291 rows per page would be
+	 * five to six times the real count); the table grows when the estimate was low */
+	est_rows = (int64) (reltuples * 1.1) + 1024;
+	if (est_rows < (int64) nblocks * 8)
+		est_rows = (int64) nblocks * 8;
+	GX_CHECK(gx_table_create(backend_ctx, info->ncols, info->types, est_rows, out));
 
 	for (blk = 0; blk < nblocks; blk++)
 	{
 		CHECK_FOR_INTERRUPTS();
+		if (nbatch == 0)
+		{
+			GX_CHECK(gx_stage_acquire(backend_ctx, slot_bytes, (void **) &slot));
+			pages = slot;
+			vis = (uint16 *) (slot + pages_bytes);
+			cnt = (int32 *) (slot + pages_bytes + vis_bytes);
+		}
 		heapgetpage(scan, blk);
 		LockBuffer(scan->rs_cbuf, BUFFER_LOCK_SHARE);
 		memcpy(pages + (size_t) nbatch * BLCKSZ, BufferGetPage(scan->rs_cbuf), BLCKSZ);
@@ -260,16 +307,12 @@ gpuexec_load_relation(Relation rel, EState *estate, GpuRelInfo *info, gx_table *
 
 			if (st != GX_OK)
 			{
-				gx_host_free(backend_ctx, pages);
 				heap_endscan(scan);
 				GX_CHECK(st);
 			}
 			nbatch = 0;
 		}
 	}
-	gx_host_free(backend_ctx, pages);
-	pfree(vis);
-	pfree(cnt);
 	heap_endscan(scan);
 }
 
@@ -279,7 +322,27 @@ gpuexec_load_relation(Relation rel, EState *estate, GpuRelInfo *info, gx_table *
 static List *
 put_int(List *l, int64 v)
 {
-	return lappend(l, makeInteger((int) v));
+	Assert(v == (int64) (int32) v);		/* small enumerations and column numbers only */
+	return lappend(l, makeInteger((long) v));
+}
+
+/* 64-bit integers travel as decimal strings: nodeRead() turns any integer token that does
+ * not fit int32 into a T_Float node anyway (nodes/read.c), and a double would round above 2^53 */
+static List *
+put_int64(List *l, int64 v)
+{
+	char		buf[32];
+
+	snprintf(buf, sizeof(buf), INT64_FORMAT, v);
+	return lappend(l, makeFloat(pstrdup(buf)));
+}
+static int64
+get_int64(ListCell **lc)
+{
+	int64		v = (int64) strtoll(strVal(lfirst(*lc)), NULL, 10);
+
+	*lc = lnext(*lc);
+	return v;
 }
 static List *
 put_double(List *l, double v)
@@ -353,14 +416,23 @@ gpuexec_serialise(const GpuExecState *st)
 		for (i = 0; i < st->n_payload; i++)
 			l = put_int(l, st->payload_cols[i]);
 		l = put_int(l, st->inner_unique);
+		l = put_int(l, st->n_inner_preds);
+		for (i = 0; i < st->n_inner_preds; i++)
+		{
+			l = put_int(l, st->inner_preds[i].col);
+			l = put_int(l, st->inner_preds[i].op);
+			l = put_int64(l, st->inner_preds[i].ival);
+			l = put_double(l, st->inner_preds[i].fval);
+		}
 	}
+	l = put_int(l, st->partial);
 	l = put_int(l, p->n_preds);
 	l = put_int(l, p->outer_key_col);
 	for (i = 0; i < p->n_preds; i++)
 	{
 		l = put_int(l, p->preds[i].col);
 		l = put_int(l, p->preds[i].op);
-		l = put_double(l, (double) p->preds[i].ival);
+		l = put_int64(l, p->preds[i].ival);
 		l = put_double(l, p->preds[i].fval);
 	}
 	l = put_int(l, p->n_group_cols);
@@ -381,7 +453,7 @@ gpuexec_serialise(const GpuExecState *st)
 			l = put_double(l, p->aggs[i].arg.ops[j].k);
 		}
 	}
-	l = put_double(l, (double) p->est_groups);
+	l = put_int64(l, p->est_groups);
 	return l;
 }
 
@@ -406,14 +478,23 @@ gpuexec_deserialise(List *priv, GpuExecState *st)
 		for (i = 0; i < st->n_payload; i++)
 			st->payload_cols[i] = get_int(&lc);
 		st->inner_unique = get_int(&lc);
+		st->n_inner_preds = get_int(&lc);
+		for (i = 0; i < st->n_inner_preds; i++)
+		{
+			st->inner_preds[i].col = get_int(&lc);
+			st->inner_preds[i].op = get_int(&lc);
+			st->inner_preds[i].ival = get_int64(&lc);
+			st->inner_preds[i].fval = get_double(&lc);
+		}
 	}
+	st->partial = get_int(&lc);
 	p->n_preds = get_int(&lc);
 	p->outer_key_col = get_int(&lc);
 	for (i = 0; i < p->n_preds; i++)
 	{
 		p->preds[i].col = get_int(&lc);
 		p->preds[i].op = get_int(&lc);
-		p->preds[i].ival = (int64) get_double(&lc);
+		p->preds[i].ival = get_int64(&lc);
 		p->preds[i].fval = get_double(&lc);
 	}
 	p->n_group_cols = get_int(&lc);
@@ -434,7 +515,7 @@ gpuexec_deserialise(List *priv, GpuExecState *st)
 			p->aggs[i].arg.ops[j].k = get_double(&lc);
 		}
 	}
-	p->est_groups = (int64) get_double(&lc);
+	p->est_groups = get_int64(&lc);
 }
 
 /* ------------------------------------------------------ executor methods */
@@ -509,19 +590,25 @@ gpuexec_run(GpuExecState *st, EState *estate)
 
 	INSTR_TIME_SET_CURRENT(t0);
 	if (st->has_join)
-		GX_CHECK(gx_hash_build(backend_ctx, st->inner_tab, st->inner_key_col, 0, NULL,
+		GX_CHECK(gx_hash_build(backend_ctx, st->inner_tab, st->inner_key_col, st->n_inner_preds, st->inner_preds,
 							   st->n_payload, st->payload_cols, st->inner_unique, &st->hash));
 	CHECK_FOR_INTERRUPTS();
 	GX_CHECK(gx_hash_agg(backend_ctx, st->outer_tab, st->hash, &st->plan, &st->result));
-	/* Partial -> Distribute -> Finalize happens in the planner's own RemoteSubplan
-	 * above us unless all datanodes share one box; then gx_result_combine() does it
-	 * over NVLink (no-op without a communicator). */
-	GX_CHECK(gx_result_combine(backend_ctx, st->result));
+	/* The result holds this datanode's groups only.  Whether they are final is the PLANNER's
+	 * business: the hook offers the pushed-down path only when the GROUP BY covers the
+	 * distribution key, and otherwise asks for partial states, which the reference's own
+	 * RemoteSubplan + Finalize Agg above us combine (st->partial). */
 	n = gx_result_ngroups(st->result);
 	st->keys = (int64 *) palloc(sizeof(int64) * Max(n * ng, 1));
 	st->aggs = (double *) palloc(sizeof(double) * Max(n * na, 1));
 	st->nulls = (uint8 *) palloc(Max(n * (ng + na), 1));
-	GX_CHECK(gx_result_fetch(st->result, n, st->keys, st->aggs, st->nulls));
+	if (st->partial)
+	{
+		st->cnts = (int64 *) palloc(sizeof(int64) * Max(n * na, 1));
+		GX_CHECK(gx_result_fetch_states(st->result, n, st->keys, st->aggs, st->cnts, st->nulls));
+	}
+	else
+		GX_CHECK(gx_result_fetch(st->result, n, st->keys, st->aggs, st->nulls));
 	st->ngroups = n;
 	st->next = 0;
 	INSTR_TIME_SET_CURRENT(t1);
@@ -532,14 +619,20 @@ gpuexec_run(GpuExecState *st, EState *estate)
 	st->done_exec = true;
 }
 
-/* Returns one group per call as a virtual tuple: the custom_scan_tlist is
- * (group columns..., aggregates...) in plan order. */
+/* Returns one group per call as a virtual tuple.  The SCAN tuple is described by
+ * custom_scan_tlist, which PlanCustomPath builds as (group columns in GROUP BY order,
+ * aggregates in descriptor order) — whatever order the query's own target list has; the
+ * plan's targetlist is projected over it (ExecAssignScanProjectionInfoWithVarno,
+ * nodeCustom.c:100-101) below.  In partial mode an aggregate column carries the transition
+ * value the reference's combine function expects (pg_aggregate.h:178-252): int8 for
+ * count/sum(int4), float8 for sum/min/max(float8), float8[3] {N, Sx, Sxx} for avg(float8). */
 static TupleTableSlot *
 gpuexec_exec(CustomScanState *node)
 {
 	GpuExecState *st = (GpuExecState *) node;
 	TupleTableSlot *slot = node->ss.ss_ScanTupleSlot;
 	TupleDesc	desc = slot->tts_tupleDescriptor;
+	ExprContext *econtext = node->ss.ps.ps_ExprContext;
 	int			ng = st->plan.n_group_cols,
 				na = st->plan.n_aggs;
 	int			i;
@@ -550,6 +643,8 @@ gpuexec_exec(CustomScanState *node)
 	ExecClearTuple(slot);
 	if (st->next >= st->ngroups)
 		return slot;			/* empty slot = end of scan */
+	if (econtext)
+		ResetExprContext(econtext);	/* by-reference datums of the previous row die here */
 	g = st->next++;
 	for (i = 0; i < ng + na; i++)
 	{
@@ -582,6 +677,16 @@ gpuexec_exec(CustomScanState *node)
 				case CHAROID:
 					slot->tts_values[i] = CharGetDatum((char) v);
 					break;
+				case BPCHAROID:
+					{
+						/* bpchar(1) was staged as its one byte: rebuild the varlena */
+						MemoryContext old = MemoryContextSwitchTo(econtext->ecxt_per_tuple_memory);
+						char		c = (char) v;
+
+						slot->tts_values[i] = PointerGetDatum(cstring_to_text_with_len(&c, 1));
+						MemoryContextSwitchTo(old);
+						break;
+					}
 				default:
 					slot->tts_values[i] = Int32GetDatum((int32) v);
 					break;
@@ -589,9 +694,26 @@ gpuexec_exec(CustomScanState *node)
 		}
 		else
 		{
-			double		d = st->aggs[g * na + (i - ng)];
+			int			a = i - ng;
+			double		d = st->aggs[g * na + a];
+			int			fn = st->plan.aggs[a].fn;
 
-			if (typid == INT8OID)
+			if (st->partial && fn == GX_AGG_AVG_F8)
+			{
+				/* float8_accum's transition value {N, Sx, Sxx}; Sxx is not carried (only
+				 * var/stddev read it; float8_combine, float.c:2725, keeps it finite) */
+				MemoryContext old = MemoryContextSwitchTo(econtext->ecxt_per_tuple_memory);
+				Datum		elems[3];
+
+				elems[0] = Float8GetDatum((double) st->cnts[g * na + a]);
+				elems[1] = Float8GetDatum(d);
+				elems[2] = Float8GetDatum(0.0);
+				slot->tts_values[i] = PointerGetDatum(construct_array(elems, 3, FLOAT8OID, sizeof(float8), FLOAT8PASSBYVAL, 'd'));
+				MemoryContextSwitchTo(old);
+			}
+			else if (st->partial && (fn == GX_AGG_COUNT_STAR || fn == GX_AGG_COUNT))
+				slot->tts_values[i] = Int64GetDatum(st->cnts[g * na + a]);
+			else if (typid == INT8OID)
 			{
 				int64		v;
 
@@ -602,7 +724,13 @@ gpuexec_exec(CustomScanState *node)
 				slot->tts_values[i] = Float8GetDatum(d);
 		}
 	}
-	return ExecStoreVirtualTuple(slot);
+	ExecStoreVirtualTuple(slot);
+	if (node->ss.ps.ps_ProjInfo)
+	{
+		econtext->ecxt_scantuple = slot;
+		return ExecProject(node->ss.ps.ps_ProjInfo);
+	}
+	return slot;
 }
 
 static void
@@ -645,6 +773,7 @@ gpuexec_explain(CustomScanState *node, List *ancestors, ExplainState *es)
 	GpuExecState *st = (GpuExecState *) node;
 
 	ExplainPropertyText("GPU Strategy", st->has_join ? "hash build + fused probe/aggregate" : "scan + hash aggregate", es);
+	ExplainPropertyText("GPU Output", st->partial ? "partial states (Finalize above the redistribute)" : "final values (GROUP BY covers the distribution key)", es);
 	if (es->analyze && st->done_exec)
 	{
 		ExplainPropertyFloat("GPU Load", "ms", st->load_ms, 3, es);
@@ -662,35 +791,45 @@ static const CustomPathMethods gpuexec_path_methods = {
 	.PlanCustomPath = gpuexec_plan_path,
 };
 
-/* PlanCustomPath: the CustomPath carries the serialised descriptor; the scan
- * tuple is described by custom_scan_tlist = the upper rel's target list
- * (scanrelid = 0: nodeCustom.c:81-94 requires it). */
+/* PlanCustomPath.  CustomPath.custom_private = (serialised descriptor, scan-tuple expressions):
+ * the second list holds the GROUP BY expressions in groupClause order followed by the
+ * (final or partial) Aggrefs in descriptor order — exactly the columns gpuexec_exec() fills —
+ * and becomes custom_scan_tlist.  The plan's own targetlist (SELECT order, resjunk entries,
+ * whatever) is then resolved against it by set_customscan_references (setrefs.c:1805) and
+ * projected at run time; nothing relies on the two orders coinciding. */
 static Plan *
 gpuexec_plan_path(PlannerInfo *root, RelOptInfo *rel, CustomPath *best_path,
 				  List *tlist, List *clauses, List *custom_plans)
 {
 	CustomScan *cscan = makeNode(CustomScan);
+	List	   *scan_exprs = (List *) lsecond(best_path->custom_private);
+	List	   *stl = NIL;
+	ListCell   *lc;
+	AttrNumber	resno = 1;
 
+	foreach(lc, scan_exprs)
+		stl = lappend(stl, makeTargetEntry((Expr *) copyObject(lfirst(lc)), resno++, NULL, false));
 	cscan->scan.plan.targetlist = tlist;
 	cscan->scan.plan.qual = NIL;	/* HAVING is declined by the hook */
 	cscan->scan.scanrelid = 0;
 	cscan->flags = best_path->flags;
 	cscan->custom_plans = NIL;
 	cscan->custom_exprs = NIL;
-	cscan->custom_private = best_path->custom_private;
-	cscan->custom_scan_tlist = tlist;
+	cscan->custom_private = (List *) linitial(best_path->custom_private);
+	cscan->custom_scan_tlist = stl;
 	cscan->custom_relids = NULL;
 	cscan->methods = &gpuexec_scan_methods;
 	return &cscan->scan.plan;
 }
 
 /* ---- plan-shape analysis -------------------------------------------------
- * Accepts:   Agg(HASHED/PLAIN) over  SeqScan(R)                       (configs 1, 2)
+ * Accepts:   Agg(HASHED/PLAIN) over  SeqScan(R)                       (configs 1, 2, Q1)
  *            Agg over HashJoin[INNER, one int4/int8 equi-key](SeqScan(R), SeqScan(S))   (config 3)
- * with Var group keys, no HAVING / grouping sets / DISTINCT / ORDER BY aggregates /
- * FILTER, and aggregates count(*), count(x), sum/avg/min/max(float8 expr),
- * sum(int4).  Anything else returns false and the CPU paths stay untouched —
- * the same "eligibility test" idea as jit_compile_hashjoin (jit/jit.c:253-303). */
+ * with "Var op Const" quals on the scans, Var group keys, no HAVING / grouping sets /
+ * DISTINCT / ORDER BY aggregates / FILTER, and aggregates count(*), count(x),
+ * sum/avg/min/max(float8 expr), sum(int4); every target-list entry must be a group Var or a
+ * bare Aggref.  Anything else returns false and the CPU paths stay untouched — the same
+ * "eligibility test" idea as jit_compile_hashjoin (jit/jit.c:253-303). */
 #define AGG_COUNT_STAR 2803
 #define AGG_COUNT_ANY  2147
 #define AGG_SUM_F8     2111
@@ -782,14 +921,169 @@ match_f8_expr(Node *n, GpuRelInfo *outer, gx_expr *e)
 	return false;
 }
 
+/* comparison function oid -> (GX_* operator, operand class: 'i' integer-like, 'f' float8, 'c' one byte) */
+static bool
+qual_operator(Oid funcid, int *op, char *cls)
+{
+	static const struct { Oid fn; int op; char cls; } tab[] = {
+		{F_INT4LT, GX_LT, 'i'}, {F_INT4LE, GX_LE, 'i'}, {F_INT4EQ, GX_EQ, 'i'}, {F_INT4GE, GX_GE, 'i'}, {F_INT4GT, GX_GT, 'i'}, {F_INT4NE, GX_NE, 'i'},
+		{F_INT8LT, GX_LT, 'i'}, {F_INT8LE, GX_LE, 'i'}, {F_INT8EQ, GX_EQ, 'i'}, {F_INT8GE, GX_GE, 'i'}, {F_INT8GT, GX_GT, 'i'}, {F_INT8NE, GX_NE, 'i'},
+		{F_DATE_LT, GX_LT, 'i'}, {F_DATE_LE, GX_LE, 'i'}, {F_DATE_EQ, GX_EQ, 'i'}, {F_DATE_GE, GX_GE, 'i'}, {F_DATE_GT, GX_GT, 'i'}, {F_DATE_NE, GX_NE, 'i'},
+		{F_FLOAT8LT, GX_LT, 'f'}, {F_FLOAT8LE, GX_LE, 'f'}, {F_FLOAT8EQ, GX_EQ, 'f'}, {F_FLOAT8GE, GX_GE, 'f'}, {F_FLOAT8GT, GX_GT, 'f'}, {F_FLOAT8NE, GX_NE, 'f'},
+		{F_CHARLT, GX_LT, 'c'}, {F_CHARLE, GX_LE, 'c'}, {F_CHAREQ, GX_EQ, 'c'}, {F_CHARGE, GX_GE, 'c'}, {F_CHARGT, GX_GT, 'c'}, {F_CHARNE, GX_NE, 'c'},
+		{F_BPCHAREQ, GX_EQ, 'b'}, {F_BPCHARNE, GX_NE, 'b'},
+	};
+	int			i;
+
+	for (i = 0; i < (int) lengthof(tab); i++)
+		if (tab[i].fn == funcid)
+		{
+			*op = tab[i].op;
+			*cls = tab[i].cls;
+			return true;
+		}
+	return false;
+}
+
+/* baserestrictinfo -> gx_pred[]: every clause must be "Var op Const" (either order) with both
+ * sides of the SAME type (no cross-type int48/int84 operators); false = decline the plan */
+static bool
+match_quals(List *restrictinfo, GpuRelInfo *rel, gx_pred *preds, int *n_preds)
+{
+	ListCell   *lc;
+
+	foreach(lc, restrictinfo)
+	{
+		RestrictInfo *ri = (RestrictInfo *) lfirst(lc);
+		OpExpr	   *o = (OpExpr *) ri->clause;
+		Node	   *l,
+				   *r;
+		Var		   *v;
+		Const	   *k;
+		int			op,
+					c;
+		char		cls;
+		bool		flipped = false;
+
+		if (ri->pseudoconstant || !IsA(o, OpExpr) || list_length(o->args) != 2 || *n_preds >= GX_MAX_PREDS)
+			return false;
+		l = (Node *) linitial(o->args);
+		r = (Node *) lsecond(o->args);
+		if (IsA(l, RelabelType))
+			l = (Node *) ((RelabelType *) l)->arg;
+		if (IsA(r, RelabelType))
+			r = (Node *) ((RelabelType *) r)->arg;
+		if (IsA(l, Const) && IsA(r, Var))
+		{
+			Node	   *t = l;
+
+			l = r;
+			r = t;
+			flipped = true;
+		}
+		if (!IsA(l, Var) || !IsA(r, Const) || !qual_operator(o->opfuncid, &op, &cls))
+			return false;
+		v = (Var *) l;
+		k = (Const *) r;
+		if (k->constisnull || v->varlevelsup != 0 || k->consttype != v->vartype)
+			return false;
+		c = rel_column(rel, v->varno, v->varattno, v->vartype, v->vartypmod);
+		if (c < 0)
+			return false;
+		if (flipped)			/* const op var  ==  var op' const */
+			op = op == GX_LT ? GX_GT : op == GX_LE ? GX_GE : op == GX_GT ? GX_LT : op == GX_GE ? GX_LE : op;
+		preds[*n_preds].col = c;
+		preds[*n_preds].op = op;
+		preds[*n_preds].ival = 0;
+		preds[*n_preds].fval = 0;
+		switch (cls)
+		{
+			case 'i':
+				preds[*n_preds].ival = v->vartype == INT8OID ? DatumGetInt64(k->constvalue) : (int64) DatumGetInt32(k->constvalue);
+				break;
+			case 'f':
+				preds[*n_preds].fval = DatumGetFloat8(k->constvalue);
+				break;
+			case 'c':
+				preds[*n_preds].ival = (int64) (unsigned char) DatumGetChar(k->constvalue);
+				break;
+			default:			/* bpchar(1) = 'x' */
+				{
+					struct varlena *t = (struct varlena *) DatumGetPointer(k->constvalue);
+
+					if (VARSIZE_ANY_EXHDR(t) != 1)
+						return false;
+					preds[*n_preds].ival = (int64) (unsigned char) VARDATA_ANY(t)[0];
+					break;
+				}
+		}
+		(*n_preds)++;
+	}
+	return true;
+}
+
+/* Relations the GPU path must not read around the row-level machinery ExecScan applies per
+ * tuple (execScan.c:185-200,261,313-325): data masking, CLS policies, FGA audit policies. */
+static bool
+relation_is_protected(PlannerInfo *root, Index rti)
+{
+	RangeTblEntry *rte = planner_rt_fetch(rti, root);
+	List	   *fga = NIL;
+
+	if (rte->rtekind != RTE_RELATION)
+		return true;
+	if (g_enable_data_mask && datamask_check_table_has_datamask(rte->relid))
+		return true;
+	if (g_enable_cls && cls_check_table_has_policy(rte->relid))
+		return true;
+	if (enable_fga && get_audit_fga_quals(rte->relid, "select", root->parse->targetList, &fga) && fga != NIL)
+		return true;
+	return false;
+}
+
+/* GROUP BY covers the distribution key: groups on different datanodes cannot overlap, so the
+ * whole aggregation may run below the RemoteSubplan.  Restates the rule of
+ * grouping_distribution_match (planner.c:8588-8668) with plain equal() — stricter than the
+ * reference's exprs_known_equal(), so it can only decline more often. */
+static bool
+grouping_covers_distribution(Query *parse, Distribution *d)
+{
+	int			j;
+
+	if (d == NULL || IsLocatorReplicated(d->distributionType))
+		return true;
+	if (!IsValidDistribution(d))
+		return false;
+	for (j = 0; j < d->nExprs; j++)
+	{
+		ListCell   *lc;
+		bool		found = false;
+
+		foreach(lc, parse->groupClause)
+		{
+			TargetEntry *tle = get_sortgroupclause_tle((SortGroupClause *) lfirst(lc), parse->targetList);
+
+			if (d->disExprs[j] && equal(tle->expr, d->disExprs[j]))
+			{
+				found = true;
+				break;
+			}
+		}
+		if (!found)
+			return false;
+	}
+	return true;
+}
+
 static bool
 gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_rel, GpuExecState *out,
-				   double *est_rows, double *est_groups)
+				   List **agg_refs, double *est_rows, double *est_groups, double *est_bytes)
 {
 	Query	   *parse = root->parse;
 	Path	   *in = input_rel->cheapest_total_path;
 	gx_agg_plan *plan = &out->plan;
 	ListCell   *lc;
+	int			i;
 
 	if (parse->groupingSets || parse->havingQual || parse->hasWindowFuncs || parse->hasTargetSRFs || in == NULL)
 		return false;
@@ -797,9 +1091,11 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 
 	if (in->pathtype == T_SeqScan && input_rel->reloptkind == RELOPT_BASEREL)
 	{
-		if (input_rel->baserestrictinfo != NIL)
-			return false;		/* quals: a later version maps "Var op Const" onto gx_pred */
 		out->outer.rti = input_rel->relid;
+		if (relation_is_protected(root, input_rel->relid) ||
+			!match_quals(input_rel->baserestrictinfo, &out->outer, plan->preds, &plan->n_preds))
+			return false;
+		*est_bytes = input_rel->tuples;
 	}
 	else if (IsA(in, HashPath))
 	{
@@ -814,8 +1110,9 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 		if (hp->jpath.jointype != JOIN_INNER || list_length(hp->path_hashclauses) != 1 || hp->jpath.joinrestrictinfo == NIL ||
 			list_length(hp->jpath.joinrestrictinfo) != 1)
 			return false;
-		if (op->pathtype != T_SeqScan || ip->pathtype != T_SeqScan ||
-			op->parent->baserestrictinfo != NIL || ip->parent->baserestrictinfo != NIL)
+		/* both inputs must be plain scans of co-located shards: a RemoteSubplan below the join
+		 * (pathtype T_RemoteSubplan) means the reference redistributes first — decline */
+		if (op->pathtype != T_SeqScan || ip->pathtype != T_SeqScan)
 			return false;
 		ri = (RestrictInfo *) linitial(hp->path_hashclauses);
 		clause = (OpExpr *) ri->clause;
@@ -837,11 +1134,17 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 		out->has_join = true;
 		out->outer.rti = op->parent->relid;
 		out->inner.rti = ip->parent->relid;
+		if (relation_is_protected(root, out->outer.rti) || relation_is_protected(root, out->inner.rti))
+			return false;
 		plan->outer_key_col = rel_column(&out->outer, lv->varno, lv->varattno, lv->vartype, lv->vartypmod);
 		out->inner_key_col = rel_column(&out->inner, rv->varno, rv->varattno, rv->vartype, rv->vartypmod);
 		out->inner_unique = hp->jpath.inner_unique;
 		if (plan->outer_key_col < 0 || out->inner_key_col < 0)
 			return false;
+		if (!match_quals(op->parent->baserestrictinfo, &out->outer, plan->preds, &plan->n_preds) ||
+			!match_quals(ip->parent->baserestrictinfo, &out->inner, out->inner_preds, &out->n_inner_preds))
+			return false;
+		*est_bytes = op->parent->tuples;
 	}
 	else
 		return false;
@@ -878,7 +1181,8 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 		plan->n_group_cols++;
 	}
 
-	/* aggregates of the target list, in order (they follow the group columns in the scan tuple) */
+	/* every target-list entry is either one of the GROUP BY expressions or a bare Aggref; the
+	 * Aggrefs, in target-list order, are the descriptor's aggregates and the tail of the scan tuple */
 	foreach(lc, parse->targetList)
 	{
 		TargetEntry *tle = (TargetEntry *) lfirst(lc);
@@ -886,7 +1190,17 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 		gx_agg	   *g;
 
 		if (IsA(a, Var))
-			continue;			/* a group column */
+		{
+			ListCell   *gc;
+			bool		is_group = false;
+
+			foreach(gc, parse->groupClause)
+				if (equal(get_sortgroupclause_tle((SortGroupClause *) lfirst(gc), parse->targetList)->expr, a))
+					is_group = true;
+			if (!is_group)
+				return false;	/* functionally dependent column: not carried */
+			continue;
+		}
 		if (!IsA(a, Aggref) || a->aggdistinct || a->aggorder || a->aggfilter || a->aggdirectargs || plan->n_aggs >= GX_MAX_AGGS)
 			return false;
 		g = &plan->aggs[plan->n_aggs];
@@ -928,6 +1242,7 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 			if ((g->fn == GX_AGG_SUM_I4 || g->fn == GX_AGG_COUNT) && g->arg.nops != 1)
 				return false;
 		}
+		*agg_refs = lappend(*agg_refs, a);
 		plan->n_aggs++;
 	}
 	if (plan->n_aggs == 0 && plan->n_group_cols == 0)
@@ -935,6 +1250,23 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 	*est_rows = in->rows;
 	*est_groups = output_rel->rows > 0 ? output_rel->rows : 1;
 	plan->est_groups = (int64) *est_groups;
+	/* HBM the plan needs: the referenced columns of every row, plus 16 B x 2 per build row */
+	{
+		double		bytes = 0;
+		double		outer_rows = *est_bytes;
+
+		for (i = 0; i < out->outer.ncols; i++)
+			bytes += outer_rows * (out->outer.types[i] == GX_INT8 || out->outer.types[i] == GX_FLOAT8 ? 8 : out->outer.types[i] == GX_CHAR ? 1 : 4);
+		if (out->has_join)
+		{
+			double		inner_rows = ((HashPath *) in)->jpath.innerjoinpath->parent->tuples;
+
+			for (i = 0; i < out->inner.ncols; i++)
+				bytes += inner_rows * (out->inner.types[i] == GX_INT8 || out->inner.types[i] == GX_FLOAT8 ? 8 : out->inner.types[i] == GX_CHAR ? 1 : 4);
+			bytes += inner_rows * 32;
+		}
+		*est_bytes = bytes * 1.25;
+	}
 	return true;
 }
 
@@ -942,23 +1274,59 @@ static void
 gpuexec_upper_paths_hook(PlannerInfo *root, UpperRelationKind stage, RelOptInfo *input_rel, RelOptInfo *output_rel)
 {
 	GpuExecState desc;
+	Query	   *parse = root->parse;
+	List	   *agg_refs = NIL;
+	List	   *scan_exprs = NIL;
 	double		rows,
-				groups;
+				groups,
+				bytes = 0;
+	ListCell   *lc;
 
 	if (prev_upper_paths_hook)
 		prev_upper_paths_hook(root, stage, input_rel, output_rel);
 	if (!gpuexec_enabled || stage != UPPERREL_GROUP_AGG)
 		return;
 	memset(&desc, 0, sizeof(desc));
-	if (!gpuexec_match_plan(root, input_rel, output_rel, &desc, &rows, &groups))
+	if (!gpuexec_match_plan(root, input_rel, output_rel, &desc, &agg_refs, &rows, &groups, &bytes))
 		return;					/* decline: the CPU paths stay as they are */
+	/* capacity (the analogue of ExecChooseHashTableSize deciding on batches, nodeHash.c:864): there is
+	 * no spill path on the device, so a plan that would not fit is left to the CPU executor */
+	if (bytes > (double) gpuexec_hbm_limit_mb * 1024.0 * 1024.0)
+		return;
 	{
 		CustomPath *cpath = makeNode(CustomPath);
 		Path	   *cheapest_in = input_rel->cheapest_total_path;
+		bool		pushdown = grouping_covers_distribution(parse, cheapest_in->distribution);
+		PathTarget *scan_target;
+
+		desc.partial = !pushdown;
+		/* the scan tuple: GROUP BY expressions, then the aggregates (partial Aggrefs in two-phase mode) */
+		scan_target = create_empty_pathtarget();
+		foreach(lc, parse->groupClause)
+		{
+			SortGroupClause *sgc = (SortGroupClause *) lfirst(lc);
+			TargetEntry *tle = get_sortgroupclause_tle(sgc, parse->targetList);
+
+			scan_exprs = lappend(scan_exprs, tle->expr);
+			add_column_to_pathtarget(scan_target, tle->expr, sgc->tleSortGroupRef);
+		}
+		foreach(lc, agg_refs)
+		{
+			Aggref	   *a = (Aggref *) lfirst(lc);
+
+			if (desc.partial)
+			{
+				a = (Aggref *) copyObject(a);
+				mark_partial_aggref(a, AGGSPLIT_INITIAL_SERIAL);
+			}
+			scan_exprs = lappend(scan_exprs, a);
+			if (desc.partial)
+				add_column_to_pathtarget(scan_target, (Expr *) a, 0);
+		}
 
 		cpath->path.pathtype = T_CustomScan;
 		cpath->path.parent = output_rel;
-		cpath->path.pathtarget = output_rel->reltarget;
+		cpath->path.pathtarget = desc.partial ? scan_target : output_rel->reltarget;
 		cpath->path.param_info = NULL;
 		cpath->path.parallel_aware = false;
 		cpath->path.parallel_safe = false;	/* the GPU replaces intra-node parallelism */
@@ -966,15 +1334,34 @@ gpuexec_upper_paths_hook(PlannerInfo *root, UpperRelationKind stage, RelOptInfo 
 		/* staging dominates: charge the sequential page reads, nothing per tuple */
 		cpath->path.startup_cost = cheapest_in->total_cost * 0.25;
 		cpath->path.total_cost = cpath->path.startup_cost + groups * 0.01;
-		/* the aggregate runs where the data lives: keep the input's distribution, the XL
-		 * planner then adds the RemoteSubplan above us exactly as for a CPU HashAggregate
-		 * (optimizer/util/pathnode.c:4575) */
+		/* the aggregate runs where the data lives */
 		cpath->path.distribution = cheapest_in->distribution;
 		cpath->flags = 0;
 		cpath->custom_paths = NIL;
-		cpath->custom_private = gpuexec_serialise(&desc);
+		cpath->custom_private = list_make2(gpuexec_serialise(&desc), scan_exprs);
 		cpath->methods = &gpuexec_path_methods;
-		add_path(output_rel, &cpath->path);
+		if (pushdown)
+			add_path(output_rel, &cpath->path);
+		else
+		{
+			/* Partial GpuExecHashAgg -> Distribute results by the group key -> Finalize HashAggregate:
+			 * the shape of planner.c:9045-9075 with our node in place of the partial AggPath
+			 * (xc_groupby.out:193-205).  Aggregates whose transition state cannot travel decline. */
+			AggClauseCosts final_costs;
+			Path	   *remote;
+
+			MemSet(&final_costs, 0, sizeof(final_costs));
+			get_agg_clause_costs(root, (Node *) output_rel->reltarget->exprs, AGGSPLIT_FINAL_DESERIAL, &final_costs);
+			if (final_costs.hasNonPartial || final_costs.hasNonSerial)
+				return;
+			remote = create_redistribute_grouping_path(root, parse, &cpath->path);
+			if (remote == NULL)
+				return;
+			add_path(output_rel, (Path *)
+					 create_agg_path(root, output_rel, remote, output_rel->reltarget,
+									 parse->groupClause ? AGG_HASHED : AGG_PLAIN, AGGSPLIT_FINAL_DESERIAL,
+									 parse->groupClause, NIL, &final_costs, groups));
+		}
 	}
 }
 
@@ -985,6 +1372,8 @@ _PG_init(void)
 							 &gpuexec_enabled, true, PGC_USERSET, 0, NULL, NULL, NULL);
 	DefineCustomIntVariable("gpuexec.device", "CUDA device ordinal used by this datanode.", NULL,
 							&gpuexec_device, 0, 0, 63, PGC_BACKEND, 0, NULL, NULL, NULL);
+	DefineCustomIntVariable("gpuexec.hbm_limit_mb", "Decline plans whose staged columns and join table are estimated above this many MB of HBM.", NULL,
+							&gpuexec_hbm_limit_mb, 150 * 1024, 64, 1024 * 1024, PGC_USERSET, 0, NULL, NULL, NULL);
 	RegisterCustomScanMethods(&gpuexec_scan_methods);
 	RegisterResourceReleaseCallback(gpuexec_resowner_callback, NULL);
 	prev_upper_paths_hook = create_upper_paths_hook;
