@@ -574,10 +574,17 @@ __global__ void __launch_bounds__(LPT_K == 8 ? 640 : 1024, 1) gx_k_agg_lptile(co
 // general kernels — the result never depends on the estimate.
 // Plan shape (checked by the host): no join; group key <= 8 bytes without NULLs; aggregates are
 // count(*) or sum/avg over chain expressions of NOT-NULL float8 columns and constants.
+template <int K> __device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K]);
 #define FG_G  4
 #define FG_NV 5
 #define FG_K  4                         /* rows per lane and tile: independent loads in flight */
-struct gx_fewgroups_args { int nv; int _pad; int vagg[FG_NV], vword[FG_NV]; };
+#define FG_NC 4                         /* distinct float8 columns the aggregate arguments may read */
+struct gx_fewgroups_args {
+    int nv, nc;
+    const double *col[FG_NC];           // the distinct argument columns: loaded ONCE per row into registers
+    int vagg[FG_NV], vword[FG_NV];
+    signed char tslot[FG_NV][4];        // column slot of term t of value w (-1: constant)
+};
 
 __device__ __forceinline__ int fg_insert(unsigned long long *s_keys, unsigned int *s_state, unsigned long long key)
 {
@@ -594,6 +601,48 @@ __device__ __forceinline__ int fg_insert(unsigned long long *s_keys, unsigned in
         }
     }
     return -1;
+}
+
+// one term of a chain expression over a register tile
+template <int K>
+__device__ __forceinline__ void reg_term(int kind, double k, const double (&x)[K], double (&out)[K])
+{
+    switch (kind) {
+        case GXT_COL:
+#pragma unroll
+            for (int j = 0; j < K; j++) out[j] = x[j];
+            break;
+        case GXT_K_SUB_COL:
+#pragma unroll
+            for (int j = 0; j < K; j++) out[j] = __dsub_rn(k, x[j]);
+            break;
+        case GXT_K_ADD_COL:
+#pragma unroll
+            for (int j = 0; j < K; j++) out[j] = __dadd_rn(k, x[j]);
+            break;
+        case GXT_K_MUL_COL:
+#pragma unroll
+            for (int j = 0; j < K; j++) out[j] = __dmul_rn(k, x[j]);
+            break;
+        default:                                               // GXT_COL_SUB_K
+#pragma unroll
+            for (int j = 0; j < K; j++) out[j] = __dsub_rn(x[j], k);
+            break;
+    }
+}
+template <int K, int NC>
+__device__ __forceinline__ void slot_term(const gx_dterm &t, int slot, const double (&x)[NC][K], double (&out)[K])
+{
+    if (slot < 0) {
+#pragma unroll
+        for (int j = 0; j < K; j++) out[j] = t.k;
+        return;
+    }
+    // warp-uniform: picks the register tile of the column
+    if (slot == 0 || NC == 1) reg_term<K>(t.kind, t.k, x[0], out);
+    else if (slot == 1 || NC == 2) reg_term<K>(t.kind, t.k, x[NC > 1 ? 1 : 0], out);
+    else if (slot == 2 || NC == 3) reg_term<K>(t.kind, t.k, x[NC > 2 ? 2 : 0], out);
+    else reg_term<K>(t.kind, t.k, x[NC > 3 ? 3 : 0], out);
 }
 
 __global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_fewgroups_args F)
@@ -623,10 +672,15 @@ __global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__
         long long r[FG_K]; bool ok[FG_K]; int gi[FG_K];
 #pragma unroll
         for (int j = 0; j < FG_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < A.row1; }
-        for (int p = 0; p < P.npreds; p++) {
+        // ---- every column the tile needs is requested before anything is used: argument columns first (no use
+        // until the arithmetic below), then the qual columns, then the group columns
+        double x[FG_NC][FG_K];
 #pragma unroll
-            for (int j = 0; j < FG_K; j++) if (ok[j]) ok[j] = gx_eval_pred(P.preds[p], r[j]);
+        for (int c = 0; c < FG_NC; c++) {
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) x[c][j] = (c < F.nc && ok[j]) ? __ldg(F.col[c] + r[j]) : 0.0;
         }
+        for (int p = 0; p < P.npreds; p++) pred_tile<FG_K>(P.preds[p], r, ok);
         // group of every row: compare with the keys this CTA knows
         unsigned long long key[FG_K];
         bool miss = false;
@@ -657,20 +711,20 @@ __global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__
             if (w >= nv) break;
             const gx_dexpr &e = P.aggs[F.vagg[w]].expr;
             double v[FG_K];
-            lpt_term<FG_K>(e.t[0], r, ok, v);
+            slot_term<FG_K, FG_NC>(e.t[0], F.tslot[w][0], x, v);
             for (int i = 1; i < e.nterms; i++) {
-                double x[FG_K];
-                lpt_term<FG_K>(e.t[i], r, ok, x);
+                double y[FG_K];
+                slot_term<FG_K, FG_NC>(e.t[i], F.tslot[w][i], x, y);
                 const int op = e.t[i].op;
                 if (op == GX_OP_ADD) {
 #pragma unroll
-                    for (int j = 0; j < FG_K; j++) v[j] = __dadd_rn(v[j], x[j]);
+                    for (int j = 0; j < FG_K; j++) v[j] = __dadd_rn(v[j], y[j]);
                 } else if (op == GX_OP_SUB) {
 #pragma unroll
-                    for (int j = 0; j < FG_K; j++) v[j] = __dsub_rn(v[j], x[j]);
+                    for (int j = 0; j < FG_K; j++) v[j] = __dsub_rn(v[j], y[j]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < FG_K; j++) v[j] = __dmul_rn(v[j], x[j]);
+                    for (int j = 0; j < FG_K; j++) v[j] = __dmul_rn(v[j], y[j]);
                 }
             }
 #pragma unroll
@@ -690,10 +744,10 @@ __global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__
 #pragma unroll
         for (int w = 0; w < FG_NV; w++) {
             if (w >= nv) break;
-            double x = acc[gI][w];
+            double xx = acc[gI][w];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_down_sync(0xffffffffu, x, o));
-            if (lane == 0) atomicAdd((double *) &s_acc[gI][1 + w], x);
+            for (int o = 16; o > 0; o >>= 1) xx = __dadd_rn(xx, __shfl_down_sync(0xffffffffu, xx, o));
+            if (lane == 0) atomicAdd((double *) &s_acc[gI][1 + w], xx);
         }
     }
     __syncthreads();
@@ -1142,8 +1196,10 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
 #define RA_LIST 136
 #define RA_BND  0x80000000u
 struct gx_runagg_args {
-    int nv, need_cnt, nthreads_unused, _pad;
+    int nv, nc, _pad0, _pad1;
     int vagg[RA_NV], vword[RA_NV];
+    const double *col[FG_NC];           // distinct argument columns, loaded once per row (as in gx_k_fewgroups)
+    signed char tslot[RA_NV][4];
     unsigned long long *out; long long out_cap; long long *cursor;   // dense final records + cursor
     long long rows_per_warp;
     // group-key packing: the join key and/or payload bit fields
@@ -1188,8 +1244,8 @@ __device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r
 }
 
 #define RA_K 4                           /* slabs (of 32 rows) per tile: their loads are issued together */
-template <int NV>
-__global__ void __launch_bounds__(512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_runagg_args R)
+template <int NV, int NC>
+__global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_runagg_args R)
 {
     extern __shared__ unsigned long long smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1275,6 +1331,14 @@ __global__ void __launch_bounds__(512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid
         for (int j = 0; j < RA_K; j++) { r[j] = tb + j * 32 + lane; ok[j] = r[j] < c1; }
 #pragma unroll
         for (int j = 0; j < RA_K; j++) kk[j] = ok[j] ? __ldg(okey + r[j]) : 0;
+        // argument columns next, unconditionally for the rows of the tile (a row that fails the quals shares its
+        // sectors with rows that pass): nothing below waits for the quals before its loads are in flight
+        double x[NC][RA_K];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int j = 0; j < RA_K; j++) x[c][j] = (c < R.nc && ok[j]) ? __ldg(R.col[c] + r[j]) : 0.0;
+        }
         for (int p = 0; p < P.npreds; p++) pred_tile<RA_K>(P.preds[p], r, ok);
 #pragma unroll
         for (int q = 0; q < NV; q++) {
@@ -1282,13 +1346,13 @@ __global__ void __launch_bounds__(512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid
             for (int j = 0; j < RA_K; j++) vv[q][j] = 0.0;
             if (q < nv) {
                 const gx_dexpr &e = P.aggs[R.vagg[q]].expr;
-                lpt_term<RA_K>(e.t[0], r, ok, vv[q]);
+                slot_term<RA_K, NC>(e.t[0], R.tslot[q][0], x, vv[q]);
                 for (int i = 1; i < e.nterms; i++) {
-                    double x[RA_K];
-                    lpt_term<RA_K>(e.t[i], r, ok, x);
+                    double y[RA_K];
+                    slot_term<RA_K, NC>(e.t[i], R.tslot[q][i], x, y);
                     const int op = e.t[i].op;
 #pragma unroll
-                    for (int j = 0; j < RA_K; j++) vv[q][j] = op == GX_OP_ADD ? __dadd_rn(vv[q][j], x[j]) : (op == GX_OP_SUB ? __dsub_rn(vv[q][j], x[j]) : __dmul_rn(vv[q][j], x[j]));
+                    for (int j = 0; j < RA_K; j++) vv[q][j] = op == GX_OP_ADD ? __dadd_rn(vv[q][j], y[j]) : (op == GX_OP_SUB ? __dsub_rn(vv[q][j], y[j]) : __dmul_rn(vv[q][j], y[j]));
                 }
 #pragma unroll
                 for (int j = 0; j < RA_K; j++) vv[q][j] = ok[j] ? vv[q][j] : 0.0;
@@ -1951,6 +2015,16 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
     for (int a = 0; a < A.P.nagg && fewgroups_ok; a++) {
         if (A.P.aggs[a].kind == GXU_NONE) continue;
         if (FG.nv >= FG_NV) { fewgroups_ok = false; break; }
+        const gx_dexpr &e = A.P.aggs[a].expr;
+        for (int t = 0; t < e.nterms && fewgroups_ok; t++) {
+            int slot = -1;
+            if (e.t[t].kind != GXT_CONST) {
+                const double *cp = (const double *) e.t[t].col.data;
+                for (int c = 0; c < FG.nc; c++) if (FG.col[c] == cp) slot = c;
+                if (slot < 0) { if (FG.nc < FG_NC) { slot = FG.nc; FG.col[FG.nc++] = cp; } else fewgroups_ok = false; }
+            }
+            FG.tslot[FG.nv][t] = (signed char) slot;
+        }
         FG.vagg[FG.nv] = a; FG.vword[FG.nv] = A.P.aggs[a].word; FG.nv++;
     }
     { const char *e = getenv("GX_NO_FEWGROUPS"); if (e && e[0] == '1') fewgroups_ok = false; }
@@ -1979,20 +2053,30 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             ok = ga.kind == GXU_ADD_F64 && !ga.is_int && ga.cnt_word == 0 && RA.nv < RA_NV && ga.expr.nterms >= 1;
             for (int t = 0; t < ga.expr.nterms && ok; t++)
                 ok = ga.expr.t[t].kind == GXT_CONST || (ga.expr.t[t].col.type == GX_FLOAT8 && ga.expr.t[t].col.nulls == nullptr);
+            for (int t = 0; t < ga.expr.nterms && ok; t++) {
+                int slot = -1;
+                if (ga.expr.t[t].kind != GXT_CONST) {
+                    const double *cp = (const double *) ga.expr.t[t].col.data;
+                    for (int c = 0; c < RA.nc; c++) if (RA.col[c] == cp) slot = c;
+                    if (slot < 0) { if (RA.nc < FG_NC) { slot = RA.nc; RA.col[RA.nc++] = cp; } else ok = false; }
+                }
+                RA.tslot[RA.nv][t] = (signed char) slot;
+            }
             if (ok) { RA.vagg[RA.nv] = a; RA.vword[RA.nv] = ga.word; RA.nv++; }
         }
         if (ok) {
             rc = need_wide(); if (rc) return rc;
             static bool attr = false;
-            const int threads = 512, nwarps = threads / 32;
+            const bool small = RA.nv <= 2 && RA.nc <= 2;           // two CTAs of 384 threads per SM (85 registers each)
+            const int threads = small ? 384 : 512, nwarps = threads / 32;
             const size_t smem = (size_t) nwarps * ((size_t) RA_LIST * (1 + RA.nv) + RA_LIST / 2) * 8;
             if (!attr) {
-                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
-                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
-                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<RA_NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<RA_NV, FG_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
                 attr = true;
             }
-            const long long nrows = outer->nrows, total_warps = (long long) ctx->sm_count * (RA.nv <= 2 ? 2 : 1) * nwarps;
+            const long long nrows = outer->nrows, total_warps = (long long) ctx->sm_count * (small ? 2 : 1) * nwarps;
             long long rpw = (nrows + total_warps - 1) / total_warps; rpw = (rpw + 31) / 32 * 32; if (rpw < 128) rpw = 128;
             const long long nchunks = (nrows + rpw - 1) / rpw;
             const unsigned grid = (unsigned) ((nchunks + nwarps - 1) / nwarps);
@@ -2009,9 +2093,9 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             RA.out = d_out; RA.out_cap = out_cap; RA.cursor = ctx->d_scratch + 12;
             {
                 gx_launch_scope ls(ctx, "runagg");
-                if (RA.nv <= 1) gx_k_runagg<1><<<grid, threads, smem, ctx->stream>>>(A, RA);
-                else if (RA.nv == 2) gx_k_runagg<2><<<grid, threads, smem, ctx->stream>>>(A, RA);
-                else gx_k_runagg<RA_NV><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                if (small && RA.nv <= 1) gx_k_runagg<1, 2><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                else if (small) gx_k_runagg<2, 2><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                else gx_k_runagg<RA_NV, FG_NC><<<grid, threads, smem, ctx->stream>>>(A, RA);
             }
             GX_CUDA(ctx, cudaGetLastError());
             long long c[4], direct = 0;

@@ -237,6 +237,115 @@ static int partition_impl(gx_ctx *ctx, const gx_table *in, int key_col, gx_table
     return GX_OK;
 }
 
+// ---- one pass: route + scatter into fixed-capacity per-destination regions ----------------
+// The two-pass form above reads the key column twice and the rows once more (histogram, scan,
+// scatter).  For the redistribute itself the destinations only have to be contiguous PER
+// DESTINATION, not densely packed: region d starts at d * cap rows, so a tile can claim its
+// ranges with one global atomic per destination as soon as it has its own counts.  A CTA takes
+// tiles of 2048 rows: destination and tile-local position of every row (warp-aggregated shared
+// atomics), one claim per destination, then the copy.  cap = rows / N * 1.25 (SHARD placement of
+// the default map is balanced to a percent); a region that would overflow raises a flag and the
+// caller falls back to the exact two-pass form.
+#define RP_THREADS 256
+#define RP_K 8
+struct gx_route1_args {
+    gx_dcol key; long long nrows; const int32_t *shardmap; int nnodes, ncols;
+    gx_dcol in[GX_MAX_COLS]; void *out[GX_MAX_COLS]; uint8_t *out_nulls[GX_MAX_COLS];
+    long long cap; unsigned long long *cursor;   // [nnodes] rows claimed per destination; [GX_MAX_NODES] overflow flag
+};
+__global__ void __launch_bounds__(RP_THREADS) gx_k_route_onepass(gx_route1_args a)
+{
+    __shared__ unsigned int cur[GX_MAX_NODES];
+    __shared__ long long tbase[GX_MAX_NODES];
+    const int lane = threadIdx.x & 31;
+    const long long tile_rows = (long long) RP_THREADS * RP_K;
+    for (long long base = (long long) blockIdx.x * tile_rows; base < a.nrows; base += (long long) gridDim.x * tile_rows) {
+        if (threadIdx.x < GX_MAX_NODES) cur[threadIdx.x] = 0;
+        __syncthreads();
+        int d[RP_K]; unsigned int lp[RP_K];
+#pragma unroll
+        for (int k = 0; k < RP_K; k++) {
+            const long long r = base + k * RP_THREADS + threadIdx.x;
+            d[k] = -1; lp[k] = 0;
+            if (r < a.nrows) {
+                const bool isnull = gx_is_null(a.key, r);
+                const long long datum = isnull ? 0 : gx_load_int(a.key, r);
+                d[k] = a.shardmap[gx_shard_index(gx_route_hash(a.key.type, datum, isnull))];
+                const unsigned int m = __match_any_sync(__activemask(), d[k]);
+                const int leader = __ffs(m) - 1;
+                unsigned int off = 0;
+                if (lane == leader) off = atomicAdd(&cur[d[k]], (unsigned int) __popc(m));
+                lp[k] = __shfl_sync(m, off, leader) + __popc(m & ((1u << lane) - 1));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < a.nnodes) {
+            const unsigned int n = cur[threadIdx.x];
+            long long b = n ? (long long) atomicAdd(&a.cursor[threadIdx.x], (unsigned long long) n) : 0;
+            if (b + n > a.cap) { atomicExch(&a.cursor[GX_MAX_NODES], 1ULL); b = -1; }
+            tbase[threadIdx.x] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RP_K; k++) {
+            if (d[k] < 0 || tbase[d[k]] < 0) continue;
+            const long long r = base + k * RP_THREADS + threadIdx.x;
+            const long long dst = (long long) d[k] * a.cap + tbase[d[k]] + lp[k];
+            for (int c = 0; c < a.ncols; c++) {
+                switch (a.in[c].type) {
+                    case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = __ldg((const int *) a.in[c].data + r); break;
+                    case GX_CHAR: ((signed char *) a.out[c])[dst] = __ldg((const signed char *) a.in[c].data + r); break;
+                    default: ((long long *) a.out[c])[dst] = __ldg((const long long *) a.in[c].data + r); break;
+                }
+                if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// regions of `cap` rows per destination; returns GX_OK with *overflowed = 1 when a region was too small
+static int partition_regions(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out, int64_t *host_counts, long long *cap_out, int *overflowed)
+{
+    GX_CHECK_ARG(ctx, key_col >= 0 && key_col < in->ncols, "route: key column %d out of range", key_col);
+    const int kt = in->types[key_col], N = ctx->nnodes;
+    GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "route: distribution column type %d not supported (int4/int8/date)", kt);
+    const long long cap = N == 1 ? (in->nrows > 0 ? in->nrows : 1) : in->nrows / N + in->nrows / (4 * N) + 4096;
+    bool hn[GX_MAX_COLS];
+    for (int c = 0; c < in->ncols; c++) hn[c] = in->nulls[c] != nullptr;
+    gx_table *t;
+    int rc = gx_table_alloc_like(ctx, in->ncols, in->types, hn, cap * N, &t); if (rc) return rc;
+    gx_route1_args a; memset(&a, 0, sizeof(a));
+    a.key.data = in->cols[key_col]; a.key.nulls = in->nulls[key_col]; a.key.type = kt;
+    a.nrows = in->nrows; a.shardmap = ctx->d_shardmap; a.nnodes = N; a.ncols = in->ncols; a.cap = cap;
+    for (int c = 0; c < in->ncols; c++) {
+        a.in[c].data = in->cols[c]; a.in[c].nulls = in->nulls[c]; a.in[c].type = in->types[c];
+        a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c];
+    }
+    unsigned long long *d_cur;
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_cur, (GX_MAX_NODES + 1) * 8));
+    GX_CUDA(ctx, cudaMemsetAsync(d_cur, 0, (GX_MAX_NODES + 1) * 8, ctx->stream));
+    a.cursor = d_cur;
+    if (in->nrows > 0) {
+        const long long tiles = (in->nrows + RP_THREADS * RP_K - 1) / (RP_THREADS * RP_K), maxb = (long long) ctx->sm_count * 8;
+        gx_launch_scope ls(ctx, "partition");
+        gx_k_route_onepass<<<(unsigned) (tiles < maxb ? tiles : maxb), RP_THREADS, 0, ctx->stream>>>(a);
+    }
+    unsigned long long h_cur[GX_MAX_NODES + 1];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cur, d_cur, sizeof(h_cur), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    gx_tmp_free(ctx, d_cur);
+    if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "partition: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    *overflowed = h_cur[GX_MAX_NODES] != 0;
+    if (*overflowed) { gx_table_free(t); *out = nullptr; return GX_OK; }
+    for (int n = 0; n < N; n++) host_counts[n] = (int64_t) h_cur[n];
+    t->nrows = N == 1 ? in->nrows : cap * N;
+    *cap_out = cap;
+    *out = t;
+    return GX_OK;
+}
+
 extern "C" int gx_partition_by_node(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out, int64_t *host_counts)
 {
     if (!ctx || !in || !out || !host_counts) return GX_ERR_ARG;
@@ -276,8 +385,12 @@ extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_
     const int N = ctx->nranks;
     GX_CHECK_ARG(ctx, ctx->nnodes == N, "redistribute: shard map covers %d nodes but the communicator has %d ranks", ctx->nnodes, N);
     int64_t counts[GX_MAX_NODES + 1];
-    gx_table *part;
-    int rc = partition_impl(ctx, in, key_col, &part, counts); if (rc) return rc;
+    gx_table *part = nullptr;
+    long long cap = 0; int overflowed = 0;
+    const char *two = getenv("GX_PARTITION_TWO_PASS");
+    int rc = GX_OK;
+    if (!(two && two[0] == '1') && (N == 1 || ctx->comm)) { rc = partition_regions(ctx, in, key_col, &part, counts, &cap, &overflowed); if (rc) return rc; }
+    if (!part) { rc = partition_impl(ctx, in, key_col, &part, counts); if (rc) return rc; cap = 0; }
     if (N == 1 || !ctx->comm) { *out = part; return GX_OK; }
     // counts first (+ which columns carry NULL arrays, so every rank agrees)
     int64_t nullbits = 0;
@@ -288,7 +401,7 @@ extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_
     if (rc) { free(all); gx_table_free(part); return rc; }
     int64_t sendoff[GX_MAX_NODES], recvcnt[GX_MAX_NODES], recvoff[GX_MAX_NODES], total = 0, anynull = 0;
     for (int p = 0; p < N; p++) {
-        sendoff[p] = p ? sendoff[p - 1] + counts[p - 1] : 0;
+        sendoff[p] = cap ? (int64_t) p * cap : (p ? sendoff[p - 1] + counts[p - 1] : 0);   // regions, or densely packed (two-pass)
         recvcnt[p] = all[(size_t) p * (N + 1) + ctx->rank];
         recvoff[p] = total; total += recvcnt[p];
         anynull |= all[(size_t) p * (N + 1) + N];
@@ -310,7 +423,7 @@ extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_
                 // a rank without a NULL array for this column sends zeros
                 uint8_t *src = part->nulls[c];
                 uint8_t *tmp = nullptr;
-                if (!src) { gx_tmp_alloc(ctx, (void **) &tmp, (size_t) (in->nrows > 0 ? in->nrows : 1)); cudaMemsetAsync(tmp, 0, (size_t) in->nrows, ctx->stream); src = tmp; }
+                if (!src) { gx_tmp_alloc(ctx, (void **) &tmp, (size_t) (part->nrows > 0 ? part->nrows : 1)); cudaMemsetAsync(tmp, 0, (size_t) part->nrows, ctx->stream); src = tmp; }
                 rc = alltoallv_bytes(ctx, (const char *) src, sendoff, counts, (char *) t->nulls[c], recvoff, recvcnt);
                 if (tmp) { cudaStreamSynchronize(ctx->stream); gx_tmp_free(ctx, tmp); }
             }

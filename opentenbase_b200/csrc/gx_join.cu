@@ -1178,6 +1178,69 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe(gx_probe_args a)
     }
 }
 
+// Unique build side (inner_unique, nodeHashjoin.c:859-861): at most one match per outer row.  A warp takes
+// tiles of 4 x 32 rows: the four key loads and then the four home-pair loads (one 32-byte sector each) are in
+// flight together, matches are numbered with ballots and the warp claims its output range with ONE atomic per
+// tile; the surviving rows are copied column by column.
+#define PT_K 4
+__device__ __forceinline__ void ld_pair(const gx_slot *p, long long &k0, unsigned long long &p0, long long &k1, unsigned long long &p1)
+{
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(p0), "=l"(k1), "=l"(p1) : "l"(p));
+}
+__global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = (1u << lane) - 1;
+    const long long nwarp = ((long long) gridDim.x * blockDim.x) >> 5, wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long tile = 32LL * PT_K;
+    for (long long base = wid * tile; base < a.nrows; base += nwarp * tile) {
+        long long r[PT_K], key[PT_K]; bool ok[PT_K], hit[PT_K]; unsigned long long pay[PT_K], s[PT_K];
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < a.nrows && !gx_is_null(a.key, r[j]); }
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) key[j] = ok[j] ? gx_load_int(a.key, r[j]) : 0;
+        for (int p = 0; p < a.npreds; p++) {
+#pragma unroll
+            for (int j = 0; j < PT_K; j++) if (ok[j]) ok[j] = gx_eval_pred(a.preds[p], r[j]);
+        }
+        long long k0[PT_K], k1[PT_K]; unsigned long long p0[PT_K], p1[PT_K];
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) {
+            s[j] = gx_slot_index(key[j], a.sf);
+            k0[j] = k1[j] = GX_EMPTY_KEY; p0[j] = p1[j] = 0;
+            if (ok[j] && key[j] != GX_EMPTY_KEY) ld_pair(a.slots + s[j], k0[j], p0[j], k1[j], p1[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) {
+            hit[j] = false; pay[j] = 0;
+            if (!ok[j]) continue;
+            if (key[j] == GX_EMPTY_KEY) { hit[j] = a.special_count > 0; if (hit[j]) pay[j] = a.special[0]; continue; }
+            for (;;) {
+                if (k0[j] == key[j]) { hit[j] = true; pay[j] = p0[j]; break; }
+                if (k0[j] == GX_EMPTY_KEY) break;
+                if (k1[j] == key[j]) { hit[j] = true; pay[j] = p1[j]; break; }
+                if (k1[j] == GX_EMPTY_KEY) break;
+                s[j] = gx_next_pair(s[j], a.mask);
+                ld_pair(a.slots + s[j], k0[j], p0[j], k1[j], p1[j]);
+            }
+        }
+        __syncwarp();
+        unsigned int m[PT_K]; int total = 0;
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) { m[j] = __ballot_sync(0xffffffffu, hit[j]); total += __popc(m[j]); }
+        if (total == 0) continue;
+        long long dst0 = 0;
+        if (lane == 0) dst0 = (long long) atomicAdd((unsigned long long *) a.cursor, (unsigned long long) total);
+        dst0 = __shfl_sync(0xffffffffu, dst0, 0);
+        if (a.count_only) continue;
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) {
+            if (hit[j]) { const long long dst = dst0 + __popc(m[j] & lt); if (dst < a.out_cap) emit_row(a, dst, r[j], pay[j]); }
+            dst0 += __popc(m[j]);
+        }
+    }
+}
+
 extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, int n_preds, const gx_pred *preds,
                              const gx_hash *h, int n_out_outer, const int32_t *out_outer_cols, gx_table **out)
 {
@@ -1222,7 +1285,13 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
     for (int c = 0; c < t->ncols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
     a.count_only = 0; a.out_cap = out_cap;
     GX_CUDA(ctx, cudaMemsetAsync(a.cursor, 0, sizeof(long long), ctx->stream));
-    { gx_launch_scope ls(ctx, "probe"); gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a); }
+    {
+        gx_launch_scope ls(ctx, "probe");
+        if (h->unique) {
+            long long nt = (outer->nrows + 32 * PT_K * 8 - 1) / (32 * PT_K * 8);
+            gx_k_hash_probe_unique<<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
+        } else gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a);
+    }
     cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, a.cursor, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "hash_probe: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }

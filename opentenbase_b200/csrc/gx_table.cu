@@ -291,7 +291,21 @@ struct gx_filter_args {
     long long nrows;
 };
 
-#define FILTER_ROWS_PER_THREAD 4
+// ---- one pass, order preserving: quals -> compaction -> projection ------------------------
+// A CTA takes tiles of FT_ROWS rows in ticket order.  Per tile: evaluate the quals (8 rows per
+// thread, coalesced), rank the survivors (warp ballots + a 64-entry scan of the per-warp
+// counts), publish the tile's count, obtain the tile's output offset by decoupled look-back
+// over the tile-status array (a tile never waits for a tile that has not started: tickets are
+// handed out in order), then copy the surviving rows of every projected column.  One kernel, no
+// count pass, no host round trip between counting and writing; the row order of the input is
+// kept (a key-ordered table stays key-ordered, which the join build and the run kernels use).
+#define FT_THREADS 256
+#define FT_K       8
+#define FT_ROWS    (FT_THREADS * FT_K)
+#define FT_AGG     (1ULL << 62)        /* tile's own count is available */
+#define FT_INC     (2ULL << 62)        /* inclusive prefix is available */
+#define FT_VAL     ((1ULL << 62) - 1)
+
 __device__ __forceinline__ bool filter_pass(const gx_filter_args &a, long long r)
 {
     bool ok = true;
@@ -299,37 +313,82 @@ __device__ __forceinline__ bool filter_pass(const gx_filter_args &a, long long r
     for (int p = 0; p < GX_MAX_PREDS; p++) if (p < a.npreds) ok = ok && gx_eval_pred(a.preds[p], r);
     return ok;
 }
-__global__ void gx_k_filter_count(gx_filter_args a, long long *blocksums)
+
+__global__ void __launch_bounds__(FT_THREADS) gx_k_filter_onepass(gx_filter_args a, unsigned long long *tile_state, unsigned int *ticket, long long ntiles, long long *total_out)
 {
-    __shared__ long long sm[33];
-    long long base = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * FILTER_ROWS_PER_THREAD;
-    long long n = 0, tot;
+    __shared__ unsigned int wc[FT_K][FT_THREADS / 32];
+    __shared__ unsigned int woff[FT_K][FT_THREADS / 32];
+    __shared__ long long s_tile, s_prefix;
+    __shared__ unsigned int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = (long long) atomicAdd(ticket, 1u);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= ntiles) return;
+        const long long base = tile * FT_ROWS;
+        bool keep[FT_K]; unsigned int rank[FT_K];
 #pragma unroll
-    for (int k = 0; k < FILTER_ROWS_PER_THREAD; k++) { long long r = base + k; if (r < a.nrows && filter_pass(a, r)) n++; }
-    gx_block_exscan(n, &tot, sm);
-    if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
-}
-__global__ void gx_k_filter_write(gx_filter_args a, const long long *blockoffs)
-{
-    __shared__ long long sm[33];
-    long long base = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * FILTER_ROWS_PER_THREAD;
-    bool keep[FILTER_ROWS_PER_THREAD]; long long n = 0, tot;
-#pragma unroll
-    for (int k = 0; k < FILTER_ROWS_PER_THREAD; k++) { long long r = base + k; keep[k] = r < a.nrows && filter_pass(a, r); n += keep[k]; }
-    long long dst = blockoffs[blockIdx.x] + gx_block_exscan(n, &tot, sm);
-#pragma unroll
-    for (int k = 0; k < FILTER_ROWS_PER_THREAD; k++) {
-        if (!keep[k]) continue;
-        long long r = base + k;
-        for (int c = 0; c < a.ncols; c++) {
-            switch (a.in[c].type) {
-                case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = ((const int *) a.in[c].data)[r]; break;
-                case GX_CHAR: ((signed char *) a.out[c])[dst] = ((const signed char *) a.in[c].data)[r]; break;
-                default: ((long long *) a.out[c])[dst] = ((const long long *) a.in[c].data)[r]; break;
-            }
-            if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
+        for (int k = 0; k < FT_K; k++) {
+            const long long r = base + k * FT_THREADS + threadIdx.x;
+            keep[k] = r < a.nrows && filter_pass(a, r);
+            const unsigned int m = __ballot_sync(0xffffffffu, keep[k]);
+            rank[k] = __popc(m & lt);
+            if (lane == 0) wc[k][warp] = __popc(m);
         }
-        dst++;
+        __syncthreads();
+        if (threadIdx.x < 32) {                                 // exclusive scan of the 64 (k, warp) counts, k-major
+            const int i0 = 2 * lane, i1 = 2 * lane + 1;
+            const unsigned int c0 = ((unsigned int *) wc)[i0], c1 = ((unsigned int *) wc)[i1];
+            unsigned int x = c0 + c1, inc = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+            ((unsigned int *) woff)[i0] = inc - x; ((unsigned int *) woff)[i1] = inc - x + c0;
+            const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
+            // ---- publish, then look back (warp-parallel: 32 predecessors per round)
+            long long prefix = 0;
+            if (lane == 0) {
+                s_total = total;
+                __threadfence();
+                atomicExch(&tile_state[tile], (tile == 0 ? FT_INC : FT_AGG) | (unsigned long long) total);
+            }
+            if (tile > 0) {
+                long long look = tile - 1;
+                for (;;) {
+                    const long long t = look - lane;
+                    unsigned long long st = FT_INC;                       // tiles before 0: inclusive prefix 0
+                    if (t >= 0) { do { st = *(volatile unsigned long long *) &tile_state[t]; } while ((st >> 62) == 0); }
+                    const unsigned int incm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                    const int first = incm ? __ffs((int) incm) - 1 : 32;  // nearest predecessor holding an inclusive prefix
+                    unsigned long long v = lane <= first ? (st & FT_VAL) : 0ULL;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                    prefix += (long long) __shfl_sync(0xffffffffu, v, 0);
+                    if (incm) break;
+                    look -= 32;
+                }
+                if (lane == 0) { __threadfence(); atomicExch(&tile_state[tile], FT_INC | (unsigned long long) (prefix + total)); }
+            }
+            if (lane == 0) { s_prefix = prefix; if (tile == ntiles - 1) *total_out = prefix + total; }
+        }
+        __syncthreads();
+        const long long prefix = s_prefix;
+#pragma unroll
+        for (int k = 0; k < FT_K; k++) {
+            if (!keep[k]) continue;
+            const long long r = base + k * FT_THREADS + threadIdx.x;
+            const long long dst = prefix + woff[k][warp] + rank[k];
+            for (int c = 0; c < a.ncols; c++) {
+                switch (a.in[c].type) {
+                    case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = __ldg((const int *) a.in[c].data + r); break;
+                    case GX_CHAR: ((signed char *) a.out[c])[dst] = __ldg((const signed char *) a.in[c].data + r); break;
+                    default: ((long long *) a.out[c])[dst] = __ldg((const long long *) a.in[c].data + r); break;
+                }
+                if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
+            }
+        }
+        __syncthreads();                                        // wc / woff / s_* are reused by the next tile
     }
 }
 
@@ -362,35 +421,29 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
         GX_CHECK_ARG(ctx, out_cols[c] >= 0 && out_cols[c] < in->ncols, "scan_filter: column %d out of range", out_cols[c]);
         a.in[c] = make_dcol(in, out_cols[c]); types[c] = in->types[out_cols[c]]; hn[c] = in->nulls[out_cols[c]] != nullptr;
     }
-    const int BS = 256;
-    long long rows_per_block = (long long) BS * FILTER_ROWS_PER_THREAD;
-    long long nblocks = (in->nrows + rows_per_block - 1) / rows_per_block;
-    long long total = 0;
-    long long *d_sums = nullptr;
-    if (nblocks > 0) {
-        GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_sums, (size_t) nblocks * sizeof(long long)));
-        {
-            gx_launch_scope ls(ctx, "filter", 2);
-            gx_k_filter_count<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
-            gx_k_scan_inplace<<<1, 1024, 0, ctx->stream>>>(d_sums, nblocks, ctx->d_scratch);
-        }
-        cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { gx_tmp_free(ctx, d_sums); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
-        total = ctx->h_scratch[0];
-    }
+    // the output is sized for the worst case (every row survives): stream-ordered pool memory, untouched pages cost nothing
     gx_table *t;
-    rc = gx_table_alloc_like(ctx, n_out_cols, types, hn, total, &t);
-    if (rc) { if (d_sums) gx_tmp_free(ctx, d_sums); return rc; }
-    if (nblocks > 0) {
+    rc = gx_table_alloc_like(ctx, n_out_cols, types, hn, in->nrows > 0 ? in->nrows : 1, &t);
+    if (rc) return rc;
+    long long total = 0;
+    if (in->nrows > 0) {
         for (int c = 0; c < n_out_cols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
-        {
-            gx_launch_scope ls(ctx, "filter", 1);
-            gx_k_filter_write<<<(unsigned) nblocks, BS, 0, ctx->stream>>>(a, d_sums);
+        const long long ntiles = (in->nrows + FT_ROWS - 1) / FT_ROWS;
+        unsigned long long *d_state = nullptr;
+        cudaError_t e = gx_tmp_alloc(ctx, (void **) &d_state, (size_t) (ntiles + 1) * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_state, 0, (size_t) (ntiles + 1) * sizeof(unsigned long long), ctx->stream);
+        if (e == cudaSuccess) {
+            gx_launch_scope ls(ctx, "filter");
+            long long maxb = (long long) ctx->sm_count * 8;
+            gx_k_filter_onepass<<<(unsigned) (ntiles < maxb ? ntiles : maxb), FT_THREADS, 0, ctx->stream>>>(
+                a, d_state, (unsigned int *) (d_state + ntiles), ntiles, ctx->d_scratch);
+            e = cudaGetLastError();
         }
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        gx_tmp_free(ctx, d_sums);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        gx_tmp_free(ctx, d_state);
         if (e != cudaSuccess) { gx_table_free(t); GX_SET_ERR(ctx, "scan_filter: %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+        total = ctx->h_scratch[0];
     }
     t->nrows = total;
     *out = t;
