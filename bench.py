@@ -434,6 +434,34 @@ def run_ours(args):
             extras[name] = {"ms_per_step": ms, "rows_per_s": rows1 / (ms / 1e3), "groups_total": allsum(float(len(out[0]))),
                             "frac_hbm": bpr * rows1 / world / (ms / 1e3) / 1e9 / peak, "phases_ms": ph}
 
+    # ---- the same configs[2] query over UNCLUSTERED copies of both tables (rows permuted): neither the key-ordered
+    # build nor the run-folding probe applies; every probe is a random 32-byte sector of a table far larger than L2
+    if not args.no_extras and not args.no_unclustered:
+        lp = ctx.scan_filter(lt, [], [g.L_ORDERKEY, g.L_EXTENDEDPRICE]); lu = lp.permuted(7); lp.free()
+        op_ = ctx.scan_filter(ot, [], [g.O_ORDERKEY, g.O_ORDERDATE]); ou = op_.permuted(11); op_.free()
+        uplan = P.config3_plan(0, 1)
+
+        def ustep():
+            ht = ctx.hash_build(ou, 0, [1], unique=True)
+            r = ctx.hash_agg(lu, uplan, ht)
+            r.combine()
+            out = r.fetch()
+            r.free(); ht.free()
+            return out
+        ms, ph, out, nlaunch = timed_block(ustep, xsteps, warm=1)
+        ucount = allsum(float(out[1][:, 0].view(np.int64).sum()))
+        pm = ph.get("probe_agg", {}).get("ms_per_step")
+        extras["unclustered"] = {"workload": "configs[2] query, both tables row-permuted (out[i] = in[(i*A+B) mod n])",
+                                 "ms_per_step": ms, "value_unclustered": rows_all / (ms / 1e3), "launches_per_step": nlaunch,
+                                 "count_star_equals_lineitem_rows": int(ucount) == int(nl_total),
+                                 "probe_sectors_gb_s": (nl * 32.0 / (pm / 1e3) / 1e9) if pm else None,
+                                 "probe_alg_frac_hbm": (nl * 24.0 / (pm / 1e3) / 1e9 / peak) if pm else None,
+                                 "note": "one 32-byte DRAM sector per probe is the floor for an unpartitioned probe of a table larger than L2 "
+                                         "(B200 delivers ~42 G random gathers/s, profiles/r01_ubench_random_access.txt)",
+                                 "phases_ms": ph}
+        checks["unclustered_count_star_equals_lineitem_rows"] = extras["unclustered"]["count_star_equals_lineitem_rows"]
+        lu.free(); ou.free()
+
     # ---- parity against the oracle on a slice, through the same calls (all datanodes take part)
     nslice = min(args.cpu_sample_orders, n_orders_total)
     os_ = ctx.table(g.SCHEMAS[g.T_ORDERS], nslice + 1024).generate(g.T_ORDERS, sf_total, 0, nslice, rank, world)
@@ -605,6 +633,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--extra-steps", type=int, default=5, help="timed steps of the Q3/Q1/config1/config2 extras")
     ap.add_argument("--no-extras", action="store_true", help="headline only (profiling runs)")
+    ap.add_argument("--no-unclustered", action="store_true", help="skip the row-permuted variant")
     ap.add_argument("--cpu-sample-orders", type=int, default=1_500_000)
     args = ap.parse_args()
     if args.warmup < 3:

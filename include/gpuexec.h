@@ -210,6 +210,9 @@ int  gx_table_truncate(gx_table *t);         /* keep capacity, nrows = 0      */
  * list, execScan.c:237); later columns move down by one */
 int  gx_table_drop_column(gx_table *t, int col);
 void gx_table_free(gx_table *t);
+/* an UNCLUSTERED copy: out[i] = in[(i * A + B) mod n], A coprime to n (bench/test plumbing:
+ * the layout the run-folding and key-ordered fast paths must not depend on) */
+int  gx_table_permute(gx_ctx *ctx, const gx_table *in, int64_t seed, gx_table **out);
 /* raw device pointer of a column (bench/test plumbing; not used by the provider) */
 int  gx_table_column_devptr(gx_table *t, int col, void **dptr);
 
@@ -253,6 +256,23 @@ int64_t gx_hash_nslots(const gx_hash *h);
  * exceed 4 is redone with the mixing hash before this call returns). */
 int  gx_hash_info(const gx_hash *h, int *slot_mode, double *avg_chain);
 void gx_hash_free(gx_hash *h);
+
+/* ---- the hash join's bloom filter ------------------------------------------
+ * BlockBloomFilterInit / Insert / Find (utils/misc/bloomfilter.c:54,140,162), filled while
+ * the join builds (nodeHash.c:717-726) and asked per outer tuple (ExecHashJoinBloomFilter,
+ * nodeHashjoin.c:1862).  Bit-identical directory: same sizing (MinLogSpace at 0.05, given up
+ * above 2^20 buckets: *out = NULL), same bucket and bit positions, hash = the join's
+ * CRC32C "new hash" of the key (hashfunc.c:112-175).  NULL keys and rows failing the
+ * build-side quals are not inserted. */
+typedef struct gx_bloom gx_bloom;
+int  gx_bloom_build(gx_ctx *ctx, const gx_table *inner, int key_col, int n_preds,
+                    const gx_pred *preds, gx_bloom **out);
+int  gx_bloom_log_num_buckets(const gx_bloom *b);
+int  gx_bloom_read_words(gx_bloom *b, uint32_t *host_out /* 8 << log_num_buckets words */);
+/* host_pass[i] = 1 when row i's key may have a partner; b == NULL passes every row */
+int  gx_bloom_test(gx_ctx *ctx, const gx_bloom *b, const gx_table *outer, int key_col,
+                   uint8_t *host_pass);
+void gx_bloom_free(gx_bloom *b);
 
 /* ---- K3: probe, materialising the join ----------------------------------
  * ExecHashJoinImpl INNER join (executor/nodeHashjoin.c:446-666) +

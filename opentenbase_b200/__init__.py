@@ -138,6 +138,7 @@ def _declare(L):
         "gx_table_drop_column": (C.c_int, [vp, C.c_int]),
         "gx_table_free": (None, [vp]),
         "gx_table_column_devptr": (C.c_int, [vp, C.c_int, pp]),
+        "gx_table_permute": (C.c_int, [vp, vp, i64, pp]),
         "gx_table_generate": (C.c_int, [vp, C.c_int, C.c_int, i64, i64, C.c_int, C.c_int]),
         "gx_table_generate_cols": (C.c_int, [vp, C.c_int, C.c_int, i64, i64, C.c_int, C.c_int, C.POINTER(i32)]),
         "gx_scan_filter": (C.c_int, [vp, vp, C.c_int, C.POINTER(GxPred), C.c_int, C.POINTER(i32), pp]),
@@ -146,6 +147,11 @@ def _declare(L):
         "gx_hash_nslots": (i64, [vp]),
         "gx_hash_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(dbl)]),
         "gx_hash_free": (None, [vp]),
+        "gx_bloom_build": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), pp]),
+        "gx_bloom_log_num_buckets": (C.c_int, [vp]),
+        "gx_bloom_read_words": (C.c_int, [vp, vp]),
+        "gx_bloom_test": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+        "gx_bloom_free": (None, [vp]),
         "gx_hash_probe": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), vp, C.c_int, C.POINTER(i32), pp]),
         "gx_hash_agg": (C.c_int, [vp, vp, vp, C.POINTER(GxAggPlan), pp]),
         "gx_result_combine": (C.c_int, [vp, vp]),
@@ -260,6 +266,11 @@ class Table:
         nl = np.zeros(n, np.uint8) if with_nulls else None
         self.ctx._chk(lib().gx_table_read_column(self.h, col, 0, n, out.ctypes.data, None if nl is None else nl.ctypes.data))
         return (out, nl) if with_nulls else out
+
+    def permuted(self, seed=1) -> "Table":
+        h = C.c_void_p()
+        self.ctx._chk(lib().gx_table_permute(self.ctx.h, self.h, seed, C.byref(h)))
+        return Table(self.ctx, h, self.types)
 
     def drop_column(self, col):
         self.ctx._chk(lib().gx_table_drop_column(self.h, col))
@@ -445,6 +456,24 @@ class Context:
         h = C.c_void_p()
         self._chk(lib().gx_hash_probe(self.h, outer.h, key_col, len(preds), pr, ht.h, len(out_outer_cols), oc, C.byref(h)))
         return Table(self, h, [outer.types[c] for c in out_outer_cols] + ht.payload_types)
+
+    # ---- bloom filter of the hash join
+    def bloom_build(self, inner: Table, key_col, preds=()):
+        """returns an opaque handle (int) or None when the reference would give up (> 2^20 buckets)"""
+        pr = (GxPred * max(len(preds), 1))(*[mk_pred(*p) for p in preds])
+        h = C.c_void_p()
+        self._chk(lib().gx_bloom_build(self.h, inner.h, key_col, len(preds), pr, C.byref(h)))
+        return h if h.value else None
+
+    def bloom_words(self, b) -> np.ndarray:
+        out = np.empty(8 << lib().gx_bloom_log_num_buckets(b), np.uint32)
+        self._chk(lib().gx_bloom_read_words(b, out.ctypes.data))
+        return out
+
+    def bloom_test(self, b, outer: Table, key_col) -> np.ndarray:
+        out = np.zeros(outer.nrows, np.uint8)
+        self._chk(lib().gx_bloom_test(self.h, b, outer.h, key_col, out.ctypes.data))
+        return out
 
     # ---- aggregate
     def hash_agg(self, outer: Table, plan: GxAggPlan, ht: HashTable | None = None) -> Result:

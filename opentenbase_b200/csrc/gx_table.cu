@@ -130,6 +130,54 @@ extern "C" int gx_table_read_column(gx_table *t, int col, int64_t row0, int64_t 
     return GX_OK;
 }
 
+// ------------------------------------------------------------ permute (bench / test plumbing)
+// out[i] = in[(i * A + B) mod n] with A coprime to n near n / golden ratio: a bijection that sends
+// neighbouring rows far apart — what an UNCLUSTERED copy of a table looks like to the join kernels.
+struct gx_permute_args { long long n, A, B; int ncols; gx_dcol in[GX_MAX_COLS]; void *out[GX_MAX_COLS]; uint8_t *out_nulls[GX_MAX_COLS]; };
+__global__ void gx_k_permute(gx_permute_args a)
+{
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const long long r = (long long) (((unsigned __int128) (unsigned long long) i * (unsigned long long) a.A + (unsigned long long) a.B) % (unsigned long long) a.n);
+        for (int c = 0; c < a.ncols; c++) {
+            switch (a.in[c].type) {
+                case GX_INT4: case GX_DATE: ((int *) a.out[c])[i] = ((const int *) a.in[c].data)[r]; break;
+                case GX_CHAR: ((signed char *) a.out[c])[i] = ((const signed char *) a.in[c].data)[r]; break;
+                default: ((long long *) a.out[c])[i] = ((const long long *) a.in[c].data)[r]; break;
+            }
+            if (a.out_nulls[c]) a.out_nulls[c][i] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
+        }
+    }
+}
+static long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+extern "C" int gx_table_permute(gx_ctx *ctx, const gx_table *in, int64_t seed, gx_table **out)
+{
+    if (!ctx || !in || !out) return GX_ERR_ARG;
+    bool hn[GX_MAX_COLS];
+    for (int c = 0; c < in->ncols; c++) hn[c] = in->nulls[c] != nullptr;
+    gx_table *t;
+    int rc = gx_table_alloc_like(ctx, in->ncols, in->types, hn, in->nrows > 0 ? in->nrows : 1, &t); if (rc) return rc;
+    if (in->nrows > 1) {
+        gx_permute_args a; memset(&a, 0, sizeof(a));
+        a.n = in->nrows; a.ncols = in->ncols;
+        a.A = (long long) ((double) in->nrows * 0.6180339887498949) | 1;
+        while (gcd_ll(a.A, a.n) != 1) a.A += 2;
+        a.B = (long long) ((unsigned long long) seed * 0x9E3779B97F4A7C15ULL % (unsigned long long) a.n);
+        for (int c = 0; c < in->ncols; c++) { a.in[c].data = in->cols[c]; a.in[c].nulls = in->nulls[c]; a.in[c].type = in->types[c]; a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
+        gx_launch_scope ls(ctx, "permute");
+        gx_k_permute<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a);
+        GX_CUDA(ctx, cudaGetLastError());
+    } else if (in->nrows == 1) {
+        for (int c = 0; c < in->ncols; c++) {
+            GX_CUDA(ctx, cudaMemcpyAsync(t->cols[c], in->cols[c], (size_t) gx_type_size(in->types[c]), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (t->nulls[c]) GX_CUDA(ctx, cudaMemcpyAsync(t->nulls[c], in->nulls[c], 1, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    t->nrows = in->nrows;
+    *out = t;
+    return GX_OK;
+}
+
 // ------------------------------------------------------------ block scan
 // exclusive scan of n int64 values in place; total written to *total
 __global__ void gx_k_scan_inplace(long long *v, long long n, long long *total)

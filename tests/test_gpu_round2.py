@@ -217,3 +217,64 @@ def test_few_groups_register_kernels(gx, ndistinct):
         assert_agg_equal(plans[0], gx.hash_agg(sub, to_gpu_plan(plans[0])).fetch(), O.exec_agg(O.Rel(types, [c[:m] for c in cols]), plans[0]))
         sub.free()
     t.free()
+
+
+def test_permuted_tables_give_the_same_answer(gx, ):
+    """gx_table_permute is a bijection, and the join + aggregate does not depend on the row order of either side
+    (key-ordered build and run-folding probe are optimisations that verify their precondition)."""
+    sf, nord = 1, 50000
+    o, l = O.gen_orders(sf, 0, nord), O.gen_lineitem(sf, 0, nord)
+    ot = gx.table_from(g.SCHEMAS[g.T_ORDERS], o); lt = gx.table_from(g.SCHEMAS[g.T_LINEITEM], l)
+    ou, lu = ot.permuted(3), lt.permuted(5)
+    assert sorted(ou.read(0).tolist()) == sorted(o[0].tolist())
+    assert not np.array_equal(lu.read(0), l[0])
+    plan = P.config3_plan(g.L_ORDERKEY, g.L_EXTENDEDPRICE)
+    want = O.exec_agg(lineitem_rel(l), O.GxAggPlan.from_buffer_copy(bytes(plan)), orders_rel(o),
+                      O.make_join(g.O_ORDERKEY, payload_cols=[g.O_ORDERDATE], inner_unique=1))
+    ht = gx.hash_build(ou, g.O_ORDERKEY, [g.O_ORDERDATE], unique=True)
+    assert_agg_equal(plan, gx.hash_agg(lu, plan, ht).fetch(), want)
+    for t in (ot, lt, ou, lu):
+        t.free()
+
+
+def test_bloom_filter_bit_identical_with_the_reference_geometry(gx):
+    """gx_bloom_build / gx_bloom_test against the oracle's BlockBloomFilter (itself pinned to the reference's
+    bloomfilter.o): same number of buckets, the SAME directory words bit for bit, the same Find answers — for int8
+    and int4 keys, NULL keys, a build-side qual, and the size at which the reference gives the filter up."""
+    import ctypes as C
+    L = O.lib()
+    rng = np.random.default_rng(8)
+    n = 60000
+    keys = rng.choice(np.arange(1, 10**7), n, replace=False).astype(np.int64)
+    nulls = (rng.random(n) < 0.05).astype(np.uint8)
+    flag = rng.integers(0, 2, n).astype(np.int32)
+    t = gx.table_from([g.GX_INT8, g.GX_INT4], [keys, flag], [nulls, None])
+    for preds, keep in (((), nulls == 0), (((1, g.GX_EQ, 1),), (nulls == 0) & (flag == 1))):
+        b = gx.bloom_build(t, 0, preds)
+        ob = L.orc_bloom_create(n)
+        assert g.lib().gx_bloom_log_num_buckets(b) == L.orc_bloom_log_num_buckets(ob)
+        for k in keys[keep].tolist():
+            L.orc_bloom_insert(ob, L.orc_hashint8new(k))
+        nw = C.c_int64()
+        L.orc_bloom_words.restype = C.POINTER(C.c_uint32)
+        want = np.ctypeslib.as_array(L.orc_bloom_words(ob, C.byref(nw)), (8 << L.orc_bloom_log_num_buckets(ob),)).copy()
+        np.testing.assert_array_equal(gx.bloom_words(b), want)
+        probe = np.concatenate([keys[:2000], rng.integers(10**7, 2 * 10**7, 20000)]).astype(np.int64)
+        pt = gx.table_from([g.GX_INT8], [probe])
+        got = gx.bloom_test(b, pt, 0)
+        exp = np.array([L.orc_bloom_find(ob, L.orc_hashint8new(k)) for k in probe.tolist()], np.uint8)
+        np.testing.assert_array_equal(got, exp)
+        assert got[:2000][keep[:2000]].all()                       # no false negatives
+        assert got[2000:].mean() < 0.12                            # false positives near the 5 % the sizing aims at
+        # an int4 probe column of the same values hashes alike (hashint4new widens to int64)
+        small = rng.integers(1, 10**7, 5000).astype(np.int32)
+        p4 = gx.table_from([g.GX_INT4], [small])
+        exp4 = np.array([L.orc_bloom_find(ob, L.orc_hashint4new(int(k))) for k in small.tolist()], np.uint8)
+        np.testing.assert_array_equal(gx.bloom_test(b, p4, 0), exp4)
+        g.lib().gx_bloom_free(b); L.orc_bloom_free(ob)
+        pt.free(); p4.free()
+    t.free()
+    # "give up using bloom filter": more than 2^20 buckets wanted (bloomfilter.c:68)
+    big = gx.table([g.GX_INT8], 60_000_000).generate(g.T_ORDERS, 40, 0, 60_000_000, colmap=[g.O_ORDERKEY])
+    assert gx.bloom_build(big, 0) is None and not L.orc_bloom_create(60_000_000)
+    big.free()
