@@ -282,6 +282,15 @@ int  gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col,
                    int n_preds, const gx_pred *preds, const gx_hash *h,
                    int n_out_outer, const int32_t *out_outer_cols,
                    gx_table **out);
+/* Join types of ExecHashJoinImpl beyond INNER (JoinType, nodes/nodes.h): LEFT emits an unmatched
+ * outer row with a NULL inner side (HJ_FILL_OUTER_TUPLE, nodeHashjoin.c:668-689; unique build sides
+ * only), SEMI emits an outer row once on its first match, ANTI emits the outer rows without a match
+ * (nodeHashjoin.c:628-634); SEMI/ANTI output carries no inner columns.  A NULL outer key never
+ * matches.  RIGHT/FULL (HJ_FILL_INNER_TUPLES) are declined. */
+enum { GX_JOIN_INNER = 0, GX_JOIN_LEFT = 1, GX_JOIN_SEMI = 4, GX_JOIN_ANTI = 5 };
+int  gx_hash_probe_ex(gx_ctx *ctx, const gx_table *outer, int key_col,
+                      int n_preds, const gx_pred *preds, const gx_hash *h, int join_type,
+                      int n_out_outer, const int32_t *out_outer_cols, gx_table **out);
 
 /* ---- K3+K4: [probe ->] hash aggregate ------------------------------------
  * agg_fill_hash_table / lookup_hash_entries / advance_aggregates /

@@ -25,6 +25,7 @@ GX_LT, GX_LE, GX_EQ, GX_GE, GX_GT, GX_NE = 1, 2, 3, 4, 5, 6
 (GX_AGG_COUNT_STAR, GX_AGG_COUNT, GX_AGG_SUM_F8, GX_AGG_AVG_F8, GX_AGG_SUM_I4,
  GX_AGG_MIN_F8, GX_AGG_MAX_F8, GX_AGG_SUM_I8) = 1, 2, 3, 4, 5, 6, 7, 8
 GX_OP_COL, GX_OP_CONST, GX_OP_ADD, GX_OP_SUB, GX_OP_MUL = 1, 2, 3, 4, 5
+GX_JOIN_INNER, GX_JOIN_LEFT, GX_JOIN_SEMI, GX_JOIN_ANTI = 0, 1, 4, 5
 T_ORDERS, T_LINEITEM, T_CUSTOMER = 1, 2, 3
 # fixed schemas of include/gx_tpch_gen.h
 O_ORDERKEY, O_CUSTKEY, O_ORDERDATE, O_SHIPPRIORITY = 0, 1, 2, 3
@@ -153,6 +154,7 @@ def _declare(L):
         "gx_bloom_test": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "gx_bloom_free": (None, [vp]),
         "gx_hash_probe": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), vp, C.c_int, C.POINTER(i32), pp]),
+        "gx_hash_probe_ex": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), vp, C.c_int, C.c_int, C.POINTER(i32), pp]),
         "gx_hash_agg": (C.c_int, [vp, vp, vp, C.POINTER(GxAggPlan), pp]),
         "gx_result_combine": (C.c_int, [vp, vp]),
         "gx_result_ngroups": (i64, [vp]),
@@ -450,12 +452,13 @@ class Context:
         ht.payload_types = [inner.types[c] for c in payload_cols] or [GX_INT8]
         return ht
 
-    def hash_probe(self, outer: Table, key_col, ht: HashTable, out_outer_cols, preds=()) -> Table:
+    def hash_probe(self, outer: Table, key_col, ht: HashTable, out_outer_cols, preds=(), join_type=0) -> Table:
         pr = (GxPred * max(len(preds), 1))(*[mk_pred(*p) for p in preds])
         oc = (C.c_int32 * max(len(out_outer_cols), 1))(*out_outer_cols)
         h = C.c_void_p()
-        self._chk(lib().gx_hash_probe(self.h, outer.h, key_col, len(preds), pr, ht.h, len(out_outer_cols), oc, C.byref(h)))
-        return Table(self, h, [outer.types[c] for c in out_outer_cols] + ht.payload_types)
+        self._chk(lib().gx_hash_probe_ex(self.h, outer.h, key_col, len(preds), pr, ht.h, join_type, len(out_outer_cols), oc, C.byref(h)))
+        inner = [] if join_type in (GX_JOIN_SEMI, GX_JOIN_ANTI) else ht.payload_types
+        return Table(self, h, [outer.types[c] for c in out_outer_cols] + inner)
 
     # ---- bloom filter of the hash join
     def bloom_build(self, inner: Table, key_col, preds=()):

@@ -1103,10 +1103,10 @@ struct gx_probe_args {
     int payload_types[GX_MAX_PAYLOAD];
     long long *cursor;             // global output cursor
     long long out_cap;
-    int count_only; int _pad;
+    int count_only; int join_type;  // GX_JOIN_*
 };
 
-__device__ __forceinline__ void emit_row(const gx_probe_args &a, long long dst, long long r, unsigned long long payload)
+__device__ __forceinline__ void emit_row(const gx_probe_args &a, long long dst, long long r, unsigned long long payload, bool matched = true)
 {
     for (int c = 0; c < a.n_out_outer; c++) {
         switch (a.out_src[c].type) {
@@ -1116,6 +1116,11 @@ __device__ __forceinline__ void emit_row(const gx_probe_args &a, long long dst, 
         }
         if (a.out_nulls[c]) a.out_nulls[c][dst] = a.out_src[c].nulls ? a.out_src[c].nulls[r] : 0;
     }
+    if (a.join_type == GX_JOIN_SEMI || a.join_type == GX_JOIN_ANTI) return;      // the inner side is not part of the target list
+    const int npo = a.n_payload ? a.n_payload : 1;
+    if (a.join_type == GX_JOIN_LEFT)                                               // hj_NullInnerTupleSlot for an unmatched outer row
+        for (int i = 0; i < npo; i++) if (a.out_nulls[a.n_out_outer + i]) a.out_nulls[a.n_out_outer + i][dst] = matched ? 0 : 1;
+    if (!matched) payload = 0;
     if (a.n_payload == 0) { ((long long *) a.out[a.n_out_outer])[dst] = (long long) payload; return; }
     int shift = 0;
     for (int i = 0; i < a.n_payload; i++) {
@@ -1194,15 +1199,17 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
     const long long nwarp = ((long long) gridDim.x * blockDim.x) >> 5, wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long tile = 32LL * PT_K;
     for (long long base = wid * tile; base < a.nrows; base += nwarp * tile) {
-        long long r[PT_K], key[PT_K]; bool ok[PT_K], hit[PT_K]; unsigned long long pay[PT_K], s[PT_K];
+        long long r[PT_K], key[PT_K]; bool ok[PT_K], hit[PT_K], quals_ok[PT_K]; unsigned long long pay[PT_K], s[PT_K];
 #pragma unroll
-        for (int j = 0; j < PT_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < a.nrows && !gx_is_null(a.key, r[j]); }
-#pragma unroll
-        for (int j = 0; j < PT_K; j++) key[j] = ok[j] ? gx_load_int(a.key, r[j]) : 0;
+        for (int j = 0; j < PT_K; j++) { r[j] = base + j * 32 + lane; quals_ok[j] = r[j] < a.nrows; }
         for (int p = 0; p < a.npreds; p++) {
 #pragma unroll
-            for (int j = 0; j < PT_K; j++) if (ok[j]) ok[j] = gx_eval_pred(a.preds[p], r[j]);
+            for (int j = 0; j < PT_K; j++) if (quals_ok[j]) quals_ok[j] = gx_eval_pred(a.preds[p], r[j]);
         }
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) ok[j] = quals_ok[j] && !gx_is_null(a.key, r[j]);      // a NULL key never matches (hashStrict)
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) key[j] = ok[j] ? gx_load_int(a.key, r[j]) : 0;
         long long k0[PT_K], k1[PT_K]; unsigned long long p0[PT_K], p1[PT_K];
 #pragma unroll
         for (int j = 0; j < PT_K; j++) {
@@ -1225,6 +1232,16 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
             }
         }
         __syncwarp();
+        // which rows produce output (nodeHashjoin.c:569-668): INNER/SEMI the matched ones, ANTI the unmatched ones
+        // (HJ_FILL_OUTER_TUPLE without a match), LEFT all of them (unmatched with a NULL inner side)
+        bool matched[PT_K];
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) {
+            matched[j] = hit[j];
+            const bool scanned = r[j] < a.nrows && (ok[j] || (gx_is_null(a.key, r[j]) && quals_ok[j]));   // passed the scan quals
+            if (a.join_type == GX_JOIN_ANTI) hit[j] = scanned && !matched[j];
+            else if (a.join_type == GX_JOIN_LEFT) hit[j] = scanned;
+        }
         unsigned int m[PT_K]; int total = 0;
 #pragma unroll
         for (int j = 0; j < PT_K; j++) { m[j] = __ballot_sync(0xffffffffu, hit[j]); total += __popc(m[j]); }
@@ -1235,24 +1252,35 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
         if (a.count_only) continue;
 #pragma unroll
         for (int j = 0; j < PT_K; j++) {
-            if (hit[j]) { const long long dst = dst0 + __popc(m[j] & lt); if (dst < a.out_cap) emit_row(a, dst, r[j], pay[j]); }
+            if (hit[j]) { const long long dst = dst0 + __popc(m[j] & lt); if (dst < a.out_cap) emit_row(a, dst, r[j], pay[j], matched[j]); }
             dst0 += __popc(m[j]);
         }
     }
 }
 
+extern "C" int gx_hash_probe_ex(gx_ctx *ctx, const gx_table *outer, int key_col, int n_preds, const gx_pred *preds,
+                                const gx_hash *h, int join_type, int n_out_outer, const int32_t *out_outer_cols, gx_table **out);
 extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, int n_preds, const gx_pred *preds,
                              const gx_hash *h, int n_out_outer, const int32_t *out_outer_cols, gx_table **out)
+{
+    return gx_hash_probe_ex(ctx, outer, key_col, n_preds, preds, h, GX_JOIN_INNER, n_out_outer, out_outer_cols, out);
+}
+extern "C" int gx_hash_probe_ex(gx_ctx *ctx, const gx_table *outer, int key_col, int n_preds, const gx_pred *preds,
+                                const gx_hash *h, int join_type, int n_out_outer, const int32_t *out_outer_cols, gx_table **out)
 {
     if (!ctx || !outer || !h || !out) return GX_ERR_ARG;
     GX_CHECK_ARG(ctx, key_col >= 0 && key_col < outer->ncols, "hash_probe: key column %d out of range", key_col);
     int kt = outer->types[key_col];
     GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "hash_probe: key type %d not supported", kt);
-    int n_pay_out = h->n_payload ? h->n_payload : 1;
-    GX_CHECK_ARG(ctx, n_out_outer >= 0 && n_out_outer + n_pay_out <= GX_MAX_COLS, "hash_probe: too many output columns");
+    GX_CHECK_ARG(ctx, join_type == GX_JOIN_INNER || join_type == GX_JOIN_LEFT || join_type == GX_JOIN_SEMI || join_type == GX_JOIN_ANTI,
+                 "hash_probe: join type %d not supported (inner, left, semi, anti)", join_type);
+    GX_CHECK_ARG(ctx, join_type != GX_JOIN_LEFT || h->unique, "hash_probe: LEFT JOIN needs a unique build side (inner_unique)");
+    const bool no_inner_cols = join_type == GX_JOIN_SEMI || join_type == GX_JOIN_ANTI;
+    int n_pay_out = no_inner_cols ? 0 : (h->n_payload ? h->n_payload : 1);
+    GX_CHECK_ARG(ctx, n_out_outer >= 0 && n_out_outer + n_pay_out <= GX_MAX_COLS && n_out_outer + n_pay_out > 0, "hash_probe: bad output column count");
     gx_probe_args a; memset(&a, 0, sizeof(a));
     a.key.data = outer->cols[key_col]; a.key.nulls = outer->nulls[key_col]; a.key.type = kt;
-    a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique;
+    a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique; a.join_type = join_type;
     { int wrc = gx_hash_wide(ctx, const_cast<gx_hash *>(h)); if (wrc) return wrc; }
     a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
     a.special = h->special_payload; a.special_count = h->special_count;
@@ -1265,13 +1293,15 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
         a.out_src[c].data = outer->cols[oc]; a.out_src[c].nulls = outer->nulls[oc]; a.out_src[c].type = outer->types[oc];
         types[c] = outer->types[oc]; hn[c] = outer->nulls[oc] != nullptr;
     }
-    if (h->n_payload == 0) { types[n_out_outer] = GX_INT8; hn[n_out_outer] = false; }
-    for (int i = 0; i < h->n_payload; i++) { types[n_out_outer + i] = h->payload_types[i]; hn[n_out_outer + i] = false; a.payload_types[i] = h->payload_types[i]; }
+    const bool left = join_type == GX_JOIN_LEFT;
+    if (!no_inner_cols && h->n_payload == 0) { types[n_out_outer] = GX_INT8; hn[n_out_outer] = left; }
+    for (int i = 0; i < h->n_payload; i++) { if (!no_inner_cols) { types[n_out_outer + i] = h->payload_types[i]; hn[n_out_outer + i] = left; } a.payload_types[i] = h->payload_types[i]; }
     a.cursor = ctx->d_scratch + 2;
     long long nb = (outer->nrows + 255) / 256, maxb = (long long) ctx->sm_count * 8;
     unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
     long long out_cap = outer->nrows;
-    if (!h->unique) {
+    const bool first_match_only = h->unique || join_type != GX_JOIN_INNER;      // semi/anti stop at the first match
+    if (!first_match_only) {
         // size the output first
         a.count_only = 1; a.out_cap = 0;
         GX_CUDA(ctx, cudaMemsetAsync(a.cursor, 0, sizeof(long long), ctx->stream));
@@ -1287,7 +1317,7 @@ extern "C" int gx_hash_probe(gx_ctx *ctx, const gx_table *outer, int key_col, in
     GX_CUDA(ctx, cudaMemsetAsync(a.cursor, 0, sizeof(long long), ctx->stream));
     {
         gx_launch_scope ls(ctx, "probe");
-        if (h->unique) {
+        if (first_match_only) {
             long long nt = (outer->nrows + 32 * PT_K * 8 - 1) / (32 * PT_K * 8);
             gx_k_hash_probe_unique<<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
         } else gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a);

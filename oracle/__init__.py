@@ -76,7 +76,7 @@ class OrcJoinSpec(C.Structure):
     _fields_ = [("inner_key_col", C.c_int32), ("n_inner_preds", C.c_int32),
                 ("inner_preds", GxPred * 4),
                 ("n_payload", C.c_int32), ("payload_cols", C.c_int32 * 2),
-                ("inner_unique", C.c_int32)]
+                ("inner_unique", C.c_int32), ("jointype", C.c_int32)]
 
 
 class OrcResult(C.Structure):
@@ -278,8 +278,9 @@ def mk_pred(col, op, const, is_float=False) -> GxPred:
     return q
 
 
-def make_join(inner_key_col, payload_cols=(), inner_unique=0, inner_preds=()) -> OrcJoinSpec:
+def make_join(inner_key_col, payload_cols=(), inner_unique=0, inner_preds=(), jointype=0) -> OrcJoinSpec:
     j = OrcJoinSpec()
+    j.jointype = jointype
     j.inner_key_col = inner_key_col
     j.n_inner_preds = len(inner_preds)
     for i, pr in enumerate(inner_preds):

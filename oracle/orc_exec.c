@@ -353,7 +353,8 @@ static HashJoinTable *MultiExecHash(PlanState *inner_scan, const orc_rel *inner,
 }
 
 /* ------------------------------------------------------------ HashJoin */
-enum { HJ_BUILD_HASHTABLE = 1, HJ_NEED_NEW_OUTER, HJ_SCAN_BUCKET };   /* nodeHashjoin.c:139-144 */
+enum { HJ_BUILD_HASHTABLE = 1, HJ_NEED_NEW_OUTER, HJ_SCAN_BUCKET, HJ_FILL_OUTER_TUPLE };   /* nodeHashjoin.c:139-144 */
+enum { ORC_JOIN_INNER = 0, ORC_JOIN_LEFT = 1, ORC_JOIN_SEMI = 4, ORC_JOIN_ANTI = 5 };   /* JoinType, nodes/nodes.h */
 
 typedef struct HashJoinState {
     PlanState ps;
@@ -368,7 +369,9 @@ typedef struct HashJoinState {
     HashJoinTuple cur_tuple;          /* hj_CurTuple */
     int64_t   cur_key;
     orc_slot  hashtup_slot;           /* hj_HashTupleSlot (minimal tuple) */
-    int       single_match;           /* inner_unique, nodeHashjoin.c:859-861 */
+    int       single_match;           /* inner_unique || JOIN_SEMI, nodeHashjoin.c:859-861 */
+    int       jointype;
+    int       matched_outer;          /* hj_MatchedOuter */
     cmp_fn    key_cmp;
     /* projection: result slot = [needed outer attrs..., inner key, payload...] */
     int       n_outer_atts;
@@ -397,7 +400,8 @@ static int ExecScanHashBucket(HashJoinState *hj)
     return 0;
 }
 
-/* ExecHashJoinImpl, nodeHashjoin.c:186-742, JOIN_INNER arms only */
+/* ExecHashJoinImpl, nodeHashjoin.c:186-742: JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI arms
+ * (HJ_FILL_INNER_TUPLES — right/full joins — is not restated) */
 static orc_slot *ExecHashJoin(PlanState *ps)
 {
     HashJoinState *hj = (HashJoinState *) ps;
@@ -415,14 +419,21 @@ static orc_slot *ExecHashJoin(PlanState *ps)
                 if (TupIsNull(o)) { hj->result.empty = 1; return &hj->result; }
                 uint8_t knull;
                 int64_t key = orc_slot_getattr(o, hj->outer_key_col, &knull);
-                if (!ExecHashGetHashValue(hj->outer_key_type, key, knull, &hj->cur_hash))
-                    continue;                       /* NULL outer key never matches */
-                hj->outer_slot = o; hj->cur_key = key; hj->cur_tuple = NULL;
+                hj->outer_slot = o; hj->matched_outer = 0;
+                if (!ExecHashGetHashValue(hj->outer_key_type, key, knull, &hj->cur_hash)) {
+                    /* NULL outer key never matches: ExecHashJoinOuterGetTuple skips the tuple unless the join
+                     * fills outer tuples (HJ_FILL_OUTER, nodeHashjoin.c:1079-1090: keep_nulls) */
+                    if (hj->jointype == ORC_JOIN_LEFT || hj->jointype == ORC_JOIN_ANTI) { hj->state = HJ_FILL_OUTER_TUPLE; continue; }
+                    continue;
+                }
+                hj->cur_key = key; hj->cur_tuple = NULL;
                 hj->state = HJ_SCAN_BUCKET;
             }   /* FALLTHROUGH */
             case HJ_SCAN_BUCKET: {
-                if (!ExecScanHashBucket(hj)) { hj->state = HJ_NEED_NEW_OUTER; continue; }
-                if (hj->single_match) hj->state = HJ_NEED_NEW_OUTER;
+                if (!ExecScanHashBucket(hj)) { hj->state = HJ_FILL_OUTER_TUPLE; continue; }      /* :543-557 */
+                hj->matched_outer = 1;                                                             /* :578 */
+                if (hj->jointype == ORC_JOIN_ANTI) { hj->state = HJ_NEED_NEW_OUTER; continue; }    /* :628-634 */
+                if (hj->single_match) hj->state = HJ_NEED_NEW_OUTER;                              /* :640-643 */
                 /* ExecProject into the virtual result slot */
                 orc_slot *r = &hj->result, *o = hj->outer_slot, *in = &hj->hashtup_slot;
                 for (int a = 0; a < hj->n_outer_atts; a++)
@@ -430,6 +441,18 @@ static orc_slot *ExecHashJoin(PlanState *ps)
                         r->values[a] = orc_slot_getattr(o, a, &r->isnull[a]);
                 for (int a = 0; a < hj->ht->ninner; a++)
                     r->values[hj->n_outer_atts + a] = orc_slot_getattr(in, a, &r->isnull[hj->n_outer_atts + a]);
+                r->empty = 0;
+                return r;
+            }
+            case HJ_FILL_OUTER_TUPLE: {                                                            /* :668-689 */
+                hj->state = HJ_NEED_NEW_OUTER;
+                if (hj->matched_outer || !(hj->jointype == ORC_JOIN_LEFT || hj->jointype == ORC_JOIN_ANTI)) continue;
+                /* the outer tuple joined with hj_NullInnerTupleSlot */
+                orc_slot *r = &hj->result, *o = hj->outer_slot;
+                for (int a = 0; a < hj->n_outer_atts; a++)
+                    if (hj->outer_needed[a])
+                        r->values[a] = orc_slot_getattr(o, a, &r->isnull[a]);
+                for (int a = 0; a < hj->ht->ninner; a++) { r->values[hj->n_outer_atts + a] = 0; r->isnull[hj->n_outer_atts + a] = 1; }
                 r->empty = 0;
                 return r;
             }
@@ -448,7 +471,8 @@ static HashJoinState *ExecInitHashJoin(PlanState *outer, const orc_rel *outer_re
     hj->outer_key_col = outer_key_col;
     hj->outer_key_type = outer_rel->attrs[outer_key_col].type;
     hj->key_cmp = cmp_for_type(hj->outer_key_type);
-    hj->single_match = js->inner_unique;
+    hj->jointype = js->jointype;
+    hj->single_match = js->inner_unique || js->jointype == ORC_JOIN_SEMI;      /* nodeHashjoin.c:859-861 */
     hj->n_outer_atts = outer_rel->natts;
     int nres = outer_rel->natts + 1 + js->n_payload;
     hj->result.natts = nres; hj->result.nvalid = nres; hj->result.tuple = NULL;

@@ -113,6 +113,7 @@ typedef struct orc_join_spec {
     int32_t  n_payload;
     int32_t  payload_cols[GX_MAX_PAYLOAD];
     int32_t  inner_unique;
+    int32_t  jointype;          /* JoinType (nodes/nodes.h): 0 INNER, 1 LEFT, 4 SEMI, 5 ANTI */
 } orc_join_spec;
 
 /* Volcano, one tuple per ExecProcNode call:

@@ -278,3 +278,55 @@ def test_bloom_filter_bit_identical_with_the_reference_geometry(gx):
     big = gx.table([g.GX_INT8], 60_000_000).generate(g.T_ORDERS, 40, 0, 60_000_000, colmap=[g.O_ORDERKEY])
     assert gx.bloom_build(big, 0) is None and not L.orc_bloom_create(60_000_000)
     big.free()
+
+
+def test_left_semi_anti_joins(gx):
+    """gx_hash_probe_ex against the oracle's ExecHashJoinImpl restatement (nodeHashjoin.c:466-689): LEFT emits the
+    unmatched outer rows with a NULL inner side, SEMI each outer row once, ANTI the rows without a partner — with
+    NULL outer keys (never match), duplicate build keys (SEMI/ANTI), outer quals, and unmatched keys."""
+    rng = np.random.default_rng(12)
+    ni, no = 30000, 120000
+    uk = rng.choice(np.arange(1, 200000), ni, replace=False).astype(np.int64)
+    dk = np.concatenate([uk[:ni // 2], uk[:ni // 2]])                       # every key twice
+    ipay = rng.integers(0, 1000, ni).astype(np.int32)
+    okey = rng.integers(1, 200000, no).astype(np.int64)
+    onull = (rng.random(no) < 0.03).astype(np.uint8)
+    oval = np.arange(no, dtype=np.int32)
+    types = [g.GX_INT8, g.GX_INT4]
+    ot = gx.table_from(types, [okey, oval], [onull, None])
+    orel = O.Rel(types, [okey, oval], [onull, None])
+    preds = [(1, g.GX_GE, 1000)]
+    NULL = np.iinfo(np.int64).min
+
+    def gpu_rows(t, with_inner):
+        cols = [t.read(c, with_nulls=True) for c in range(len(t.types))]
+        n = t.nrows
+        out = np.full((n, len(cols)), NULL, np.int64)
+        for c, (v, nl) in enumerate(cols):
+            out[:, c] = np.where(nl == 0, v.astype(np.int64), NULL)
+        return out[np.lexsort(out.T[::-1])]
+
+    def want_rows(cols):
+        w = np.stack(cols, 1) if len(cols[0]) else np.zeros((0, len(cols)), np.int64)
+        return w[np.lexsort(w.T[::-1])]
+
+    for keys, unique, jts in ((uk, True, (g.GX_JOIN_INNER, g.GX_JOIN_LEFT, g.GX_JOIN_SEMI, g.GX_JOIN_ANTI)),
+                              (dk, False, (g.GX_JOIN_INNER, g.GX_JOIN_SEMI, g.GX_JOIN_ANTI))):
+        it = gx.table_from(types, [keys, ipay])
+        irel = O.Rel(types, [keys, ipay])
+        ht = gx.hash_build(it, 0, [1], unique=unique)
+        for jt in jts:
+            got = gx.hash_probe(ot, 0, ht, [0, 1], preds=preds, join_type=jt)
+            w = O.exec_join(orel, 0, irel, O.make_join(0, payload_cols=[1], inner_unique=int(unique), jointype=jt), [0, 1], outer_preds=preds)
+            if jt in (g.GX_JOIN_SEMI, g.GX_JOIN_ANTI):
+                w = w[:2]                                                   # the inner side is not part of the target list
+            np.testing.assert_array_equal(gpu_rows(got, jt), want_rows(w), err_msg=f"join type {jt}, unique={unique}")
+            got.free()
+        ht.free(); it.free()
+    # LEFT over a non-unique build side is declined, RIGHT/FULL are declined
+    it = gx.table_from(types, [dk, ipay]); ht = gx.hash_build(it, 0, [1], unique=False)
+    for jt in (g.GX_JOIN_LEFT, 2, 3):
+        with pytest.raises(g.GxError) as ei:
+            gx.hash_probe(ot, 0, ht, [0, 1], join_type=jt)
+        assert ei.value.status == g.GX_ERR_ARG
+    ot.free(); it.free()
