@@ -187,6 +187,9 @@ typedef struct gx_heap_desc {
     int16_t att_len[64];
     int8_t  att_align[64];
     int32_t attnums[GX_MAX_COLS];
+    int8_t  att_notnull[64];   /* pg_attribute.attnotnull: such a column is staged WITHOUT a NULL array (an
+                                * error if a tuple nevertheless lacks the value), which keeps the no-NULL
+                                * fast paths of the join and aggregate kernels open for heap-loaded tables */
 } gx_heap_desc;
 /* With vis_offsets the call only ENQUEUES (copies + the deform kernel; row offsets are
  * scanned on the host from vis_counts) and grows the table if needed; `pages`, if it came
@@ -195,6 +198,9 @@ int  gx_table_append_heap_pages(gx_table *t, const void *pages, int64_t npages,
                                 const gx_heap_desc *desc,
                                 const uint16_t *vis_offsets, const int32_t *vis_counts,
                                 int32_t vis_stride);
+/* End of a load: waits for the enqueued appends; GX_ERR_STATE if a NULL arrived in a column
+ * the descriptor declared NOT NULL. */
+int  gx_table_load_finish(gx_table *t);
 /* Pinned staging for the loader above: one of two library-owned buffers; the call waits
  * until the previous copy out of that buffer has completed.  Filling one buffer while the
  * other one's DMA and deform run is how the provider overlaps heapgetpage() with the GPU. */

@@ -79,7 +79,7 @@ class GxAggPlan(C.Structure):
 class GxHeapDesc(C.Structure):
     _fields_ = [("natts", C.c_int32), ("ncols", C.c_int32),
                 ("att_len", C.c_int16 * 64), ("att_align", C.c_int8 * 64),
-                ("attnums", C.c_int32 * 16)]
+                ("attnums", C.c_int32 * 16), ("att_notnull", C.c_int8 * 64)]
 
 
 class GxHostTable(C.Structure):
@@ -132,6 +132,7 @@ def _declare(L):
         "gx_table_append_heap_pages": (C.c_int, [vp, vp, i64, C.POINTER(GxHeapDesc), vp, vp, i32]),
         "gx_stage_acquire": (C.c_int, [vp, sz, pp]),
         "gx_table_reserve": (C.c_int, [vp, i64]),
+        "gx_table_load_finish": (C.c_int, [vp]),
         "gx_table_nrows": (i64, [vp]),
         "gx_table_ncols": (C.c_int, [vp]),
         "gx_table_read_column": (C.c_int, [vp, C.c_int, i64, i64, vp, vp]),
@@ -235,9 +236,11 @@ class Table:
         self.ctx.sync()
         return self
 
-    def append_heap_pages(self, pages: np.ndarray, att_len, att_align, attnums, vis=None, vis_counts=None):
+    def append_heap_pages(self, pages: np.ndarray, att_len, att_align, attnums, vis=None, vis_counts=None, notnull=None):
         d = GxHeapDesc()
         d.natts, d.ncols = len(att_len), len(attnums)
+        for i, nn in enumerate(notnull or ()):
+            d.att_notnull[i] = 1 if nn else 0
         for i, (l, a) in enumerate(zip(att_len, att_align)):
             d.att_len[i], d.att_align[i] = l, a
         for i, a in enumerate(attnums):
@@ -252,6 +255,7 @@ class Table:
             stride = vis.shape[1]
             vo, vc = vis.ctypes.data, vis_counts.ctypes.data
         self.ctx._chk(lib().gx_table_append_heap_pages(self.h, pages.ctypes.data, npages, C.byref(d), vo, vc, stride))
+        self.ctx._chk(lib().gx_table_load_finish(self.h))
         return self
 
     def generate(self, table_id, sf, o0, o1, node=0, nnodes=1, colmap=None):

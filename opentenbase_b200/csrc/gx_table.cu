@@ -44,6 +44,17 @@ extern "C" void gx_table_free(gx_table *t)
 extern "C" int64_t gx_table_nrows(const gx_table *t) { return t ? t->nrows : -1; }
 extern "C" int gx_table_ncols(const gx_table *t) { return t ? t->ncols : -1; }
 extern "C" int gx_table_truncate(gx_table *t) { if (!t) return GX_ERR_ARG; t->nrows = 0; return GX_OK; }
+// End of a load: wait for the enqueued appends and report a NULL that arrived in a column staged as NOT NULL
+extern "C" int gx_table_load_finish(gx_table *t)
+{
+    if (!t) return GX_ERR_ARG;
+    gx_ctx *ctx = t->ctx;
+    GX_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 20, ctx->d_scratch + 20, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + 20, 0, sizeof(long long), ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_scratch[20] != 0) { GX_SET_ERR(ctx, "heap pages: a NULL value arrived in a column declared NOT NULL (att_notnull)"); return GX_ERR_STATE; }
+    return GX_OK;
+}
 extern "C" int gx_table_drop_column(gx_table *t, int col)
 {
     if (!t || col < 0 || col >= t->ncols || t->ncols < 2) return GX_ERR_ARG;
@@ -518,6 +529,7 @@ struct gx_deform_args {
     signed char col_of_att[64];          // table column fed by attribute a, or -1
     void *out[GX_MAX_COLS]; uint8_t *out_nulls[GX_MAX_COLS]; int out_type[GX_MAX_COLS];
     long long base_row;
+    int *notnull_violation;              // a NULL arrived in a column declared NOT NULL
 };
 
 __device__ __forceinline__ int page_nvisible(const gx_deform_args &a, long long p)
@@ -577,7 +589,7 @@ __global__ void gx_k_deform(gx_deform_args a, const long long *pageoffs)
             int c = a.col_of_att[att];
             if (att >= tnatts || (hasnulls && !(bp[att >> 3] & (1 << (att & 7))))) {
                 if (c >= 0) {
-                    if (a.out_nulls[c]) a.out_nulls[c][row] = 1;
+                    if (a.out_nulls[c]) a.out_nulls[c][row] = 1; else *a.notnull_violation = 1;
                     switch (a.out_type[c]) { case GX_INT4: case GX_DATE: ((int *) a.out[c])[row] = 0; break;
                                              case GX_CHAR: ((signed char *) a.out[c])[row] = 0; break;
                                              default: ((long long *) a.out[c])[row] = 0; }
@@ -627,6 +639,7 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
     if (npages == 0) return GX_OK;
     gx_deform_args a; memset(&a, 0, sizeof(a));
     a.npages = npages; a.natts = desc->natts; a.ncols = desc->ncols; a.vis_stride = vis_stride; a.base_row = t->nrows;
+    a.notnull_violation = (int *) (ctx->d_scratch + 20);     // reported by gx_table_load_finish()
     for (int i = 0; i < desc->natts; i++) {
         a.att_len[i] = desc->att_len[i]; a.att_align[i] = desc->att_align[i]; a.col_of_att[i] = -1;
         GX_CHECK_ARG(ctx, a.att_len[i] == -1 || a.att_len[i] == 1 || a.att_len[i] == 2 || a.att_len[i] == 4 || a.att_len[i] == 8, "heap desc: attribute %d has unsupported attlen %d", i, a.att_len[i]);
@@ -637,7 +650,8 @@ extern "C" int gx_table_append_heap_pages(gx_table *t, const void *pages, int64_
         GX_CHECK_ARG(ctx, att >= 0 && att < desc->natts, "heap desc: attnum %d out of range", att);
         a.col_of_att[att] = (signed char) c;
         if (att + 1 > a.maxatt) a.maxatt = att + 1;
-        int rc = ensure_null_array(t, c); if (rc) return rc;
+        // a NOT NULL attribute gets no NULL array (unless the table already has one for it)
+        if (!desc->att_notnull[att] || t->nulls[c]) { int rc = ensure_null_array(t, c); if (rc) return rc; }
         a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; a.out_type[c] = t->types[c];
     }
     // With visibility lists the host knows every page's row count: the row offsets are scanned here and

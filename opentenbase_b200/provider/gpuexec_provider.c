@@ -267,6 +267,7 @@ gpuexec_load_relation(Relation rel, EState *estate, GpuRelInfo *info, gx_table *
 
 		hd.att_len[i] = att->attlen;
 		hd.att_align[i] = att->attalign == 'd' ? 8 : att->attalign == 'i' ? 4 : att->attalign == 's' ? 2 : 1;
+		hd.att_notnull[i] = att->attnotnull ? 1 : 0;	/* no NULL array: the kernels' no-NULL fast paths stay open */
 	}
 	for (i = 0; i < info->ncols; i++)
 	{
@@ -314,6 +315,7 @@ gpuexec_load_relation(Relation rel, EState *estate, GpuRelInfo *info, gx_table *
 		}
 	}
 	heap_endscan(scan);
+	GX_CHECK(gx_table_load_finish(*out));
 }
 
 /* ------------------------------------------- custom_private (de)serialisation

@@ -247,13 +247,14 @@ int main(int argc, char **argv)
 		for (i = 0; i < natts; i++)
 		{
 			Form_pg_attribute a = TupleDescAttr(d, i);
-			int32		len = rd32(f), align = rd32(f), typid = rd32(f);
+			int32		len = rd32(f), align = rd32(f), typid = rd32(f), notnull = rd32(f);
 
 			a->attlen = (int16) len;
 			a->attalign = align == 8 ? 'd' : align == 4 ? 'i' : align == 2 ? 's' : 'c';
 			a->atttypid = (Oid) typid;
 			a->attnum = i + 1;
 			a->attbyval = len > 0;
+			a->attnotnull = notnull != 0;
 			a->atttypmod = typid == BPCHAROID ? VARHDRSZ + 1 : -1;
 			snprintf(NameStr(a->attname), NAMEDATALEN, "a%d", i + 1);
 		}

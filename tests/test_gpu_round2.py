@@ -330,3 +330,28 @@ def test_left_semi_anti_joins(gx):
             gx.hash_probe(ot, 0, ht, [0, 1], join_type=jt)
         assert ei.value.status == g.GX_ERR_ARG
     ot.free(); it.free()
+
+
+def test_not_null_columns_are_staged_without_null_arrays(gx):
+    """pg_attribute.attnotnull reaches the loader (gx_heap_desc.att_notnull): such a column gets no NULL array, so the
+    no-NULL fast paths stay open for heap-loaded tables; a NULL arriving in it is reported, not silently kept."""
+    rng = np.random.default_rng(4)
+    n = 4000
+    types = [O.GX_INT8, O.GX_FLOAT8]
+    cols = [rng.integers(0, 2**40, n), rng.random(n)]
+    rel = O.Rel(types, cols)
+    t = gx.table([g.GX_INT8, g.GX_FLOAT8], n)
+    t.append_heap_pages(rel.pages(), [8, 8], [8, 8], [0, 1], notnull=[True, True])
+    k, kn = t.read(0, with_nulls=True)
+    np.testing.assert_array_equal(k, cols[0]); assert not kn.any()
+    # the same relation with a NULL in the "NOT NULL" column
+    rel2 = O.Rel(types, cols, [None, (np.arange(n) == 17).astype(np.uint8)])
+    t2 = gx.table([g.GX_INT8, g.GX_FLOAT8], n)
+    with pytest.raises(g.GxError) as ei:
+        t2.append_heap_pages(rel2.pages(), [8, 8], [8, 8], [0, 1], notnull=[True, True])
+    assert ei.value.status == g.GX_ERR_STATE
+    t3 = gx.table([g.GX_INT8, g.GX_FLOAT8], n)
+    t3.append_heap_pages(rel2.pages(), [8, 8], [8, 8], [0, 1], notnull=[True, False])
+    assert t3.read(1, with_nulls=True)[1].sum() == 1
+    for x in (t, t2, t3):
+        x.free()

@@ -28,15 +28,15 @@ GXT = {O.GX_INT4: g.GX_INT4, O.GX_INT8: g.GX_INT8, O.GX_FLOAT8: g.GX_FLOAT8, O.G
 INT8OID, FLOAT8OID, FLOAT8ARRAYOID = 20, 701, 1022
 
 
-def write_case(path, rels, outer, inner, plan, partial, out_types):
-    """rels: [(oracle types, O.Rel)]; outer/inner: dict(rti, attnums); inner also key_col, payload_cols, unique, preds"""
+def write_case(path, rels, outer, inner, plan, partial, out_types, notnull=True):
+    """rels: [(oracle types, O.Rel)]; notnull: the columns are declared NOT NULL (as in the TPC-H DDL); outer/inner: dict(rti, attnums); inner also key_col, payload_cols, unique, preds"""
     with open(path, "wb") as f:
         f.write(b"GXH1")
         f.write(struct.pack("<i", len(rels)))
         for types, rel in rels:
             f.write(struct.pack("<i", len(types)))
             for t in types:
-                f.write(struct.pack("<iii", *PG[t]))
+                f.write(struct.pack("<iiii", *PG[t], 1 if notnull else 0))
             f.write(struct.pack("<q", rel.npages))
             f.write(struct.pack("<f", float(rel.ntuples)))
             f.write(rel.pages().tobytes())
