@@ -386,7 +386,7 @@ def run_ours(args):
 
         def q3():
             r = P.q3_datanode(ctx, ct, ot, lt, cols["c"], cols["o"], cols["l"], q3stats)
-            out = r.fetch()
+            out = r.fetch(pinned=True)            # a million groups: the result lands in reusable pinned buffers
             r.free()
             return out
         ms, ph, out, nlaunch = timed_block(q3, xsteps)

@@ -336,12 +336,19 @@ class Result:
         self.ctx._chk(lib().gx_result_combine(self.ctx.h, self.h))
         return self
 
-    def fetch(self):
-        """keys int64[n, ng], aggs float64[n, na] (int results bit-cast), nulls uint8[n, ng+na]"""
+    def fetch(self, pinned=False):
+        """keys int64[n, ng], aggs float64[n, na] (int results bit-cast), nulls uint8[n, ng+na].
+        pinned=True: the arrays are views of the context's reusable pinned result buffers (valid until the
+        next pinned fetch) — what a caller that fetches large results repeatedly would hand in."""
         n, ng, na = self.ngroups, self.plan.n_group_cols, self.plan.n_aggs
-        keys = np.zeros((n, ng), np.int64)
-        aggs = np.zeros((n, na), np.float64)
-        nulls = np.zeros((n, ng + na), np.uint8)
+        if pinned:
+            keys = self.ctx.pinned_array("keys", (n, ng), np.int64)
+            aggs = self.ctx.pinned_array("aggs", (n, na), np.float64)
+            nulls = self.ctx.pinned_array("nulls", (n, ng + na), np.uint8)
+        else:
+            keys = np.zeros((n, ng), np.int64)
+            aggs = np.zeros((n, na), np.float64)
+            nulls = np.zeros((n, ng + na), np.uint8)
         self.ctx._chk(lib().gx_result_fetch(self.h, n, keys.ctypes.data, aggs.ctypes.data, nulls.ctypes.data))
         return keys, aggs, nulls
 
@@ -379,8 +386,26 @@ class Context:
         if st != GX_OK:
             raise GxError(st, (lib().gx_last_error(self.h) or b"").decode())
 
+    def pinned_array(self, name, shape, dtype):
+        """numpy view of a cached pinned host buffer (gx_host_alloc), grown on demand"""
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        nbytes = max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 8)
+        ptr, cap = self._pinned.get(name, (None, 0))
+        if cap < nbytes:
+            if ptr:
+                self.host_free(ptr)
+            cap = int(nbytes * 1.25) + 4096
+            ptr = self.host_alloc(cap)
+            self._pinned[name] = (ptr, cap)
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def close(self):
         if self.h:
+            for ptr, _ in getattr(self, "_pinned", {}).values():
+                lib().gx_host_free(self.h, ptr)
+            self._pinned = {}
             lib().gx_shutdown(self.h)
             self.h = None
 

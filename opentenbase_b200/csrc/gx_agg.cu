@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(LPT_K == 8 ? 640 : 1024, 1) gx_k_agg_lptile(co
 template <int K> __device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K]);
 #define FG_G  4
 #define FG_NV 5
-#define FG_K  4                         /* rows per lane and tile: independent loads in flight */
+#define FG_K  8                         /* rows per lane and tile: independent loads in flight; the plan walk is paid once per tile */
 #define FG_NC 4                         /* distinct float8 columns the aggregate arguments may read */
 struct gx_fewgroups_args {
     int nv, nc;
@@ -645,52 +645,73 @@ __device__ __forceinline__ void slot_term(const gx_dterm &t, int slot, const dou
     else reg_term<K>(t.kind, t.k, x[NC > 3 ? 3 : 0], out);
 }
 
-__global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_fewgroups_args F)
+// BYTEKEY: the group key is one or two 1-byte columns without NULLs (Q1: l_returnflag, l_linestatus) — packed with
+// two byte loads instead of the generic column walk.
+#define FG_THREADS 512
+template <bool BYTEKEY>
+__global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_fewgroups_args F)
 {
+    extern __shared__ unsigned long long fg_smem[];            // [warp][word][group][lane]: a lane's own accumulators (bank == lane)
     __shared__ unsigned long long s_keys[FG_G];
     __shared__ unsigned int s_state[FG_G];
     __shared__ unsigned long long s_acc[FG_G][1 + FG_NV];
     __shared__ int s_over;
-    const int lane = threadIdx.x & 31, nv = F.nv;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nv = F.nv, nw = 1 + nv;
     if (threadIdx.x < FG_G) { s_state[threadIdx.x] = 0u; s_keys[threadIdx.x] = 0ULL; }
     if (threadIdx.x < FG_G * (1 + FG_NV)) ((unsigned long long *) s_acc)[threadIdx.x] = 0ULL;
     if (threadIdx.x == 0) s_over = 0;
+    unsigned long long *const acc = fg_smem + (size_t) warp * nw * FG_G * 32 + lane;     // + (word * FG_G + group) * 32
+    for (int i = 0; i < nw * FG_G; i++) acc[i * 32] = 0ULL;
     __syncthreads();
     const gx_dplan &P = A.P;
-    double acc[FG_G][FG_NV]; unsigned int cnt[FG_G];
-#pragma unroll
-    for (int gI = 0; gI < FG_G; gI++) { cnt[gI] = 0u;
-#pragma unroll
-        for (int w = 0; w < FG_NV; w++) acc[gI][w] = 0.0; }
+    // keys the CTA has handed out so far; an unused entry holds a value no packed key can take (BYTEKEY keys are
+    // below 2^16; the generic path also checks the valid bit)
     unsigned long long gk[FG_G]; unsigned int gvalid = 0u;
 #pragma unroll
-    for (int gI = 0; gI < FG_G; gI++) gk[gI] = 0ULL;
+    for (int gI = 0; gI < FG_G; gI++) gk[gI] = ~0ULL;
+    const unsigned char *kc0 = (const unsigned char *) P.gcols[0].col.data, *kc1 = (const unsigned char *) P.gcols[P.ngroup > 1 ? 1 : 0].col.data;
+    const int two = P.ngroup > 1, sh1 = P.gcols[P.ngroup > 1 ? 1 : 0].shift;
     const long long tile = 32LL * FG_K, nwarp_total = (long long) gridDim.x * (blockDim.x >> 5);
-    const long long wid = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long wid = (long long) blockIdx.x * (blockDim.x >> 5) + warp;
     for (long long base = A.row0 + wid * tile; base < A.row1; base += nwarp_total * tile) {
         if (*(volatile int *) &s_over) break;
         long long r[FG_K]; bool ok[FG_K]; int gi[FG_K];
 #pragma unroll
         for (int j = 0; j < FG_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < A.row1; }
         // ---- every column the tile needs is requested before anything is used: argument columns first (no use
-        // until the arithmetic below), then the qual columns, then the group columns
+        // until the arithmetic below), then the group columns, then the qual columns
         double x[FG_NC][FG_K];
 #pragma unroll
         for (int c = 0; c < FG_NC; c++) {
+            const double *pc = F.col[c < F.nc ? c : 0] + base + lane;      // row j of the tile sits at a compile-time offset
 #pragma unroll
-            for (int j = 0; j < FG_K; j++) x[c][j] = (c < F.nc && ok[j]) ? __ldg(F.col[c] + r[j]) : 0.0;
+            for (int j = 0; j < FG_K; j++) x[c][j] = (c < F.nc && ok[j]) ? __ldg(pc + j * 32) : 0.0;
+        }
+        unsigned long long key[FG_K];
+        if (BYTEKEY) {
+            unsigned int b0[FG_K], b1[FG_K];
+            const unsigned char *p0 = kc0 + base + lane, *p1 = kc1 + base + lane;
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) { b0[j] = ok[j] ? __ldg(p0 + j * 32) : 0u; b1[j] = (two && ok[j]) ? __ldg(p1 + j * 32) : 0u; }
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) key[j] = (unsigned long long) (b0[j] | (b1[j] << sh1));
+        } else {
+#pragma unroll
+            for (int j = 0; j < FG_K; j++) { unsigned long long k0 = 0, k1; unsigned int nm; if (ok[j]) pack_group_key(P, r[j], 0ULL, k0, k1, nm); key[j] = k0; }
         }
         for (int p = 0; p < P.npreds; p++) pred_tile<FG_K>(P.preds[p], r, ok);
         // group of every row: compare with the keys this CTA knows
-        unsigned long long key[FG_K];
         bool miss = false;
 #pragma unroll
         for (int j = 0; j < FG_K; j++) {
-            unsigned long long k0 = 0, k1; unsigned int nm;
-            if (ok[j]) pack_group_key(P, r[j], 0ULL, k0, k1, nm);
-            key[j] = k0; gi[j] = -1;
+            gi[j] = -1;
+            if (BYTEKEY) {
 #pragma unroll
-            for (int gI = 0; gI < FG_G; gI++) if (((gvalid >> gI) & 1u) && k0 == gk[gI]) gi[j] = gI;
+                for (int gI = 0; gI < FG_G; gI++) if ((unsigned int) key[j] == (unsigned int) gk[gI]) gi[j] = gI;      // 32-bit compare; unused entries hold 0xffffffff
+            } else {
+#pragma unroll
+                for (int gI = 0; gI < FG_G; gI++) if (((gvalid >> gI) & 1u) && key[j] == gk[gI]) gi[j] = gI;
+            }
             miss |= ok[j] && gi[j] < 0;
         }
         if (__any_sync(0xffffffffu, miss)) {                       // first sight of a key (a handful of times per CTA)
@@ -701,11 +722,10 @@ __global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__
             for (int gI = 0; gI < FG_G; gI++) if (*(volatile unsigned int *) &s_state[gI] == 2u) { gk[gI] = *(volatile unsigned long long *) &s_keys[gI]; gvalid |= 1u << gI; }
             if (*(volatile int *) &s_over) break;                  // more groups than accumulators: the host takes the general path
         }
+        // ---- accumulate: word 0 = rows, word 1 + w = sum of value w; [word][group][lane], a lane touches only its own column
+        unsigned long long *ap[FG_K];
 #pragma unroll
-        for (int j = 0; j < FG_K; j++) {
-#pragma unroll
-            for (int gI = 0; gI < FG_G; gI++) cnt[gI] += (ok[j] && gi[j] == gI) ? 1u : 0u;
-        }
+        for (int j = 0; j < FG_K; j++) { ap[j] = acc + (size_t) (gi[j] < 0 ? 0 : gi[j]) * 32; if (ok[j]) *ap[j] += 1ULL; }
 #pragma unroll
         for (int w = 0; w < FG_NV; w++) {
             if (w >= nv) break;
@@ -728,26 +748,23 @@ __global__ void __launch_bounds__(512, 1) gx_k_fewgroups(const __grid_constant__
                 }
             }
 #pragma unroll
-            for (int j = 0; j < FG_K; j++) {
-#pragma unroll
-                for (int gI = 0; gI < FG_G; gI++) if (ok[j] && gi[j] == gI) acc[gI][w] = __dadd_rn(acc[gI][w], v[j]);
-            }
+            for (int j = 0; j < FG_K; j++) if (ok[j]) { double *pp = (double *) (ap[j] + (size_t) (1 + w) * FG_G * 32); *pp = __dadd_rn(*pp, v[j]); }
         }
     }
-    // ---- threads -> warp -> CTA -> global table
+    // ---- lanes -> warp -> CTA -> global table
+    __syncwarp();
+    for (int i = 0; i < nw * FG_G; i++) {
+        const int word = i / FG_G, gI = i % FG_G;
+        unsigned long long raw = acc[i * 32];
+        if (word == 0) {
 #pragma unroll
-    for (int gI = 0; gI < FG_G; gI++) {
-        unsigned long long c = cnt[gI];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-        if (lane == 0 && c) atomicAdd(&s_acc[gI][0], c);
-#pragma unroll
-        for (int w = 0; w < FG_NV; w++) {
-            if (w >= nv) break;
-            double xx = acc[gI][w];
+            for (int o = 16; o > 0; o >>= 1) raw += __shfl_down_sync(0xffffffffu, raw, o);
+            if (lane == 0 && raw) atomicAdd(&s_acc[gI][0], raw);
+        } else {
+            double xx = __longlong_as_double((long long) raw);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) xx = __dadd_rn(xx, __shfl_down_sync(0xffffffffu, xx, o));
-            if (lane == 0) atomicAdd((double *) &s_acc[gI][1 + w], xx);
+            if (lane == 0) atomicAdd((double *) &s_acc[gI][word], xx);
         }
     }
     __syncthreads();
@@ -773,7 +790,8 @@ __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant_
     if (threadIdx.x < CC_G) { s_state[threadIdx.x] = 0u; s_keys[threadIdx.x] = 0ULL; s_cnt[threadIdx.x] = 0ULL; }
     if (threadIdx.x == 0) s_over = 0;
     __syncthreads();
-    unsigned int cnt[CC_G], rep[CC_G]; unsigned int gvalid = 0u;
+    unsigned int cnt[CC_G], rep[CC_G];
+    int ngk = 0;                                                    // keys this thread knows: a prefix of the CTA's list
 #pragma unroll
     for (int gI = 0; gI < CC_G; gI++) { cnt[gI] = 0u; rep[gI] = 0u; }
     auto insert = [&](unsigned int byte) -> bool {
@@ -789,24 +807,29 @@ __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant_
         }
         return false;
     };
-    auto reload = [&]() {
+    auto reload = [&]() {                                          // slots are claimed in order: the ready ones form a prefix
+        int n = 0;
 #pragma unroll
-        for (int gI = 0; gI < CC_G; gI++) if (*(volatile unsigned int *) &s_state[gI] == 2u) {
-            rep[gI] = (unsigned int) *(volatile unsigned long long *) &s_keys[gI] * 0x01010101u; gvalid |= 1u << gI; }
+        for (int gI = 0; gI < CC_G; gI++) if (n == gI && *(volatile unsigned int *) &s_state[gI] == 2u) {
+            rep[gI] = (unsigned int) *(volatile unsigned long long *) &s_keys[gI] * 0x01010101u; n = gI + 1; }
+        ngk = n;
     };
-    auto count_word = [&](unsigned int w, unsigned int keep /* 0xff per byte that is a row */) {
+    // bytes of w equal to the replicated key: 0x80 in every matching byte (exact zero-byte test of w ^ rep)
+    auto eqmask = [](unsigned int w, unsigned int rep) -> unsigned int { const unsigned int x = w ^ rep; return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); };
+    auto count_word = [&](unsigned int w, unsigned int keep /* 0x80 per byte that is a row */) {
         unsigned int seen = 0u;
 #pragma unroll
         for (int gI = 0; gI < CC_G; gI++) {
-            const unsigned int m = ((gvalid >> gI) & 1u) ? (__vcmpeq4(w, rep[gI]) & keep) : 0u;
-            cnt[gI] += (unsigned int) __popc(m) >> 3; seen |= m;
+            if (gI >= ngk) break;
+            const unsigned int m = eqmask(w, rep[gI]) & keep;
+            cnt[gI] += (unsigned int) __popc(m); seen |= m;
         }
         if (seen != keep) {                                        // a byte value this thread has not seen yet
-            for (int b = 0; b < 4; b++) if (((keep & ~seen) >> (8 * b)) & 0xffu) { if (!insert((w >> (8 * b)) & 0xffu)) s_over = 1; }
+            for (int b = 0; b < 4; b++) if (((keep & ~seen) >> (8 * b)) & 0x80u) { if (!insert((w >> (8 * b)) & 0xffu)) s_over = 1; }
             reload();
             const unsigned int todo = keep & ~seen;
 #pragma unroll
-            for (int gI = 0; gI < CC_G; gI++) { const unsigned int m = ((gvalid >> gI) & 1u) ? (__vcmpeq4(w, rep[gI]) & todo) : 0u; cnt[gI] += (unsigned int) __popc(m) >> 3; }
+            for (int gI = 0; gI < CC_G; gI++) { if (gI >= ngk) break; cnt[gI] += (unsigned int) __popc(eqmask(w, rep[gI]) & todo); }
         }
     };
     const long long n = A.row1 - A.row0;
@@ -815,16 +838,16 @@ __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant_
     long long head = (long long) ((16 - ((unsigned long long) p0 & 15ULL)) & 15ULL); if (head > n) head = n;
     const long long nvec = (n - head) >> 4, tail0 = head + (nvec << 4);
     const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long) gridDim.x * blockDim.x;
-    if (tid < head) count_word((unsigned int) (unsigned char) p0[tid], 0xffu);
-    if (tid < n - tail0) count_word((unsigned int) (unsigned char) p0[tail0 + tid], 0xffu);
+    if (tid < head) count_word((unsigned int) (unsigned char) p0[tid], 0x80u);
+    if (tid < n - tail0) count_word((unsigned int) (unsigned char) p0[tail0 + tid], 0x80u);
     const uint4 *pv = (const uint4 *) (p0 + head);
     for (long long i = tid; i < nvec; i += 2 * nthr) {             // two vectors in flight per thread
         uint4 v, u = make_uint4(0, 0, 0, 0);
         const bool two = i + nthr < nvec;
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pv + i));
         if (two) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(pv + i + nthr));
-        count_word(v.x, 0xffffffffu); count_word(v.y, 0xffffffffu); count_word(v.z, 0xffffffffu); count_word(v.w, 0xffffffffu);
-        if (two) { count_word(u.x, 0xffffffffu); count_word(u.y, 0xffffffffu); count_word(u.z, 0xffffffffu); count_word(u.w, 0xffffffffu); }
+        count_word(v.x, 0x80808080u); count_word(v.y, 0x80808080u); count_word(v.z, 0x80808080u); count_word(v.w, 0x80808080u);
+        if (two) { count_word(u.x, 0x80808080u); count_word(u.y, 0x80808080u); count_word(u.z, 0x80808080u); count_word(u.w, 0x80808080u); }
     }
     const int lane = threadIdx.x & 31;                             // list positions are the CTA's: every thread counts key g in cnt[g]
 #pragma unroll
@@ -1243,7 +1266,31 @@ __device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r
     }
 }
 
-#define RA_K 4                           /* slabs (of 32 rows) per tile: their loads are issued together */
+// quals of FOUR CONSECUTIVE rows starting at r0 (a multiple of 4): one 128-bit load per 4-byte column, two per 8-byte one
+__device__ __forceinline__ void pred_vec4(const gx_dpred &p, long long r0, bool (&ok)[4])
+{
+    if (p.col.nulls == nullptr && (p.col.type == GX_INT4 || p.col.type == GX_DATE)) {
+        const int4 v = ld_stream_i4((const int *) p.col.data + r0);
+        const int x[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) ok[i] = ok[i] && gx_op_holds(p.op, (long long) x[i] > p.ival ? 1 : ((long long) x[i] < p.ival ? -1 : 0));
+    } else if (p.col.nulls == nullptr && p.col.type == GX_FLOAT8) {
+        const double2 a = ld_stream_d2((const double *) p.col.data + r0), b = ld_stream_d2((const double *) p.col.data + r0 + 2);
+        const double x[4] = { a.x, a.y, b.x, b.y };
+#pragma unroll
+        for (int i = 0; i < 4; i++) ok[i] = ok[i] && gx_op_holds(p.op, gx_f8cmp(x[i], p.fval));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (ok[i]) ok[i] = gx_eval_pred(p, r0 + i);
+    }
+}
+
+// The kernel.  A lane owns FOUR CONSECUTIVE rows of a 128-row tile (128-bit loads for every column), folds them
+// serially into runs, and only the runs' boundaries meet other lanes: a warp scan numbers the run heads, a run that
+// starts in a lane is written to the per-warp list by that lane, the rows that continue a run begun further left
+// are added to its list entry with a shared-memory atomic.  Entry 0 of the list is the run left open by the previous
+// tile (the carry), so a run may span any number of lanes and tiles of the warp's chunk.  All entries but the last
+// are then complete and are processed densely, one run per lane (probe, final record); the last becomes the carry.
 template <int NV, int NC>
 __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_runagg_args R)
 {
@@ -1263,21 +1310,14 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
     const long long c0 = A.row0 + gw * R.rows_per_warp;
     long long c1 = c0 + R.rows_per_warp; if (c1 > A.row1) c1 = A.row1;
     if (c0 >= c1) return;
-    const unsigned int le = 0xffffffffu >> (31 - lane), lt = le >> 1;
+    const unsigned int lt = (1u << lane) - 1;
     bool bad = false;
-    // carry = the (unfinished) last run seen so far
-    bool carry_valid = false, first_pending = true;
-    long long carry_key = 0; unsigned int carry_c = 0; double carry_v[NV];
-#pragma unroll
-    for (int q = 0; q < NV; q++) carry_v[q] = 0.0;
-    long long prev_last = c0 > A.row0 ? __ldg(okey + c0 - 1) : __ldg(okey + c0);
-    int n_list = 0;
 
-    auto flush = [&]() {
-        __syncwarp();
-        for (int b = 0; b < n_list; b += 32) {
+    // entries [0, n) of the list: probe, then a final record (or, for a run that touches the chunk's edge, the global table)
+    auto flush = [&](int n) {
+        for (int b = 0; b < n; b += 32) {
             const int i = b + lane;
-            const bool valid = i < n_list;
+            const bool valid = i < n;
             const long long key = valid ? Qkey[i] : 0;
             const unsigned int craw = valid ? Qcnt[i] : 0u, cnt = craw & ~RA_BND;
             const bool bnd = (craw & RA_BND) != 0;
@@ -1320,115 +1360,128 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
                 }
             }
         }
-        n_list = 0;
         __syncwarp();
     };
 
-    for (long long tb = c0; tb < c1; tb += 32 * RA_K) {
-        // ---- the tile's loads: keys, qual columns, aggregate arguments of RA_K slabs, issued together
-        long long r[RA_K], kk[RA_K]; bool ok[RA_K]; double vv[NV][RA_K];
+    // entry 0 = the open run: the chunk's first key, nothing counted yet; it may have begun in the previous chunk
+    long long carry_key = __ldg(okey + c0);
+    if (c0 > A.row0) bad |= carry_key < __ldg(okey + c0 - 1);
+    if (lane == 0) {
+        Qkey[0] = carry_key; Qcnt[0] = RA_BND;
 #pragma unroll
-        for (int j = 0; j < RA_K; j++) { r[j] = tb + j * 32 + lane; ok[j] = r[j] < c1; }
+        for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST] = 0.0;
+    }
+    __syncwarp();
+
+    for (long long t0 = c0; t0 < c1; t0 += 128) {
+        const long long r0 = t0 + lane * 4;
+        long long k[4]; bool ok[4]; double x[NC][4];
+        if (t0 + 128 <= c1) {                                   // full tile: 128-bit loads, everything requested before use
+            const longlong2 ka = ld_stream_ll2(okey + r0), kb = ld_stream_ll2(okey + r0 + 2);
+            k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
 #pragma unroll
-        for (int j = 0; j < RA_K; j++) kk[j] = ok[j] ? __ldg(okey + r[j]) : 0;
-        // argument columns next, unconditionally for the rows of the tile (a row that fails the quals shares its
-        // sectors with rows that pass): nothing below waits for the quals before its loads are in flight
-        double x[NC][RA_K];
+            for (int c = 0; c < NC; c++) {
+                if (c < R.nc) { const double2 a = ld_stream_d2(R.col[c] + r0), b = ld_stream_d2(R.col[c] + r0 + 2); x[c][0] = a.x; x[c][1] = a.y; x[c][2] = b.x; x[c][3] = b.y; }
+                else { x[c][0] = x[c][1] = x[c][2] = x[c][3] = 0.0; }
+            }
+            ok[0] = ok[1] = ok[2] = ok[3] = true;
+            for (int p = 0; p < P.npreds; p++) pred_vec4(P.preds[p], r0, ok);
+        } else {                                                // the chunk's last, partial tile: rows past the end extend the last run with nothing
+            const long long last = c1 - 1;
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
+            for (int i = 0; i < 4; i++) {
+                const long long r = r0 + i < c1 ? r0 + i : last;
+                k[i] = __ldg(okey + r); ok[i] = r0 + i < c1;
 #pragma unroll
-            for (int j = 0; j < RA_K; j++) x[c][j] = (c < R.nc && ok[j]) ? __ldg(R.col[c] + r[j]) : 0.0;
+                for (int c = 0; c < NC; c++) x[c][i] = c < R.nc ? __ldg(R.col[c] + r) : 0.0;
+                for (int p = 0; p < P.npreds; p++) if (ok[i]) ok[i] = gx_eval_pred(P.preds[p], r);
+            }
         }
-        for (int p = 0; p < P.npreds; p++) pred_tile<RA_K>(P.preds[p], r, ok);
+        // aggregate arguments of the lane's four rows
+        double v[NV][4];
 #pragma unroll
         for (int q = 0; q < NV; q++) {
 #pragma unroll
-            for (int j = 0; j < RA_K; j++) vv[q][j] = 0.0;
+            for (int i = 0; i < 4; i++) v[q][i] = 0.0;
             if (q < nv) {
                 const gx_dexpr &e = P.aggs[R.vagg[q]].expr;
-                slot_term<RA_K, NC>(e.t[0], R.tslot[q][0], x, vv[q]);
-                for (int i = 1; i < e.nterms; i++) {
-                    double y[RA_K];
-                    slot_term<RA_K, NC>(e.t[i], R.tslot[q][i], x, y);
-                    const int op = e.t[i].op;
+                slot_term<4, NC>(e.t[0], R.tslot[q][0], x, v[q]);
+                for (int t = 1; t < e.nterms; t++) {
+                    double y[4];
+                    slot_term<4, NC>(e.t[t], R.tslot[q][t], x, y);
+                    const int op = e.t[t].op;
 #pragma unroll
-                    for (int j = 0; j < RA_K; j++) vv[q][j] = op == GX_OP_ADD ? __dadd_rn(vv[q][j], y[j]) : (op == GX_OP_SUB ? __dsub_rn(vv[q][j], y[j]) : __dmul_rn(vv[q][j], y[j]));
+                    for (int i = 0; i < 4; i++) v[q][i] = op == GX_OP_ADD ? __dadd_rn(v[q][i], y[i]) : (op == GX_OP_SUB ? __dsub_rn(v[q][i], y[i]) : __dmul_rn(v[q][i], y[i]));
                 }
-#pragma unroll
-                for (int j = 0; j < RA_K; j++) vv[q][j] = ok[j] ? vv[q][j] : 0.0;
             }
         }
-        // ---- slab by slab: run heads, segmented reduction, list
+        // ---- run heads, their numbering inside the warp, order check
+        long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+        if (lane == 0) prevk = carry_key;
+        bad |= (k[0] < prevk) | (k[1] < k[0]) | (k[2] < k[1]) | (k[3] < k[2]);
+        bool hd[4];
+        hd[0] = k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+        const int nh = (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3];
+        int inc = nh;
 #pragma unroll
-        for (int j = 0; j < RA_K; j++) {
-            const long long sb = tb + j * 32;
-            if (sb >= c1) break;
-            const int nvalid = (int) (c1 - sb < 32 ? c1 - sb : 32);
-            const bool in = lane < nvalid;
-            const long long klast = __shfl_sync(0xffffffffu, kk[j], nvalid - 1);
-            const long long k = in ? kk[j] : klast;                        // lanes past the end extend the last run with nothing
-            unsigned int c = (in && ok[j]) ? 1u : 0u;
-            double v[NV];
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int ebase = inc - nh;                             // list entry of the run that is open when this lane starts (0 = the carry)
+        const int nheads = __shfl_sync(0xffffffffu, inc, 31);
+        // ---- fold: runs that start in this lane are written, the rows continuing an earlier run are added to it afterwards
+        unsigned int cc = 0; double cs[NV];                    // the continuing part
 #pragma unroll
-            for (int q = 0; q < NV; q++) v[q] = vv[q][j];
-            long long prevk = __shfl_up_sync(0xffffffffu, k, 1);
-            if (lane == 0) prevk = prev_last;
-            bad |= k < prevk;
-            const bool head = lane == 0 ? (!carry_valid || k != carry_key) : (k != prevk);
-            const unsigned int heads = __ballot_sync(0xffffffffu, head);
-            const int seg = 31 - __clz((heads | 1u) & le);                 // first lane of this lane's run inside the slab
+        for (int q = 0; q < NV; q++) cs[q] = 0.0;
+        {
+            int e = ebase; unsigned int c = 0; double sacc[NV];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned int tc = __shfl_up_sync(0xffffffffu, c, d);
-                const bool take = lane - d >= seg;
-                if (take) c += tc;
+            for (int q = 0; q < NV; q++) sacc[q] = 0.0;
 #pragma unroll
-                for (int q = 0; q < NV; q++) if (q < nv) { const double tv = __shfl_up_sync(0xffffffffu, v[q], d); if (take) v[q] = __dadd_rn(v[q], tv); }
+            for (int i = 0; i < 4; i++) {
+                if (hd[i]) {
+                    if (e > ebase) { Qcnt[e] = c;
+#pragma unroll
+                        for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + e] = sacc[q]; }
+                    else { cc = c;
+#pragma unroll
+                        for (int q = 0; q < NV; q++) cs[q] = sacc[q]; }
+                    e++; Qkey[e] = k[i]; c = 0;
+#pragma unroll
+                    for (int q = 0; q < NV; q++) sacc[q] = 0.0;
+                }
+                if (ok[i]) { c++;
+#pragma unroll
+                    for (int q = 0; q < NV; q++) if (q < nv) sacc[q] = __dadd_rn(sacc[q], v[q][i]); }
             }
-            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-            const bool cont = !(heads & 1u);                               // lane 0 continues the carried run
-            if (cont && seg == 0 && tail) {
-                c += carry_c;
+            if (e > ebase) { Qcnt[e] = c;
 #pragma unroll
-                for (int q = 0; q < NV; q++) if (q < nv) v[q] = __dadd_rn(v[q], carry_v[q]);
-            }
-            // the carried run is finished when lane 0 starts a new one
-            const int carry_done = (carry_valid && !cont) ? 1 : 0;
-            if (carry_done && lane == 0) {
-                Qkey[n_list] = carry_key; Qcnt[n_list] = carry_c | (first_pending ? RA_BND : 0u);
+                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + e] = sacc[q]; }
+            else { cc = c;
 #pragma unroll
-                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + n_list] = carry_v[q];
-            }
-            const unsigned int emit = (heads >> 1) & 0x7fffffffu;         // tails except lane 31's run, which becomes the carry
-            if (tail && lane != 31) {
-                const int rank = __popc(emit & lt);
-                const int pos = n_list + carry_done + rank;
-                // the chunk's first run (the one holding row c0) may have started in the previous chunk
-                const bool is_first = first_pending && !carry_done && rank == 0;
-                Qkey[pos] = k; Qcnt[pos] = c | (is_first ? RA_BND : 0u);
-#pragma unroll
-                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + pos] = v[q];
-            }
-            const int nemit = carry_done + __popc(emit);
-            if (nemit) first_pending = false;
-            n_list += nemit;
-            // new carry = lane 31's run
-            carry_key = __shfl_sync(0xffffffffu, k, 31); carry_c = __shfl_sync(0xffffffffu, c, 31);
-#pragma unroll
-            for (int q = 0; q < NV; q++) if (q < nv) carry_v[q] = __shfl_sync(0xffffffffu, v[q], 31);
-            carry_valid = true;
-            prev_last = carry_key;
+                for (int q = 0; q < NV; q++) cs[q] = sacc[q]; }
         }
-        flush();                                                           // <= RA_K * 32 + 1 entries per tile
+        __syncwarp();
+        if (cc) {
+            atomicAdd(&Qcnt[ebase], cc);
+#pragma unroll
+            for (int q = 0; q < NV; q++) if (q < nv) atomicAdd(&Qsum[(size_t) q * RA_LIST + ebase], cs[q]);
+        }
+        __syncwarp();
+        // ---- entries [0, nheads) are complete; entry nheads is the new carry
+        if (nheads > 0) {
+            flush(nheads);
+            if (lane == 0) {
+                Qkey[0] = Qkey[nheads]; Qcnt[0] = Qcnt[nheads];
+#pragma unroll
+                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST] = Qsum[(size_t) q * RA_LIST + nheads];
+            }
+            __syncwarp();
+        }
+        carry_key = __shfl_sync(0xffffffffu, k[3], 31);
     }
     // the last run of the chunk may continue in the next chunk
-    if (lane == 0) {
-        Qkey[0] = carry_key; Qcnt[0] = carry_c | RA_BND;
-#pragma unroll
-        for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST] = carry_v[q];
-    }
-    n_list = 1;
-    flush();
+    if (lane == 0) Qcnt[0] |= RA_BND;
+    __syncwarp();
+    flush(1);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr((unsigned long long *) &A.counters[1], 8ULL);
 }
 
@@ -2160,9 +2213,20 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             gx_k_count_char<<<ctx->sm_count * 2, 512, 0, ctx->stream>>>(A, (const signed char *) A.P.gcols[0].col.data);
             rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
         } else if (use_few) {
-            long long nb = (outer->nrows + 16 * 32 * FG_K - 1) / (16 * 32 * FG_K);
+            const int fg_warps = FG_THREADS / 32;
+            const size_t fg_smem = (size_t) fg_warps * (1 + FG.nv) * FG_G * 32 * 8;
+            bool bytekey = plan->n_group_cols <= 2;
+            for (int c = 0; c < plan->n_group_cols; c++) bytekey = bytekey && A.P.gcols[c].type == GX_CHAR && A.P.gcols[c].word == 0;
+            static bool fg_attr = false;
+            if (!fg_attr) {
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin - 1024));   // static shared memory counts too
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin - 1024));
+                fg_attr = true;
+            }
+            long long nb = (outer->nrows + fg_warps * 32 * FG_K - 1) / (fg_warps * 32 * FG_K);
             gx_launch_scope ls(ctx, kname);
-            gx_k_fewgroups<<<(unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count), 512, 0, ctx->stream>>>(A, FG);
+            if (bytekey) gx_k_fewgroups<true><<<(unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count), FG_THREADS, fg_smem, ctx->stream>>>(A, FG);
+            else gx_k_fewgroups<false><<<(unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count), FG_THREADS, fg_smem, ctx->stream>>>(A, FG);
             rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
         }
         else if (strategy == 1 && gmax && lptile_ok) rc = launch_lptile(ctx, A, lp_bytes, kname, lp_warps * 32);

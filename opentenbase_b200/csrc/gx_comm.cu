@@ -286,20 +286,14 @@ __global__ void __launch_bounds__(RP_THREADS) gx_k_route_onepass(gx_route1_args 
             tbase[threadIdx.x] = b;
         }
         __syncthreads();
+        long long rr[RP_K], dd[RP_K]; bool keep[RP_K];
 #pragma unroll
         for (int k = 0; k < RP_K; k++) {
-            if (d[k] < 0 || tbase[d[k]] < 0) continue;
-            const long long r = base + k * RP_THREADS + threadIdx.x;
-            const long long dst = (long long) d[k] * a.cap + tbase[d[k]] + lp[k];
-            for (int c = 0; c < a.ncols; c++) {
-                switch (a.in[c].type) {
-                    case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = __ldg((const int *) a.in[c].data + r); break;
-                    case GX_CHAR: ((signed char *) a.out[c])[dst] = __ldg((const signed char *) a.in[c].data + r); break;
-                    default: ((long long *) a.out[c])[dst] = __ldg((const long long *) a.in[c].data + r); break;
-                }
-                if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
-            }
+            keep[k] = d[k] >= 0 && tbase[d[k] < 0 ? 0 : d[k]] >= 0;
+            rr[k] = base + k * RP_THREADS + threadIdx.x;
+            dd[k] = keep[k] ? (long long) d[k] * a.cap + tbase[d[k]] + lp[k] : 0;
         }
+        for (int c = 0; c < a.ncols; c++) gx_copy_rows<RP_K>(a.in[c], a.out[c], a.out_nulls[c], rr, dd, keep);
         __syncthreads();
     }
 }

@@ -386,6 +386,36 @@ __device__ __forceinline__ unsigned long long gx_next_slot(unsigned long long s,
     return (s & ~w) | ((s + 1) & w);
 }
 
+// Copy K selected rows of one column (row r[j] -> position dst[j]): the K loads are independent and issued together,
+// the type is decoded once per column instead of once per row (projection / compaction / scatter kernels).
+template <int K>
+__device__ __forceinline__ void gx_copy_rows(const gx_dcol &in, void *out, uint8_t *out_nulls, const long long (&r)[K], const long long (&dst)[K], const bool (&keep)[K])
+{
+    if (in.type == GX_INT4 || in.type == GX_DATE) {
+        int v[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) v[j] = keep[j] ? __ldg((const int *) in.data + r[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) if (keep[j]) ((int *) out)[dst[j]] = v[j];
+    } else if (in.type == GX_CHAR) {
+        signed char v[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) v[j] = keep[j] ? __ldg((const signed char *) in.data + r[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) if (keep[j]) ((signed char *) out)[dst[j]] = v[j];
+    } else {
+        long long v[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) v[j] = keep[j] ? __ldg((const long long *) in.data + r[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) if (keep[j]) ((long long *) out)[dst[j]] = v[j];
+    }
+    if (out_nulls) {
+#pragma unroll
+        for (int j = 0; j < K; j++) if (keep[j]) out_nulls[dst[j]] = in.nulls ? in.nulls[r[j]] : 0;
+    }
+}
+
 // block-wide exclusive scan of one value per thread (blockDim.x <= 1024)
 __device__ __forceinline__ long long gx_block_exscan(long long v, long long *total, long long *smem /* 33 */)
 {

@@ -1106,6 +1106,7 @@ struct gx_probe_args {
     int count_only; int join_type;  // GX_JOIN_*
 };
 
+__device__ __forceinline__ void emit_payload(const gx_probe_args &a, long long dst, unsigned long long payload, bool matched);
 __device__ __forceinline__ void emit_row(const gx_probe_args &a, long long dst, long long r, unsigned long long payload, bool matched = true)
 {
     for (int c = 0; c < a.n_out_outer; c++) {
@@ -1116,6 +1117,10 @@ __device__ __forceinline__ void emit_row(const gx_probe_args &a, long long dst, 
         }
         if (a.out_nulls[c]) a.out_nulls[c][dst] = a.out_src[c].nulls ? a.out_src[c].nulls[r] : 0;
     }
+    emit_payload(a, dst, payload, matched);
+}
+__device__ __forceinline__ void emit_payload(const gx_probe_args &a, long long dst, unsigned long long payload, bool matched)
+{
     if (a.join_type == GX_JOIN_SEMI || a.join_type == GX_JOIN_ANTI) return;      // the inner side is not part of the target list
     const int npo = a.n_payload ? a.n_payload : 1;
     if (a.join_type == GX_JOIN_LEFT)                                               // hj_NullInnerTupleSlot for an unmatched outer row
@@ -1250,10 +1255,14 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
         if (lane == 0) dst0 = (long long) atomicAdd((unsigned long long *) a.cursor, (unsigned long long) total);
         dst0 = __shfl_sync(0xffffffffu, dst0, 0);
         if (a.count_only) continue;
+        // outer columns: column by column, the tile's loads in flight together; then the inner side
+        long long dd[PT_K];
 #pragma unroll
-        for (int j = 0; j < PT_K; j++) {
-            if (hit[j]) { const long long dst = dst0 + __popc(m[j] & lt); if (dst < a.out_cap) emit_row(a, dst, r[j], pay[j], matched[j]); }
-            dst0 += __popc(m[j]);
+        for (int j = 0; j < PT_K; j++) { dd[j] = dst0 + __popc(m[j] & lt); hit[j] = hit[j] && dd[j] < a.out_cap; dst0 += __popc(m[j]); }
+        for (int c = 0; c < a.n_out_outer; c++) gx_copy_rows<PT_K>(a.out_src[c], a.out[c], a.out_nulls[c], r, dd, hit);
+        if (a.join_type != GX_JOIN_SEMI && a.join_type != GX_JOIN_ANTI) {
+#pragma unroll
+            for (int j = 0; j < PT_K; j++) if (hit[j]) emit_payload(a, dd[j], pay[j], matched[j]);
         }
     }
 }

@@ -433,20 +433,10 @@ __global__ void __launch_bounds__(FT_THREADS) gx_k_filter_onepass(gx_filter_args
         }
         __syncthreads();
         const long long prefix = s_prefix;
+        long long rr[FT_K], dd[FT_K];
 #pragma unroll
-        for (int k = 0; k < FT_K; k++) {
-            if (!keep[k]) continue;
-            const long long r = base + k * FT_THREADS + threadIdx.x;
-            const long long dst = prefix + woff[k][warp] + rank[k];
-            for (int c = 0; c < a.ncols; c++) {
-                switch (a.in[c].type) {
-                    case GX_INT4: case GX_DATE: ((int *) a.out[c])[dst] = __ldg((const int *) a.in[c].data + r); break;
-                    case GX_CHAR: ((signed char *) a.out[c])[dst] = __ldg((const signed char *) a.in[c].data + r); break;
-                    default: ((long long *) a.out[c])[dst] = __ldg((const long long *) a.in[c].data + r); break;
-                }
-                if (a.out_nulls[c]) a.out_nulls[c][dst] = a.in[c].nulls ? a.in[c].nulls[r] : 0;
-            }
-        }
+        for (int k = 0; k < FT_K; k++) { rr[k] = base + k * FT_THREADS + threadIdx.x; dd[k] = prefix + woff[k][warp] + rank[k]; }
+        for (int c = 0; c < a.ncols; c++) gx_copy_rows<FT_K>(a.in[c], a.out[c], a.out_nulls[c], rr, dd, keep);
         __syncthreads();                                        // wc / woff / s_* are reused by the next tile
     }
 }
