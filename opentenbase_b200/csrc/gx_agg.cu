@@ -1200,6 +1200,116 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
     smem_dense_merge(T, A);
 }
 
+// 16-byte group slots for gx_k_runjoin2: word 0 = [bit 63 occupied | bits 62..32 rows | bits 31..0 the 4-byte key], the sum
+// lives in a parallel array.  The row count is added to the word's upper half with a native 32-bit shared atomic.
+#define PK_OCC   0x8000000000000000ULL
+#define PK_MATCH 0x80000000FFFFFFFFULL
+template <bool HAS_SUM>
+__device__ __forceinline__ void packed_flush(unsigned long long *tab, double *tsum, int S, const gx_agg_dev &A, int gkey, unsigned int cnt, double sum)
+{
+    const unsigned long long want = PK_OCC | (unsigned long long) (unsigned int) gkey;
+    int s = (int) ((unsigned int) gkey & (unsigned int) (S - 1));
+    for (int n = 0;; n++) {
+        const unsigned long long t = *(volatile unsigned long long *) &tab[s];
+        if ((t & PK_MATCH) == want) break;
+        if (t == 0) { const unsigned long long old = atomicCAS(&tab[s], 0ULL, want); if (old == 0 || (old & PK_MATCH) == want) break; }
+        s = (s + 1) & (S - 1);
+        if (n >= 64) { atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
+    }
+    atomicAdd((unsigned int *) &tab[s] + 1, cnt);                  // little-endian: the upper half holds the row count
+    if (HAS_SUM) atomicAdd(&tsum[s], sum);
+}
+
+template <bool HAS_SUM, bool COMPACT>
+__global__ void __launch_bounds__(512, 2) gx_k_runjoin2(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
+{
+    extern __shared__ unsigned long long smem[];
+    // group table: 16 bytes per slot — [occupied | rows (31 bits) | 4-byte key] and the float8 sum — so that two CTAs
+    // of 512 threads fit one SM (gx_k_runjoin keeps 24-byte slots and one CTA of 1024)
+    const int S = A.s_slots;
+    unsigned long long *const tab = smem; double *const tsum = (double *) (smem + S);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gx_runlist &Q = ((gx_runlist *) (smem + (size_t) S * 2))[warp];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { tab[i] = 0ULL; tsum[i] = 0.0; }
+    __syncthreads();
+    const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    long long k[4]; double v[4];
+    bool act = q < nvec;
+    if (act) {
+        const long long r = A.row0 + (q << 2);
+        longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+        k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+        if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+    }
+    // the loop is warp-uniform: lanes past the end carry no rows
+    while (__any_sync(0xffffffffu, act)) {
+        // ---- run heads and their numbering inside the warp
+        const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+        bool hd[4];
+        hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+        const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
+        int inc = nh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int base = inc - nh, R = __shfl_sync(0xffffffffu, inc, 31);
+        // ---- fold: runs that start in this lane are stored, the rows that continue the previous
+        // lane's run are added to that run afterwards
+        unsigned int c0 = 0; double s0 = 0.0;
+        if (act) {
+            int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (hd[i]) {
+                    if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+                    rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
+                }
+                c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+            }
+            if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+        }
+        __syncwarp();
+        if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
+        __syncwarp();
+        // ---- next rows: requested now, they arrive while the runs are probed
+        q += stride; act = q < nvec;
+        if (act) {
+            const long long r = A.row0 + (q << 2);
+            longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+            k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+            if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+        }
+        // ---- one run per lane
+        for (int j = lane; j < R; j += 32) {
+            const long long key = Q.key[j];
+            const unsigned int rc = Q.cnt[j];
+            const double rs = HAS_SUM ? Q.sum[j] : 0.0;
+            int g = 0;
+            const bool hit = runjoin_probe<COMPACT>(A, key, g);
+            if (hit) packed_flush<HAS_SUM>(tab, tsum, S, A, g, rc, rs);
+        }
+        __syncwarp();
+    }
+    // the (< 4) rows after the last full vector: one thread each
+    {
+        long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < A.row1) {
+            int gk = 0;
+            if (runjoin_probe<COMPACT>(A, F.okey[r], gk)) packed_flush<HAS_SUM>(tab, tsum, S, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {             // the CTA's table into the global one
+        const unsigned long long t = tab[i];
+        if (t == 0) continue;
+        unsigned long long *rec = global_upsert(A, t & 0xFFFFFFFFULL, 0ULL, 0u);
+        if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+        merge_word(&rec[3], WK_ADD_I64, (t >> 32) & 0x7FFFFFFFULL);
+        if (HAS_SUM) merge_word(&rec[3 + F.sum_word], WK_ADD_F64, (unsigned long long) __double_as_longlong(tsum[i]));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // GROUP BY keys that CONTAIN the join key of a unique build side (the Q3 shape: GROUP BY
 // l_orderkey, o_orderdate, o_shippriority) over an outer side stored in key order: all rows of
@@ -1216,7 +1326,7 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
 // Replaces ExecHashJoinImpl's probe loop + agg_fill_hash_table for this shape
 // (nodeHashjoin.c:446-666, nodeAgg.c:2609-2648).
 #define RA_NV   4                        /* float8 sum words per group (beyond the row count) */
-#define RA_LIST 136
+#define RA_LIST 168                      /* <= 31 finished runs waiting for a full round + the carry + 128 new ones */
 #define RA_BND  0x80000000u
 struct gx_runagg_args {
     int nv, nc, _pad0, _pad1;
@@ -1363,7 +1473,9 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
         __syncwarp();
     };
 
-    // entry 0 = the open run: the chunk's first key, nothing counted yet; it may have begun in the previous chunk
+    // entry cbase = the open run (the carry); entries [0, cbase) are finished runs waiting for a full round of 32.
+    // At the start: the chunk's first key, nothing counted yet; it may have begun in the previous chunk.
+    int cbase = 0;
     long long carry_key = __ldg(okey + c0);
     if (c0 > A.row0) bad |= carry_key < __ldg(okey + c0 - 1);
     if (lane == 0) {
@@ -1425,7 +1537,7 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
         int inc = nh;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        const int ebase = inc - nh;                             // list entry of the run that is open when this lane starts (0 = the carry)
+        const int ebase = cbase + inc - nh;                     // list entry of the run that is open when this lane starts (cbase = the carry)
         const int nheads = __shfl_sync(0xffffffffu, inc, 31);
         // ---- fold: runs that start in this lane are written, the rows continuing an earlier run are added to it afterwards
         unsigned int cc = 0; double cs[NV];                    // the continuing part
@@ -1466,22 +1578,33 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
             for (int q = 0; q < NV; q++) if (q < nv) atomicAdd(&Qsum[(size_t) q * RA_LIST + ebase], cs[q]);
         }
         __syncwarp();
-        // ---- entries [0, nheads) are complete; entry nheads is the new carry
-        if (nheads > 0) {
-            flush(nheads);
-            if (lane == 0) {
-                Qkey[0] = Qkey[nheads]; Qcnt[0] = Qcnt[nheads];
+        // ---- entries [0, cbase + nheads) are finished, entry cbase + nheads is the new carry.  Finished runs are
+        // processed in FULL rounds of 32 (one run per lane); the remainder waits at the front of the list.
+        {
+            const int done = cbase + nheads, full = done & ~31;
+            if (full > 0) {
+                flush(full);
+                const int rest = done - full + 1;                   // unprocessed finished runs + the carry
+                for (int i = lane; i < rest; i += 32) {             // rest <= 32: one pass, no overlap hazards (source index >= 32)
+                    const long long kk = Qkey[full + i]; const unsigned int cq = Qcnt[full + i];
+                    double sq[NV];
 #pragma unroll
-                for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST] = Qsum[(size_t) q * RA_LIST + nheads];
+                    for (int q = 0; q < NV; q++) sq[q] = q < nv ? Qsum[(size_t) q * RA_LIST + full + i] : 0.0;
+                    __syncwarp(__activemask());
+                    Qkey[i] = kk; Qcnt[i] = cq;
+#pragma unroll
+                    for (int q = 0; q < NV; q++) if (q < nv) Qsum[(size_t) q * RA_LIST + i] = sq[q];
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            cbase = done - full;
         }
         carry_key = __shfl_sync(0xffffffffu, k[3], 31);
     }
     // the last run of the chunk may continue in the next chunk
-    if (lane == 0) Qcnt[0] |= RA_BND;
+    if (lane == 0) Qcnt[cbase] |= RA_BND;
     __syncwarp();
-    flush(1);
+    flush(cbase + 1);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr((unsigned long long *) &A.counters[1], 8ULL);
 }
 
@@ -1924,8 +2047,36 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
+template <bool HAS_SUM, bool COMPACT>
+static int launch_runjoin2_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, const char *name)
+{
+    static bool attr_set = false;
+    const size_t smem = (size_t) A.s_slots * 16 + 16 * sizeof(gx_runlist);
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin2<HAS_SUM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem > 100 * 1024 ? (int) smem : 100 * 1024));
+        attr_set = true;
+    }
+    long long nvec = (A.row1 - A.row0 + 3) / 4;
+    long long nb = (nvec + 511) / 512, maxb = (long long) ctx->sm_count * 2;
+    while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 31)) maxb *= 2;      // 31-bit row counters per CTA
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_k_runjoin2<HAS_SUM, COMPACT><<<grid, 512, smem, ctx->stream>>>(A, FA);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
 static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name, bool use_run)
 {
+    // gx_k_runjoin2: two CTAs of 512 threads per SM with 16-byte group slots (64 KB + 40 KB of run lists).  MEASURED SLOWER
+    // than one CTA of 1024 threads with 24-byte slots (3.29 vs 2.76 ms at SF100, profiles/r02_runjoin_variants.txt), like the
+    // other attempts to trade CTA size for occupancy on this kernel; kept behind GX_RUNJOIN_V2=1 for the record.
+    {
+        const char *v2 = getenv("GX_RUNJOIN_V2");
+        if (use_run && v2 && v2[0] == '1' && A.s_slots <= 4096) {
+            if (A.cslots) return sum ? launch_runjoin2_t<true, true>(ctx, A, FA, name) : launch_runjoin2_t<false, true>(ctx, A, FA, name);
+            return sum ? launch_runjoin2_t<true, false>(ctx, A, FA, name) : launch_runjoin2_t<false, false>(ctx, A, FA, name);
+        }
+    }
     // the run-folding join kernel keeps a per-warp run list next to the group table
     const size_t run_bytes = 32 * sizeof(gx_runlist);
     if (use_run) {

@@ -373,7 +373,7 @@ __device__ __forceinline__ bool filter_pass(const gx_filter_args &a, long long r
     return ok;
 }
 
-__global__ void __launch_bounds__(FT_THREADS) gx_k_filter_onepass(gx_filter_args a, unsigned long long *tile_state, unsigned int *ticket, long long ntiles, long long *total_out)
+__global__ void __launch_bounds__(FT_THREADS, 4) gx_k_filter_onepass(gx_filter_args a, unsigned long long *tile_state, unsigned int *ticket, long long ntiles, long long *total_out)
 {
     __shared__ unsigned int wc[FT_K][FT_THREADS / 32];
     __shared__ unsigned int woff[FT_K][FT_THREADS / 32];
