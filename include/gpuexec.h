@@ -145,6 +145,10 @@ const char *gx_last_error(gx_ctx *ctx);      /* ctx may be NULL: global msg   */
 int  gx_device_info(gx_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                     int64_t *hbm_bytes);
 int  gx_sync(gx_ctx *ctx);
+/* Map `bytes` of HBM into the context's stream-ordered memory pool now (0 = all that is free minus
+ * 8 GB), so that per-query temporaries never wait for the driver to create physical memory
+ * mid-query.  Call it once per context, after gx_comm_init (NCCL allocates its own buffers). */
+int  gx_pool_reserve(gx_ctx *ctx, size_t bytes);
 
 /* kernel launch counter (bench.py's gpu_launches) and CUDA-event timing of the
  * library's own stream (torch.cuda.Event cannot see it) */

@@ -118,6 +118,7 @@ def _declare(L):
         "gx_last_error": (C.c_char_p, [vp]),
         "gx_device_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
         "gx_sync": (C.c_int, [vp]),
+        "gx_pool_reserve": (C.c_int, [vp, sz]),
         "gx_launch_count": (i64, [vp]),
         "gx_timer_start": (C.c_int, [vp]),
         "gx_timer_stop": (C.c_int, [vp, C.POINTER(dbl)]),
@@ -411,6 +412,9 @@ class Context:
 
     def sync(self):
         self._chk(lib().gx_sync(self.h))
+
+    def pool_reserve(self, nbytes=0):
+        self._chk(lib().gx_pool_reserve(self.h, nbytes))
 
     def device_info(self):
         sm, ma, mi, hbm = C.c_int(), C.c_int(), C.c_int(), C.c_int64()

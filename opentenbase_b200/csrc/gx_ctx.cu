@@ -74,6 +74,29 @@ extern "C" int gx_init(int device, gx_ctx **out)
 
 extern "C" void gx_comm_destroy(gx_ctx *ctx);
 
+// Map `bytes` of HBM into the context's stream-ordered pool up front (one allocation, freed at once; 0 = everything that
+// is free minus 8 GB of headroom for NCCL and the host runtime).  Without it the pool grows on demand, and a query whose
+// temporaries do not fit the blocks already mapped waits for the driver to create and map physical memory in the middle
+// of its critical path: measured 27.8 ms instead of 1.5 ms for one hash build of the Q3 chain, 100-500 ms with two
+// ranks waiting for each other (profiles/r02_pool_reserve.txt).
+extern "C" int gx_pool_reserve(gx_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return GX_ERR_ARG;
+    if (bytes == 0) {
+        size_t fr = 0, tot = 0;
+        GX_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+        const size_t head = (size_t) 8 << 30;
+        if (fr <= head) return GX_OK;
+        bytes = fr - head;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); GX_SET_ERR(ctx, "pool_reserve: %zu bytes: %s", bytes, cudaGetErrorString(e)); return GX_ERR_NOMEM; }
+    GX_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+    GX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GX_OK;
+}
+
 extern "C" void gx_shutdown(gx_ctx *ctx)
 {
     if (!ctx) return;

@@ -82,6 +82,7 @@ void		_PG_init(void);
 
 static bool gpuexec_enabled = true;
 static int	gpuexec_device = 0;
+static int	gpuexec_pool_reserve_mb = 0;	/* HBM mapped into the library's pool when the backend's context is created */
 static int	gpuexec_hbm_limit_mb = 150 * 1024;	/* decline plans whose staged columns + join table would not fit */
 static create_upper_paths_hook_type prev_upper_paths_hook = NULL;
 
@@ -200,6 +201,9 @@ gpuexec_ensure_context(void)
 			ereport(ERROR,
 					(errcode(ERRCODE_EXTERNAL_ROUTINE_EXCEPTION),
 					 errmsg("gpuexec: %s", gx_last_error(NULL))));
+		/* several backends share one GPU: each reserves only what the DBA grants it */
+		if (gpuexec_pool_reserve_mb > 0)
+			GX_CHECK(gx_pool_reserve(backend_ctx, (size_t) gpuexec_pool_reserve_mb << 20));
 	}
 }
 
@@ -1374,6 +1378,8 @@ _PG_init(void)
 							 &gpuexec_enabled, true, PGC_USERSET, 0, NULL, NULL, NULL);
 	DefineCustomIntVariable("gpuexec.device", "CUDA device ordinal used by this datanode.", NULL,
 							&gpuexec_device, 0, 0, 63, PGC_BACKEND, 0, NULL, NULL, NULL);
+	DefineCustomIntVariable("gpuexec.pool_reserve_mb", "HBM (MB) mapped into the GPU memory pool when a backend first uses the GPU (0 = grow on demand).", NULL,
+							&gpuexec_pool_reserve_mb, 0, 0, 1024 * 1024, PGC_BACKEND, 0, NULL, NULL, NULL);
 	DefineCustomIntVariable("gpuexec.hbm_limit_mb", "Decline plans whose staged columns and join table are estimated above this many MB of HBM.", NULL,
 							&gpuexec_hbm_limit_mb, 150 * 1024, 64, 1024 * 1024, PGC_USERSET, 0, NULL, NULL, NULL);
 	RegisterCustomScanMethods(&gpuexec_scan_methods);

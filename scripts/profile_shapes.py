@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--shapes", default="config1,q1,q3,config2,config3")
     a = ap.parse_args()
     ctx = g.Context(0)
+    ctx.pool_reserve(0)
     no = 1_500_000 * a.sf
     lt = ctx.table(g.SCHEMAS[g.T_LINEITEM], no * 4 + no // 8).generate(g.T_LINEITEM, a.sf, 0, no)
     ot = ctx.table(g.SCHEMAS[g.T_ORDERS], no).generate(g.T_ORDERS, a.sf, 0, no)

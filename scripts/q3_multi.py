@@ -41,6 +41,7 @@ def main():
     dist.broadcast_object_list(box, src=0)
     ctx.comm_init(rank, world, box[0])
     ctx.set_shardmap(world)
+    ctx.pool_reserve(0)
 
     from opentenbase_b200 import plans as P
     nord = a.orders or 1_500_000 * a.sf
@@ -60,8 +61,8 @@ def main():
         res.free()
         ctx.sync(); dist.barrier()
         dt = time.perf_counter() - t0
-        if rank == 0 and a.iters > 1:
-            print(f"q3 iteration {it}: {dt * 1e3:.2f} ms")
+        if a.iters > 1:
+            print(f"rank {rank} q3 iteration {it}: {dt * 1e3:.2f} ms; " + ", ".join(f"{k} {v:.2f}" for k, v in stats["host_ms_per_call"].items()), flush=True)
     rows_in = cust.nrows + orders.nrows + line.nrows
 
     gathered = [None] * world

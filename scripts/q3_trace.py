@@ -6,6 +6,7 @@ from opentenbase_b200 import plans as P
 
 sf = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 ctx = g.Context(0)
+ctx.pool_reserve(0)
 ctx.set_shardmap(1)
 no = 1_500_000 * sf
 lt = ctx.table(g.SCHEMAS[g.T_LINEITEM], no * 4 + no // 8).generate(g.T_LINEITEM, sf, 0, no)
