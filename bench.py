@@ -483,6 +483,13 @@ def run_ours(args):
     except g.GxError as ex:
         e2e = {"value": None, "unit": "rows/s", "error": str(ex)}
 
+    e2e_pages = None
+    if rank == 0 and not args.no_extras and args.pages_gb > 0:
+        try:
+            e2e_pages = run_e2e_pages(ctx, g, args)
+        except (g.GxError, OSError) as ex:
+            e2e_pages = {"error": str(ex)}
+
     if rank != 0:
         ctx.close()
         if dist is not None:
@@ -540,6 +547,10 @@ def run_ours(args):
             "float_determinism": "float8 sums use shared-memory atomics: not bit-identical run to run, within 1e-9 relative of the reference",
             "phases_ms": phases}
     line.update(extras)
+    if e2e_pages is not None:
+        line["e2e_pages"] = e2e_pages
+        if e2e_pages.get("rows_match_oracle") is False:
+            failed.append("e2e_pages.rows_match_oracle")
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
     ctx.close()
     if dist is not None:
@@ -598,6 +609,72 @@ def run_e2e(ctx, g, ot, lt, no, nl, plan, args, barrier, allmax, rows_all):
                     "staging buffer in the same run"}
 
 
+def run_e2e_pages(ctx, g, args):
+    """The plug-in's real ingest path at scale: raw 8 KB heap pages (built by the oracle's page writer, TPC-H lineitem
+    layout, 8 attributes) + heapgetpage()-style visibility lists -> gx_stage_acquire ring -> gx_table_append_heap_pages ->
+    device deform of the 4 referenced attributes, 32 MB batches, no synchronisation per batch.  The page set (~0.5 GB)
+    is replayed until `--pages-gb` GB have gone through, like a relation that many pages long."""
+    import ctypes as C
+    import oracle as O
+    nord = 1_250_000
+    l = O.gen_lineitem(100, 0, nord)
+    ltypes = [O.GX_INT8, O.GX_FLOAT8, O.GX_FLOAT8, O.GX_FLOAT8, O.GX_FLOAT8, O.GX_DATE, O.GX_CHAR, O.GX_CHAR]
+    rel = O.Rel(ltypes, l)
+    pages = rel.pages()
+    npages, ntup = rel.npages, rel.ntuples
+    L = O.lib()
+    L.orc_heapgetpage.restype = C.c_int
+    L.orc_heapgetpage.argtypes = [C.c_void_p, C.c_void_p]
+    stride = 291                                                  # MaxHeapTuplesPerPage
+    vis = np.zeros((npages, stride), np.uint16); cnt = np.zeros(npages, np.int32)
+    for p in range(npages):
+        cnt[p] = L.orc_heapgetpage(pages[p * 8192:].ctypes.data, vis[p].ctypes.data)
+    reps = max(1, int(round(args.pages_gb * 1e9 / (npages * 8192.0))))
+    attnums = [0, 2, 3, 5]                                        # l_orderkey, l_extendedprice, l_discount, l_shipdate
+    d = g.GxHeapDesc()
+    d.natts, d.ncols = 8, 4
+    for i, (ln, al) in enumerate(zip([8, 8, 8, 8, 8, 4, 1, 1], [8, 8, 8, 8, 8, 4, 1, 1])):
+        d.att_len[i], d.att_align[i], d.att_notnull[i] = ln, al, 1
+    for i, a in enumerate(attnums):
+        d.attnums[i] = a
+    t = ctx.table([g.GX_INT8, g.GX_FLOAT8, g.GX_FLOAT8, g.GX_DATE], int(ntup * reps * 1.01) + 1024)
+    B = 4096
+    pb, vb = B * 8192, B * stride * 2
+    slot_bytes = pb + vb + B * 4
+
+    def load():
+        t.truncate()
+        for _ in range(reps):
+            for p0 in range(0, npages, B):
+                n = min(B, npages - p0)
+                slot = ctx.stage_acquire(slot_bytes)
+                C.memmove(slot, pages[p0 * 8192:].ctypes.data, n * 8192)               # the provider's memcpy out of shared_buffers
+                C.memmove(slot + pb, vis[p0].ctypes.data, n * stride * 2)
+                C.memmove(slot + pb + vb, cnt[p0:].ctypes.data, n * 4)
+                ctx._chk(g.lib().gx_table_append_heap_pages(t.h, slot, n, C.byref(d), slot + pb, slot + pb + vb, stride))
+        ctx._chk(g.lib().gx_table_load_finish(t.h))
+    load()                                                        # warm-up (pins the ring, grows nothing afterwards)
+    t0 = time.perf_counter()
+    load()
+    dt = time.perf_counter() - t0
+    # host-side copy rate alone (what heapgetpage + memcpy can feed at best from one backend process)
+    slot = ctx.stage_acquire(slot_bytes)
+    t1 = time.perf_counter()
+    for p0 in range(0, npages, B):
+        C.memmove(slot, pages[p0 * 8192:].ctypes.data, min(B, npages - p0) * 8192)
+    host_gbs = npages * 8192 / (time.perf_counter() - t1) / 1e9
+    ok = t.nrows == ntup * reps
+    first = np.empty(ntup, np.int64)
+    ctx._chk(g.lib().gx_table_read_column(t.h, 0, 0, ntup, first.ctypes.data, None))
+    ok = ok and bool(np.array_equal(first, l[0]))
+    t.free()
+    gb = npages * 8192.0 * reps / 1e9
+    return {"page_gb": gb, "rows": int(ntup * reps), "seconds": dt, "page_gb_per_s": gb / dt, "rows_per_s": ntup * reps / dt,
+            "host_memcpy_gb_per_s": host_gbs, "rows_match_oracle": ok,
+            "note": "one host thread copies every page into the pinned ring (as gpuexec_load_relation does out of shared_buffers) while the "
+                    "previous batch's DMA and deform run; the ceiling of this leg is that single-thread memcpy, not PCIe"}
+
+
 def staging_placement(bufs):
     """Where the pinned staging buffers ended up (pages per NUMA node, from /proc/self/numa_maps) and the
     node the GPU hangs off: the e2e figure halves when the two differ."""
@@ -636,6 +713,7 @@ def main():
     ap.add_argument("--extra-steps", type=int, default=5, help="timed steps of the Q3/Q1/config1/config2 extras")
     ap.add_argument("--no-extras", action="store_true", help="headline only (profiling runs)")
     ap.add_argument("--no-unclustered", action="store_true", help="skip the row-permuted variant")
+    ap.add_argument("--pages-gb", type=float, default=10.0, help="GB of heap pages pushed through the page loader (e2e_pages leg; 0 = skip)")
     ap.add_argument("--cpu-sample-orders", type=int, default=1_500_000)
     args = ap.parse_args()
     if args.warmup < 3:

@@ -413,6 +413,11 @@ class Context:
     def sync(self):
         self._chk(lib().gx_sync(self.h))
 
+    def stage_acquire(self, nbytes) -> int:
+        p = C.c_void_p()
+        self._chk(lib().gx_stage_acquire(self.h, nbytes, C.byref(p)))
+        return p.value
+
     def pool_reserve(self, nbytes=0):
         self._chk(lib().gx_pool_reserve(self.h, nbytes))
 

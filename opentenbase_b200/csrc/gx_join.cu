@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_b
 //    the host down the bucketing path.  (Doing the search inside the fill kernel, one sub-table
 //    ahead, was measured slower: 1.91 ms against 0.41 + 1.07 ms.)
 __device__ __forceinline__ long long sorted_lower_bound(const long long *__restrict__ keys, long long nrows, const gx_slotfn &sf,
-                                                        long long s, long long nsub, double rows_per_sub, int lane)
+                                                        long long s, long long nsub, double rows_per_sub, int lane, long long seed = -1)
 {
     if (s <= 0) return 0;
     if (s >= nsub) return nrows;
@@ -630,7 +630,9 @@ __device__ __forceinline__ long long sorted_lower_bound(const long long *__restr
         if (r < 0) return false;
         return (long long) (gx_slot_index(__ldg(keys + r), sf) >> GX_SUB_LOG2) >= s;
     };
-    long long g = (long long) ((double) s * rows_per_sub);
+    // guess: the global density, or — better — the previous bound plus one sub-table's worth of rows (a datanode's 1/N
+    // pseudo-random subset of the keys wanders off the global density by hundreds of rows, but only by a dozen per sub-table)
+    long long g = seed >= 0 ? seed + (long long) rows_per_sub : (long long) ((double) s * rows_per_sub);
     if (g > nrows) g = nrows;
     // one round when the guess is within 16 rows
     {
@@ -673,9 +675,13 @@ __global__ void __launch_bounds__(256) gx_k_sorted_bounds_search(const long long
     const int lane = threadIdx.x & 31;
     const long long nwarp = ((long long) gridDim.x * blockDim.x) >> 5, wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const double rows_per_sub = (double) nrows * (double) GX_SUB / (double) (nslots - GX_SUB);
-    for (long long s = wid; s <= nsub; s += nwarp) {
-        const long long v = sorted_lower_bound(keys, nrows, sf, s, nsub, rows_per_sub, lane);
+    // a warp takes a CONTIGUOUS block of bounds and seeds each search with the previous result
+    const long long per = (nsub + 1 + nwarp - 1) / nwarp, s0 = wid * per;
+    long long prev = -1;
+    for (long long s = s0; s < s0 + per && s <= nsub; s++) {
+        const long long v = sorted_lower_bound(keys, nrows, sf, s, nsub, rows_per_sub, lane, prev);
         if (lane == 0) start[s] = v;
+        prev = (s > 0 && s < nsub) ? v : -1;
     }
 }
 
