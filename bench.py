@@ -487,8 +487,8 @@ def run_ours(args):
     if rank == 0 and not args.no_extras and args.pages_gb > 0:
         try:
             e2e_pages = run_e2e_pages(ctx, g, args)
-        except (g.GxError, OSError) as ex:
-            e2e_pages = {"error": str(ex)}
+        except Exception as ex:                                  # an extra must never take the headline line down with it
+            e2e_pages = {"error": repr(ex)}
 
     if rank != 0:
         ctx.close()

@@ -279,6 +279,10 @@ class Table:
         self.ctx._chk(lib().gx_table_permute(self.ctx.h, self.h, seed, C.byref(h)))
         return Table(self.ctx, h, self.types)
 
+    def truncate(self):
+        self.ctx._chk(lib().gx_table_truncate(self.h))
+        return self
+
     def drop_column(self, col):
         self.ctx._chk(lib().gx_table_drop_column(self.h, col))
         del self.types[col]
