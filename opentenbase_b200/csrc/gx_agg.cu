@@ -22,6 +22,7 @@
 //      one CTA aggregates one partition in shared memory (many groups: Q3)
 //   3  global table only (atomics in L2)
 #include "gx_internal.cuh"
+#include <type_traits>
 
 int gx_fill_dpreds(gx_ctx *ctx, const gx_table *t, int n_preds, const gx_pred *preds, gx_dpred *out);
 
@@ -660,8 +661,10 @@ __global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_con
     if (threadIdx.x < FG_G) { s_state[threadIdx.x] = 0u; s_keys[threadIdx.x] = 0ULL; }
     if (threadIdx.x < FG_G * (1 + FG_NV)) ((unsigned long long *) s_acc)[threadIdx.x] = 0ULL;
     if (threadIdx.x == 0) s_over = 0;
-    unsigned long long *const acc = fg_smem + (size_t) warp * nw * FG_G * 32 + lane;     // + (word * FG_G + group) * 32
-    for (int i = 0; i < nw * FG_G; i++) acc[i * 32] = 0ULL;
+    // group slot FG_G is a trash can: rows that fail the quals are added there, so the tile body has no per-row branches
+    constexpr int GS = FG_G + 1;
+    unsigned long long *const acc = fg_smem + (size_t) warp * nw * GS * 32 + lane;     // + (word * GS + group) * 32
+    for (int i = 0; i < nw * GS; i++) acc[i * 32] = 0ULL;
     __syncthreads();
     const gx_dplan &P = A.P;
     // keys the CTA has handed out so far; an unused entry holds a value no packed key can take (BYTEKEY keys are
@@ -673,26 +676,33 @@ __global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_con
     const int two = P.ngroup > 1, sh1 = P.gcols[P.ngroup > 1 ? 1 : 0].shift;
     const long long tile = 32LL * FG_K, nwarp_total = (long long) gridDim.x * (blockDim.x >> 5);
     const long long wid = (long long) blockIdx.x * (blockDim.x >> 5) + warp;
-    for (long long base = A.row0 + wid * tile; base < A.row1; base += nwarp_total * tile) {
-        if (*(volatile int *) &s_over) break;
+    bool stop = false;
+    // FULL = every row of the tile exists: loads and arithmetic are unconditional (the compiler sees no row predicate)
+    auto tile_body = [&](long long base, auto FULL) {
+        constexpr bool full = decltype(FULL)::value;
         long long r[FG_K]; bool ok[FG_K]; int gi[FG_K];
 #pragma unroll
-        for (int j = 0; j < FG_K; j++) { r[j] = base + j * 32 + lane; ok[j] = r[j] < A.row1; }
+        for (int j = 0; j < FG_K; j++) { r[j] = base + j * 32 + lane; ok[j] = full || r[j] < A.row1; }
         // ---- every column the tile needs is requested before anything is used: argument columns first (no use
         // until the arithmetic below), then the group columns, then the qual columns
         double x[FG_NC][FG_K];
 #pragma unroll
         for (int c = 0; c < FG_NC; c++) {
             const double *pc = F.col[c < F.nc ? c : 0] + base + lane;      // row j of the tile sits at a compile-time offset
+            if (c < F.nc) {
 #pragma unroll
-            for (int j = 0; j < FG_K; j++) x[c][j] = (c < F.nc && ok[j]) ? __ldg(pc + j * 32) : 0.0;
+                for (int j = 0; j < FG_K; j++) x[c][j] = (full || ok[j]) ? __ldg(pc + j * 32) : 0.0;
+            } else {
+#pragma unroll
+                for (int j = 0; j < FG_K; j++) x[c][j] = 0.0;
+            }
         }
         unsigned long long key[FG_K];
         if (BYTEKEY) {
             unsigned int b0[FG_K], b1[FG_K];
             const unsigned char *p0 = kc0 + base + lane, *p1 = kc1 + base + lane;
 #pragma unroll
-            for (int j = 0; j < FG_K; j++) { b0[j] = ok[j] ? __ldg(p0 + j * 32) : 0u; b1[j] = (two && ok[j]) ? __ldg(p1 + j * 32) : 0u; }
+            for (int j = 0; j < FG_K; j++) { b0[j] = (full || ok[j]) ? __ldg(p0 + j * 32) : 0u; b1[j] = (two && (full || ok[j])) ? __ldg(p1 + j * 32) : 0u; }
 #pragma unroll
             for (int j = 0; j < FG_K; j++) key[j] = (unsigned long long) (b0[j] | (b1[j] << sh1));
         } else {
@@ -720,12 +730,12 @@ __global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_con
             __syncwarp();
 #pragma unroll
             for (int gI = 0; gI < FG_G; gI++) if (*(volatile unsigned int *) &s_state[gI] == 2u) { gk[gI] = *(volatile unsigned long long *) &s_keys[gI]; gvalid |= 1u << gI; }
-            if (*(volatile int *) &s_over) break;                  // more groups than accumulators: the host takes the general path
+            if (*(volatile int *) &s_over) { stop = true; return; }    // more groups than accumulators: the host takes the general path
         }
         // ---- accumulate: word 0 = rows, word 1 + w = sum of value w; [word][group][lane], a lane touches only its own column
         unsigned long long *ap[FG_K];
 #pragma unroll
-        for (int j = 0; j < FG_K; j++) { ap[j] = acc + (size_t) (gi[j] < 0 ? 0 : gi[j]) * 32; if (ok[j]) *ap[j] += 1ULL; }
+        for (int j = 0; j < FG_K; j++) { ap[j] = acc + (size_t) ((ok[j] && gi[j] >= 0) ? gi[j] : FG_G) * 32; *ap[j] += 1ULL; }
 #pragma unroll
         for (int w = 0; w < FG_NV; w++) {
             if (w >= nv) break;
@@ -748,13 +758,19 @@ __global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_con
                 }
             }
 #pragma unroll
-            for (int j = 0; j < FG_K; j++) if (ok[j]) { double *pp = (double *) (ap[j] + (size_t) (1 + w) * FG_G * 32); *pp = __dadd_rn(*pp, v[j]); }
+            for (int j = 0; j < FG_K; j++) { double *pp = (double *) (ap[j] + (size_t) (1 + w) * GS * 32); *pp = __dadd_rn(*pp, v[j]); }
         }
+    };
+    for (long long base = A.row0 + wid * tile; base < A.row1 && !stop; base += nwarp_total * tile) {
+        if (*(volatile int *) &s_over) break;
+        if (base + tile <= A.row1) tile_body(base, std::true_type());
+        else tile_body(base, std::false_type());
     }
     // ---- lanes -> warp -> CTA -> global table
     __syncwarp();
-    for (int i = 0; i < nw * FG_G; i++) {
-        const int word = i / FG_G, gI = i % FG_G;
+    for (int i = 0; i < nw * GS; i++) {
+        const int word = i / GS, gI = i % GS;
+        if (gI == FG_G) continue;                                  // the trash can
         unsigned long long raw = acc[i * 32];
         if (word == 0) {
 #pragma unroll
@@ -777,45 +793,44 @@ __global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_con
     }
 }
 
-// config 1's shape exactly: count(*) GROUP BY one 1-byte column, no quals.  16 rows per 128-bit
-// load; every byte is compared with the (<= 8) keys the CTA knows, four bytes per instruction
-// (__vcmpeq4), matches are counted with a population count.  1 B/row of traffic.
+// config 1's shape exactly: count(*) GROUP BY one 1-byte column, no quals.  16 rows per 128-bit load; every byte is
+// compared with the (<= 8) keys the CTA knows four bytes at a time (exact zero-byte test of word ^ replicated key:
+// 0x80 in every matching byte), matches are counted with a population count.  1 B/row of traffic.  The key list is
+// claimed with a single compare-and-swap per new key (0 = free, 0x100 | byte = taken): no lock, nothing spins.
 #define CC_G 8
+// a byte value this thread has not seen: claim / find it in the CTA's list; returns the number of keys now known
+// (the ready slots form a prefix), or -1 when a ninth distinct value turns up
+__device__ __noinline__ int cc_learn(unsigned int *s_keys, unsigned int w, unsigned int unseen)
+{
+    for (int b = 0; b < 4; b++) {
+        if (!((unseen >> (8 * b)) & 0x80u)) continue;
+        const unsigned int want = 0x100u | ((w >> (8 * b)) & 0xffu);
+        int gI = 0;
+        for (; gI < CC_G; gI++) {
+            unsigned int cur = *(volatile unsigned int *) &s_keys[gI];
+            if (cur == 0u) { cur = atomicCAS(&s_keys[gI], 0u, want); if (cur == 0u) cur = want; }
+            if (cur == want) break;
+        }
+        if (gI == CC_G) return -1;
+    }
+    int n = 0;
+    while (n < CC_G && *(volatile unsigned int *) &s_keys[n] != 0u) n++;
+    return n;
+}
 __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant__ gx_agg_dev A, const signed char *__restrict__ col)
 {
-    __shared__ unsigned long long s_keys[CC_G];
-    __shared__ unsigned int s_state[CC_G];
+    __shared__ unsigned int s_keys[CC_G];
     __shared__ unsigned long long s_cnt[CC_G];
     __shared__ int s_over;
-    if (threadIdx.x < CC_G) { s_state[threadIdx.x] = 0u; s_keys[threadIdx.x] = 0ULL; s_cnt[threadIdx.x] = 0ULL; }
+    if (threadIdx.x < CC_G) { s_keys[threadIdx.x] = 0u; s_cnt[threadIdx.x] = 0ULL; }
     if (threadIdx.x == 0) s_over = 0;
     __syncthreads();
     unsigned int cnt[CC_G], rep[CC_G];
     int ngk = 0;                                                    // keys this thread knows: a prefix of the CTA's list
 #pragma unroll
     for (int gI = 0; gI < CC_G; gI++) { cnt[gI] = 0u; rep[gI] = 0u; }
-    auto insert = [&](unsigned int byte) -> bool {
-        for (int gI = 0; gI < CC_G; gI++) {
-            for (;;) {
-                const unsigned int st = *(volatile unsigned int *) &s_state[gI];
-                if (st == 2u) { if (*(volatile unsigned long long *) &s_keys[gI] == (unsigned long long) byte) return true; break; }
-                if (st == 0u && atomicCAS(&s_state[gI], 0u, 1u) == 0u) {
-                    *(volatile unsigned long long *) &s_keys[gI] = (unsigned long long) byte; __threadfence_block();
-                    *(volatile unsigned int *) &s_state[gI] = 2u; return true;
-                }
-            }
-        }
-        return false;
-    };
-    auto reload = [&]() {                                          // slots are claimed in order: the ready ones form a prefix
-        int n = 0;
-#pragma unroll
-        for (int gI = 0; gI < CC_G; gI++) if (n == gI && *(volatile unsigned int *) &s_state[gI] == 2u) {
-            rep[gI] = (unsigned int) *(volatile unsigned long long *) &s_keys[gI] * 0x01010101u; n = gI + 1; }
-        ngk = n;
-    };
-    // bytes of w equal to the replicated key: 0x80 in every matching byte (exact zero-byte test of w ^ rep)
-    auto eqmask = [](unsigned int w, unsigned int rep) -> unsigned int { const unsigned int x = w ^ rep; return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); };
+    // bytes of w equal to the replicated key: 0x80 in every matching byte
+    auto eqmask = [](unsigned int w, unsigned int rp) -> unsigned int { const unsigned int x = w ^ rp; return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); };
     auto count_word = [&](unsigned int w, unsigned int keep /* 0x80 per byte that is a row */) {
         unsigned int seen = 0u;
 #pragma unroll
@@ -824,12 +839,18 @@ __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant_
             const unsigned int m = eqmask(w, rep[gI]) & keep;
             cnt[gI] += (unsigned int) __popc(m); seen |= m;
         }
-        if (seen != keep) {                                        // a byte value this thread has not seen yet
-            for (int b = 0; b < 4; b++) if (((keep & ~seen) >> (8 * b)) & 0x80u) { if (!insert((w >> (8 * b)) & 0xffu)) s_over = 1; }
-            reload();
+        if (seen != keep) {                                        // rare: a value not seen by this thread before
             const unsigned int todo = keep & ~seen;
+            const int n = cc_learn(s_keys, w, todo);
+            if (n < 0) { s_over = 1; return; }
+            const int old = ngk;
+            ngk = n;
 #pragma unroll
-            for (int gI = 0; gI < CC_G; gI++) { if (gI >= ngk) break; cnt[gI] += (unsigned int) __popc(eqmask(w, rep[gI]) & todo); }
+            for (int gI = 0; gI < CC_G; gI++) {
+                if (gI >= ngk) break;
+                if (gI >= old) rep[gI] = (s_keys[gI] & 0xffu) * 0x01010101u;
+                if (gI >= old) cnt[gI] += (unsigned int) __popc(eqmask(w, rep[gI]) & todo);
+            }
         }
     };
     const long long n = A.row1 - A.row0;
@@ -837,17 +858,20 @@ __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant_
     // head: bytes up to the first 16-byte boundary; body: vectors; tail: the rest
     long long head = (long long) ((16 - ((unsigned long long) p0 & 15ULL)) & 15ULL); if (head > n) head = n;
     const long long nvec = (n - head) >> 4, tail0 = head + (nvec << 4);
-    const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long) gridDim.x * blockDim.x;
+    const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < head) count_word((unsigned int) (unsigned char) p0[tid], 0x80u);
     if (tid < n - tail0) count_word((unsigned int) (unsigned char) p0[tail0 + tid], 0x80u);
     const uint4 *pv = (const uint4 *) (p0 + head);
-    for (long long i = tid; i < nvec; i += 2 * nthr) {             // two vectors in flight per thread
+    // a CTA reads one contiguous range of vectors, its threads two vectors at a time
+    const long long per = (nvec + gridDim.x - 1) / gridDim.x, v0 = per * blockIdx.x, v1 = v0 + per < nvec ? v0 + per : nvec;
+    for (long long i = v0 + threadIdx.x; i < v1; i += 2 * blockDim.x) {
         uint4 v, u = make_uint4(0, 0, 0, 0);
-        const bool two = i + nthr < nvec;
+        const bool two = i + blockDim.x < v1;
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pv + i));
-        if (two) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(pv + i + nthr));
+        if (two) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(pv + i + blockDim.x));
         count_word(v.x, 0x80808080u); count_word(v.y, 0x80808080u); count_word(v.z, 0x80808080u); count_word(v.w, 0x80808080u);
         if (two) { count_word(u.x, 0x80808080u); count_word(u.y, 0x80808080u); count_word(u.z, 0x80808080u); count_word(u.w, 0x80808080u); }
+        if (*(volatile int *) &s_over) break;
     }
     const int lane = threadIdx.x & 31;                             // list positions are the CTA's: every thread counts key g in cnt[g]
 #pragma unroll
@@ -859,9 +883,9 @@ __global__ void __launch_bounds__(512, 2) gx_k_count_char(const __grid_constant_
     }
     __syncthreads();
     if (s_over) { if (threadIdx.x == 0) atomicOr((unsigned long long *) &A.counters[1], 1ULL); return; }
-    if (threadIdx.x < CC_G && s_state[threadIdx.x] == 2u && s_cnt[threadIdx.x]) {
-        // group key = the byte sign-extended the way pack_group_key packs a 1-byte column
-        unsigned long long *rec = global_upsert(A, s_keys[threadIdx.x] & 0xffULL, 0ULL, 0u);
+    if (threadIdx.x < CC_G && s_keys[threadIdx.x] != 0u && s_cnt[threadIdx.x]) {
+        // group key = the byte the way pack_group_key packs a 1-byte column
+        unsigned long long *rec = global_upsert(A, (unsigned long long) (s_keys[threadIdx.x] & 0xffu), 0ULL, 0u);
         if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); return; }
         atomicAdd(&rec[3], s_cnt[threadIdx.x]);
     }
@@ -2365,7 +2389,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
         } else if (use_few) {
             const int fg_warps = FG_THREADS / 32;
-            const size_t fg_smem = (size_t) fg_warps * (1 + FG.nv) * FG_G * 32 * 8;
+            const size_t fg_smem = (size_t) fg_warps * (1 + FG.nv) * (FG_G + 1) * 32 * 8;
             bool bytekey = plan->n_group_cols <= 2;
             for (int c = 0; c < plan->n_group_cols; c++) bytekey = bytekey && A.P.gcols[c].type == GX_CHAR && A.P.gcols[c].word == 0;
             static bool fg_attr = false;

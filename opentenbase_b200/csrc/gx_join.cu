@@ -1102,6 +1102,7 @@ struct gx_probe_args {
     gx_dpred preds[GX_MAX_PREDS];
     long long nrows;
     const gx_slot *slots; unsigned long long mask;
+    const gx_cslot *cslots; unsigned long long cspan;       // compact 8-byte form (half the bytes: an L2-resident table more often)
     const unsigned long long *special; int special_count; int _pad2; gx_slotfn sf;
     gx_dcol out_src[GX_MAX_COLS];
     void *out[GX_MAX_COLS];
@@ -1199,10 +1200,12 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe(gx_probe_args a)
 // flight together, matches are numbered with ballots and the warp claims its output range with ONE atomic per
 // tile; the surviving rows are copied column by column.
 #define PT_K 4
+template <bool COMPACT> __global__ void gx_k_hash_probe_unique(gx_probe_args a);
 __device__ __forceinline__ void ld_pair(const gx_slot *p, long long &k0, unsigned long long &p0, long long &k1, unsigned long long &p1)
 {
     asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(p0), "=l"(k1), "=l"(p1) : "l"(p));
 }
+template <bool COMPACT>
 __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
 {
     const int lane = threadIdx.x & 31;
@@ -1222,10 +1225,36 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
 #pragma unroll
         for (int j = 0; j < PT_K; j++) key[j] = ok[j] ? gx_load_int(a.key, r[j]) : 0;
         long long k0[PT_K], k1[PT_K]; unsigned long long p0[PT_K], p1[PT_K];
+        if (COMPACT) {
+            // four 8-byte slots {d, payload} per 32-byte sector; d = ((key - kmin) << 1) | 1 truncated to 32 bits, 0 = empty
+            unsigned int d[PT_K];
+#pragma unroll
+            for (int j = 0; j < PT_K; j++) {
+                const bool inspan = ok[j] && ((unsigned long long) key[j] - (unsigned long long) a.sf.kmin) < a.cspan;   // outside the build side's key span: no partner
+                s[j] = gx_slot_index(key[j], a.sf);
+                d[j] = GX_CSLOT_D(key[j], a.sf.kmin);
+                k0[j] = k1[j] = 0; p0[j] = p1[j] = 0;
+                if (inspan) ld_pair((const gx_slot *) (a.cslots + s[j]), k0[j], p0[j], k1[j], p1[j]);
+                else d[j] = 0xfffffffeu;                               // even: matches no stored d (they are odd), the all-zero group ends the walk
+            }
+#pragma unroll
+            for (int j = 0; j < PT_K; j++) {
+                hit[j] = false; pay[j] = 0;
+                if (!ok[j]) continue;
+                for (;;) {
+                    const unsigned int d0 = (unsigned int) k0[j], d1 = (unsigned int) p0[j], d2 = (unsigned int) k1[j], d3 = (unsigned int) p1[j];
+                    const unsigned long long m = d0 == d[j] ? (unsigned long long) k0[j] : d1 == d[j] ? p0[j] : d2 == d[j] ? (unsigned long long) k1[j] : p1[j];
+                    hit[j] = (d0 == d[j]) | (d1 == d[j]) | (d2 == d[j]) | (d3 == d[j]);
+                    pay[j] = m >> 32;
+                    if (hit[j] | (d0 == 0u) | (d1 == 0u) | (d2 == 0u) | (d3 == 0u)) break;
+                    s[j] = gx_next_quad(s[j], a.mask);
+                    ld_pair((const gx_slot *) (a.cslots + s[j]), k0[j], p0[j], k1[j], p1[j]);
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < PT_K; j++) {
-            s[j] = gx_slot_index(key[j], a.sf);
-            k0[j] = k1[j] = GX_EMPTY_KEY; p0[j] = p1[j] = 0;
+            s[j] = gx_slot_index(key[j], a.sf);            k0[j] = k1[j] = GX_EMPTY_KEY; p0[j] = p1[j] = 0;
             if (ok[j] && key[j] != GX_EMPTY_KEY) ld_pair(a.slots + s[j], k0[j], p0[j], k1[j], p1[j]);
         }
 #pragma unroll
@@ -1242,6 +1271,7 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
                 ld_pair(a.slots + s[j], k0[j], p0[j], k1[j], p1[j]);
             }
         }
+        }
         __syncwarp();
         // which rows produce output (nodeHashjoin.c:569-668): INNER/SEMI the matched ones, ANTI the unmatched ones
         // (HJ_FILL_OUTER_TUPLE without a match), LEFT all of them (unmatched with a NULL inner side)
@@ -1249,7 +1279,7 @@ __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
 #pragma unroll
         for (int j = 0; j < PT_K; j++) {
             matched[j] = hit[j];
-            const bool scanned = r[j] < a.nrows && (ok[j] || (gx_is_null(a.key, r[j]) && quals_ok[j]));   // passed the scan quals
+            const bool scanned = quals_ok[j];                   // passed the scan quals (a NULL key included: it just never matches)
             if (a.join_type == GX_JOIN_ANTI) hit[j] = scanned && !matched[j];
             else if (a.join_type == GX_JOIN_LEFT) hit[j] = scanned;
         }
@@ -1296,8 +1326,11 @@ extern "C" int gx_hash_probe_ex(gx_ctx *ctx, const gx_table *outer, int key_col,
     gx_probe_args a; memset(&a, 0, sizeof(a));
     a.key.data = outer->cols[key_col]; a.key.nulls = outer->nulls[key_col]; a.key.type = kt;
     a.npreds = n_preds; a.n_out_outer = n_out_outer; a.n_payload = h->n_payload; a.unique = h->unique; a.join_type = join_type;
-    { int wrc = gx_hash_wide(ctx, const_cast<gx_hash *>(h)); if (wrc) return wrc; }
+    const bool first_match_only_c = h->unique || join_type != GX_JOIN_INNER;
+    const bool use_compact = h->cslots != nullptr && first_match_only_c;       // the 8-byte slots are probed as they are
+    if (!use_compact) { int wrc = gx_hash_wide(ctx, const_cast<gx_hash *>(h)); if (wrc) return wrc; }
     a.nrows = outer->nrows; a.slots = h->slots; a.mask = (unsigned long long) h->nslots - 1;
+    a.cslots = h->cslots; a.cspan = h->cspan;
     a.special = h->special_payload; a.special_count = h->special_count;
     a.sf.mode = h->mode; a.sf.win = h->win; a.sf.shift = h->shift; a.sf.amask = h->amask; a.sf.kmin = h->kmin; a.sf.scale = h->scale; a.sf.mask = (unsigned long long) h->nslots - 1;
     int rc = gx_fill_dpreds(ctx, outer, n_preds, preds, a.preds); if (rc) return rc;
@@ -1334,7 +1367,8 @@ extern "C" int gx_hash_probe_ex(gx_ctx *ctx, const gx_table *outer, int key_col,
         gx_launch_scope ls(ctx, "probe");
         if (first_match_only) {
             long long nt = (outer->nrows + 32 * PT_K * 8 - 1) / (32 * PT_K * 8);
-            gx_k_hash_probe_unique<<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
+            if (use_compact) gx_k_hash_probe_unique<true><<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
+            else gx_k_hash_probe_unique<false><<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
         } else gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a);
     }
     cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, a.cursor, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
