@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(LPT_K == 8 ? 640 : 1024, 1) gx_k_agg_lptile(co
 template <int K> __device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K]);
 #define FG_G  4
 #define FG_NV 5
-#define FG_K  8                         /* rows per lane and tile: independent loads in flight; the plan walk is paid once per tile */
+/* FG_K = rows per lane and tile (independent loads in flight; the plan walk is paid once per tile) and the CTA size are
+ * template parameters of gx_k_fewgroups: <8, 512> (128 registers, 16 warps/SM) and <4, 768> (85 registers, 24 warps/SM) */
 #define FG_NC 4                         /* distinct float8 columns the aggregate arguments may read */
 struct gx_fewgroups_args {
     int nv, nc;
@@ -648,8 +649,7 @@ __device__ __forceinline__ void slot_term(const gx_dterm &t, int slot, const dou
 
 // BYTEKEY: the group key is one or two 1-byte columns without NULLs (Q1: l_returnflag, l_linestatus) — packed with
 // two byte loads instead of the generic column walk.
-#define FG_THREADS 512
-template <bool BYTEKEY>
+template <bool BYTEKEY, int FG_K, int FG_THREADS>
 __global__ void __launch_bounds__(FG_THREADS, 1) gx_k_fewgroups(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_fewgroups_args F)
 {
     extern __shared__ unsigned long long fg_smem[];            // [warp][word][group][lane]: a lane's own accumulators (bank == lane)
@@ -2388,20 +2388,26 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             gx_k_count_char<<<ctx->sm_count * 2, 512, 0, ctx->stream>>>(A, (const signed char *) A.P.gcols[0].col.data);
             rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
         } else if (use_few) {
-            const int fg_warps = FG_THREADS / 32;
+            const char *fv = getenv("GX_FG_VARIANT");
+            const bool v768 = !(fv && fv[0] == '0');                 // <4, 768> unless GX_FG_VARIANT=0 asks for <8, 512> (profiles/r02_fewgroups_variants.txt)
+            const int fg_threads = v768 ? 768 : 512, fg_k = v768 ? 4 : 8, fg_warps = fg_threads / 32;
             const size_t fg_smem = (size_t) fg_warps * (1 + FG.nv) * (FG_G + 1) * 32 * 8;
             bool bytekey = plan->n_group_cols <= 2;
             for (int c = 0; c < plan->n_group_cols; c++) bytekey = bytekey && A.P.gcols[c].type == GX_CHAR && A.P.gcols[c].word == 0;
             static bool fg_attr = false;
             if (!fg_attr) {
-                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin - 1024));   // static shared memory counts too
-                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin - 1024));
+                const int lim = (int) ctx->smem_optin - 1024;        // static shared memory counts too
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<true, 8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<false, 8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<true, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_fewgroups<false, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
                 fg_attr = true;
             }
-            long long nb = (outer->nrows + fg_warps * 32 * FG_K - 1) / (fg_warps * 32 * FG_K);
+            long long nb = (outer->nrows + (long long) fg_warps * 32 * fg_k - 1) / ((long long) fg_warps * 32 * fg_k);
+            const unsigned fg_grid = (unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count);
             gx_launch_scope ls(ctx, kname);
-            if (bytekey) gx_k_fewgroups<true><<<(unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count), FG_THREADS, fg_smem, ctx->stream>>>(A, FG);
-            else gx_k_fewgroups<false><<<(unsigned) (nb < ctx->sm_count ? nb : ctx->sm_count), FG_THREADS, fg_smem, ctx->stream>>>(A, FG);
+            if (v768) { if (bytekey) gx_k_fewgroups<true, 4, 768><<<fg_grid, 768, fg_smem, ctx->stream>>>(A, FG); else gx_k_fewgroups<false, 4, 768><<<fg_grid, 768, fg_smem, ctx->stream>>>(A, FG); }
+            else { if (bytekey) gx_k_fewgroups<true, 8, 512><<<fg_grid, 512, fg_smem, ctx->stream>>>(A, FG); else gx_k_fewgroups<false, 8, 512><<<fg_grid, 512, fg_smem, ctx->stream>>>(A, FG); }
             rc = cudaGetLastError() == cudaSuccess ? GX_OK : GX_ERR_CUDA;
         }
         else if (strategy == 1 && gmax && lptile_ok) rc = launch_lptile(ctx, A, lp_bytes, kname, lp_warps * 32);

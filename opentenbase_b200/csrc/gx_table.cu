@@ -359,8 +359,6 @@ struct gx_filter_args {
 // count pass, no host round trip between counting and writing; the row order of the input is
 // kept (a key-ordered table stays key-ordered, which the join build and the run kernels use).
 #define FT_THREADS 256
-#define FT_K       8
-#define FT_ROWS    (FT_THREADS * FT_K)
 #define FT_AGG     (1ULL << 62)        /* tile's own count is available */
 #define FT_INC     (2ULL << 62)        /* inclusive prefix is available */
 #define FT_VAL     ((1ULL << 62) - 1)
@@ -373,8 +371,12 @@ __device__ __forceinline__ bool filter_pass(const gx_filter_args &a, long long r
     return ok;
 }
 
+// FT_K rows per thread and tile (8: tiles of 2048 rows; 16: tiles of 4096 rows, half the barriers and look-backs per row)
+template <int FT_K>
 __global__ void __launch_bounds__(FT_THREADS, 4) gx_k_filter_onepass(gx_filter_args a, unsigned long long *tile_state, unsigned int *ticket, long long ntiles, long long *total_out)
 {
+    constexpr int FT_ROWS = FT_THREADS * FT_K;
+    constexpr int NCNT = FT_K * (FT_THREADS / 32);          // (k, warp) counts per tile: 64 or 128
     __shared__ unsigned int wc[FT_K][FT_THREADS / 32];
     __shared__ unsigned int woff[FT_K][FT_THREADS / 32];
     __shared__ long long s_tile, s_prefix;
@@ -397,13 +399,17 @@ __global__ void __launch_bounds__(FT_THREADS, 4) gx_k_filter_onepass(gx_filter_a
             if (lane == 0) wc[k][warp] = __popc(m);
         }
         __syncthreads();
-        if (threadIdx.x < 32) {                                 // exclusive scan of the 64 (k, warp) counts, k-major
-            const int i0 = 2 * lane, i1 = 2 * lane + 1;
-            const unsigned int c0 = ((unsigned int *) wc)[i0], c1 = ((unsigned int *) wc)[i1];
-            unsigned int x = c0 + c1, inc = x;
+        if (threadIdx.x < 32) {                                 // exclusive scan of the NCNT (k, warp) counts, k-major
+            constexpr int PER = NCNT / 32;                      // consecutive counts per lane: 2 or 4
+            unsigned int cv[PER], x = 0;
+#pragma unroll
+            for (int q = 0; q < PER; q++) { cv[q] = ((unsigned int *) wc)[PER * lane + q]; x += cv[q]; }
+            unsigned int inc = x;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-            ((unsigned int *) woff)[i0] = inc - x; ((unsigned int *) woff)[i1] = inc - x + c0;
+            unsigned int run = inc - x;
+#pragma unroll
+            for (int q = 0; q < PER; q++) { ((unsigned int *) woff)[PER * lane + q] = run; run += cv[q]; }
             const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
             // ---- publish, then look back (warp-parallel: 32 predecessors per round)
             long long prefix = 0;
@@ -433,10 +439,13 @@ __global__ void __launch_bounds__(FT_THREADS, 4) gx_k_filter_onepass(gx_filter_a
         }
         __syncthreads();
         const long long prefix = s_prefix;
-        long long rr[FT_K], dd[FT_K];
 #pragma unroll
-        for (int k = 0; k < FT_K; k++) { rr[k] = base + k * FT_THREADS + threadIdx.x; dd[k] = prefix + woff[k][warp] + rank[k]; }
-        for (int c = 0; c < a.ncols; c++) gx_copy_rows<FT_K>(a.in[c], a.out[c], a.out_nulls[c], rr, dd, keep);
+        for (int h8 = 0; h8 < FT_K; h8 += 8) {                  // eight rows at a time: their loads in flight together
+            long long rr[8], dd[8]; bool kp[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { rr[k] = base + (h8 + k) * FT_THREADS + threadIdx.x; dd[k] = prefix + woff[h8 + k][warp] + rank[h8 + k]; kp[k] = keep[h8 + k]; }
+            for (int c = 0; c < a.ncols; c++) gx_copy_rows<8>(a.in[c], a.out[c], a.out_nulls[c], rr, dd, kp);
+        }
         __syncthreads();                                        // wc / woff / s_* are reused by the next tile
     }
 }
@@ -477,14 +486,19 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
     long long total = 0;
     if (in->nrows > 0) {
         for (int c = 0; c < n_out_cols; c++) { a.out[c] = t->cols[c]; a.out_nulls[c] = t->nulls[c]; }
-        const long long ntiles = (in->nrows + FT_ROWS - 1) / FT_ROWS;
+        const char *k16 = getenv("GX_FILTER_K16");
+        const bool big = !(k16 && k16[0] == '0');                 // 4096-row tiles unless GX_FILTER_K16=0 (2.24 vs 2.39 ms for the Q3 scans at SF100)
+        const long long tile_rows = (long long) FT_THREADS * (big ? 16 : 8);
+        const long long ntiles = (in->nrows + tile_rows - 1) / tile_rows;
         unsigned long long *d_state = nullptr;
         cudaError_t e = gx_tmp_alloc(ctx, (void **) &d_state, (size_t) (ntiles + 1) * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemsetAsync(d_state, 0, (size_t) (ntiles + 1) * sizeof(unsigned long long), ctx->stream);
         if (e == cudaSuccess) {
             gx_launch_scope ls(ctx, "filter");
             long long maxb = (long long) ctx->sm_count * 8;
-            gx_k_filter_onepass<<<(unsigned) (ntiles < maxb ? ntiles : maxb), FT_THREADS, 0, ctx->stream>>>(
+            if (big) gx_k_filter_onepass<16><<<(unsigned) (ntiles < maxb ? ntiles : maxb), FT_THREADS, 0, ctx->stream>>>(
+                a, d_state, (unsigned int *) (d_state + ntiles), ntiles, ctx->d_scratch);
+            else gx_k_filter_onepass<8><<<(unsigned) (ntiles < maxb ? ntiles : maxb), FT_THREADS, 0, ctx->stream>>>(
                 a, d_state, (unsigned int *) (d_state + ntiles), ntiles, ctx->d_scratch);
             e = cudaGetLastError();
         }
