@@ -246,7 +246,7 @@ def phase_table(ctx, names, steps):
 PHASES = ("build_sample", "build_bounds", "build_scatter", "build", "build_clear", "build_expand", "probe_agg", "agg",
           "agg_compact", "probe_records", "scan_records", "runagg", "runagg_merge", "radix_partition", "radix_agg", "radix_overflow",
           "filter", "partition", "alltoall", "probe", "probe_count", "combine_pack", "allgather", "combine_merge",
-          "combine_partition")
+          "combine_partition", "peer_wait_ack", "peer_scatter", "peer_publish", "peer_wait", "peer_gather", "peer_ack")
 
 
 def run_ours(args):
@@ -397,12 +397,18 @@ def run_ours(args):
         builds = allsum(float(q3stats["cust_kept"] + q3stats["build_rows"]))
         alg = 28.0 * allsum(float(nl)) + 20.0 * allsum(float(no)) + 5.0 * allsum(float(nc)) + 16.0 * builds + 2.0 * sent
         a2a_ms = ph.get("alltoall", {}).get("ms_per_step", 0.0)
+        peer_ms = sum(ph.get(k, {}).get("ms_per_step", 0.0) for k in ("peer_scatter", "peer_publish", "peer_wait"))
+        transport = "nccl send/recv after a local partition"
+        if peer_ms and not a2a_ms:
+            # rows were stored straight into the destinations' windows by the routing kernel: the exchange is that kernel
+            # plus the wait for the slowest peer's rows
+            a2a_ms, transport = peer_ms, "peer windows: the routing kernel stores into the destination's HBM over NVLink (no partition, no collective)"
         extras["q3"] = {"workload": "configs[3] shape: customer JOIN orders JOIN lineitem, Distribute by o_custkey, then by o_orderkey; "
                                     "sum(l_extendedprice*(1-l_discount)) GROUP BY l_orderkey, o_orderdate, o_shippriority",
                         "ms_per_step": ms, "rows_per_s": rows3 / (ms / 1e3), "rows_per_step": rows3, "steps": xsteps,
                         "groups_total": allsum(float(len(out[0]))), "launches_per_step": nlaunch,
                         "redistributed_rows": allsum(float(q3stats["redistributed_custkey"] + q3stats["redistributed_orderkey"])),
-                        "alltoall_bytes_per_gpu": sent / world, "alltoall_ms": a2a_ms,
+                        "alltoall_bytes_per_gpu": sent / world, "alltoall_ms": a2a_ms, "transport": transport if world > 1 else None,
                         "nvlink_gb_s_per_gpu": (sent / world * (world - 1) / world / (a2a_ms / 1e3) / 1e9) if (a2a_ms and world > 1) else None,
                         "nvlink_peak_gb_s": 900.0,
                         "algorithmic_bytes": alg, "hbm_gb_s_per_gpu": alg / world / (ms / 1e3) / 1e9,

@@ -1224,6 +1224,106 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
     smem_dense_merge(T, A);
 }
 
+struct gx_runlist3 { long long key[160]; double sum[160]; unsigned int cnt[160]; };   // 31 waiting + 128 new runs
+template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
+__global__ void __launch_bounds__(1024, 1) gx_k_runjoin3(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
+{
+    extern __shared__ unsigned long long smem[];
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = 1; T.tagkey = 1; T.gmax = 0;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0; T.w = T.k0; T.gidx = nullptr; T.gcount = nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gx_runlist3 &Q = ((gx_runlist3 *) (smem + (size_t) T.S * (1 + T.nwords)))[warp];
+    int nl = 0;                                                 // finished runs waiting at the front of the list for a full round of 32
+    for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+        T.tag[i] = 0;
+        for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+    }
+    __syncthreads();
+    const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    long long k[4]; double v[4];
+    bool act = q < nvec;
+    if (act) {
+        const long long r = A.row0 + (q << 2);
+        longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+        k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+        if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+    }
+    // the loop is warp-uniform: lanes past the end carry no rows
+    while (__any_sync(0xffffffffu, act)) {
+        // ---- run heads and their numbering inside the warp
+        const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+        bool hd[4];
+        hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+        const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
+        int inc = nh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int base = nl + inc - nh, R = __shfl_sync(0xffffffffu, inc, 31);      // this tile's runs go behind the waiting ones
+        // ---- fold: runs that start in this lane are stored, the rows that continue the previous
+        // lane's run are added to that run afterwards
+        unsigned int c0 = 0; double s0 = 0.0;
+        if (act) {
+            int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (hd[i]) {
+                    if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+                    rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
+                }
+                c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+            }
+            if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+        }
+        __syncwarp();
+        if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
+        __syncwarp();
+        // ---- next rows: requested now, they arrive while the runs are probed
+        q += stride; act = q < nvec;
+        if (act) {
+            const long long r = A.row0 + (q << 2);
+            longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+            k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+            if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+        }
+        // ---- one run per lane, in FULL rounds of 32 only: a tile of 128 rows holds ~33 runs, and a second round for
+        // the last one or two of them costs the warp as many issue slots as a full one
+        const int total = nl + R, full = total & ~31;
+        for (int j = lane; j < full; j += 32) {
+            const long long key = Q.key[j];
+            const unsigned int rc = Q.cnt[j];
+            const double rs = HAS_SUM ? Q.sum[j] : 0.0;
+            int g = 0;
+            const bool hit = runjoin_probe<COMPACT>(A, key, g);
+            if (hit) fast_flush<HAS_CNT, HAS_SUM>(T, A, g, rc, rs, F.sum_word);
+        }
+        __syncwarp();
+        nl = total - full;
+        if (full > 0 && lane < nl) {                                // the remainder moves to the front (sources lie at index >= 32)
+            const long long kk = Q.key[full + lane]; const unsigned int cq = Q.cnt[full + lane]; const double sq = HAS_SUM ? Q.sum[full + lane] : 0.0;
+            Q.key[lane] = kk; Q.cnt[lane] = cq; if (HAS_SUM) Q.sum[lane] = sq;
+        }
+        __syncwarp();
+    }
+    for (int j = lane; j < nl; j += 32) {                           // what was still waiting when the rows ran out
+        int g = 0;
+        const bool hit = runjoin_probe<COMPACT>(A, Q.key[j], g);
+        if (hit) fast_flush<HAS_CNT, HAS_SUM>(T, A, g, Q.cnt[j], HAS_SUM ? Q.sum[j] : 0.0, F.sum_word);
+    }
+    __syncwarp();
+    // the (< 4) rows after the last full vector: one thread each
+    {
+        long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < A.row1) {
+            int gk = 0;
+            if (runjoin_probe<COMPACT>(A, F.okey[r], gk)) fast_flush<HAS_CNT, HAS_SUM>(T, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0, F.sum_word);
+        }
+    }
+    __syncthreads();
+    smem_dense_merge(T, A);
+}
+
 // 16-byte group slots for gx_k_runjoin2: word 0 = [bit 63 occupied | bits 62..32 rows | bits 31..0 the 4-byte key], the sum
 // lives in a parallel array.  The row count is added to the word's upper half with a native 32-bit shared atomic.
 #define PK_OCC   0x8000000000000000ULL
@@ -2071,6 +2171,23 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
+template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
+static int launch_runjoin3_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t table_bytes, const char *name)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin3<HAS_CNT, HAS_SUM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set = true;
+    }
+    long long nvec = (A.row1 - A.row0 + 3) / 4;
+    long long nb = (nvec + 1023) / 1024, maxb = (long long) ctx->sm_count;
+    while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 32)) maxb *= 2;
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_k_runjoin3<HAS_CNT, HAS_SUM, COMPACT><<<grid, 1024, table_bytes + 32 * sizeof(gx_runlist3), ctx->stream>>>(A, FA);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
 template <bool HAS_SUM, bool COMPACT>
 static int launch_runjoin2_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, const char *name)
 {
@@ -2091,6 +2208,20 @@ static int launch_runjoin2_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_arg
 }
 static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name, bool use_run)
 {
+    // gx_k_runjoin3: finished runs wait for a full round of 32 (GX_RUNJOIN_CARRY=1; A/B against gx_k_runjoin)
+    {
+        const char *cv = getenv("GX_RUNJOIN_CARRY");
+        if (use_run && cv && cv[0] == '1' && smem + 32 * sizeof(gx_runlist3) <= ctx->smem_optin - 1024) {
+            if (A.cslots) {
+                if (cnt && sum) return launch_runjoin3_t<true, true, true>(ctx, A, FA, smem, name);
+                if (cnt) return launch_runjoin3_t<true, false, true>(ctx, A, FA, smem, name);
+                return launch_runjoin3_t<false, true, true>(ctx, A, FA, smem, name);
+            }
+            if (cnt && sum) return launch_runjoin3_t<true, true, false>(ctx, A, FA, smem, name);
+            if (cnt) return launch_runjoin3_t<true, false, false>(ctx, A, FA, smem, name);
+            return launch_runjoin3_t<false, true, false>(ctx, A, FA, smem, name);
+        }
+    }
     // gx_k_runjoin2: two CTAs of 512 threads per SM with 16-byte group slots (64 KB + 40 KB of run lists).  MEASURED SLOWER
     // than one CTA of 1024 threads with 24-byte slots (3.29 vs 2.76 ms at SF100, profiles/r02_runjoin_variants.txt), like the
     // other attempts to trade CTA size for occupancy on this kernel; kept behind GX_RUNJOIN_V2=1 for the record.

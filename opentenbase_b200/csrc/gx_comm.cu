@@ -76,6 +76,9 @@ extern "C" int gx_set_shardmap(gx_ctx *ctx, const int32_t *shardmap, int nnodes)
     return GX_OK;
 }
 
+static int peer_setup(gx_ctx *ctx);
+static void peer_teardown(gx_ctx *ctx);
+
 extern "C" int gx_comm_init(gx_ctx *ctx, int rank, int nranks, const void *uid)
 {
     if (!ctx || !uid) return GX_ERR_ARG;
@@ -86,8 +89,8 @@ extern "C" int gx_comm_init(gx_ctx *ctx, int rank, int nranks, const void *uid)
     GX_CUDA(ctx, cudaSetDevice(ctx->device));
     GX_NCCL(ctx, g_nccl.CommInitRank(&comm, nranks, id, rank));
     ctx->nccl = &g_nccl; ctx->comm = comm; ctx->rank = rank; ctx->nranks = nranks;
-    if (ctx->nnodes != nranks) return gx_set_shardmap(ctx, nullptr, nranks);
-    return GX_OK;
+    if (ctx->nnodes != nranks) { rc = gx_set_shardmap(ctx, nullptr, nranks); if (rc) return rc; }
+    return peer_setup(ctx);
 }
 extern "C" int gx_comm_rank(const gx_ctx *ctx, int *rank, int *nranks)
 {
@@ -98,6 +101,7 @@ extern "C" int gx_comm_rank(const gx_ctx *ctx, int *rank, int *nranks)
 }
 extern "C" void gx_comm_destroy(gx_ctx *ctx)
 {
+    if (ctx) peer_teardown(ctx);
     if (ctx && ctx->comm && ctx->nccl) { ctx->nccl->CommDestroy(ctx->comm); ctx->comm = nullptr; ctx->nranks = 1; ctx->rank = 0; }
 }
 
@@ -373,6 +377,364 @@ static int allgather_i64(gx_ctx *ctx, const int64_t *mine, int n, int64_t *all /
     return GX_OK;
 }
 
+
+// ------------------------------------------------------------- redistribute over peer memory
+// The reference's sender copies each tuple into the destination's FnPage and hands the page to the
+// forwarder (ExecSendRemoteFragment, execFragment.c:3505-3652; FnPageAddItem, fnbufpage.c:50-85).
+// On one NVSwitch node the destination's memory is addressable: every rank owns a window, all windows
+// are mapped into all processes (CUDA IPC), and the routing kernel stores each row straight into the
+// destination's window - routing, serialisation and transport are one kernel, nothing is staged locally
+// and no collective runs.  Window of rank d: N regions, region s written only by rank s (columnar, `cap`
+// rows per column, cap chosen by the writer).  Control words of rank d: hdr[s] = {epoch, rows, cap,
+// nullbits} written by s after its rows; ack[d'] written by d' once it has copied epoch's rows out of
+// ITS window, so the writer knows the regions it owns there may be overwritten.
+// All ranks see all headers, so "someone's region overflowed" is common knowledge and every rank takes
+// the NCCL path for that call together.
+#define PEER_CTL_BYTES 4096
+#define PEER_HDR(base, s) ((unsigned long long *) (base) + (size_t) (s) * 4)
+#define PEER_ACK(base, d) ((unsigned long long *) (base) + 256 + (d))
+#define PEER_FALLBACK 0xffffffffffffffffULL
+
+static inline long long peer_align(long long b) { return (b + 255) & ~255LL; }
+// byte offset of column c (or of its NULL array) inside a region laid out for `cap` rows; c == ncols: region size
+__host__ __device__ static inline long long peer_layout(long long cap, int ncols, const int *sizes, unsigned long long nullbits, int c, int want_null)
+{
+    long long off = 0;
+    for (int i = 0; i < ncols; i++) { if (!want_null && i == c) return off; off += (cap * sizes[i] + 255) & ~255LL; }
+    for (int i = 0; i < ncols; i++) if ((nullbits >> i) & 1ULL) { if (want_null && i == c) return off; off += (cap + 255) & ~255LL; }
+    return off;
+}
+
+static void peer_teardown(gx_ctx *ctx)
+{
+    if (ctx->peer_ready != 1) { ctx->peer_ready = 0; return; }
+    cudaStreamSynchronize(ctx->stream);
+    for (int p = 0; p < ctx->nranks; p++) if (p != ctx->rank && ctx->peer_base[p]) cudaIpcCloseMemHandle(ctx->peer_base[p]);
+    if (ctx->peer_base[ctx->rank]) cudaFree(ctx->peer_base[ctx->rank]);
+    memset(ctx->peer_base, 0, sizeof(ctx->peer_base));
+    ctx->peer_ready = 0;
+}
+
+static int allgather_i64(gx_ctx *ctx, const int64_t *mine, int n, int64_t *all);
+
+// Collective (called from gx_comm_init): allocate the window, exchange IPC handles through the communicator,
+// map the peers.  Any rank failing any step makes every rank give the windows up (peer_ready = -1): the
+// decision must be the same everywhere.  GX_PEER_WINDOW_MB (default 4096; 0 = no windows), GX_NO_PEER=1.
+static int peer_setup(gx_ctx *ctx)
+{
+    const int N = ctx->nranks;
+    ctx->peer_ready = -1; ctx->peer_epoch = 0;
+    if (N < 2) return GX_OK;
+    const char *no = getenv("GX_NO_PEER"), *mb = getenv("GX_PEER_WINDOW_MB");
+    long long win_mb = mb ? atoll(mb) : 4096;
+    if ((no && no[0] == '1') || win_mb <= 0) win_mb = 0;
+    int64_t mine[16], *all = (int64_t *) calloc((size_t) N * 16, 8);
+    memset(mine, 0, sizeof(mine));
+    char *own = nullptr;
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle travels as 8 int64");
+    if (win_mb > 0 && cudaMalloc((void **) &own, PEER_CTL_BYTES + ((size_t) win_mb << 20)) == cudaSuccess &&
+        cudaMemset(own, 0, PEER_CTL_BYTES) == cudaSuccess && cudaIpcGetMemHandle(&h, own) == cudaSuccess) {
+        memcpy(mine, &h, 64); mine[8] = 1; mine[9] = win_mb;
+    } else {
+        cudaGetLastError();
+        if (own) { cudaFree(own); own = nullptr; }
+    }
+    int rc = allgather_i64(ctx, mine, 16, all);
+    if (rc) { if (own) cudaFree(own); free(all); return rc; }
+    bool ok = true;
+    for (int p = 0; p < N; p++) ok = ok && all[(size_t) p * 16 + 8] == 1 && all[(size_t) p * 16 + 9] == win_mb;
+    memset(ctx->peer_base, 0, sizeof(ctx->peer_base));
+    int64_t mapped = ok ? 1 : 0;
+    if (ok) {
+        ctx->peer_base[ctx->rank] = own;
+        for (int p = 0; p < N && mapped; p++) {
+            if (p == ctx->rank) continue;
+            cudaIpcMemHandle_t hp; memcpy(&hp, all + (size_t) p * 16, 64);
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hp, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = 0; }
+            else ctx->peer_base[p] = (char *) ptr;
+        }
+    }
+    // second round: did everybody map everybody?
+    int64_t *all2 = (int64_t *) calloc((size_t) N, 8);
+    rc = allgather_i64(ctx, &mapped, 1, all2);
+    bool all_mapped = rc == GX_OK;
+    for (int p = 0; p < N && all_mapped; p++) all_mapped = all2[p] == 1;
+    free(all); free(all2);
+    if (!all_mapped) {
+        for (int p = 0; p < N; p++) if (p != ctx->rank && ctx->peer_base[p]) cudaIpcCloseMemHandle(ctx->peer_base[p]);
+        if (own) cudaFree(own);
+        memset(ctx->peer_base, 0, sizeof(ctx->peer_base));
+        return rc;
+    }
+    ctx->peer_win_bytes = (size_t) win_mb << 20;
+    ctx->peer_ready = 1;
+    return GX_OK;
+}
+
+__device__ __forceinline__ unsigned long long peer_load(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_store(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long peer_now_ns()
+{
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+
+struct gx_peer_ptrs { char *base[GX_MAX_NODES]; };
+
+// thread i waits until word i of `words` (own control block) reaches `want`; *timed_out is raised instead of hanging
+__global__ void gx_k_peer_wait(const unsigned long long *words, int stride, int n, unsigned long long want, unsigned long long timeout_ns,
+                               int *timed_out, unsigned long long *hdr_out)
+{
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long *w = words + (size_t) i * stride;
+    const unsigned long long t0 = peer_now_ns();
+    unsigned int spins = 0;
+    while (peer_load(w) < want) {
+        if ((++spins & 1023u) == 0 && peer_now_ns() - t0 > timeout_ns) { atomicExch(timed_out, 1); return; }
+        __nanosleep(200);
+    }
+    if (hdr_out) { hdr_out[i * 3 + 0] = w[1]; hdr_out[i * 3 + 1] = w[2]; hdr_out[i * 3 + 2] = w[3]; }
+}
+
+// after the routing kernel: thread d tells rank d how many rows of this rank lie in its window (or that this
+// rank cannot use the windows for this call)
+__global__ void gx_k_peer_publish(gx_peer_ptrs P, int n, int self, unsigned long long epoch, const unsigned long long *cursor, int feasible,
+                                  unsigned long long cap, unsigned long long nullbits)
+{
+    const int d = threadIdx.x;
+    if (d >= n) return;
+    const bool bad = !feasible || cursor[GX_MAX_NODES] != 0;
+    unsigned long long *h = PEER_HDR(P.base[d], self);
+    h[1] = bad ? PEER_FALLBACK : cursor[d]; h[2] = cap; h[3] = nullbits;
+    __threadfence_system();
+    peer_store(h, epoch);
+}
+
+// after the copy-out: thread s tells rank s that its region in this rank's window is free again
+__global__ void gx_k_peer_ack(gx_peer_ptrs P, int n, int self, unsigned long long epoch)
+{
+    const int s = threadIdx.x;
+    if (s >= n) return;
+    __threadfence_system();
+    peer_store(PEER_ACK(P.base[s], self), epoch);
+}
+
+// Route + serialise + transport in one kernel.  Tiles of 2048 rows: destination and tile-local position of every
+// row, one claim per destination in this rank's region there, then per column the tile is grouped by destination
+// in shared memory and leaves as contiguous runs (full 128-byte lines on the NVLink side, not 8-byte scatters).
+#define PR_THREADS 256
+#define PR_K 8
+struct gx_peer_route_args {
+    gx_dcol key; long long nrows; const int32_t *shardmap; int nnodes, ncols;
+    gx_dcol in[GX_MAX_COLS];
+    long long coff[GX_MAX_COLS], noff[GX_MAX_COLS];     // byte offset of the column / its NULL array inside a region (noff < 0: none)
+    char *dst[GX_MAX_NODES];                             // this rank's region in the window of each destination
+    long long cap; unsigned long long *cursor;           // [nnodes] rows claimed per destination; [GX_MAX_NODES] overflow flag
+};
+__global__ void __launch_bounds__(PR_THREADS) gx_k_route_peer(const __grid_constant__ gx_peer_route_args a)
+{
+    __shared__ unsigned int cur[GX_MAX_NODES];
+    __shared__ unsigned int toff[GX_MAX_NODES + 1];
+    __shared__ long long tbase[GX_MAX_NODES];
+    __shared__ long long stage[PR_THREADS * PR_K];
+    const int lane = threadIdx.x & 31;
+    const long long tile_rows = (long long) PR_THREADS * PR_K;
+    for (long long base = (long long) blockIdx.x * tile_rows; base < a.nrows; base += (long long) gridDim.x * tile_rows) {
+        if (threadIdx.x < GX_MAX_NODES) cur[threadIdx.x] = 0;
+        __syncthreads();
+        int d[PR_K]; unsigned int lp[PR_K];
+#pragma unroll
+        for (int k = 0; k < PR_K; k++) {
+            const long long r = base + k * PR_THREADS + threadIdx.x;
+            d[k] = -1; lp[k] = 0;
+            if (r < a.nrows) {
+                const bool isnull = gx_is_null(a.key, r);
+                const long long datum = isnull ? 0 : gx_load_int(a.key, r);
+                d[k] = a.shardmap[gx_shard_index(gx_route_hash(a.key.type, datum, isnull))];
+                const unsigned int m = __match_any_sync(__activemask(), d[k]);
+                const int leader = __ffs(m) - 1;
+                unsigned int off = 0;
+                if (lane == leader) off = atomicAdd(&cur[d[k]], (unsigned int) __popc(m));
+                lp[k] = __shfl_sync(m, off, leader) + __popc(m & ((1u << lane) - 1));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < a.nnodes) {
+            const unsigned int n = cur[threadIdx.x];
+            long long b = n ? (long long) atomicAdd(&a.cursor[threadIdx.x], (unsigned long long) n) : 0;
+            if (b + n > a.cap) { atomicExch(&a.cursor[GX_MAX_NODES], 1ULL); b = -1; }
+            tbase[threadIdx.x] = b;
+        }
+        if (threadIdx.x == 32) {
+            unsigned int run = 0;
+            for (int n = 0; n < a.nnodes; n++) { toff[n] = run; run += cur[n]; }
+            toff[a.nnodes] = run;
+        }
+        __syncthreads();
+        unsigned int si[PR_K];
+#pragma unroll
+        for (int k = 0; k < PR_K; k++) si[k] = d[k] >= 0 ? toff[d[k]] + lp[k] : 0xffffffffu;
+        const unsigned int total = toff[a.nnodes];
+        for (int c = 0; c < a.ncols; c++) {
+            const int ty = a.in[c].type;
+            const int sz = (ty == GX_INT4 || ty == GX_DATE) ? 4 : (ty == GX_CHAR ? 1 : 8);
+            for (int pass = 0; pass < 2; pass++) {                  // 0: the column, 1: its NULL bytes
+                if (pass == 1 && a.noff[c] < 0) break;
+                const int esz = pass ? 1 : sz;
+                if (pass == 0 && sz == 8) {
+                    long long v[PR_K];
+#pragma unroll
+                    for (int k = 0; k < PR_K; k++) v[k] = d[k] >= 0 ? __ldg((const long long *) a.in[c].data + base + k * PR_THREADS + threadIdx.x) : 0;
+#pragma unroll
+                    for (int k = 0; k < PR_K; k++) if (d[k] >= 0) stage[si[k]] = v[k];
+                } else if (pass == 0 && sz == 4) {
+                    int v[PR_K];
+#pragma unroll
+                    for (int k = 0; k < PR_K; k++) v[k] = d[k] >= 0 ? __ldg((const int *) a.in[c].data + base + k * PR_THREADS + threadIdx.x) : 0;
+#pragma unroll
+                    for (int k = 0; k < PR_K; k++) if (d[k] >= 0) ((int *) stage)[si[k]] = v[k];
+                } else {
+                    const unsigned char *src = pass ? a.in[c].nulls : (const unsigned char *) a.in[c].data;
+#pragma unroll
+                    for (int k = 0; k < PR_K; k++) if (d[k] >= 0) ((unsigned char *) stage)[si[k]] = src ? src[base + k * PR_THREADS + threadIdx.x] : 0;
+                }
+                __syncthreads();
+                const long long coff = pass ? a.noff[c] : a.coff[c];
+                int n = 0;
+                for (unsigned int i = threadIdx.x; i < total; i += PR_THREADS) {
+                    while (i >= toff[n + 1]) n++;
+                    const long long tb = tbase[n];
+                    if (tb < 0) continue;
+                    char *out = a.dst[n] + coff;
+                    const long long pos = tb + (long long) (i - toff[n]);
+                    if (esz == 8) ((long long *) out)[pos] = stage[i];
+                    else if (esz == 4) ((int *) out)[pos] = ((const int *) stage)[i];
+                    else ((unsigned char *) out)[pos] = ((const unsigned char *) stage)[i];
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// copy-out on the receiving side: region s of the own window -> rows [sum of earlier counts, +count[s]) of the table
+struct gx_peer_gather_args {
+    int nnodes, ncols; int sizes[GX_MAX_COLS];
+    const char *win; long long region_stride;
+    long long count[GX_MAX_NODES], cap[GX_MAX_NODES]; unsigned long long nullbits[GX_MAX_NODES];
+    void *out[GX_MAX_COLS]; uint8_t *out_nulls[GX_MAX_COLS];
+};
+__global__ void __launch_bounds__(256) gx_k_peer_gather(const __grid_constant__ gx_peer_gather_args a)
+{
+    const int s = blockIdx.y, c = blockIdx.z % a.ncols, want_null = blockIdx.z / a.ncols;
+    if (want_null && !a.out_nulls[c]) return;
+    long long first = 0;
+    for (int i = 0; i < s; i++) first += a.count[i];
+    const long long n = a.count[s];
+    const bool src_has = !want_null || ((a.nullbits[s] >> c) & 1ULL);
+    const char *src = a.win + (long long) s * a.region_stride + peer_layout(a.cap[s], a.ncols, a.sizes, a.nullbits[s], c, want_null);
+    const int sz = want_null ? 1 : a.sizes[c];
+    const long long step = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (sz == 8) ((long long *) a.out[c])[first + i] = ((const long long *) src)[i];
+        else if (sz == 4) ((int *) a.out[c])[first + i] = ((const int *) src)[i];
+        else if (!want_null) ((unsigned char *) a.out[c])[first + i] = ((const unsigned char *) src)[i];
+        else a.out_nulls[c][first + i] = src_has ? ((const unsigned char *) src)[i] : 0;
+    }
+}
+
+// Returns GX_OK with *done = 1 and *out set when the rows travelled through the windows; *done = 0 when the ranks
+// agreed (through the headers) that this call must take the NCCL path.
+static int redistribute_peer(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out, int *done)
+{
+    *done = 0;
+    const int N = ctx->nranks, kt = in->types[key_col];
+    GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "route: distribution column type %d not supported (int4/int8/date)", kt);
+    const unsigned long long epoch = ++ctx->peer_epoch;
+    const char *tmo = getenv("GX_PEER_TIMEOUT_MS");
+    const unsigned long long timeout_ns = (unsigned long long) (tmo ? atoll(tmo) : 20000) * 1000000ULL;
+    gx_peer_ptrs P; memset(&P, 0, sizeof(P));
+    for (int p = 0; p < N; p++) P.base[p] = ctx->peer_base[p];
+    char *own = ctx->peer_base[ctx->rank];
+    const long long region_stride = (long long) (ctx->peer_win_bytes / N) & ~255LL;
+    int sizes[GX_MAX_COLS]; unsigned long long nullbits = 0;
+    for (int c = 0; c < in->ncols; c++) { sizes[c] = gx_type_size(in->types[c]); if (in->nulls[c]) nullbits |= 1ULL << c; }
+    const long long cap = in->nrows / N + in->nrows / (4 * N) + 4096;
+    const int feasible = peer_layout(cap, in->ncols, sizes, nullbits, in->ncols, 0) <= region_stride;
+
+    unsigned long long *d_cur; int *d_flag; unsigned long long *d_hdr;
+    GX_CUDA(ctx, gx_tmp_alloc(ctx, (void **) &d_cur, (GX_MAX_NODES + 2) * 8 + (size_t) GX_MAX_NODES * 3 * 8));
+    GX_CUDA(ctx, cudaMemsetAsync(d_cur, 0, (GX_MAX_NODES + 2) * 8, ctx->stream));
+    d_flag = (int *) (d_cur + GX_MAX_NODES + 1); d_hdr = d_cur + GX_MAX_NODES + 2;
+    // the regions this rank owns in the peers' windows must have been emptied (previous call)
+    { gx_launch_scope ls(ctx, "peer_wait_ack"); gx_k_peer_wait<<<1, GX_MAX_NODES, 0, ctx->stream>>>(PEER_ACK(own, 0), 1, N, epoch - 1, timeout_ns, d_flag, nullptr); }
+    if (feasible && in->nrows > 0) {
+        gx_peer_route_args a; memset(&a, 0, sizeof(a));
+        a.key.data = in->cols[key_col]; a.key.nulls = in->nulls[key_col]; a.key.type = kt;
+        a.nrows = in->nrows; a.shardmap = ctx->d_shardmap; a.nnodes = N; a.ncols = in->ncols; a.cap = cap; a.cursor = d_cur;
+        for (int c = 0; c < in->ncols; c++) {
+            a.in[c].data = in->cols[c]; a.in[c].nulls = in->nulls[c]; a.in[c].type = in->types[c];
+            a.coff[c] = peer_layout(cap, in->ncols, sizes, nullbits, c, 0);
+            a.noff[c] = in->nulls[c] ? peer_layout(cap, in->ncols, sizes, nullbits, c, 1) : -1;
+        }
+        for (int p = 0; p < N; p++) a.dst[p] = ctx->peer_base[p] + PEER_CTL_BYTES + (long long) ctx->rank * region_stride;
+        const long long tiles = (in->nrows + PR_THREADS * PR_K - 1) / (PR_THREADS * PR_K), maxb = (long long) ctx->sm_count * 8;
+        gx_launch_scope ls(ctx, "peer_scatter");
+        gx_k_route_peer<<<(unsigned) (tiles < maxb ? tiles : maxb), PR_THREADS, 0, ctx->stream>>>(a);
+    }
+    { gx_launch_scope ls(ctx, "peer_publish"); gx_k_peer_publish<<<1, GX_MAX_NODES, 0, ctx->stream>>>(P, N, ctx->rank, epoch, d_cur, feasible, (unsigned long long) cap, nullbits); }
+    { gx_launch_scope ls(ctx, "peer_wait"); gx_k_peer_wait<<<1, GX_MAX_NODES, 0, ctx->stream>>>(PEER_HDR(own, 0), 4, N, epoch, timeout_ns, d_flag, d_hdr); }
+    unsigned long long h_hdr[GX_MAX_NODES * 3]; int h_flag = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hdr, d_hdr, (size_t) N * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    gx_tmp_free(ctx, d_cur);
+    if (e != cudaSuccess) { GX_SET_ERR(ctx, "redistribute (peer windows): %s", cudaGetErrorString(e)); return GX_ERR_CUDA; }
+    if (h_flag) { GX_SET_ERR(ctx, "redistribute (peer windows): rank %d waited %llu ms for its peers", ctx->rank, timeout_ns / 1000000ULL); return GX_ERR_NCCL; }
+    bool fallback = false; long long total = 0; unsigned long long anynull = 0;
+    for (int s = 0; s < N; s++) {
+        if (h_hdr[s * 3] == PEER_FALLBACK) fallback = true; else total += (long long) h_hdr[s * 3];
+        anynull |= h_hdr[s * 3 + 2];
+    }
+    if (fallback) {
+        // nothing of this epoch will be read from the windows: release them and let the caller take the NCCL path
+        gx_launch_scope ls(ctx, "peer_ack"); gx_k_peer_ack<<<1, GX_MAX_NODES, 0, ctx->stream>>>(P, N, ctx->rank, epoch);
+        return GX_OK;
+    }
+    bool hn[GX_MAX_COLS];
+    for (int c = 0; c < in->ncols; c++) hn[c] = (anynull >> c) & 1ULL;
+    gx_table *t;
+    int rc = gx_table_alloc_like(ctx, in->ncols, in->types, hn, total, &t);
+    if (rc == GX_OK && total > 0) {
+        gx_peer_gather_args g; memset(&g, 0, sizeof(g));
+        g.nnodes = N; g.ncols = in->ncols; g.win = own + PEER_CTL_BYTES; g.region_stride = region_stride;
+        long long most = 0;
+        for (int s = 0; s < N; s++) { g.count[s] = (long long) h_hdr[s * 3]; g.cap[s] = (long long) h_hdr[s * 3 + 1]; g.nullbits[s] = h_hdr[s * 3 + 2]; if (g.count[s] > most) most = g.count[s]; }
+        for (int c = 0; c < in->ncols; c++) { g.sizes[c] = sizes[c]; g.out[c] = t->cols[c]; g.out_nulls[c] = t->nulls[c]; }
+        long long bx = (most + 256 * 8 - 1) / (256 * 8); if (bx < 1) bx = 1; if (bx > ctx->sm_count * 2) bx = ctx->sm_count * 2;
+        gx_launch_scope ls(ctx, "peer_gather");
+        gx_k_peer_gather<<<dim3((unsigned) bx, (unsigned) N, (unsigned) (anynull ? 2 * in->ncols : in->ncols)), 256, 0, ctx->stream>>>(g);
+    }
+    // the ack goes out even when the allocation failed: the peers must not wait for this rank
+    { gx_launch_scope ls(ctx, "peer_ack"); gx_k_peer_ack<<<1, GX_MAX_NODES, 0, ctx->stream>>>(P, N, ctx->rank, epoch); }
+    if (rc) return rc;
+    GX_CUDA(ctx, cudaGetLastError());
+    t->nrows = total;
+    *out = t; *done = 1;
+    return GX_OK;
+}
+
 extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_table **out)
 {
     if (!ctx || !in || !out) return GX_ERR_ARG;
@@ -383,6 +745,12 @@ extern "C" int gx_redistribute(gx_ctx *ctx, const gx_table *in, int key_col, gx_
     long long cap = 0; int overflowed = 0;
     const char *two = getenv("GX_PARTITION_TWO_PASS");
     int rc = GX_OK;
+    if (N > 1 && ctx->comm && ctx->peer_ready == 1) {
+        GX_CHECK_ARG(ctx, key_col >= 0 && key_col < in->ncols, "route: key column %d out of range", key_col);
+        int done = 0;
+        rc = redistribute_peer(ctx, in, key_col, out, &done);
+        if (rc || done) return rc;
+    }
     if (!(two && two[0] == '1') && (N == 1 || ctx->comm)) { rc = partition_regions(ctx, in, key_col, &part, counts, &cap, &overflowed); if (rc) return rc; }
     if (!part) { rc = partition_impl(ctx, in, key_col, &part, counts); if (rc) return rc; cap = 0; }
     if (N == 1 || !ctx->comm) { *out = part; return GX_OK; }

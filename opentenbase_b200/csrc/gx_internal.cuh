@@ -50,6 +50,9 @@ struct gx_ctx {
     int32_t *d_shardmap; int nnodes;
     // communicator
     gx_nccl_api *nccl; void *comm; int rank, nranks;
+    // peer windows (gx_comm.cu): every rank's exchange block mapped into this process over NVLink;
+    // peer_base[p] = rank p's block (control words, then the data window), peer_ready 1 = mapped, -1 = not available
+    int peer_ready; size_t peer_win_bytes; char *peer_base[GX_MAX_NODES]; unsigned long long peer_epoch;
 };
 
 struct gx_table {

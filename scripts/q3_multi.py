@@ -53,6 +53,7 @@ def main():
     ocols = {"orderkey": g.O_ORDERKEY, "custkey": g.O_CUSTKEY, "orderdate": g.O_ORDERDATE, "shippriority": g.O_SHIPPRIORITY}
     lcols = {"orderkey": g.L_ORDERKEY, "extendedprice": g.L_EXTENDEDPRICE, "discount": g.L_DISCOUNT, "shipdate": g.L_SHIPDATE}
     stats = {}
+    ctx.profile(True)
     for it in range(a.iters):
         ctx.sync(); dist.barrier()
         t0 = time.perf_counter()
@@ -64,6 +65,10 @@ def main():
         if a.iters > 1:
             print(f"rank {rank} q3 iteration {it}: {dt * 1e3:.2f} ms; " + ", ".join(f"{k} {v:.2f}" for k, v in stats["host_ms_per_call"].items()), flush=True)
     rows_in = cust.nrows + orders.nrows + line.nrows
+    npeer, nnccl = ctx.profile_get("peer_gather")[1], ctx.profile_get("alltoall")[1]
+    ctx.profile(False)
+    if rank == 0:
+        print(f"transport: peer windows x{npeer}, nccl all-to-all x{nnccl}", flush=True)
 
     gathered = [None] * world
     dist.all_gather_object(gathered, (keys, aggs, rows_in, stats["redistributed_custkey"], stats["redistributed_orderkey"]))
