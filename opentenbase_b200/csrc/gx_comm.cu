@@ -644,11 +644,33 @@ __global__ void __launch_bounds__(256) gx_k_peer_gather(const __grid_constant__ 
     const bool src_has = !want_null || ((a.nullbits[s] >> c) & 1ULL);
     const char *src = a.win + (long long) s * a.region_stride + peer_layout(a.cap[s], a.ncols, a.sizes, a.nullbits[s], c, want_null);
     const int sz = want_null ? 1 : a.sizes[c];
-    const long long step = (long long) gridDim.x * blockDim.x;
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        if (sz == 8) ((long long *) a.out[c])[first + i] = ((const long long *) src)[i];
-        else if (sz == 4) ((int *) a.out[c])[first + i] = ((const int *) src)[i];
-        else if (!want_null) ((unsigned char *) a.out[c])[first + i] = ((const unsigned char *) src)[i];
+    const long long step = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (sz == 8 || sz == 4) {
+        // four independent loads in flight per thread
+        long long i = i0;
+        for (; i + 3 * step < n; i += 4 * step) {
+            if (sz == 8) {
+                long long v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = ((const long long *) src)[i + j * step];
+#pragma unroll
+                for (int j = 0; j < 4; j++) ((long long *) a.out[c])[first + i + j * step] = v[j];
+            } else {
+                int v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = ((const int *) src)[i + j * step];
+#pragma unroll
+                for (int j = 0; j < 4; j++) ((int *) a.out[c])[first + i + j * step] = v[j];
+            }
+        }
+        for (; i < n; i += step) {
+            if (sz == 8) ((long long *) a.out[c])[first + i] = ((const long long *) src)[i];
+            else ((int *) a.out[c])[first + i] = ((const int *) src)[i];
+        }
+        return;
+    }
+    for (long long i = i0; i < n; i += step) {
+        if (!want_null) ((unsigned char *) a.out[c])[first + i] = ((const unsigned char *) src)[i];
         else a.out_nulls[c][first + i] = src_has ? ((const unsigned char *) src)[i] : 0;
     }
 }
