@@ -907,7 +907,7 @@ struct gx_fast_args {
     const int *gcol;            // !JOIN: group column (int4/date)
     const double *vcol;         // value column of sum/avg (may be NULL)
     int sum_word;               // state word of the sum
-    int _pad;
+    int pf;                     // gx_k_runjoin: 1/2 = prefetch the join-table lines of a tile into L2/L1 before its runs are folded
 };
 
 __device__ __forceinline__ longlong2 ld_stream_ll2(const long long *p)
@@ -1166,6 +1166,14 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
     }
     // the loop is warp-uniform: lanes past the end carry no rows
     while (__any_sync(0xffffffffu, act)) {
+        // ---- the join-table lines this tile's runs will read: requested now, they arrive while the runs are folded
+        if (COMPACT && F.pf && act) {
+            const unsigned long long dd = (unsigned long long) k[0] - (unsigned long long) A.sf.kmin;
+            if (dd < A.cspan) {
+                const gx_cslot *pa = A.cslots + gx_slot_index(k[0], A.sf);
+                if (F.pf == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(pa)); else asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
+            }
+        }
         // ---- run heads and their numbering inside the warp
         const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
         bool hd[4];
@@ -1453,7 +1461,7 @@ __global__ void __launch_bounds__(512, 2) gx_k_runjoin2(const __grid_constant__ 
 #define RA_LIST 168                      /* <= 31 finished runs waiting for a full round + the carry + 128 new ones */
 #define RA_BND  0x80000000u
 struct gx_runagg_args {
-    int nv, nc, _pad0, _pad1;
+    int nv, nc, pf, _pad1;            // pf: bit 0 = rows two tiles ahead into L2, bit 1 = this tile's join-table lines into L2 before the fold
     int vagg[RA_NV], vword[RA_NV];
     const double *col[FG_NC];           // distinct argument columns, loaded once per row (as in gx_k_fewgroups)
     signed char tslot[RA_NV][4];
@@ -1612,6 +1620,20 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
     for (long long t0 = c0; t0 < c1; t0 += 128) {
         const long long r0 = t0 + lane * 4;
         long long k[4]; bool ok[4]; double x[NC][4];
+        if ((R.pf & 1) && t0 + 384 <= c1) {
+            // the warp walks its chunk front to back: the lines of the tile after the next one are asked for now
+            // (8 lanes per column, one 128-byte line each), so the loads below find their rows in L2
+            const long long tp = t0 + 256;
+            const int items = 1 + R.nc + P.npreds;
+            for (int it = lane >> 3; it < items; it += 4) {
+                const char *b; int sz = 8;
+                if (it == 0) b = (const char *) okey;
+                else if (it <= R.nc) b = (const char *) R.col[it - 1];
+                else { const gx_dcol &pc = P.preds[it - 1 - R.nc].col; b = (const char *) pc.data; sz = (pc.type == GX_INT4 || pc.type == GX_DATE) ? 4 : (pc.type == GX_CHAR ? 1 : 8); }
+                const int li = lane & 7;
+                if (li * 128 < 128 * sz) asm volatile("prefetch.global.L2 [%0];" :: "l"(b + tp * sz + li * 128));
+            }
+        }
         if (t0 + 128 <= c1) {                                   // full tile: 128-bit loads, everything requested before use
             const longlong2 ka = ld_stream_ll2(okey + r0), kb = ld_stream_ll2(okey + r0 + 2);
             k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
@@ -1633,6 +1655,7 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
                 for (int p = 0; p < P.npreds; p++) if (ok[i]) ok[i] = gx_eval_pred(P.preds[p], r);
             }
         }
+        if ((R.pf & 2) && k[0] != GX_EMPTY_KEY) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.slots + gx_slot_index(k[0], A.sf)));
         // aggregate arguments of the lane's four rows
         double v[NV][4];
 #pragma unroll
@@ -2324,6 +2347,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
 
     // ---- does the plan have the shape the specialised kernel was written for?
     gx_fast_args FA; memset(&FA, 0, sizeof(FA));
+    { const char *pf = getenv("GX_RUNJOIN_PF"); FA.pf = pf ? atoi(pf) : 0; }
     bool fast_ok = plan->n_preds == 0 && plan->n_group_cols == 1 && tagkey && outer->nrows > 0;
     if (fast_ok) {
         const gx_dgroupcol &gc = A.P.gcols[0];
@@ -2394,6 +2418,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
     // plan down the general path below.
     {
         gx_runagg_args RA; memset(&RA, 0, sizeof(RA));
+        { const char *pf = getenv("GX_RUNAGG_PF"); RA.pf = pf ? atoi(pf) : 1; }     // Q3 chain at SF100: 5.68 ms without, 5.52 with the rows, 5.59 with rows + table lines
         const char *e = getenv("GX_NO_RUNAGG");
         bool ok = !(e && e[0] == '1') && plan->strategy == 0 && A.P.has_join && h->unique && A.P.key_type == GX_INT8 && A.P.okey.nulls == nullptr &&
                   outer->nrows > 0 && plan->n_group_cols >= 1;

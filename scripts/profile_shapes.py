@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--sf", type=int, default=100)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--shapes", default="config1,q1,q3,config2,config3")
+    ap.add_argument("--envs", default="", help="A/B runs: ';'-separated settings, each a ','-separated list of NAME=VALUE "
+                                               "(the library reads its switches per call); an empty setting is the default build")
     a = ap.parse_args()
     ctx = g.Context(0)
     ctx.pool_reserve(0)
@@ -41,25 +43,41 @@ def main():
         h.free()
         return r
     shapes["config3"] = c3
-    for name in a.shapes.split(","):
-        fn = shapes[name]
+    if "q3chain" in a.shapes:
+        ctx.set_shardmap(1)
+        ct = ctx.table(g.SCHEMAS[g.T_CUSTOMER], no // 10).generate(g.T_CUSTOMER, a.sf, 0, no // 10)
+        cc = {"custkey": g.C_CUSTKEY, "mktsegment": g.C_MKTSEGMENT}
+        oc = {"orderkey": g.O_ORDERKEY, "custkey": g.O_CUSTKEY, "orderdate": g.O_ORDERDATE, "shippriority": g.O_SHIPPRIORITY}
+        lc = {"orderkey": g.L_ORDERKEY, "extendedprice": g.L_EXTENDEDPRICE, "discount": g.L_DISCOUNT, "shipdate": g.L_SHIPDATE}
+        shapes["q3chain"] = lambda: P.q3_datanode(ctx, ct, ot, lt, cc, oc, lc)
+    for setting, name in [(e, n) for e in a.envs.split(";") for n in a.shapes.split(",")]:
+        pairs = [kv.split("=", 1) for kv in setting.split(",") if kv]
+        for k, v in pairs:
+            os.environ[k] = v
+        _run(ctx, name, shapes[name], a.iters, setting)
+        for k, _ in pairs:
+            del os.environ[k]
+    ctx.close()
+
+
+def _run(ctx, name, fn, iters, setting):
+    if True:
         fn().free()
         ctx.sync()
         ctx.profile(True)
         ctx.timer_start()
-        for _ in range(a.iters):
+        for _ in range(iters):
             r = fn()
             n = r.ngroups
             r.free()
-        ms = ctx.timer_stop() / a.iters
+        ms = ctx.timer_stop() / iters
         ph = {}
-        for lab in ("agg", "probe_agg", "runagg", "build", "build_scatter", "agg_compact", "runagg_merge"):
+        for lab in ("agg", "probe_agg", "runagg", "build", "build_scatter", "agg_compact", "runagg_merge", "filter", "partition", "probe"):
             t, k = ctx.profile_get(lab)
             if k:
-                ph[lab] = round(t / a.iters, 3)
+                ph[lab] = round(t / iters, 3)
         ctx.profile(False)
-        print(f"{name}: {ms:.3f} ms per call, {n} groups, kernels {ph}", flush=True)
-    ctx.close()
+        print(f"{name} [{setting or 'default'}]: {ms:.3f} ms per call, {n} groups, kernels {ph}", flush=True)
 
 
 if __name__ == "__main__":
