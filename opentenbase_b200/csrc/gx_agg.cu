@@ -575,7 +575,6 @@ __global__ void __launch_bounds__(LPT_K == 8 ? 640 : 1024, 1) gx_k_agg_lptile(co
 // general kernels — the result never depends on the estimate.
 // Plan shape (checked by the host): no join; group key <= 8 bytes without NULLs; aggregates are
 // count(*) or sum/avg over chain expressions of NOT-NULL float8 columns and constants.
-template <int K> __device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K]);
 #define FG_G  4
 #define FG_NV 5
 /* FG_K = rows per lane and tile (independent loads in flight; the plan walk is paid once per tile) and the CTA size are
@@ -1484,28 +1483,6 @@ __device__ __forceinline__ bool runagg_probe(const gx_agg_dev &A, long long key,
         p = gx_next_pair(p, A.mask);
     }
     return found;
-}
-
-// quals of a tile of K rows per lane: the predicate descriptor is decoded once, the K column loads are independent
-template <int K>
-__device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K])
-{
-    if (p.col.nulls == nullptr && (p.col.type == GX_INT4 || p.col.type == GX_DATE)) {
-        const int *c = (const int *) p.col.data; int x[K];
-#pragma unroll
-        for (int j = 0; j < K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) ok[j] = ok[j] && gx_op_holds(p.op, (long long) x[j] > p.ival ? 1 : ((long long) x[j] < p.ival ? -1 : 0));
-    } else if (p.col.nulls == nullptr && p.col.type == GX_FLOAT8) {
-        const double *c = (const double *) p.col.data; double x[K];
-#pragma unroll
-        for (int j = 0; j < K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0.0;
-#pragma unroll
-        for (int j = 0; j < K; j++) ok[j] = ok[j] && gx_op_holds(p.op, gx_f8cmp(x[j], p.fval));
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; j++) if (ok[j]) ok[j] = gx_eval_pred(p, r[j]);
-    }
 }
 
 // quals of FOUR CONSECUTIVE rows starting at r0 (a multiple of 4): one 128-bit load per 4-byte column, two per 8-byte one

@@ -405,17 +405,25 @@ __host__ __device__ static inline long long peer_layout(long long cap, int ncols
     return off;
 }
 
+static int allgather_i64(gx_ctx *ctx, const int64_t *mine, int n, int64_t *all);
+
+// Collective like the set-up: an exporter must not free its block while a peer still has it mapped (or has an
+// acknowledgement store in flight towards it), so the ranks meet once before the imports are closed and once before
+// the blocks are freed.  GX_PEER_TEARDOWN_SYNC=0 skips the two rendezvous (a rank that is known to be alone).
 static void peer_teardown(gx_ctx *ctx)
 {
     if (ctx->peer_ready != 1) { ctx->peer_ready = 0; return; }
+    const char *ts = getenv("GX_PEER_TEARDOWN_SYNC");
+    const bool meet = ctx->comm && !(ts && ts[0] == '0');
+    int64_t one = 1, all[GX_MAX_NODES];
     cudaStreamSynchronize(ctx->stream);
+    if (meet) allgather_i64(ctx, &one, 1, all);                 // every rank's stores into the peers' blocks have completed
     for (int p = 0; p < ctx->nranks; p++) if (p != ctx->rank && ctx->peer_base[p]) cudaIpcCloseMemHandle(ctx->peer_base[p]);
+    if (meet) allgather_i64(ctx, &one, 1, all);                 // nobody has this rank's block mapped any more
     if (ctx->peer_base[ctx->rank]) cudaFree(ctx->peer_base[ctx->rank]);
     memset(ctx->peer_base, 0, sizeof(ctx->peer_base));
     ctx->peer_ready = 0;
 }
-
-static int allgather_i64(gx_ctx *ctx, const int64_t *mine, int n, int64_t *all);
 
 // Collective (called from gx_comm_init): allocate the window, exchange IPC handles through the communicator,
 // map the peers.  Any rank failing any step makes every rank give the windows up (peer_ready = -1): the
@@ -684,7 +692,7 @@ static int redistribute_peer(gx_ctx *ctx, const gx_table *in, int key_col, gx_ta
     GX_CHECK_ARG(ctx, kt == GX_INT4 || kt == GX_INT8 || kt == GX_DATE, "route: distribution column type %d not supported (int4/int8/date)", kt);
     const unsigned long long epoch = ++ctx->peer_epoch;
     const char *tmo = getenv("GX_PEER_TIMEOUT_MS");
-    const unsigned long long timeout_ns = (unsigned long long) (tmo ? atoll(tmo) : 20000) * 1000000ULL;
+    const unsigned long long timeout_ns = (unsigned long long) (tmo ? atoll(tmo) : 60000) * 1000000ULL;
     gx_peer_ptrs P; memset(&P, 0, sizeof(P));
     for (int p = 0; p < N; p++) P.base[p] = ctx->peer_base[p];
     char *own = ctx->peer_base[ctx->rank];

@@ -295,12 +295,14 @@ __device__ __forceinline__ int gx_f8cmp(double a, double b)
     if (isnan(b)) return -1;
     return a > b ? 1 : (a < b ? -1 : 0);
 }
+// does "x op y" hold, given c = sign(x - y)?  Branch-free: three bits per operator (c = -1, 0, +1), looked up in one word -
+// the switch this replaces compiled to a jump table inside every tile loop (ncu: 8 % of gx_k_runagg's instructions)
+#define GX_OP_BITS(op, lt, eq, gt) ((unsigned int) ((lt) | ((eq) << 1) | ((gt) << 2)) << (3 * (op)))
 __device__ __forceinline__ bool gx_op_holds(int op, int c)
 {
-    switch (op) {
-        case GX_LT: return c < 0;  case GX_LE: return c <= 0; case GX_EQ: return c == 0;
-        case GX_GE: return c >= 0; case GX_GT: return c > 0;  default: return c != 0;
-    }
+    constexpr unsigned int T = GX_OP_BITS(GX_LT, 1, 0, 0) | GX_OP_BITS(GX_LE, 1, 1, 0) | GX_OP_BITS(GX_EQ, 0, 1, 0) |
+                               GX_OP_BITS(GX_GE, 0, 1, 1) | GX_OP_BITS(GX_GT, 0, 0, 1) | GX_OP_BITS(GX_NE, 1, 0, 1);
+    return (T >> (3 * op + c + 1)) & 1u;
 }
 __device__ __forceinline__ bool gx_eval_pred(const gx_dpred &p, long long r)
 {
@@ -312,6 +314,28 @@ __device__ __forceinline__ bool gx_eval_pred(const gx_dpred &p, long long r)
         c = x > y ? 1 : (x < y ? -1 : 0);
     } else { long long x = gx_load_int(p.col, r); c = x > p.ival ? 1 : (x < p.ival ? -1 : 0); }
     return gx_op_holds(p.op, c);
+}
+
+// quals of a tile of K rows per lane: the predicate descriptor is decoded once, the K column loads are independent
+template <int K>
+__device__ __forceinline__ void pred_tile(const gx_dpred &p, const long long (&r)[K], bool (&ok)[K])
+{
+    if (p.col.nulls == nullptr && (p.col.type == GX_INT4 || p.col.type == GX_DATE)) {
+        const int *c = (const int *) p.col.data; int x[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) ok[j] = ok[j] && gx_op_holds(p.op, (long long) x[j] > p.ival ? 1 : ((long long) x[j] < p.ival ? -1 : 0));
+    } else if (p.col.nulls == nullptr && p.col.type == GX_FLOAT8) {
+        const double *c = (const double *) p.col.data; double x[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) x[j] = ok[j] ? __ldg(c + r[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < K; j++) ok[j] = ok[j] && gx_op_holds(p.op, gx_f8cmp(x[j], p.fval));
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; j++) if (ok[j]) ok[j] = gx_eval_pred(p, r[j]);
+    }
 }
 
 // IEEE fp64 ops that ptxas must never contract into FMA: the reference computes

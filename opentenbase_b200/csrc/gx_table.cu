@@ -390,10 +390,16 @@ __global__ void __launch_bounds__(FT_THREADS, 4) gx_k_filter_onepass(gx_filter_a
         if (tile >= ntiles) return;
         const long long base = tile * FT_ROWS;
         bool keep[FT_K]; unsigned int rank[FT_K];
+        {
+            // quals column by column: a descriptor is decoded once per tile and its FT_K loads are in flight together
+            long long rr[FT_K];
+#pragma unroll
+            for (int k = 0; k < FT_K; k++) { rr[k] = base + k * FT_THREADS + threadIdx.x; keep[k] = rr[k] < a.nrows; }
+#pragma unroll
+            for (int p = 0; p < GX_MAX_PREDS; p++) if (p < a.npreds) pred_tile<FT_K>(a.preds[p], rr, keep);
+        }
 #pragma unroll
         for (int k = 0; k < FT_K; k++) {
-            const long long r = base + k * FT_THREADS + threadIdx.x;
-            keep[k] = r < a.nrows && filter_pass(a, r);
             const unsigned int m = __ballot_sync(0xffffffffu, keep[k]);
             rank[k] = __popc(m & lt);
             if (lane == 0) wc[k][warp] = __popc(m);
