@@ -1460,7 +1460,8 @@ __global__ void __launch_bounds__(512, 2) gx_k_runjoin2(const __grid_constant__ 
 #define RA_LIST 168                      /* <= 31 finished runs waiting for a full round + the carry + 128 new ones */
 #define RA_BND  0x80000000u
 struct gx_runagg_args {
-    int nv, nc, pf, _pad1;            // pf: bit 0 = rows two tiles ahead into L2, bit 1 = this tile's join-table lines into L2 before the fold
+    int nv, nc, pf, pf_n;             // pf_n: columns listed for the row prefetch (the first four the tile reads)
+    const char *pf_ptr[4]; int pf_size[4], pf_lines[4];            // pf: bit 0 = rows two tiles ahead into L2, bit 1 = this tile's join-table lines into L2 before the fold
     int vagg[RA_NV], vword[RA_NV];
     const double *col[FG_NC];           // distinct argument columns, loaded once per row (as in gx_k_fewgroups)
     signed char tslot[RA_NV][4];
@@ -1599,17 +1600,9 @@ __global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_run
         long long k[4]; bool ok[4]; double x[NC][4];
         if ((R.pf & 1) && t0 + 384 <= c1) {
             // the warp walks its chunk front to back: the lines of the tile after the next one are asked for now
-            // (8 lanes per column, one 128-byte line each), so the loads below find their rows in L2
-            const long long tp = t0 + 256;
-            const int items = 1 + R.nc + P.npreds;
-            for (int it = lane >> 3; it < items; it += 4) {
-                const char *b; int sz = 8;
-                if (it == 0) b = (const char *) okey;
-                else if (it <= R.nc) b = (const char *) R.col[it - 1];
-                else { const gx_dcol &pc = P.preds[it - 1 - R.nc].col; b = (const char *) pc.data; sz = (pc.type == GX_INT4 || pc.type == GX_DATE) ? 4 : (pc.type == GX_CHAR ? 1 : 8); }
-                const int li = lane & 7;
-                if (li * 128 < 128 * sz) asm volatile("prefetch.global.L2 [%0];" :: "l"(b + tp * sz + li * 128));
-            }
+            // (8 lanes per column, one 128-byte line each; the host lists the columns), so the loads below find their rows in L2
+            const int it = lane >> 3, li = lane & 7;
+            if (it < R.pf_n && li < R.pf_lines[it]) asm volatile("prefetch.global.L2 [%0];" :: "l"(R.pf_ptr[it] + (t0 + 256) * R.pf_size[it] + li * 128));
         }
         if (t0 + 128 <= c1) {                                   // full tile: 128-bit loads, everything requested before use
             const longlong2 ka = ld_stream_ll2(okey + r0), kb = ld_stream_ll2(okey + r0 + 2);
@@ -2442,6 +2435,15 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             const long long nchunks = (nrows + rpw - 1) / rpw;
             const unsigned grid = (unsigned) ((nchunks + nwarps - 1) / nwarps);
             RA.rows_per_warp = rpw;
+            {
+                // what a tile reads, for the row prefetch: the key, the argument columns, the qual columns (first four)
+                auto list = [&](const void *ptr, int size) {
+                    if (RA.pf_n < 4 && ptr) { RA.pf_ptr[RA.pf_n] = (const char *) ptr; RA.pf_size[RA.pf_n] = size; RA.pf_lines[RA.pf_n] = size; RA.pf_n++; }
+                };
+                list(A.P.okey.data, 8);
+                for (int c = 0; c < RA.nc; c++) list(RA.col[c], 8);
+                for (int q = 0; q < A.P.npreds; q++) list(A.P.preds[q].col.data, gx_type_size(A.P.preds[q].col.type));
+            }
             const long long out_cap = (h->nentries < nrows ? h->nentries : nrows) + 64;
             const long long g_cap = gx_pow2_ceil(8 * nchunks + 1024);
             unsigned long long *g_tab, *d_out;

@@ -86,6 +86,12 @@ class OrcResult(C.Structure):
                 ("nulls", C.POINTER(C.c_uint8)), ("states", C.POINTER(C.c_double))]
 
 
+class OrcFnPageId(C.Structure):
+    """what FnPageInit stamps on every page of a fragment's stream (forward/fnbufpage.h:54-65)"""
+    _fields_ = [("qid_timestamp_nodeid", C.c_int64), ("qid_sequence", C.c_int64), ("fid", C.c_uint16), ("nodeid", C.c_uint16),
+                ("workerid", C.c_uint16), ("virtualid", C.c_uint8), ("pad", C.c_uint8)]
+
+
 def _declare(L: C.CDLL) -> None:
     u32, i32, i64, dbl, vp = C.c_uint32, C.c_int32, C.c_int64, C.c_double, C.c_void_p
     for name, res, args in [
@@ -123,6 +129,8 @@ def _declare(L: C.CDLL) -> None:
         ("orc_bloom_create", vp, [i64]), ("orc_bloom_insert", None, [vp, u32]),
         ("orc_bloom_find", C.c_int, [vp, u32]), ("orc_bloom_log_num_buckets", C.c_int, [vp]),
         ("orc_bloom_words", vp, [vp, vp]), ("orc_bloom_free", None, [vp]),
+        ("orc_fnpage_pack", i64, [C.c_int, vp, vp, vp, i64, C.POINTER(OrcFnPageId), C.c_int, vp, i64]),
+        ("orc_fnpage_unpack", i64, [vp, i64, C.c_int, vp, vp, vp, i64]),
     ]:
         f = getattr(L, name)
         f.restype = res
@@ -241,6 +249,42 @@ class Rel:
             self.free()
         except Exception:
             pass
+
+
+def fnpage_pack(types, cols, nulls=None, page_id=None, end_marker=True) -> np.ndarray:
+    """columns -> forward-node pages as the reference's sender fills them; returns a (npages, 8192) uint8 array"""
+    n = len(cols[0]) if cols else 0
+    keep = [np.ascontiguousarray(c, NP_DTYPES[t]) for c, t in zip(cols, types)]
+    cp = (C.c_void_p * len(keep))(*[c.ctypes.data for c in keep])
+    npp, kn = None, None
+    if nulls is not None:
+        kn = [None if x is None else np.ascontiguousarray(x, np.uint8) for x in nulls]
+        npp = (C.c_void_p * len(kn))(*[None if x is None else x.ctypes.data for x in kn])
+    tarr = (C.c_int32 * len(types))(*types)
+    pid = page_id or OrcFnPageId()
+    cap = n // 20 + 4                                   # a tuple takes at least 24 bytes: <= 340 per page
+    while True:
+        out = np.empty((cap, 8192), np.uint8)
+        k = lib().orc_fnpage_pack(len(types), tarr, cp, npp, n, C.byref(pid), int(bool(end_marker)), _ptr(out), cap)
+        if k == -1:
+            cap *= 2
+            continue
+        assert k >= 0, k
+        return out[:k].copy()
+
+
+def fnpage_unpack(pages: np.ndarray, types):
+    """forward-node pages -> (columns, null arrays) as the reference's receiver reads them"""
+    pages = np.ascontiguousarray(pages, np.uint8).reshape(-1, 8192)
+    cap = len(pages) * 510 + 1                          # a tuple takes at least 16 bytes (header only: every attribute NULL)
+    cols = [np.empty(cap, NP_DTYPES[t]) for t in types]
+    nulls = [np.zeros(cap, np.uint8) for _ in types]
+    tarr = (C.c_int32 * len(types))(*types)
+    cp = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    npp = (C.c_void_p * len(cols))(*[c.ctypes.data for c in nulls])
+    k = lib().orc_fnpage_unpack(_ptr(pages), len(pages), len(types), tarr, cp, npp, cap)
+    assert k >= 0, k
+    return [c[:k] for c in cols], [x[:k] for x in nulls]
 
 
 def make_plan(preds=(), outer_key_col=-1, group_cols=(), aggs=(), est_groups=0, strategy=0) -> GxAggPlan:

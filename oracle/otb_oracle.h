@@ -93,6 +93,18 @@ int      orc_rel_delete_tuple(orc_rel *r, int64_t pageno, int lineoff /* 1-based
 int64_t  orc_rel_scan_columns(const orc_rel *r, int ncols, const int32_t *attnums,
                               void *const *cols_out, uint8_t *const *nulls_out);
 
+/* ------------------------------------------------------- forward-node pages */
+/* The redistribute wire format (forward/fnbufpage.h:54-65): 8192-byte pages of MAXALIGNed minimal tuples.
+ * pack follows the sender (FragmentSendAttrs + FragmentGetPage's fit rule, execFragment.c:2067-2136, :1857-1876;
+ * end_marker adds FragmentSendNullTuple's MAX_UINT32 word + FNPAGE_END); returns the number of pages,
+ * -1 if cap_pages is too small, -2 for a tuple that would need FragmentSendHuge.  unpack follows the receiver's
+ * iterator (fnbufpage.h:107-127, tqueueThread.c:913-925) and slot_deform_tuple; returns the rows, -1 / -2 likewise. */
+typedef struct orc_fnpage_id { int64_t qid_timestamp_nodeid, qid_sequence; uint16_t fid, nodeid, workerid; uint8_t virtualid, pad; } orc_fnpage_id;
+int64_t orc_fnpage_pack(int natts, const int32_t *types, const void *const *cols, const uint8_t *const *nulls, int64_t nrows,
+                        const orc_fnpage_id *id, int end_marker, uint8_t *pages, int64_t cap_pages);
+int64_t orc_fnpage_unpack(const uint8_t *pages, int64_t npages, int natts, const int32_t *types,
+                          void *const *cols_out, uint8_t *const *nulls_out, int64_t cap_rows);
+
 /* ------------------------------------------------------- executor */
 typedef struct orc_result {
     int32_t  n_group_cols, n_aggs;

@@ -22,6 +22,8 @@
 #include "utils/bloomfilter.h"
 #include "utils/builtins.h"
 #include "utils/hashutils.h"
+#include "forward/fnbufpage.h"
+#include "pgxc/squeue.h"          /* MAX_UINT32, the end-of-stream length word */
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -267,3 +269,100 @@ void ref_debug_array(void)
             ARR_NDIM(a), ARR_DIMS(a)[0], ARR_HASNULL(a), ARR_ELEMTYPE(a), FLOAT8OID, sizeof(ArrayType), (size_t) ARR_OVERHEAD_NONULLS(1));
 }
 int ref_fcinfo_arg_offset(void) { return (int) offsetof(FunctionCallInfoData, arg); }
+
+/* ---- forward-node pages (the redistribute wire format) ----------------------
+ * Sender side as FragmentSendAttrs does it (executor/execFragment.c:2067-2136): header size and data size from
+ * heap_minimal_tuple_header_size / heap_compute_data_size, the tuple formed in place by heap_form_minimal_tuple_ptr,
+ * lower advanced by MAXALIGN(len); a new page when the aligned tuple does not fit (FragmentGetPage's rule,
+ * execFragment.c:1858, restated here because that function is static and drags the whole buffer manager in);
+ * pages initialised by FnPageInit (+ virtualid as FragmentGetPage sets it); the end of the stream is a MAX_UINT32
+ * length word and FNPAGE_END (FragmentSendNullTuple, execFragment.c:1963-1975).  values/isnull are row-major. */
+static Datum glue_datum(int16 attlen, int64 v)
+{
+    if (attlen == -1) {
+        struct varlena *t = (struct varlena *) calloc(1, VARHDRSZ + 1);
+        SET_VARSIZE(t, VARHDRSZ + 1);
+        VARDATA(t)[0] = (char) v;
+        return PointerGetDatum(t);
+    }
+    return (Datum) v;
+}
+int64 ref_fnpage_pack(int natts, const int16 *attlen, const int8 *attalign, const int64 *values, const uint8 *isnull, int64 nrows,
+                      int64 qid_ts, int64 qid_seq, int fid, int nodeid, int workerid, int virtualid, int end_marker,
+                      uint8 *pages, int64 cap_pages)
+{
+    TupleDesc d = make_desc(natts, attlen, attalign);
+    Datum *v = (Datum *) calloc(natts, sizeof(Datum));
+    bool *n = (bool *) calloc(natts, sizeof(bool));
+    FNQueryId qid; qid.timestamp_nodeid = qid_ts; qid.sequence = qid_seq;
+    int64 npages = 0;
+    char *page = NULL;
+#define GLUE_NEW_PAGE() do { if (npages >= cap_pages) { npages = -1; goto done; } page = (char *) pages + npages * BLCKSZ; npages++; \
+        memset(page, 0, BLCKSZ); FnPageInit(page, qid, (uint16) fid, (uint16) nodeid, (uint16) workerid); \
+        ((FnPageHeader) page)->virtualid = (uint8) virtualid; } while (0)
+    for (int64 r = 0; r < nrows; r++) {
+        bool hasnull = false;
+        for (int i = 0; i < natts; i++) { n[i] = isnull[r * natts + i] != 0; hasnull |= n[i]; v[i] = n[i] ? (Datum) 0 : glue_datum(attlen[i], values[r * natts + i]); }
+        int hoff = heap_minimal_tuple_header_size(d, hasnull);
+        Size len = hoff + heap_compute_data_size(d, v, n);
+        Size aligned = MAXALIGN(len);
+        if (page == NULL || aligned > BLCKSZ - ((FnPageHeader) page)->lower) GLUE_NEW_PAGE();
+        void *tuple = page + ((FnPageHeader) page)->lower;
+        heap_form_minimal_tuple_ptr(d, v, n, hasnull, len, hoff, (MinimalTuple *) &tuple);
+        ((FnPageHeader) page)->lower += MAXALIGN(len);
+        for (int i = 0; i < natts; i++) if (attlen[i] == -1 && !n[i]) free(DatumGetPointer(v[i]));
+    }
+    if (end_marker) {
+        uint32 n32 = MAX_UINT32;
+        if (page == NULL || sizeof(uint32) > BLCKSZ - ((FnPageHeader) page)->lower) GLUE_NEW_PAGE();
+        memcpy(page + ((FnPageHeader) page)->lower, &n32, sizeof(uint32));
+        ((FnPageHeader) page)->lower += sizeof(uint32);
+        FnPageSetFlag(page, FNPAGE_END);
+    }
+done:
+    free(v); free(n); free(d);
+    return npages;
+}
+/* Receiver side: the iterator macros of fnbufpage.h as the forward receiver uses them (executor/tqueueThread.c:913-925),
+ * each item handed to heap_deform_tuple the way ExecStoreMinimalTuple presents a minimal tuple (t_data =
+ * tuple - MINIMAL_TUPLE_OFFSET, executor/execTuples.c).  Returns the number of rows, -1 if cap_rows is too small,
+ * -2 on a page carrying FNPAGE_HUGE. */
+int64 ref_fnpage_unpack(const uint8 *pages, int64 npages, int natts, const int16 *attlen, const int8 *attalign,
+                        int64 *values_out, uint8 *isnull_out, int64 cap_rows)
+{
+    TupleDesc d = make_desc(natts, attlen, attalign);
+    Datum *v = (Datum *) calloc(natts, sizeof(Datum));
+    bool *n = (bool *) calloc(natts, sizeof(bool));
+    int64 rows = 0;
+    for (int64 p = 0; p < npages && rows >= 0; p++) {
+        char *page = (char *) pages + p * BLCKSZ;
+        FnPageIterator iter;
+        if (((FnPageHeader) page)->flag & FNPAGE_HUGE) { rows = -2; break; }
+        InitFnPageIterator(&iter);
+        while (!FnPageIterateDone(page, &iter)) {
+            uint32 len; Pointer data;
+            FnPageIterateNext(page, &iter, len, data);
+            if (len == MAX_UINT32) break;
+            if (rows >= cap_rows) { rows = -1; break; }
+            HeapTupleData htup;
+            memset(&htup, 0, sizeof(htup));
+            htup.t_len = len + MINIMAL_TUPLE_OFFSET;
+            htup.t_data = (HeapTupleHeader) ((char *) data - MINIMAL_TUPLE_OFFSET);
+            heap_deform_tuple(&htup, d, v, n);
+            for (int i = 0; i < natts; i++) {
+                isnull_out[rows * natts + i] = n[i];
+                if (n[i]) { values_out[rows * natts + i] = 0; continue; }
+                if (attlen[i] == -1) values_out[rows * natts + i] = (int64) (int8) VARDATA_ANY((struct varlena *) DatumGetPointer(v[i]))[0];
+                else if (attlen[i] == 1) values_out[rows * natts + i] = (int64) DatumGetChar(v[i]);
+                else if (attlen[i] == 2) values_out[rows * natts + i] = (int64) DatumGetInt16(v[i]);
+                else if (attlen[i] == 4) values_out[rows * natts + i] = (int64) DatumGetInt32(v[i]);
+                else values_out[rows * natts + i] = DatumGetInt64(v[i]);
+            }
+            rows++;
+        }
+    }
+    free(v); free(n); free(d);
+    return rows;
+}
+int ref_sizeof_fnpage_header(void) { return (int) SizeOfFnPageHeaderData; }
+int ref_invalid_shardid(void) { return (int) InvalidShardID; }

@@ -196,3 +196,48 @@ def test_heap_tuples_and_pages_against_reference_objects(R):
     # and the next tuple really does not fit (heap_insert's fill rule)
     lp = int(pages[1][44:48].copy().view(np.uint32)[0])
     assert ((lp >> 17) + 7) // 8 * 8 > upper - lower - 4
+
+
+def test_fnpages_against_reference_objects(R):
+    """Forward-node pages (the redistribute wire format): the oracle's sender writes the bytes that heaptuple.o's
+    heap_form_minimal_tuple_ptr + fnbufpage.o's FnPageInit write under FragmentSendAttrs' control flow, and each side's
+    receiver reads the other side's pages (iterator macros of fnbufpage.h + heap_deform_tuple)."""
+    R.ref_fnpage_pack.restype = C.c_int64
+    R.ref_fnpage_pack.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    R.ref_fnpage_unpack.restype = C.c_int64
+    R.ref_fnpage_unpack.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    assert R.ref_sizeof_fnpage_header() == 32 and R.ref_invalid_shardid() == 4096
+    rng = np.random.default_rng(99)
+    for types, n, frac in [([O.GX_INT8, O.GX_INT8, O.GX_DATE, O.GX_INT4], 5000, 0.0),
+                           ([O.GX_INT8, O.GX_INT4, O.ORC_BPCHAR1, O.GX_FLOAT8, O.GX_CHAR, O.GX_DATE, O.ORC_BPCHAR1, O.GX_INT8, O.GX_INT4], 3000, 0.2),
+                           ([O.GX_CHAR], 700, 0.5), ([O.GX_FLOAT8] * 12, 900, 0.1)]:
+        vals = np.zeros((n, len(types)), np.int64)
+        for i, t in enumerate(types):
+            vals[:, i] = (rng.integers(-2**62, 2**62, n) if t in (O.GX_INT8, O.GX_FLOAT8) else
+                          rng.integers(-2**31, 2**31 - 1, n) if t in (O.GX_INT4, O.GX_DATE) else rng.integers(-128, 127, n))
+        isn = (rng.random((n, len(types))) < frac).astype(np.uint8)
+        isn[:40] = 0
+        attlen = (C.c_int16 * len(types))(*[ATT[t][0] for t in types])
+        attalign = (C.c_int8 * len(types))(*[ATT[t][1] for t in types])
+        cap = n // 20 + 4
+        ref = np.zeros((cap, 8192), np.uint8)
+        k = R.ref_fnpage_pack(len(types), attlen, attalign, vals.ctypes.data, isn.ctypes.data, n, 123456789012345, -7, 12, 3, 1, 2, 1, ref.ctypes.data, cap)
+        assert k > 0
+        cols = [vals[:, i].astype(O.NP_DTYPES[t]) if t != O.GX_FLOAT8 else vals[:, i].copy().view(np.float64) for i, t in enumerate(types)]
+        nulls = [isn[:, i].copy() for i in range(len(types))] if frac else None
+        mine = O.fnpage_pack(types, cols, nulls, O.OrcFnPageId(123456789012345, -7, 12, 3, 1, 2, 0), True)
+        assert len(mine) == k
+        np.testing.assert_array_equal(mine, ref[:k])
+        # the reference's receiver on the oracle's pages
+        vo = np.zeros((n, len(types)), np.int64); no = np.zeros((n, len(types)), np.uint8)
+        got = R.ref_fnpage_unpack(mine.ctypes.data, len(mine), len(types), attlen, attalign, vo.ctypes.data, no.ctypes.data, n)
+        assert got == n
+        np.testing.assert_array_equal(no, isn)
+        np.testing.assert_array_equal(vo[isn == 0], vals[isn == 0])
+        # the oracle's receiver on the reference's pages
+        c2, n2 = O.fnpage_unpack(ref[:k], types)
+        for i in range(len(types)):
+            np.testing.assert_array_equal(n2[i], isn[:, i])
+            keep = isn[:, i] == 0
+            np.testing.assert_array_equal(np.asarray(c2[i])[keep].view(np.uint8), np.asarray(cols[i])[keep].view(np.uint8))
