@@ -202,6 +202,32 @@ int  gx_table_append_heap_pages(gx_table *t, const void *pages, int64_t npages,
                                 const gx_heap_desc *desc,
                                 const uint16_t *vis_offsets, const int32_t *vis_counts,
                                 int32_t vis_stride);
+/* ---- forward-node pages: the reference's redistribute wire format --------------------------------
+ * What FragmentSendAttrs writes and the forward receiver reads (executor/execFragment.c:2067-2136,
+ * forward/fnbufpage.h:54-127, executor/tqueueThread.c:913-925): 8192-byte pages, a 32-byte header
+ * (FnPageHeaderData) and MAXALIGNed minimal tuples (heap_form_minimal_tuple_ptr, heaptuple.c:1852).
+ * These two calls are what a GPU datanode needs to exchange rows with stock CPU datanodes through their
+ * forwarder; between GPU datanodes gx_redistribute() moves columns instead.
+ * `desc` describes the tuple (att_len/att_align per attribute; attlen -1 = bpchar(1) carried in a GX_CHAR
+ * column).  gx_fnpage_id is what FnPageInit/FragmentGetPage stamp on every page of the stream. */
+typedef struct gx_fnpage_id {
+    int64_t  qid_timestamp_nodeid, qid_sequence;   /* FNQueryId */
+    uint16_t fid, nodeid, workerid;                /* fragment id, source node, source parallel worker */
+    uint8_t  virtualid, _pad;                      /* destination virtual datanode */
+} gx_fnpage_id;
+/* Sender.  Every table column is attribute c of the tuple (desc->natts == ncols, attnums[c] == c).
+ * host_pages == NULL: only *npages is computed.  end_marker adds FragmentSendNullTuple's MAX_UINT32 word and
+ * FNPAGE_END.  Without NULL arrays the pages equal the reference's byte for byte; with NULLs the rows per page
+ * are fixed at the worst-case tuple size (valid pages, not the reference's greedy fill).  Bytes past `lower`
+ * are zero. */
+int  gx_fnpage_pack(gx_ctx *ctx, const gx_table *t, const gx_heap_desc *desc, const gx_fnpage_id *id, int end_marker,
+                    void *host_pages, int64_t cap_pages, int64_t *npages);
+/* Receiver: pages of one stream (any fill, NULL bitmaps, short tuples, an end marker) -> a new table with
+ * desc->ncols columns of col_types; attributes declared att_notnull get no NULL array.  GX_ERR_ARG for
+ * FNPAGE_HUGE pages or a corrupt length chain. */
+int  gx_fnpage_unpack(gx_ctx *ctx, const void *host_pages, int64_t npages, const gx_heap_desc *desc,
+                      const int32_t *col_types, gx_table **out);
+
 /* End of a load: waits for the enqueued appends; GX_ERR_STATE if a NULL arrived in a column
  * the descriptor declared NOT NULL. */
 int  gx_table_load_finish(gx_table *t);

@@ -82,6 +82,12 @@ class GxHeapDesc(C.Structure):
                 ("attnums", C.c_int32 * 16), ("att_notnull", C.c_int8 * 64)]
 
 
+class GxFnPageId(C.Structure):
+    """FNQueryId + fragment / node / worker ids that FnPageInit stamps on every page (forward/fnbufpage.h:54-65)"""
+    _fields_ = [("qid_timestamp_nodeid", C.c_int64), ("qid_sequence", C.c_int64), ("fid", C.c_uint16), ("nodeid", C.c_uint16),
+                ("workerid", C.c_uint16), ("virtualid", C.c_uint8), ("_pad", C.c_uint8)]
+
+
 class GxHostTable(C.Structure):
     _fields_ = [("ncols", C.c_int32), ("_pad", C.c_int32), ("nrows", C.c_int64),
                 ("types", C.POINTER(C.c_int32)), ("cols", C.POINTER(C.c_void_p)),
@@ -150,6 +156,8 @@ def _declare(L):
         "gx_hash_nslots": (i64, [vp]),
         "gx_hash_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(dbl)]),
         "gx_hash_free": (None, [vp]),
+        "gx_fnpage_pack": (C.c_int, [vp, vp, C.POINTER(GxHeapDesc), C.POINTER(GxFnPageId), C.c_int, vp, i64, C.POINTER(i64)]),
+        "gx_fnpage_unpack": (C.c_int, [vp, vp, i64, C.POINTER(GxHeapDesc), vp, pp]),
         "gx_bloom_build": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(GxPred), pp]),
         "gx_bloom_log_num_buckets": (C.c_int, [vp]),
         "gx_bloom_read_words": (C.c_int, [vp, vp]),
@@ -501,6 +509,39 @@ class Context:
         self._chk(lib().gx_hash_probe_ex(self.h, outer.h, key_col, len(preds), pr, ht.h, join_type, len(out_outer_cols), oc, C.byref(h)))
         inner = [] if join_type in (GX_JOIN_SEMI, GX_JOIN_ANTI) else ht.payload_types
         return Table(self, h, [outer.types[c] for c in out_outer_cols] + inner)
+
+    # ---- forward-node pages (the reference's redistribute wire format)
+    @staticmethod
+    def _wire_desc(att_len, att_align, attnums, notnull=None):
+        d = GxHeapDesc()
+        d.natts, d.ncols = len(att_len), len(attnums)
+        for i, (l, a) in enumerate(zip(att_len, att_align)):
+            d.att_len[i], d.att_align[i] = l, a
+        for i, a in enumerate(attnums):
+            d.attnums[i] = a
+        for i, nn in enumerate(notnull or ()):
+            d.att_notnull[i] = 1 if nn else 0
+        return d
+
+    def fnpage_pack(self, t: Table, att_len, att_align, page_id: GxFnPageId = None, end_marker=True) -> np.ndarray:
+        """table -> (npages, 8192) uint8 array of FnPages as the reference's sender would hand them to the forwarder"""
+        d = self._wire_desc(att_len, att_align, list(range(len(att_len))))
+        pid = page_id or GxFnPageId()
+        n = C.c_int64()
+        self._chk(lib().gx_fnpage_pack(self.h, t.h, C.byref(d), C.byref(pid), int(bool(end_marker)), None, 0, C.byref(n)))
+        out = np.empty((n.value, 8192), np.uint8)
+        if n.value:
+            self._chk(lib().gx_fnpage_pack(self.h, t.h, C.byref(d), C.byref(pid), int(bool(end_marker)), out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def fnpage_unpack(self, pages: np.ndarray, att_len, att_align, attnums, col_types, notnull=None) -> Table:
+        """FnPages of one stream -> a new table (columns attnums of the tuple)"""
+        d = self._wire_desc(att_len, att_align, attnums, notnull)
+        pages = np.ascontiguousarray(pages, np.uint8)
+        tarr = (C.c_int32 * len(col_types))(*col_types)
+        h = C.c_void_p()
+        self._chk(lib().gx_fnpage_unpack(self.h, pages.ctypes.data if pages.size else None, pages.size // 8192, C.byref(d), tarr, C.byref(h)))
+        return Table(self, h, list(col_types))
 
     # ---- bloom filter of the hash join
     def bloom_build(self, inner: Table, key_col, preds=()):
