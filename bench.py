@@ -496,6 +496,13 @@ def run_ours(args):
         except Exception as ex:                                  # an extra must never take the headline line down with it
             e2e_pages = {"error": repr(ex)}
 
+    fnpage = None
+    if rank == 0 and not args.no_extras:
+        try:
+            fnpage = run_fnpage(ctx, g, ot, cols["o"], peak)
+        except Exception as ex:
+            fnpage = {"error": repr(ex)}
+
     if rank != 0:
         ctx.close()
         if dist is not None:
@@ -557,6 +564,10 @@ def run_ours(args):
         line["e2e_pages"] = e2e_pages
         if e2e_pages.get("rows_match_oracle") is False:
             failed.append("e2e_pages.rows_match_oracle")
+    if fnpage is not None:
+        line["fnpage"] = fnpage
+        if fnpage.get("round_trip_equal") is False:
+            failed.append("fnpage.round_trip_equal")
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
     ctx.close()
     if dist is not None:
@@ -613,6 +624,35 @@ def run_e2e(ctx, g, ot, lt, no, nl, plan, args, barrier, allmax, rows_all):
             "note": "gx_exec_host: pinned host columns -> HBM (chunked over the copy streams, the build overlaps the outer upload) -> "
                     "build -> probe+agg -> result on the host, every step; pcie_ceiling = cudaMemcpyAsync of 2 GB from the same "
                     "staging buffer in the same run"}
+
+
+def run_fnpage(ctx, g, ot, ocols, peak, rows=20_000_000):
+    """The reference's redistribute wire format on the device: `rows` orders rows (orderkey, custkey, orderdate, shippriority -
+    the tuple of Q3's first Distribute) -> FnPages -> rows.  Kernel times from the library's launch profile; the calls also
+    move the pages over PCIe (pageable host memory here), which is not the kernels' business."""
+    keep = [ocols["orderkey"], ocols["custkey"], ocols["orderdate"], ocols["shippriority"]]
+    # TPC-H order keys use 8 of every 32 values: key <= 4 * rows keeps about `rows` rows (of this datanode's share)
+    t = ctx.scan_filter(ot, [(ocols["orderkey"], g.GX_LE, 4 * rows)], keep)
+    sizes = {g.GX_INT8: (8, 8), g.GX_INT4: (4, 4), g.GX_DATE: (4, 4), g.GX_FLOAT8: (8, 8), g.GX_CHAR: (1, 1)}
+    al, ag = [sizes[x][0] for x in t.types], [sizes[x][1] for x in t.types]
+    ctx.profile(True)
+    pages = ctx.fnpage_pack(t, al, ag, g.GxFnPageId(1, 1, 1, 0, 0, 0, 0), True)
+    pack_ms, _ = ctx.profile_get("fnpage_pack")
+    ctx.profile(False); ctx.profile(True)
+    back = ctx.fnpage_unpack(pages, al, ag, list(range(len(al))), list(t.types), notnull=[1] * len(al))
+    unpack_ms, _ = ctx.profile_get("fnpage_unpack")
+    ctx.profile(False)
+    ok = back.nrows == t.nrows and all(np.array_equal(back.read(c), t.read(c)) for c in range(len(al)))
+    row_bytes = sum(al)
+    out = {"workload": "orders rows of Q3's first Distribute as FnPages (forward/fnbufpage.h): columns -> pages -> columns",
+           "rows": int(t.nrows), "pages": int(len(pages)), "tuple_bytes_on_the_wire": int(pages[0, 32:36].copy().view(np.uint32)[0]),
+           "pack_kernel_ms": pack_ms, "unpack_kernels_ms": unpack_ms, "round_trip_equal": bool(ok),
+           # sender: read the columns, write the pages (+ the memset that defines every byte); receiver: read the pages twice (count, deform), write the columns
+           "pack_gb_s": (t.nrows * row_bytes + 2 * len(pages) * 8192) / (pack_ms / 1e3) / 1e9 if pack_ms else None,
+           "unpack_gb_s": (t.nrows * row_bytes + 2 * len(pages) * 8192) / (unpack_ms / 1e3) / 1e9 if unpack_ms else None,
+           "hbm_peak_gb_s": peak}
+    back.free(); t.free()
+    return out
 
 
 def run_e2e_pages(ctx, g, args):
