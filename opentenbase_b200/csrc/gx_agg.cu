@@ -1511,8 +1511,8 @@ __device__ __forceinline__ void pred_vec4(const gx_dpred &p, long long r0, bool 
 // are added to its list entry with a shared-memory atomic.  Entry 0 of the list is the run left open by the previous
 // tile (the carry), so a run may span any number of lanes and tiles of the warp's chunk.  All entries but the last
 // are then complete and are processed densely, one run per lane (probe, final record); the last becomes the carry.
-template <int NV, int NC>
-__global__ void __launch_bounds__(NV <= 2 ? 384 : 512, NV <= 2 ? 2 : 1) gx_k_runagg(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_runagg_args R)
+template <int NV, int NC, int DENSE = 0>                      // DENSE: two CTAs of 512 threads per SM (64 registers) instead of two of 384 (80)
+__global__ void __launch_bounds__(DENSE ? 512 : (NV <= 2 ? 384 : 512), (DENSE || NV <= 2) ? 2 : 1) gx_k_runagg(const __grid_constant__ gx_agg_dev A, const __grid_constant__ gx_runagg_args R)
 {
     extern __shared__ unsigned long long smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -2422,11 +2422,15 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             rc = need_wide(); if (rc) return rc;
             static bool attr = false;
             const bool small = RA.nv <= 2 && RA.nc <= 2;           // two CTAs of 384 threads per SM (85 registers each)
-            const int threads = small ? 384 : 512, nwarps = threads / 32;
+            const char *dn = getenv("GX_RUNAGG_DENSE");
+            // 2 x 384 threads: 5.03 ms for the Q3 chain's lineitem side at SF100; 2 x 512 (28 bytes of spills): 4.49 ms
+            const int dense = (small && RA.nv <= 1) ? (dn ? atoi(dn) != 0 : 1) : 0;      // 2 x 640 (48 registers): 4.80 ms, profiles/r02_occupancy_variants.txt
+            const int threads = (small && !dense) ? 384 : 512, nwarps = threads / 32;
             const size_t smem = (size_t) nwarps * ((size_t) RA_LIST * (1 + RA.nv) + RA_LIST / 2) * 8;
             if (!attr) {
                 GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
                 GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+                GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
                 GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runagg<RA_NV, FG_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
                 attr = true;
             }
@@ -2456,7 +2460,8 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             RA.out = d_out; RA.out_cap = out_cap; RA.cursor = ctx->d_scratch + 12;
             {
                 gx_launch_scope ls(ctx, "runagg");
-                if (small && RA.nv <= 1) gx_k_runagg<1, 2><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                if (dense) gx_k_runagg<1, 2, 1><<<grid, threads, smem, ctx->stream>>>(A, RA);
+                else if (small && RA.nv <= 1) gx_k_runagg<1, 2><<<grid, threads, smem, ctx->stream>>>(A, RA);
                 else if (small) gx_k_runagg<2, 2><<<grid, threads, smem, ctx->stream>>>(A, RA);
                 else gx_k_runagg<RA_NV, FG_NC><<<grid, threads, smem, ctx->stream>>>(A, RA);
             }

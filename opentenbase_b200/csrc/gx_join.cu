@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) gx_k_sorted_bounds_i8(const long long *__
 // PK selects the row loader: 0 generic (any key type, NULLs, build-side quals, packed payload),
 // 1 = int8 key without NULLs or quals + one 4-byte payload column, 2 = the same without payload
 template <int PK, bool C, bool VERIFY>
-__global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_bbuild_args a)
+__global__ void __launch_bounds__(FILL_THREADS, C ? 5 : 4) gx_k_sorted_fill(gx_bbuild_args a)      // 5 CTAs/SM: profiles/r02_occupancy_variants.txt
 {
     extern __shared__ __align__(16) unsigned char fill_smem_raw[];
     gx_fill_smem_t<C> &sm = *(gx_fill_smem_t<C> *) fill_smem_raw;
@@ -1206,6 +1206,8 @@ __device__ __forceinline__ void ld_pair(const gx_slot *p, long long &k0, unsigne
     asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(p0), "=l"(k1), "=l"(p1) : "l"(p));
 }
 template <bool COMPACT>
+// no min-blocks on purpose: any value (even 1 or 4, which leave the occupancy as it is) changes ptxas' schedule and costs
+// 20-35 % here (profiles/r02_occupancy_variants.txt)
 __global__ void __launch_bounds__(256) gx_k_hash_probe_unique(gx_probe_args a)
 {
     const int lane = threadIdx.x & 31;
@@ -1367,8 +1369,9 @@ extern "C" int gx_hash_probe_ex(gx_ctx *ctx, const gx_table *outer, int key_col,
         gx_launch_scope ls(ctx, "probe");
         if (first_match_only) {
             long long nt = (outer->nrows + 32 * PT_K * 8 - 1) / (32 * PT_K * 8);
-            if (use_compact) gx_k_hash_probe_unique<true><<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
-            else gx_k_hash_probe_unique<false><<<(unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb), 256, 0, ctx->stream>>>(a);
+            const unsigned pgrid = (unsigned) (nt < maxb ? (nt > 0 ? nt : 1) : maxb);
+            if (use_compact) gx_k_hash_probe_unique<true><<<pgrid, 256, 0, ctx->stream>>>(a);
+            else gx_k_hash_probe_unique<false><<<pgrid, 256, 0, ctx->stream>>>(a);
         } else gx_k_hash_probe<<<grid, 256, 0, ctx->stream>>>(a);
     }
     cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, a.cursor, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);

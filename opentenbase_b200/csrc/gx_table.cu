@@ -502,10 +502,10 @@ extern "C" int gx_scan_filter(gx_ctx *ctx, const gx_table *in, int n_preds, cons
         if (e == cudaSuccess) {
             gx_launch_scope ls(ctx, "filter");
             long long maxb = (long long) ctx->sm_count * 8;
-            if (big) gx_k_filter_onepass<16><<<(unsigned) (ntiles < maxb ? ntiles : maxb), FT_THREADS, 0, ctx->stream>>>(
-                a, d_state, (unsigned int *) (d_state + ntiles), ntiles, ctx->d_scratch);
-            else gx_k_filter_onepass<8><<<(unsigned) (ntiles < maxb ? ntiles : maxb), FT_THREADS, 0, ctx->stream>>>(
-                a, d_state, (unsigned int *) (d_state + ntiles), ntiles, ctx->d_scratch);
+            const unsigned fgrid = (unsigned) (ntiles < maxb ? ntiles : maxb);
+            unsigned int *tk = (unsigned int *) (d_state + ntiles);
+            if (big) gx_k_filter_onepass<16><<<fgrid, FT_THREADS, 0, ctx->stream>>>(a, d_state, tk, ntiles, ctx->d_scratch);
+            else gx_k_filter_onepass<8><<<fgrid, FT_THREADS, 0, ctx->stream>>>(a, d_state, tk, ntiles, ctx->d_scratch);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
