@@ -635,13 +635,16 @@ def run_fnpage(ctx, g, ot, ocols, peak, rows=20_000_000):
     t = ctx.scan_filter(ot, [(ocols["orderkey"], g.GX_LE, 4 * rows)], keep)
     sizes = {g.GX_INT8: (8, 8), g.GX_INT4: (4, 4), g.GX_DATE: (4, 4), g.GX_FLOAT8: (8, 8), g.GX_CHAR: (1, 1)}
     al, ag = [sizes[x][0] for x in t.types], [sizes[x][1] for x in t.types]
-    ctx.profile(True)
-    pages = ctx.fnpage_pack(t, al, ag, g.GxFnPageId(1, 1, 1, 0, 0, 0, 0), True)
-    pack_ms, _ = ctx.profile_get("fnpage_pack")
-    ctx.profile(False); ctx.profile(True)
-    back = ctx.fnpage_unpack(pages, al, ag, list(range(len(al))), list(t.types), notnull=[1] * len(al))
-    unpack_ms, _ = ctx.profile_get("fnpage_unpack")
-    ctx.profile(False)
+    for it in range(2):                                 # the first pass loads the kernels (lazy module loading) and is not reported
+        ctx.profile(True)
+        pages = ctx.fnpage_pack(t, al, ag, g.GxFnPageId(1, 1, 1, 0, 0, 0, 0), True)
+        pack_ms, _ = ctx.profile_get("fnpage_pack")
+        ctx.profile(False); ctx.profile(True)
+        back = ctx.fnpage_unpack(pages, al, ag, list(range(len(al))), list(t.types), notnull=[1] * len(al))
+        unpack_ms, _ = ctx.profile_get("fnpage_unpack")
+        ctx.profile(False)
+        if it == 0:
+            back.free()
     ok = back.nrows == t.nrows and all(np.array_equal(back.read(c), t.read(c)) for c in range(len(al)))
     row_bytes = sum(al)
     out = {"workload": "orders rows of Q3's first Distribute as FnPages (forward/fnbufpage.h): columns -> pages -> columns",
