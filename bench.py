@@ -335,6 +335,7 @@ def run_ours(args):
     launches = ctx.launches - launches0
     clk = clocks.stop(wall0, wall1) if clocks else None
     probe_ms, probe_n = ctx.profile_get("probe_agg")
+    _, seg_n = ctx.profile_get("probe_agg_seg")          # > 0: the streamed-table variant (gx_k_runjoin_seg) ran
     build_ms, build_n = ctx.profile_get("build")
     phases = phase_table(ctx, PHASES, args.steps)
     ctx.profile(False)
@@ -515,11 +516,16 @@ def run_ours(args):
     traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "probe_agg_traffic.json")))
+        if seg_n:
+            tj = tj.get("gx_k_runjoin_seg") or {}
         traffic = tj.get("dram_bytes_per_launch_sf100")
-        traffic_src = "profiles/probe_agg_traffic.json (ncu --set full capture of this kernel at SF100, " + str(tj.get("source", "")) + "); not measured in this run"
+        if traffic:
+            traffic_src = "profiles/probe_agg_traffic.json (ncu --set full capture of this kernel at SF100, " + str(tj.get("source", "")) + "); not measured in this run"
     except (OSError, ValueError):
         pass
-    roofline = {"kernel": "gx_k_runjoin (fused hash probe + hash aggregate over lineitem)", "bound": "hbm",
+    probe_kernel = ("gx_k_runjoin_seg (fused hash probe + hash aggregate over lineitem; join table streamed through a cp.async.bulk/mbarrier ring)"
+                    if seg_n else "gx_k_runjoin (fused hash probe + hash aggregate over lineitem)")
+    roofline = {"kernel": probe_kernel, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "frac_dram": (traffic * (nl / 600_000_105.0) / (probe_avg_ms / 1e3) / 1e9 / peak) if (traffic and probe_n) else None,

@@ -1231,6 +1231,237 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin(const __grid_constant__ 
     smem_dense_merge(T, A);
 }
 
+// ---------------------------------------------------------------------------
+// gx_k_runjoin_seg: the same join + aggregate, with the join table STREAMED instead of gathered.
+//
+// What ncu said about gx_k_runjoin (profiles/r01_ncu_final_sf100_raw.csv, r02_runjoin_variants.txt): 54 % issue
+// utilisation, 64 % of the DRAM peak, the warps parked on the dependent 256-bit slot load of their runs.  But with an
+// order-preserving slot function and an outer side in key order those loads are not random at all: the CTA's 31 tiles
+// of one iteration are 3968 consecutive rows, their keys lie in [first key, last key] of that chunk, and every home
+// slot of such a key lies in ONE contiguous piece of the table — about 14 KB at TPC-H's densities.  So a producer warp
+// reads the chunk's first and last key one chunk ahead, computes the slot range and copies it into shared memory with a
+// single bulk-async copy (TMA, cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) into a two-deep ring guarded by
+// full/empty mbarriers; the 31 consumer warps fold their tiles exactly as gx_k_runjoin does and then probe SHARED memory.
+// The table is still read from DRAM exactly once, now front to back in large requests, and no warp waits on a gather.
+// Nothing depends on the layout for correctness: a probe whose slot group is not inside the staged window (keys out
+// of order, a chain that walks past the window, a chunk denser than the ring buffer) reads global memory as before,
+// and a chunk whose key range is far wider than the buffer is not staged at all.
+// Every wait is bounded (GX_SEG_SPIN_LIMIT polls): a protocol error raises flag 16 and the host redoes the query with
+// gx_k_runjoin instead of hanging the device.
+#define GX_SEG_CW          31                     /* consumer warps; warp 31 is the producer */
+#define GX_SEG_SPIN_LIMIT  (1u << 22)
+#define GX_SEG_MAXBUF      4
+struct gx_seg_ctl { unsigned long long full[GX_SEG_MAXBUF], empty[GX_SEG_MAXBUF], lo[GX_SEG_MAXBUF]; unsigned int len[GX_SEG_MAXBUF]; };
+
+__device__ __forceinline__ unsigned int gx_smem_u32(const void *p) { return (unsigned int) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gx_mbar_init(void *bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(gx_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gx_mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(gx_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gx_mbar_arrive_expect_tx(void *bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(gx_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// false when the phase did not complete within the poll budget (try_wait itself sleeps in hardware between polls)
+__device__ __forceinline__ bool gx_mbar_wait(void *bar, unsigned int parity)
+{
+    const unsigned int a = gx_smem_u32(bar);
+    for (unsigned int n = 0; n < GX_SEG_SPIN_LIMIT; n++) {
+        unsigned int ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+// one bulk-async copy global -> shared (16-byte aligned addresses, size a multiple of 16); completion is counted on `bar`
+__device__ __forceinline__ void gx_bulk_g2s(void *dst, const void *src, unsigned int bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(gx_smem_u32(dst)), "l"(src), "r"(bytes), "r"(gx_smem_u32(bar)) : "memory");
+}
+
+// one key against the compact join table, the slot groups inside [lo, lo + len) taken from the staged copy `sg`
+__device__ __forceinline__ bool runjoin_probe_seg(const gx_agg_dev &A, long long key, int &g,
+                                                  const unsigned long long *sg, unsigned long long lo, unsigned int len)
+{
+    bool found = false;
+    const unsigned long long dd = (unsigned long long) key - (unsigned long long) A.sf.kmin;
+    if (dd < A.cspan) {
+        const unsigned int d = GX_CSLOT_D(key, A.sf.kmin);
+        unsigned long long p = gx_slot_index(key, A.sf);
+        for (;;) {
+            const unsigned long long off = p - lo;                 // p < lo wraps to a huge value
+            unsigned long long s0, s1, s2, s3;                     // four 8-byte slots {d, payload}
+            if (off < (unsigned long long) len) {                  // lo, len and p are multiples of 4: the group is inside or outside as a whole
+                const ulonglong2 a = *(const ulonglong2 *) (sg + off), b = *(const ulonglong2 *) (sg + off + 2);
+                s0 = a.x; s1 = a.y; s2 = b.x; s3 = b.y;
+            } else {
+                const gx_slot2 c = ld_slot2((const gx_slot *) (A.cslots + p));
+                s0 = (unsigned long long) c.k0; s1 = c.p0; s2 = (unsigned long long) c.k1; s3 = c.p1;
+            }
+            const unsigned int d0 = (unsigned int) s0, d1 = (unsigned int) s1, d2 = (unsigned int) s2, d3 = (unsigned int) s3;
+            const unsigned long long m = d0 == d ? s0 : d1 == d ? s1 : d2 == d ? s2 : s3;
+            found = (d0 == d) | (d1 == d) | (d2 == d) | (d3 == d);
+            g = (int) (m >> 32);
+            if (found | (d0 == 0u) | (d1 == 0u) | (d2 == 0u) | (d3 == 0u)) break;
+            p = gx_next_quad(p, A.mask);
+        }
+    }
+    return found;
+}
+
+template <bool HAS_CNT, bool HAS_SUM>
+__global__ void __launch_bounds__(1024, 1) gx_k_runjoin_seg(const __grid_constant__ gx_agg_dev A, const gx_fast_args F, const unsigned int seg_slots, const int nbuf)
+{
+    extern __shared__ __align__(128) unsigned long long smem_seg[];
+    unsigned long long *const smem = smem_seg;
+    SmemTable T; T.S = A.s_slots; T.log2S = A.s_log2; T.nwords = A.P.nwords; T.nkw = 1; T.tagkey = 1; T.gmax = 0;
+    T.tag = smem; T.k0 = T.tag + T.S; T.k1 = T.k0; T.w = T.k0; T.gidx = nullptr; T.gcount = nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gx_runlist *const lists = (gx_runlist *) (smem + (size_t) T.S * (1 + T.nwords));
+    // table (S >= 16 slots of >= 16 bytes) and run lists (31 x 2560 bytes) are multiples of 128 bytes: the ring starts 128-byte aligned
+    unsigned long long *const seg0 = smem + (size_t) T.S * (1 + T.nwords) + GX_SEG_CW * (sizeof(gx_runlist) / 8);
+    gx_seg_ctl *const ctl = (gx_seg_ctl *) (seg0 + (size_t) nbuf * seg_slots);
+    for (int i = threadIdx.x; i < T.S; i += blockDim.x) {
+        T.tag[i] = 0;
+        for (int j = 0; j < T.nwords; j++) T.w[(size_t) i * T.nwords + j] = (unsigned long long) A.winit[j];
+    }
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < nbuf; b++) { gx_mbar_init(&ctl->full[b], 1); gx_mbar_init(&ctl->empty[b], GX_SEG_CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
+    const long long cvec = (long long) GX_SEG_CW * 32;          // vectors per chunk: one 128-row tile per consumer warp
+    const long long nchunks = (nvec + cvec - 1) / cvec;
+    const long long niter = (long long) blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks blockIdx.x + j * gridDim.x
+    bool stuck = false;
+    if (warp == GX_SEG_CW) {
+        // ---- producer: chunk j's slot range into ring buffer j % nbuf, up to nbuf chunks ahead of the slowest consumer
+        int b = 0; unsigned int use = 0;                       // buffer of chunk j, how often it has been filled before
+        long long klo_n = 0, khi_n = 0;
+        if (lane == 0 && niter > 0) {
+            const long long v0 = (long long) blockIdx.x * cvec, v1 = v0 + cvec < nvec ? v0 + cvec : nvec;
+            klo_n = __ldg(F.okey + A.row0 + (v0 << 2)); khi_n = __ldg(F.okey + A.row0 + (v1 << 2) - 1);
+        }
+        for (long long j = 0; j < niter; j++) {
+            if (lane == 0 && !stuck) {
+                const long long klo = klo_n, khi = khi_n;
+                if (j + 1 < niter) {                             // the next chunk's end keys travel while this one is set up
+                    const long long v0 = ((long long) blockIdx.x + (j + 1) * gridDim.x) * cvec, v1 = v0 + cvec < nvec ? v0 + cvec : nvec;
+                    klo_n = __ldg(F.okey + A.row0 + (v0 << 2)); khi_n = __ldg(F.okey + A.row0 + (v1 << 2) - 1);
+                }
+                // the part of the chunk's key range that lies inside the build side's key span
+                const long long kmax = (long long) ((unsigned long long) A.sf.kmin + A.cspan - 1ULL);
+                const long long ka = klo < A.sf.kmin ? A.sf.kmin : klo, kz = khi > kmax ? kmax : khi;
+                unsigned long long lo = 0; unsigned int len = 0;
+                if (ka <= kz) {
+                    const unsigned long long wm = (unsigned long long) (A.sf.win | A.sf.amask);     // the scatter window keeps a key inside its aligned block
+                    lo = gx_slot_index(ka, A.sf) & ~wm;
+                    unsigned long long hi = (gx_slot_index(kz, A.sf) | wm) + 1ULL + 32ULL;          // + one block for chains that walk on
+                    if (hi > A.mask + 1ULL) hi = A.mask + 1ULL;
+                    if (hi > lo) {
+                        const unsigned long long n = hi - lo;
+                        if (n <= 4ULL * seg_slots) len = (unsigned int) (n < seg_slots ? n : seg_slots);   // far wider: not clustered, stage nothing
+                    }
+                }
+                if (use > 0 && !gx_mbar_wait(&ctl->empty[b], (use - 1) & 1u)) stuck = true;
+                if (!stuck) {
+                    ctl->lo[b] = lo; ctl->len[b] = len;
+                    if (len) {
+                        gx_mbar_arrive_expect_tx(&ctl->full[b], len * 8u);
+                        gx_bulk_g2s(seg0 + (size_t) b * seg_slots, A.cslots + lo, len * 8u, &ctl->full[b]);
+                    } else gx_mbar_arrive(&ctl->full[b]);
+                }
+            }
+            if (++b == nbuf) { b = 0; use++; }
+            __syncwarp();
+        }
+    } else {
+        gx_runlist &Q = lists[warp];
+        long long q = ((long long) blockIdx.x * GX_SEG_CW + warp) * 32 + lane;
+        const long long qstride = (long long) gridDim.x * cvec;
+        long long k[4]; double v[4];
+        bool act = q < nvec;
+        if (act) {
+            const long long r = A.row0 + (q << 2);
+            longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+            k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+            if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+        }
+        int b = 0; unsigned int use = 0;
+        for (long long j = 0; j < niter; j++) {
+            // ---- run heads and their numbering inside the warp (as in gx_k_runjoin)
+            const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+            bool hd[4];
+            hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+            const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
+            int inc = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int base = inc - nh, R = __shfl_sync(0xffffffffu, inc, 31);
+            unsigned int c0 = 0; double s0 = 0.0;
+            if (act) {
+                int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (hd[i]) {
+                        if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+                        rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
+                    }
+                    c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+                }
+                if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+            }
+            __syncwarp();
+            if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
+            __syncwarp();
+            // ---- next rows: requested now, they arrive while the runs are probed
+            q += qstride; act = q < nvec;
+            if (act) {
+                const long long r = A.row0 + (q << 2);
+                longlong2 ka = ld_stream_ll2(F.okey + r), kb = ld_stream_ll2(F.okey + r + 2);
+                k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+                if (HAS_SUM) { double2 a = ld_stream_d2(F.vcol + r), b = ld_stream_d2(F.vcol + r + 2); v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+            }
+            // ---- this chunk's piece of the join table has landed (or the wait gives up and the host is told)
+            unsigned long long lo = 0; unsigned int len = 0;
+            if (!stuck && !gx_mbar_wait(&ctl->full[b], use & 1u)) stuck = true;
+            if (!stuck) { lo = ctl->lo[b]; len = ctl->len[b]; }
+            const unsigned long long *const sg = seg0 + (size_t) b * seg_slots;
+            // ---- one run per lane
+            for (int jj = lane; jj < R; jj += 32) {
+                const long long key = Q.key[jj];
+                const unsigned int rc = Q.cnt[jj];
+                const double rs = HAS_SUM ? Q.sum[jj] : 0.0;
+                int g = 0;
+                const bool hit = runjoin_probe_seg(A, key, g, sg, lo, len);
+                if (hit) fast_flush<HAS_CNT, HAS_SUM>(T, A, g, rc, rs, F.sum_word);
+            }
+            __syncwarp();
+            if (lane == 0) gx_mbar_arrive(&ctl->empty[b]);      // the buffer may be refilled for chunk j + nbuf
+            if (++b == nbuf) { b = 0; use++; }
+        }
+        // the (< 4) rows after the last full vector: one thread each
+        {
+            long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+            if (r < A.row1) {
+                int gk = 0;
+                if (runjoin_probe<true>(A, F.okey[r], gk)) fast_flush<HAS_CNT, HAS_SUM>(T, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0, F.sum_word);
+            }
+        }
+    }
+    if (stuck) atomicOr((unsigned long long *) &A.counters[1], 16ULL);
+    __syncthreads();
+    smem_dense_merge(T, A);
+}
+
 struct gx_runlist3 { long long key[160]; double sum[160]; unsigned int cnt[160]; };   // 31 waiting + 128 new runs
 template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
 __global__ void __launch_bounds__(1024, 1) gx_k_runjoin3(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
@@ -2164,6 +2395,44 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
+// gx_k_runjoin_seg: 31 consumer warps + 1 producer warp, the rest of the CTA's shared memory is the two-deep ring of
+// join-table pieces.  0 slots = the ring does not fit next to this group table (the caller keeps gx_k_runjoin).
+// Ring depth 3 when three buffers of the size a chunk is expected to need fit (table slots per outer row x 3968 rows, + 15 %
+// and the two edge blocks), else 2 larger ones.
+static unsigned int runjoin_seg_slots(const gx_ctx *ctx, size_t table_bytes, const gx_agg_dev &A, int *nbuf)
+{
+    const size_t fixed = table_bytes + GX_SEG_CW * sizeof(gx_runlist) + sizeof(gx_seg_ctl) + 1024;
+    *nbuf = 2;
+    if (fixed + 2 * 512 * 8 > ctx->smem_optin) return 0;
+    const size_t avail = (ctx->smem_optin - fixed) / 8;
+    const long long nrows = A.row1 - A.row0 > 0 ? A.row1 - A.row0 : 1;
+    const double need = 1.15 * (double) (A.mask + 1ULL) / (double) nrows * (GX_SEG_CW * 128) + 96.0;
+    const char *e = getenv("GX_RUNJOIN_SEG_BUFS");
+    if (e && e[0]) { int v = atoi(e); if (v >= 2 && v <= GX_SEG_MAXBUF) *nbuf = v; }
+    else if (need * 3.0 <= (double) avail) *nbuf = 3;
+    size_t slots = avail / (size_t) *nbuf;
+    if (slots > 4096) slots = 4096;                              // 32 KB per buffer
+    return (unsigned int) (slots & ~(size_t) 31);
+}
+template <bool HAS_CNT, bool HAS_SUM>
+static int launch_runjoin_seg_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t table_bytes, unsigned int seg_slots, int nbuf, const char *name)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_seg<HAS_CNT, HAS_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set = true;
+    }
+    const size_t smem = table_bytes + GX_SEG_CW * sizeof(gx_runlist) + (size_t) nbuf * seg_slots * 8 + sizeof(gx_seg_ctl);
+    const long long nvec = (A.row1 - A.row0) >> 2, cvec = (long long) GX_SEG_CW * 32;
+    long long nb = (nvec + cvec - 1) / cvec, maxb = (long long) ctx->sm_count;
+    while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 32)) maxb *= 2;      // 32-bit row counters per CTA
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_launch_scope which(ctx, "probe_agg_seg", 0);              // same kernel under a second profile name: tells gx_profile_get() which variant ran
+    gx_k_runjoin_seg<HAS_CNT, HAS_SUM><<<grid, 1024, smem, ctx->stream>>>(A, FA, seg_slots, nbuf);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
 template <bool HAS_CNT, bool HAS_SUM, bool COMPACT>
 static int launch_runjoin3_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t table_bytes, const char *name)
 {
@@ -2199,6 +2468,16 @@ static int launch_runjoin2_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_arg
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
+// GX_RUNJOIN_SEG=1/0 selects / forbids gx_k_runjoin_seg; a run that raised flag 16 (a bounded mbarrier wait gave up)
+// switches it off for the rest of the process
+#define GX_RUNJOIN_SEG_DEFAULT 0
+static bool g_runjoin_seg_broken = false;
+static bool gx_runjoin_seg_enabled()
+{
+    if (g_runjoin_seg_broken) return false;
+    const char *e = getenv("GX_RUNJOIN_SEG");
+    return e && e[0] ? e[0] != '0' : GX_RUNJOIN_SEG_DEFAULT != 0;
+}
 static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name, bool use_run)
 {
     // gx_k_runjoin3: finished runs wait for a full round of 32 (GX_RUNJOIN_CARRY=1; A/B against gx_k_runjoin)
@@ -2227,6 +2506,16 @@ static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA,
     }
     // the run-folding join kernel keeps a per-warp run list next to the group table
     const size_t run_bytes = 32 * sizeof(gx_runlist);
+    // compact table + order-preserving slots: the streamed-table variant (gx_k_runjoin_seg)
+    if (use_run && A.cslots && A.sf.mode != 0 && gx_runjoin_seg_enabled()) {
+        int nbuf = 2;
+        const unsigned int seg_slots = runjoin_seg_slots(ctx, smem, A, &nbuf);
+        if (seg_slots >= 512) {
+            if (cnt && sum) return launch_runjoin_seg_t<true, true>(ctx, A, FA, smem, seg_slots, nbuf, name);
+            if (cnt) return launch_runjoin_seg_t<true, false>(ctx, A, FA, smem, seg_slots, nbuf, name);
+            return launch_runjoin_seg_t<false, true>(ctx, A, FA, smem, seg_slots, nbuf, name);
+        }
+    }
     if (use_run) {
         if (A.cslots) {
             if (cnt && sum) return launch_runjoin_t<true, true, true>(ctx, A, FA, smem + run_bytes, name);
@@ -2564,6 +2853,10 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
             return rc;
         }
         gx_tmp_free(ctx, g_tab);
+        if (c[1] & 16) {                                          // gx_k_runjoin_seg gave up on a barrier: same plan again with gx_k_runjoin
+            fprintf(stderr, "gpuexec: gx_k_runjoin_seg timed out on its table ring; continuing with gx_k_runjoin\n");
+            g_runjoin_seg_broken = true; continue;
+        }
         if (use_few) { fewgroups_ok = false; continue; }          // more than FG_G groups: same estimate, general kernels
         // the planner's estimate was too low: grow, then fall over to radix
         est = est < 8 ? 9 : est < 16 ? 17 : est * 8;
