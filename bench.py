@@ -336,6 +336,7 @@ def run_ours(args):
     clk = clocks.stop(wall0, wall1) if clocks else None
     probe_ms, probe_n = ctx.profile_get("probe_agg")
     _, seg_n = ctx.profile_get("probe_agg_seg")          # > 0: the streamed-table variant (gx_k_runjoin_seg) ran
+    _, tma_n = ctx.profile_get("probe_agg_tma")          # > 0: the rows-by-copy-engine variant (gx_k_runjoin_tma) ran
     build_ms, build_n = ctx.profile_get("build")
     phases = phase_table(ctx, PHASES, args.steps)
     ctx.profile(False)
@@ -516,15 +517,17 @@ def run_ours(args):
     traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "probe_agg_traffic.json")))
-        if seg_n:
-            tj = tj.get("gx_k_runjoin_seg") or {}
+        if seg_n or tma_n:
+            tj = tj.get("gx_k_runjoin_seg" if seg_n else "gx_k_runjoin_tma") or {}
         traffic = tj.get("dram_bytes_per_launch_sf100")
         if traffic:
             traffic_src = "profiles/probe_agg_traffic.json (ncu --set full capture of this kernel at SF100, " + str(tj.get("source", "")) + "); not measured in this run"
     except (OSError, ValueError):
         pass
     probe_kernel = ("gx_k_runjoin_seg (fused hash probe + hash aggregate over lineitem; join table streamed through a cp.async.bulk/mbarrier ring)"
-                    if seg_n else "gx_k_runjoin (fused hash probe + hash aggregate over lineitem)")
+                    if seg_n else
+                    "gx_k_runjoin_tma (fused hash probe + hash aggregate over lineitem; outer rows delivered by cp.async.bulk onto per-warp mbarriers)"
+                    if tma_n else "gx_k_runjoin (fused hash probe + hash aggregate over lineitem)")
     roofline = {"kernel": probe_kernel, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "traffic_source": traffic_src,

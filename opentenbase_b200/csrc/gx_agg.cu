@@ -1270,6 +1270,7 @@ __device__ __forceinline__ void gx_mbar_arrive_expect_tx(void *bar, unsigned int
 __device__ __forceinline__ bool gx_mbar_wait(void *bar, unsigned int parity)
 {
     const unsigned int a = gx_smem_u32(bar);
+#pragma unroll 1
     for (unsigned int n = 0; n < GX_SEG_SPIN_LIMIT; n++) {
         unsigned int ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -1653,6 +1654,131 @@ __global__ void __launch_bounds__(512, 2) gx_k_runjoin2(const __grid_constant__ 
         }
         __syncwarp();
     }
+    // the (< 4) rows after the last full vector: one thread each
+    {
+        long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < A.row1) {
+            int gk = 0;
+            if (runjoin_probe<COMPACT>(A, F.okey[r], gk)) packed_flush<HAS_SUM>(tab, tsum, S, A, gk, 1u, HAS_SUM ? F.vcol[r] : 0.0);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {             // the CTA's table into the global one
+        const unsigned long long t = tab[i];
+        if (t == 0) continue;
+        unsigned long long *rec = global_upsert(A, t & 0xFFFFFFFFULL, 0ULL, 0u);
+        if (!rec) { atomicOr((unsigned long long *) &A.counters[1], 2ULL); continue; }
+        merge_word(&rec[3], WK_ADD_I64, (t >> 32) & 0x7FFFFFFFULL);
+        if (HAS_SUM) merge_word(&rec[3 + F.sum_word], WK_ADD_F64, (unsigned long long) __double_as_longlong(tsum[i]));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gx_k_runjoin_tma: gx_k_runjoin with the outer rows delivered by the copy engine.
+//
+// The per-instruction stall samples of gx_k_runjoin (profiles/r01_ncu_final_sf100.ncu-rep, source page) put 14 % of all
+// samples on ONE register move right behind the "prefetch" loads of the next tile: ptxas lands half of the 128-bit
+// loads in temporaries and copies them into the loop-carried registers at once, so the warp waits out the DRAM latency
+// of its rows BEFORE it starts the probe, whose dependent slot load then costs a second one (27 % of the samples).
+// Here the rows never pass through registers on their way in: lane 0 of every warp asks the copy engine for the warp's
+// next tile (two 1 KB cp.async.bulk transfers, keys and values, completion counted on the warp's own mbarrier) as soon
+// as the lanes have read the current one out of shared memory — before the fold, a whole tile ahead — and nobody waits
+// for anybody else: a warp only ever waits on its own barrier.  The 64 KB of row stages fit because the group table
+// uses gx_k_runjoin2's packed 16-byte slots (64 KB instead of 96 KB for 4096 slots).
+// Bounded waits as in gx_k_runjoin_seg: flag 16 sends the plan back to gx_k_runjoin.
+struct gx_rowstage { long long key[128]; double val[128]; };
+
+template <bool HAS_SUM, bool COMPACT>
+__global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
+{
+    extern __shared__ __align__(128) unsigned long long smem_tma[];
+    const int S = A.s_slots;
+    unsigned long long *const tab = smem_tma; double *const tsum = (double *) (smem_tma + S);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    gx_runlist &Q = ((gx_runlist *) (smem_tma + (size_t) S * 2))[warp];
+    gx_rowstage &R = ((gx_rowstage *) (smem_tma + (size_t) S * 2 + 32 * (sizeof(gx_runlist) / 8)))[warp];
+    unsigned long long *const bar = smem_tma + (size_t) S * 2 + 32 * (sizeof(gx_runlist) / 8) + 32 * (sizeof(gx_rowstage) / 8) + warp;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { tab[i] = 0ULL; tsum[i] = 0.0; }
+    if (lane == 0) {
+        gx_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    long long qw = (long long) blockIdx.x * blockDim.x + warp * 32;     // the warp's first vector of its current tile
+    // the warp's tile [qw, qw + 32) vectors = up to 128 rows: one bulk copy per column, sized to what exists
+    auto request = [&](long long w) {
+        const long long left = nvec - w;
+        const unsigned int bytes = (unsigned int) (left < 32 ? left : 32) * 32u;
+        const long long r = A.row0 + (w << 2);
+        gx_mbar_arrive_expect_tx(bar, HAS_SUM ? 2u * bytes : bytes);
+        gx_bulk_g2s(R.key, F.okey + r, bytes, bar);
+        if (HAS_SUM) gx_bulk_g2s(R.val, F.vcol + r, bytes, bar);
+    };
+    if (lane == 0 && qw < nvec) request(qw);
+    unsigned int parity = 0;
+    bool stuck = false;
+    while (qw < nvec) {                                         // warp-uniform
+        const bool act = qw + lane < nvec;
+        long long k[4]; double v[4];
+        if (!gx_mbar_wait(bar, parity)) { stuck = true; break; }
+        parity ^= 1u;
+        if (act) {
+            const longlong2 ka = *(const longlong2 *) &R.key[lane * 4], kb = *(const longlong2 *) &R.key[lane * 4 + 2];
+            k[0] = ka.x; k[1] = ka.y; k[2] = kb.x; k[3] = kb.y;
+            if (HAS_SUM) {
+                const double2 a = *(const double2 *) &R.val[lane * 4], b = *(const double2 *) &R.val[lane * 4 + 2];
+                v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+            }
+        }
+        __syncwarp();
+        // ---- the stage is free again: the next tile travels while this one is folded and probed
+        qw += stride;
+        if (lane == 0 && qw < nvec) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the lanes' reads above before the engine's writes
+            request(qw);
+        }
+        // ---- run heads and their numbering inside the warp
+        const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+        bool hd[4];
+        hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+        const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
+        int inc = nh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int base = inc - nh, NR = __shfl_sync(0xffffffffu, inc, 31);
+        // ---- fold: runs that start in this lane are stored, the rows that continue the previous
+        // lane's run are added to that run afterwards
+        unsigned int c0 = 0; double s0 = 0.0;
+        if (act) {
+            int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (hd[i]) {
+                    if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+                    rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
+                }
+                c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+            }
+            if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+        }
+        __syncwarp();
+        if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
+        __syncwarp();
+        // ---- one run per lane
+        for (int j = lane; j < NR; j += 32) {
+            const long long key = Q.key[j];
+            const unsigned int rc = Q.cnt[j];
+            const double rs = HAS_SUM ? Q.sum[j] : 0.0;
+            int g = 0;
+            const bool hit = runjoin_probe<COMPACT>(A, key, g);
+            if (hit) packed_flush<HAS_SUM>(tab, tsum, S, A, g, rc, rs);
+        }
+        __syncwarp();
+    }
+    if (stuck) atomicOr((unsigned long long *) &A.counters[1], 16ULL);
     // the (< 4) rows after the last full vector: one thread each
     {
         long long r = A.row0 + (nvec << 2) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -2451,6 +2577,24 @@ static int launch_runjoin3_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_arg
     return GX_OK;
 }
 template <bool HAS_SUM, bool COMPACT>
+static int launch_runjoin_tma_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, size_t smem, const char *name)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        attr_set = true;
+    }
+    long long nvec = (A.row1 - A.row0 + 3) / 4;
+    long long nb = (nvec + 1023) / 1024, maxb = (long long) ctx->sm_count;
+    while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 31)) maxb *= 2;      // 31-bit row counters per CTA
+    unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
+    gx_launch_scope ls(ctx, name);
+    gx_launch_scope which(ctx, "probe_agg_tma", 0);              // second profile name: which variant ran
+    gx_k_runjoin_tma<HAS_SUM, COMPACT><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    GX_CUDA(ctx, cudaGetLastError());
+    return GX_OK;
+}
+template <bool HAS_SUM, bool COMPACT>
 static int launch_runjoin2_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, const char *name)
 {
     static bool attr_set = false;
@@ -2477,6 +2621,14 @@ static bool gx_runjoin_seg_enabled()
     if (g_runjoin_seg_broken) return false;
     const char *e = getenv("GX_RUNJOIN_SEG");
     return e && e[0] ? e[0] != '0' : GX_RUNJOIN_SEG_DEFAULT != 0;
+}
+// GX_RUNJOIN_TMA=1/0 selects / forbids gx_k_runjoin_tma (same rules as GX_RUNJOIN_SEG)
+#define GX_RUNJOIN_TMA_DEFAULT 0
+static bool gx_runjoin_tma_enabled()
+{
+    if (g_runjoin_seg_broken) return false;
+    const char *e = getenv("GX_RUNJOIN_TMA");
+    return e && e[0] ? e[0] != '0' : GX_RUNJOIN_TMA_DEFAULT != 0;
 }
 static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA, bool join, bool cnt, bool sum, size_t smem, const char *name, bool use_run)
 {
@@ -2506,6 +2658,15 @@ static int launch_fast(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args &FA,
     }
     // the run-folding join kernel keeps a per-warp run list next to the group table
     const size_t run_bytes = 32 * sizeof(gx_runlist);
+    // rows through the copy engine (gx_k_runjoin_tma): packed group slots, so at most 4096 of them; 16-byte aligned columns
+    if (use_run && gx_runjoin_tma_enabled() && A.s_slots <= 4096 && (A.row0 & 1) == 0 &&
+        ((uintptr_t) FA.okey & 15) == 0 && ((uintptr_t) FA.vcol & 15) == 0) {
+        const size_t tma_smem = (size_t) A.s_slots * 16 + 32 * sizeof(gx_runlist) + 32 * sizeof(gx_rowstage) + 32 * 8;
+        if (tma_smem + 1024 <= ctx->smem_optin) {
+            if (A.cslots) return sum ? launch_runjoin_tma_t<true, true>(ctx, A, FA, tma_smem, name) : launch_runjoin_tma_t<false, true>(ctx, A, FA, tma_smem, name);
+            return sum ? launch_runjoin_tma_t<true, false>(ctx, A, FA, tma_smem, name) : launch_runjoin_tma_t<false, false>(ctx, A, FA, tma_smem, name);
+        }
+    }
     // compact table + order-preserving slots: the streamed-table variant (gx_k_runjoin_seg)
     if (use_run && A.cslots && A.sf.mode != 0 && gx_runjoin_seg_enabled()) {
         int nbuf = 2;
@@ -2811,6 +2972,11 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         const bool use_run = use_fast && A.P.has_join && runjoin_env && dense_bytes(S) + run_bytes <= ctx->smem_optin - 1024;
         if (!use_run) { rc = need_wide(); if (rc) { gx_tmp_free(ctx, g_tab); return rc; } }
         const bool use_few = strategy == 1 && gmax && fewgroups_ok && est <= 2 * FG_G;
+        { const char *dbg = getenv("GX_DEBUG_AGG");
+          if (dbg && dbg[0] == '1')
+              fprintf(stderr, "gpuexec: hash_agg attempt %d strategy %d S %lld gmax %d fast_ok %d use_fast %d use_run %d cslots %d slot mode %d seg %d tma %d rows %lld\n",
+                      attempt, strategy, S, gmax, (int) fast_ok, (int) use_fast, (int) use_run, A.cslots != nullptr, A.sf.mode,
+                      (int) gx_runjoin_seg_enabled(), (int) gx_runjoin_tma_enabled(), (long long) outer->nrows); }
         if (use_fast) rc = launch_fast(ctx, A, FA, A.P.has_join != 0, cp.need_w0 != 0, FA.vcol != nullptr, dense_bytes(S), kname, use_run);
         else if (use_few && countchar_ok) {
             gx_launch_scope ls(ctx, kname);
@@ -2854,7 +3020,7 @@ extern "C" int gx_hash_agg(gx_ctx *ctx, const gx_table *outer, const gx_hash *h,
         }
         gx_tmp_free(ctx, g_tab);
         if (c[1] & 16) {                                          // gx_k_runjoin_seg gave up on a barrier: same plan again with gx_k_runjoin
-            fprintf(stderr, "gpuexec: gx_k_runjoin_seg timed out on its table ring; continuing with gx_k_runjoin\n");
+            fprintf(stderr, "gpuexec: a bounded mbarrier wait of gx_k_runjoin_seg / gx_k_runjoin_tma gave up; continuing with gx_k_runjoin\n");
             g_runjoin_seg_broken = true; continue;
         }
         if (use_few) { fewgroups_ok = false; continue; }          // more than FG_G groups: same estimate, general kernels

@@ -7,6 +7,8 @@ themselves are tested against the oracle by tests/test_gpu_parity.py.
 2. The warp-wide lower-bound search returns the first row of every sub-table on key-ordered data.
 3. 31 stored bits identify a key inside its sub-table, and the 16-byte slot can be rebuilt from
    the compact one and its position.
+4. The window gx_k_runjoin_seg's producer stages for a chunk of key-ordered probe rows contains the
+   home slot group of every key of the chunk, and windows of consecutive chunks tile the table.
 """
 import numpy as np
 import pytest
@@ -184,3 +186,73 @@ def test_31_bits_identify_a_key_inside_its_sub_table_and_rebuild_it():
     off = np.where(off - est > 0x40000000, off - 0x80000000, off)
     off = np.where(est - off > 0x40000000, off + 0x80000000, off)
     np.testing.assert_array_equal(kmin + off, keys)
+
+
+# ------------------------------------------------------------------ 4. the staged table window of a chunk
+CHUNK = 31 * 128          # GX_SEG_CW consumer warps x one 128-row tile (csrc/gx_agg.cu)
+
+
+def producer_window(klo, khi, slot, kmin, kmax, nslots, seg_slots, win=31, amask=3):
+    """gx_k_runjoin_seg, producer warp: (lo, len) in slots for a chunk whose first / last key are klo / khi."""
+    ka, kz = max(klo, kmin), min(khi, kmax)
+    if ka > kz:
+        return 0, 0
+    wm = win | amask
+    lo = slot(ka) & ~wm
+    hi = min((slot(kz) | wm) + 1 + 32, nslots)
+    if hi <= lo or hi - lo > 4 * seg_slots:
+        return lo, 0
+    return lo, min(hi - lo, seg_slots)
+
+
+@pytest.mark.parametrize("name,okeys", [k for k in key_sets() if not k[0].startswith("two clusters")],
+                         ids=[k[0].split(" (")[0] for k in key_sets() if not k[0].startswith("two clusters")])
+def test_staged_window_holds_every_home_group_of_a_key_ordered_chunk(name, okeys):
+    rng = np.random.default_rng(17)
+    n = len(okeys)
+    nslots = 1
+    while nslots < n + n // 2 + 16:
+        nslots *= 2
+    kmin, kmax = int(okeys[0]), int(okeys[-1])
+    slot = make_slot_fn(kmin, float(kmax - kmin + 1), nslots)
+    lkeys = np.repeat(okeys, rng.integers(1, 8, n))               # 1..7 lines per order, key order
+    # plus probe keys the build side does not hold: below, above and inside its span
+    lkeys = np.sort(np.concatenate([lkeys, rng.integers(kmin - 5000, kmax + 5000, 20_000)]))
+    avail = (232448 - 1024 - 98304 - 31 * 2560 - 112) // 8        # shared memory left of 227 KB for the ring, in 8-byte slots
+    seg_slots = (avail // 3) & ~31
+    homes = np.array([slot(int(k)) for k in np.clip(lkeys, kmin, kmax)])
+    staged = total = 0
+    prev_end = 0
+    for c0 in range(0, len(lkeys), CHUNK):
+        ks = lkeys[c0:c0 + CHUNK]
+        lo, ln = producer_window(int(ks[0]), int(ks[-1]), slot, kmin, kmax, nslots, seg_slots)
+        assert lo % 4 == 0 and ln % 4 == 0 and lo + ln <= nslots  # what cp.async.bulk needs: 32-byte pieces inside the table
+        inspan = (ks >= kmin) & (ks <= kmax)                      # keys outside the span are rejected before any slot is read
+        h = homes[c0:c0 + CHUNK][inspan]
+        inside = (h >= lo) & (h + 4 <= lo + ln)
+        total += len(h); staged += int(inside.sum())
+        if ln and ln < seg_slots:                                 # not clipped by the buffer: everything must be inside
+            assert inside.all(), (name, c0)
+        if ln:
+            assert lo <= prev_end + 64 or prev_end == 0           # consecutive windows overlap or touch: the table is read front to back
+            prev_end = lo + ln
+    assert staged >= 0.99 * total, (name, staged, total)
+
+
+def test_unordered_chunks_stage_nothing_or_little():
+    """A shuffled probe side: first and last key of a chunk are unrelated, the window is skipped when it would be
+    more than four buffers wide — the kernel then probes global memory as gx_k_runjoin does."""
+    n = 120_000
+    i = np.arange(n, dtype=np.int64)
+    okeys = ((i >> 3) << 5 | (i & 7)) + 1
+    nslots = 262144
+    slot = make_slot_fn(1, float(okeys[-1]), nslots)
+    lkeys = np.random.default_rng(2).permutation(np.repeat(okeys, 4))
+    skipped = 0
+    nchunks = 0
+    for c0 in range(0, len(lkeys), CHUNK):
+        ks = lkeys[c0:c0 + CHUNK]
+        _, ln = producer_window(int(ks[0]), int(ks[-1]), slot, 1, int(okeys[-1]), nslots, 2208)
+        skipped += ln == 0
+        nchunks += 1
+    assert skipped >= 0.9 * nchunks

@@ -1,6 +1,10 @@
-"""gx_k_runjoin_seg — the config-3 probe that streams the join table through a shared-memory ring
-(cp.async.bulk + mbarrier) instead of gathering it — against the oracle's HashJoin + HashAggregate
-(nodeHashjoin.c:186-742, nodeAgg.c:2609-2648), on the layouts that decide which of its code paths run:
+"""The two cp.async.bulk + mbarrier variants of the config-3 probe against the oracle's HashJoin + HashAggregate
+(nodeHashjoin.c:186-742, nodeAgg.c:2609-2648):
+
+* gx_k_runjoin_seg (GX_RUNJOIN_SEG=1) streams the JOIN TABLE through a shared-memory ring instead of gathering it,
+* gx_k_runjoin_tma (GX_RUNJOIN_TMA=1) has the copy engine deliver the OUTER ROWS of every warp's next tile,
+
+on the layouts that decide which of their code paths run:
 
 * both sides in key order              every probe answered from the staged window
 * outer side shuffled                  chunk key ranges far wider than the ring: nothing staged, global probes
@@ -8,8 +12,8 @@
 * build side with holes / narrow span  misses, keys below and above the build side's key span (clamped windows)
 * tiny outer sides                     fewer rows than one chunk, a tail that is not a multiple of four
 
-and with every ring depth.  The switch GX_RUNJOIN_SEG forces the variant on or off; profile name
-`probe_agg_seg` proves which kernel ran."""
+and with every ring depth.  The switches force a variant on or off; the profile names `probe_agg_seg` /
+`probe_agg_tma` prove which kernel ran."""
 import numpy as np
 import pytest
 
@@ -19,7 +23,17 @@ from helpers import assert_agg_equal, to_gpu_plan, lineitem_rel, orders_rel
 
 pytestmark = pytest.mark.gpu
 
-NORD = 200_000        # >= 64 sub-tables: interpolation slots + compact table, what the variant needs
+NORD = 200_000        # >= 64 sub-tables: interpolation slots + compact table, what the seg variant needs
+VARIANTS = {"seg": ("GX_RUNJOIN_SEG", "probe_agg_seg"), "tma": ("GX_RUNJOIN_TMA", "probe_agg_tma")}
+
+
+@pytest.fixture(params=["seg", "tma"])
+def variant(request, monkeypatch):
+    for env, _ in VARIANTS.values():
+        monkeypatch.setenv(env, "0")
+    monkeypatch.setenv(VARIANTS[request.param][0], "1")
+    monkeypatch.setenv("GX_DEBUG_AGG", "1")
+    return VARIANTS[request.param][1]
 
 
 def _plan(count=True, total=True):
@@ -31,7 +45,7 @@ def _plan(count=True, total=True):
     return O.make_plan(outer_key_col=g.L_ORDERKEY, group_cols=[(1, 0)], aggs=aggs, est_groups=2600)
 
 
-def _run(gx, o, l, plan, expect_seg=True):
+def _run(gx, o, l, plan, expect_seg=True, prof="probe_agg_seg"):
     join = O.make_join(g.O_ORDERKEY, payload_cols=[g.O_ORDERDATE], inner_unique=1)
     want = O.exec_agg(lineitem_rel(l), plan, orders_rel(o), join)
     ot = gx.table_from(g.SCHEMAS[g.T_ORDERS], o)
@@ -42,11 +56,11 @@ def _run(gx, o, l, plan, expect_seg=True):
     gx.profile(True)
     try:
         got = gx.hash_agg(lt, to_gpu_plan(plan), ht).fetch()
-        _, nseg = gx.profile_get("probe_agg_seg")
+        _, nseg = gx.profile_get(prof)
     finally:
         gx.profile(False)
     if expect_seg is not None:
-        assert (nseg > 0) == expect_seg, f"probe_agg_seg launches: {nseg}"
+        assert (nseg > 0) == expect_seg, f"{prof} launches: {nseg}"
     assert_agg_equal(plan, got, want)
     for t in (ht, lt, ot):
         t.free()
@@ -61,25 +75,24 @@ def base():
 
 
 @pytest.mark.parametrize("bufs", ["2", "3", "4"])
-def test_key_ordered_both_sides(gx, base, monkeypatch, bufs):
-    monkeypatch.setenv("GX_RUNJOIN_SEG", "1")
+def test_key_ordered_both_sides(gx, base, monkeypatch, variant, bufs):
+    if variant != "probe_agg_seg" and bufs != "2":
+        pytest.skip("ring depth only exists in the seg variant")
     monkeypatch.setenv("GX_RUNJOIN_SEG_BUFS", bufs)
     o, l = base
-    got = _run(gx, o, l, _plan())
+    got = _run(gx, o, l, _plan(), prof=variant)
     assert got[1][:, 0].view(np.int64).sum() == len(l[0])     # every line finds its order
 
 
 @pytest.mark.parametrize("aggs", ["count", "sum"])
-def test_single_aggregate_instantiations(gx, base, monkeypatch, aggs):
-    monkeypatch.setenv("GX_RUNJOIN_SEG", "1")
+def test_single_aggregate_instantiations(gx, base, variant, aggs):
     o, l = base
-    _run(gx, o, l, _plan(count=aggs == "count", total=aggs == "sum"))
+    _run(gx, o, l, _plan(count=aggs == "count", total=aggs == "sum"), prof=variant)
 
 
 @pytest.mark.parametrize("layout", ["shuffled", "descending", "block_shuffled"])
-def test_outer_side_not_in_key_order(gx, base, monkeypatch, layout):
+def test_outer_side_not_in_key_order(gx, base, variant, layout):
     """The windows are a guess from the first and last key of a chunk; the answer may not depend on it."""
-    monkeypatch.setenv("GX_RUNJOIN_SEG", "1")
     o, l = base
     n = len(l[0])
     if layout == "shuffled":
@@ -90,39 +103,39 @@ def test_outer_side_not_in_key_order(gx, base, monkeypatch, layout):
         nb = (n + 999) // 1000              # chunks straddle unrelated key ranges, some windows hold part of the keys
         order = np.random.default_rng(4).permutation(nb)
         perm = np.concatenate([np.arange(b * 1000, min((b + 1) * 1000, n)) for b in order])
-    _run(gx, o, [c[perm] for c in l], _plan())
+    _run(gx, o, [c[perm] for c in l], _plan(), prof=variant)
 
 
-def test_misses_and_keys_outside_the_build_span(gx, base, monkeypatch):
+def test_misses_and_keys_outside_the_build_span(gx, base, variant):
     """Build side = the middle half of the orders with every third order removed: lines of the first and
     last quarter carry keys below / above the build side's span (windows clamped to the span or empty),
     lines of removed orders miss inside it."""
-    monkeypatch.setenv("GX_RUNJOIN_SEG", "1")
     o, l = base
     keep = np.zeros(NORD, bool)
     keep[NORD // 4: 3 * NORD // 4] = True
     keep[::3] = False
-    got = _run(gx, [c[keep] for c in o], l, _plan(), expect_seg=None)     # a 67 k-row build side is at the edge of the interpolation rule
+    got = _run(gx, [c[keep] for c in o], l, _plan(), expect_seg=None, prof=variant)     # a 67 k-row build side is at the edge of the interpolation rule
     assert 0 < got[1][:, 0].view(np.int64).sum() < len(l[0])
 
 
 @pytest.mark.parametrize("nrows", [1, 3, 4, 127, 130, 3967, 3968, 3971, 4 * 3968 + 5])
-def test_short_outer_sides(gx, base, monkeypatch, nrows):
+def test_short_outer_sides(gx, base, variant, nrows):
     """Fewer rows than one chunk (31 tiles of 128 rows), one chunk exactly, tails of 1-3 rows."""
-    monkeypatch.setenv("GX_RUNJOIN_SEG", "1")
     o, l = base
     start = 123_457                          # somewhere inside the table, mid-run
-    _run(gx, o, [c[start:start + nrows] for c in l], _plan())
+    _run(gx, o, [c[start:start + nrows] for c in l], _plan(), prof=variant)
 
 
 def test_switch_off_keeps_the_gathering_kernel(gx, base, monkeypatch):
     monkeypatch.setenv("GX_RUNJOIN_SEG", "0")
+    monkeypatch.setenv("GX_RUNJOIN_TMA", "0")
     o, l = base
     _run(gx, o, l, _plan(), expect_seg=False)
+    _run(gx, o, l, _plan(), expect_seg=False, prof="probe_agg_tma")
 
 
 def test_same_answer_as_the_gathering_kernel_at_sf10_slice(gx, monkeypatch):
-    """10 M orders generated on the device (no oracle at this size): both variants must agree bit for bit
+    """10 M orders generated on the device (no oracle at this size): all variants must agree bit for bit
     on the counts and to 1e-9 on the sums, and count(*) must equal the lineitem rows."""
     nord = 10_000_000
     ot = gx.table(g.SCHEMAS[g.T_ORDERS], nord).generate(g.T_ORDERS, 10, 0, nord)
@@ -130,14 +143,16 @@ def test_same_answer_as_the_gathering_kernel_at_sf10_slice(gx, monkeypatch):
     ht = gx.hash_build(ot, g.O_ORDERKEY, [g.O_ORDERDATE], unique=True)
     plan = to_gpu_plan(_plan())
     res = {}
-    for sw in ("0", "1"):
-        monkeypatch.setenv("GX_RUNJOIN_SEG", sw)
+    for sw, (seg, tma) in {"0": ("0", "0"), "seg": ("1", "0"), "tma": ("0", "1")}.items():
+        monkeypatch.setenv("GX_RUNJOIN_SEG", seg)
+        monkeypatch.setenv("GX_RUNJOIN_TMA", tma)
         k, a, _ = gx.hash_agg(lt, plan, ht).fetch()
         order = np.argsort(k[:, 0])
         res[sw] = (k[order], a[order])
-    np.testing.assert_array_equal(res["0"][0], res["1"][0])
-    np.testing.assert_array_equal(res["0"][1][:, 0].view(np.int64), res["1"][1][:, 0].view(np.int64))
-    np.testing.assert_allclose(res["0"][1][:, 1], res["1"][1][:, 1], rtol=1e-9, atol=0)
-    assert res["1"][1][:, 0].view(np.int64).sum() == lt.nrows
+    for sw in ("seg", "tma"):
+        np.testing.assert_array_equal(res["0"][0], res[sw][0])
+        np.testing.assert_array_equal(res["0"][1][:, 0].view(np.int64), res[sw][1][:, 0].view(np.int64))
+        np.testing.assert_allclose(res["0"][1][:, 1], res[sw][1][:, 1], rtol=1e-9, atol=0)
+        assert res[sw][1][:, 0].view(np.int64).sum() == lt.nrows
     for t in (ht, lt, ot):
         t.free()
