@@ -1688,7 +1688,7 @@ __global__ void __launch_bounds__(512, 2) gx_k_runjoin2(const __grid_constant__ 
 // Bounded waits as in gx_k_runjoin_seg: flag 16 sends the plan back to gx_k_runjoin.
 struct gx_rowstage { long long key[128]; double val[128]; };
 
-template <bool HAS_SUM, bool COMPACT>
+template <bool HAS_SUM, bool COMPACT, bool FOLD2>
 __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
 {
     extern __shared__ __align__(128) unsigned long long smem_tma[];
@@ -1708,20 +1708,32 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constan
     const long long nvec = (A.row1 - A.row0) >> 2;              // groups of four rows
     const long long stride = (long long) gridDim.x * blockDim.x;
     long long qw = (long long) blockIdx.x * blockDim.x + warp * 32;     // the warp's first vector of its current tile
-    // the warp's tile [qw, qw + 32) vectors = up to 128 rows: one bulk copy per column, sized to what exists
-    auto request = [&](long long w) {
-        const long long left = nvec - w;
-        const unsigned int bytes = (unsigned int) (left < 32 ? left : 32) * 32u;
-        const long long r = A.row0 + (w << 2);
-        gx_mbar_arrive_expect_tx(bar, HAS_SUM ? 2u * bytes : bytes);
-        gx_bulk_g2s(R.key, F.okey + r, bytes, bar);
-        if (HAS_SUM) gx_bulk_g2s(R.val, F.vcol + r, bytes, bar);
+    // the warp's tile [qw, qw + 32) vectors = up to 128 rows: one bulk copy per column.  The request is the only per-tile
+    // code that was not in gx_k_runjoin and every instruction of it is issued by the whole warp, so it is kept short:
+    // running byte pointers, 32-bit shared addresses, a running count of the vectors left, and elect.sync so that ptxas
+    // knows a single lane feeds the uniform registers of UBLKCP (no per-operand broadcast loops).
+    const char *kp = (const char *) (F.okey + A.row0) + (qw << 5);
+    const char *vp = (const char *) (F.vcol + A.row0) + (qw << 5);
+    const long long step = stride << 5;                         // bytes between a warp's consecutive tiles
+    const unsigned int s_key = gx_smem_u32(R.key), s_val = gx_smem_u32(R.val), s_bar = gx_smem_u32(bar);
+    long long left = nvec - qw;                                 // vectors from the start of the warp's current tile to the end of the input
+    auto request = [&](unsigned int bytes) {
+        unsigned int leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        if (leader) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_bar), "r"(HAS_SUM ? 2u * bytes : bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(s_key), "l"(kp), "r"(bytes), "r"(s_bar) : "memory");
+            if (HAS_SUM)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(s_val), "l"(vp), "r"(bytes), "r"(s_bar) : "memory");
+        }
     };
-    if (lane == 0 && qw < nvec) request(qw);
+    if (left > 0) request(left >= 32 ? 1024u : (unsigned int) left << 5);
     unsigned int parity = 0;
     bool stuck = false;
-    while (qw < nvec) {                                         // warp-uniform
-        const bool act = qw + lane < nvec;
+    while (left > 0) {                                          // warp-uniform
+        const bool act = (long long) lane < left;
         long long k[4]; double v[4];
         if (!gx_mbar_wait(bar, parity)) { stuck = true; break; }
         parity ^= 1u;
@@ -1734,39 +1746,78 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constan
             }
         }
         __syncwarp();
-        // ---- the stage is free again: the next tile travels while this one is folded and probed
-        qw += stride;
-        if (lane == 0 && qw < nvec) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the lanes' reads above before the engine's writes
-            request(qw);
-        }
-        // ---- run heads and their numbering inside the warp
-        const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
-        bool hd[4];
-        hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
-        const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
-        int inc = nh;
+        // ---- the stage is free again: the next tile travels while this one is folded and probed.  No proxy fence between the
+        // lanes' reads above and the engine's writes: the reads have completed (their registers are consumed right below) a
+        // DRAM round trip before the first byte of the next tile can arrive, and the fence costs a MEMBAR.ALL.CTA per tile.
+        kp += step; vp += step; left -= stride;
+        if (left > 0) request(left >= 32 ? 1024u : (unsigned int) left << 5);
+        int NR;
+        if (FOLD2) {
+            // ---- the same fold without branches (GX_RUNJOIN_TMA=2): ptxas turned the four "if (head) { close the open run, open the
+            // next }" steps of the loop below into four branch regions full of register shuffling (~100 instructions per tile).
+            // Here every row knows its run (r_i), every run length and sum is a chain of selects that restarts at a head, and each
+            // store is a single predicated instruction.
+            const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+            const bool h0 = act && (lane == 0 || k[0] != prevk), h1 = act && k[1] != k[0], h2 = act && k[2] != k[1], h3 = act && k[3] != k[2];
+            const int nh = (int) h0 + (int) h1 + (int) h2 + (int) h3;
+            int inc = nh;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        const int base = inc - nh, NR = __shfl_sync(0xffffffffu, inc, 31);
-        // ---- fold: runs that start in this lane are stored, the rows that continue the previous
-        // lane's run are added to that run afterwards
-        unsigned int c0 = 0; double s0 = 0.0;
-        if (act) {
-            int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (hd[i]) {
-                    if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
-                    rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
-                }
-                c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int base = inc - nh;
+            NR = __shfl_sync(0xffffffffu, inc, 31);
+            const int r0 = base + (int) h0 - 1, r1 = r0 + (int) h1, r2 = r1 + (int) h2, r3 = r2 + (int) h3;   // run of row i; base - 1 = the previous lane's last run
+            const unsigned int c1 = h1 ? 1u : 2u, c2 = h2 ? 1u : c1 + 1u, c3 = h3 ? 1u : c2 + 1u;                // rows of row i's run up to row i, inside this lane
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (HAS_SUM) { s0 = v[0]; s1 = h1 ? v[1] : __dadd_rn(s0, v[1]); s2 = h2 ? v[2] : __dadd_rn(s1, v[2]); s3 = h3 ? v[3] : __dadd_rn(s2, v[3]); }
+            const bool q0 = h0, q1 = q0 || h1, q2 = q1 || h2, q3 = q2 || h3;                                     // row i's run started in this lane
+            if (h0) Q.key[r0] = k[0];
+            if (h1) Q.key[r1] = k[1];
+            if (h2) Q.key[r2] = k[2];
+            if (h3) Q.key[r3] = k[3];
+            // a run of this lane ends at row i when row i + 1 is a head, the last one at row 3
+            if (h1 && q0) { Q.cnt[r0] = 1u; if (HAS_SUM) Q.sum[r0] = s0; }
+            if (h2 && q1) { Q.cnt[r1] = c1; if (HAS_SUM) Q.sum[r1] = s1; }
+            if (h3 && q2) { Q.cnt[r2] = c2; if (HAS_SUM) Q.sum[r2] = s2; }
+            if (q3) { Q.cnt[r3] = c3; if (HAS_SUM) Q.sum[r3] = s3; }
+            // the rows before this lane's first head continue the previous lane's run: added once that run's own lane has stored it
+            unsigned int cc = 0; double sc = 0.0;
+            if (act && !h0) {
+                cc = h1 ? 1u : h2 ? c1 : h3 ? c2 : c3;
+                if (HAS_SUM) sc = h1 ? s0 : h2 ? s1 : h3 ? s2 : s3;
             }
-            if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+            __syncwarp();
+            if (cc) { atomicAdd(&Q.cnt[base - 1], cc); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], sc); }
+            __syncwarp();
+        } else {
+            // ---- run heads and their numbering inside the warp
+            const long long prevk = __shfl_up_sync(0xffffffffu, k[3], 1);
+            bool hd[4];
+            hd[0] = lane == 0 || k[0] != prevk; hd[1] = k[1] != k[0]; hd[2] = k[2] != k[1]; hd[3] = k[3] != k[2];
+            const int nh = act ? (int) hd[0] + (int) hd[1] + (int) hd[2] + (int) hd[3] : 0;
+            int inc = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int base = inc - nh;
+            NR = __shfl_sync(0xffffffffu, inc, 31);
+            // ---- fold: runs that start in this lane are stored, the rows that continue the previous
+            // lane's run are added to that run afterwards
+            unsigned int c0 = 0; double s0 = 0.0;
+            if (act) {
+                int rid = base - 1; unsigned int c = 0; double sacc = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (hd[i]) {
+                        if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+                        rid++; Q.key[rid] = k[i]; c = 0; sacc = 0.0;
+                    }
+                    c++; if (HAS_SUM) sacc = __dadd_rn(sacc, v[i]);
+                }
+                if (rid >= base) { Q.cnt[rid] = c; if (HAS_SUM) Q.sum[rid] = sacc; } else { c0 = c; s0 = sacc; }
+            }
+            __syncwarp();
+            if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
+            __syncwarp();
         }
-        __syncwarp();
-        if (c0) { atomicAdd(&Q.cnt[base - 1], c0); if (HAS_SUM) atomicAdd(&Q.sum[base - 1], s0); }
-        __syncwarp();
         // ---- one run per lane
         for (int j = lane; j < NR; j += 32) {
             const long long key = Q.key[j];
@@ -2521,6 +2572,7 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
+#define GX_RUNJOIN_TMA_DEFAULT 0          /* 0 off, 1 gx_k_runjoin_tma, 2 the same with the branch-free fold */
 // gx_k_runjoin_seg: 31 consumer warps + 1 producer warp, the rest of the CTA's shared memory is the two-deep ring of
 // join-table pieces.  0 slots = the ring does not fit next to this group table (the caller keeps gx_k_runjoin).
 // Ring depth 3 when three buffers of the size a chunk is expected to need fit (table slots per outer row x 3968 rows, + 15 %
@@ -2581,16 +2633,20 @@ static int launch_runjoin_tma_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_
 {
     static bool attr_set = false;
     if (!attr_set) {
-        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
         attr_set = true;
     }
+    const char *fv = getenv("GX_RUNJOIN_TMA");
+    const bool fold2 = fv && fv[0] ? fv[0] == '2' : GX_RUNJOIN_TMA_DEFAULT == 2;      // =2: the branch-free fold
     long long nvec = (A.row1 - A.row0 + 3) / 4;
     long long nb = (nvec + 1023) / 1024, maxb = (long long) ctx->sm_count;
     while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 31)) maxb *= 2;      // 31-bit row counters per CTA
     unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
     gx_launch_scope ls(ctx, name);
     gx_launch_scope which(ctx, "probe_agg_tma", 0);              // second profile name: which variant ran
-    gx_k_runjoin_tma<HAS_SUM, COMPACT><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    if (fold2) gx_k_runjoin_tma<HAS_SUM, COMPACT, true><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    else gx_k_runjoin_tma<HAS_SUM, COMPACT, false><<<grid, 1024, smem, ctx->stream>>>(A, FA);
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
@@ -2623,7 +2679,6 @@ static bool gx_runjoin_seg_enabled()
     return e && e[0] ? e[0] != '0' : GX_RUNJOIN_SEG_DEFAULT != 0;
 }
 // GX_RUNJOIN_TMA=1/0 selects / forbids gx_k_runjoin_tma (same rules as GX_RUNJOIN_SEG)
-#define GX_RUNJOIN_TMA_DEFAULT 0
 static bool gx_runjoin_tma_enabled()
 {
     if (g_runjoin_seg_broken) return false;

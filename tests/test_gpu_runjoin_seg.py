@@ -24,16 +24,17 @@ from helpers import assert_agg_equal, to_gpu_plan, lineitem_rel, orders_rel
 pytestmark = pytest.mark.gpu
 
 NORD = 200_000        # >= 64 sub-tables: interpolation slots + compact table, what the seg variant needs
-VARIANTS = {"seg": ("GX_RUNJOIN_SEG", "probe_agg_seg"), "tma": ("GX_RUNJOIN_TMA", "probe_agg_tma")}
+VARIANTS = {"seg": ("GX_RUNJOIN_SEG", "1", "probe_agg_seg"), "tma": ("GX_RUNJOIN_TMA", "1", "probe_agg_tma"),
+            "tma2": ("GX_RUNJOIN_TMA", "2", "probe_agg_tma")}          # tma2: gx_k_runjoin_tma with the branch-free fold
 
 
-@pytest.fixture(params=["seg", "tma"])
+@pytest.fixture(params=list(VARIANTS))
 def variant(request, monkeypatch):
-    for env, _ in VARIANTS.values():
+    for env, _, _ in VARIANTS.values():
         monkeypatch.setenv(env, "0")
-    monkeypatch.setenv(VARIANTS[request.param][0], "1")
+    monkeypatch.setenv(VARIANTS[request.param][0], VARIANTS[request.param][1])
     monkeypatch.setenv("GX_DEBUG_AGG", "1")
-    return VARIANTS[request.param][1]
+    return VARIANTS[request.param][2]
 
 
 def _plan(count=True, total=True):
@@ -143,13 +144,13 @@ def test_same_answer_as_the_gathering_kernel_at_sf10_slice(gx, monkeypatch):
     ht = gx.hash_build(ot, g.O_ORDERKEY, [g.O_ORDERDATE], unique=True)
     plan = to_gpu_plan(_plan())
     res = {}
-    for sw, (seg, tma) in {"0": ("0", "0"), "seg": ("1", "0"), "tma": ("0", "1")}.items():
+    for sw, (seg, tma) in {"0": ("0", "0"), "seg": ("1", "0"), "tma": ("0", "1"), "tma2": ("0", "2")}.items():
         monkeypatch.setenv("GX_RUNJOIN_SEG", seg)
         monkeypatch.setenv("GX_RUNJOIN_TMA", tma)
         k, a, _ = gx.hash_agg(lt, plan, ht).fetch()
         order = np.argsort(k[:, 0])
         res[sw] = (k[order], a[order])
-    for sw in ("seg", "tma"):
+    for sw in ("seg", "tma", "tma2"):
         np.testing.assert_array_equal(res["0"][0], res[sw][0])
         np.testing.assert_array_equal(res["0"][1][:, 0].view(np.int64), res[sw][1][:, 0].view(np.int64))
         np.testing.assert_allclose(res["0"][1][:, 1], res[sw][1][:, 1], rtol=1e-9, atol=0)
