@@ -1688,7 +1688,7 @@ __global__ void __launch_bounds__(512, 2) gx_k_runjoin2(const __grid_constant__ 
 // Bounded waits as in gx_k_runjoin_seg: flag 16 sends the plan back to gx_k_runjoin.
 struct gx_rowstage { long long key[128]; double val[128]; };
 
-template <bool HAS_SUM, bool COMPACT, bool FOLD2>
+template <bool HAS_SUM, bool COMPACT, bool FOLD2, bool CARRY>
 __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constant__ gx_agg_dev A, const gx_fast_args F)
 {
     extern __shared__ __align__(128) unsigned long long smem_tma[];
@@ -1732,6 +1732,20 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constan
     if (left > 0) request(left >= 32 ? 1024u : (unsigned int) left << 5);
     unsigned int parity = 0;
     bool stuck = false;
+    // one run against the join table and into the group table
+    auto probe_one = [&](int j) {
+        const long long key = Q.key[j];
+        const unsigned int rc = Q.cnt[j];
+        const double rs = HAS_SUM ? Q.sum[j] : 0.0;
+        int g = 0;
+        const bool hit = runjoin_probe<COMPACT>(A, key, g);
+        if (hit) packed_flush<HAS_SUM>(tab, tsum, S, A, g, rc, rs);
+    };
+    // CARRY (GX_RUNJOIN_TMA=3): probe rounds only ever run with 32 lanes.  A tile holds ~33 runs, so half the tiles pay a second
+    // round for one to three of them (~50 instructions per tile).  Here the list keeps its oldest T mod 32 entries at the front -
+    // nothing is moved: the rounds take the NEWEST entries [T mod 32, T), the next tile appends behind what stayed, and the last
+    // stragglers are probed when the warp runs out of rows.  (gx_k_runjoin3 moved the remainder to the front after every tile.)
+    int nc = 0;                                                 // entries waiting at the front of the list
     while (left > 0) {                                          // warp-uniform
         const bool act = (long long) lane < left;
         long long k[4]; double v[4];
@@ -1763,8 +1777,13 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constan
             int inc = nh;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            const int base = inc - nh;
             NR = __shfl_sync(0xffffffffu, inc, 31);
+            if (CARRY && nc + NR > 128) {                       // more runs than the list has room for behind the waiting ones (rare): those first
+                for (int j = lane; j < nc; j += 32) probe_one(j);
+                nc = 0;
+                __syncwarp();
+            }
+            const int base = inc - nh + (CARRY ? nc : 0);
             const int r0 = base + (int) h0 - 1, r1 = r0 + (int) h1, r2 = r1 + (int) h2, r3 = r2 + (int) h3;   // run of row i; base - 1 = the previous lane's last run
             const unsigned int c1 = h1 ? 1u : 2u, c2 = h2 ? 1u : c1 + 1u, c3 = h3 ? 1u : c2 + 1u;                // rows of row i's run up to row i, inside this lane
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -1819,16 +1838,16 @@ __global__ void __launch_bounds__(1024, 1) gx_k_runjoin_tma(const __grid_constan
             __syncwarp();
         }
         // ---- one run per lane
-        for (int j = lane; j < NR; j += 32) {
-            const long long key = Q.key[j];
-            const unsigned int rc = Q.cnt[j];
-            const double rs = HAS_SUM ? Q.sum[j] : 0.0;
-            int g = 0;
-            const bool hit = runjoin_probe<COMPACT>(A, key, g);
-            if (hit) packed_flush<HAS_SUM>(tab, tsum, S, A, g, rc, rs);
+        if (CARRY) {
+            const int T = nc + NR, first = T & 31;
+            for (int j = first + lane; j < T; j += 32) probe_one(j);
+            nc = first;
+        } else {
+            for (int j = lane; j < NR; j += 32) probe_one(j);
         }
         __syncwarp();
     }
+    if (CARRY) { for (int j = lane; j < nc; j += 32) probe_one(j); }        // what was still waiting when the rows ran out
     if (stuck) atomicOr((unsigned long long *) &A.counters[1], 16ULL);
     // the (< 4) rows after the last full vector: one thread each
     {
@@ -2572,7 +2591,9 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }
-#define GX_RUNJOIN_TMA_DEFAULT 0          /* 0 off, 1 gx_k_runjoin_tma, 2 the same with the branch-free fold */
+// Measured at SF100 on one B200 (profiles/r02_runjoin_variants.txt): gx_k_runjoin 2.787 ms, gx_k_runjoin_tma 2.660 ms, with the
+// branch-free fold 2.617 ms (parity suite and bench checks green under it) -> 2 is the default; GX_RUNJOIN_TMA=0 restores gx_k_runjoin
+#define GX_RUNJOIN_TMA_DEFAULT 2          /* 0 off, 1 gx_k_runjoin_tma, 2 the same with the branch-free fold */
 // gx_k_runjoin_seg: 31 consumer warps + 1 producer warp, the rest of the CTA's shared memory is the two-deep ring of
 // join-table pieces.  0 slots = the ring does not fit next to this group table (the caller keeps gx_k_runjoin).
 // Ring depth 3 when three buffers of the size a chunk is expected to need fit (table slots per outer row x 3968 rows, + 15 %
@@ -2633,20 +2654,22 @@ static int launch_runjoin_tma_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_
 {
     static bool attr_set = false;
     if (!attr_set) {
-        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
-        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
+        GX_CUDA(ctx, cudaFuncSetAttribute(gx_k_runjoin_tma<HAS_SUM, COMPACT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin));
         attr_set = true;
     }
     const char *fv = getenv("GX_RUNJOIN_TMA");
-    const bool fold2 = fv && fv[0] ? fv[0] == '2' : GX_RUNJOIN_TMA_DEFAULT == 2;      // =2: the branch-free fold
+    const int variant = fv && fv[0] ? fv[0] - '0' : GX_RUNJOIN_TMA_DEFAULT;           // 2: the branch-free fold, 3: + full probe rounds only
     long long nvec = (A.row1 - A.row0 + 3) / 4;
     long long nb = (nvec + 1023) / 1024, maxb = (long long) ctx->sm_count;
     while ((A.row1 - A.row0 + maxb - 1) / maxb >= (1LL << 31)) maxb *= 2;      // 31-bit row counters per CTA
     unsigned grid = (unsigned) (nb < maxb ? (nb > 0 ? nb : 1) : maxb);
     gx_launch_scope ls(ctx, name);
     gx_launch_scope which(ctx, "probe_agg_tma", 0);              // second profile name: which variant ran
-    if (fold2) gx_k_runjoin_tma<HAS_SUM, COMPACT, true><<<grid, 1024, smem, ctx->stream>>>(A, FA);
-    else gx_k_runjoin_tma<HAS_SUM, COMPACT, false><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    if (variant == 3) gx_k_runjoin_tma<HAS_SUM, COMPACT, true, true><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    else if (variant == 2) gx_k_runjoin_tma<HAS_SUM, COMPACT, true, false><<<grid, 1024, smem, ctx->stream>>>(A, FA);
+    else gx_k_runjoin_tma<HAS_SUM, COMPACT, false, false><<<grid, 1024, smem, ctx->stream>>>(A, FA);
     GX_CUDA(ctx, cudaGetLastError());
     return GX_OK;
 }

@@ -25,7 +25,8 @@ pytestmark = pytest.mark.gpu
 
 NORD = 200_000        # >= 64 sub-tables: interpolation slots + compact table, what the seg variant needs
 VARIANTS = {"seg": ("GX_RUNJOIN_SEG", "1", "probe_agg_seg"), "tma": ("GX_RUNJOIN_TMA", "1", "probe_agg_tma"),
-            "tma2": ("GX_RUNJOIN_TMA", "2", "probe_agg_tma")}          # tma2: gx_k_runjoin_tma with the branch-free fold
+            "tma2": ("GX_RUNJOIN_TMA", "2", "probe_agg_tma"),          # tma2: gx_k_runjoin_tma with the branch-free fold
+            "tma3": ("GX_RUNJOIN_TMA", "3", "probe_agg_tma")}          # tma3: + probe rounds of 32 lanes only (runs wait in the list)
 
 
 @pytest.fixture(params=list(VARIANTS))
@@ -144,16 +145,24 @@ def test_same_answer_as_the_gathering_kernel_at_sf10_slice(gx, monkeypatch):
     ht = gx.hash_build(ot, g.O_ORDERKEY, [g.O_ORDERDATE], unique=True)
     plan = to_gpu_plan(_plan())
     res = {}
-    for sw, (seg, tma) in {"0": ("0", "0"), "seg": ("1", "0"), "tma": ("0", "1"), "tma2": ("0", "2")}.items():
+    for sw, (seg, tma) in {"0": ("0", "0"), "seg": ("1", "0"), "tma": ("0", "1"), "tma2": ("0", "2"), "tma3": ("0", "3")}.items():
         monkeypatch.setenv("GX_RUNJOIN_SEG", seg)
         monkeypatch.setenv("GX_RUNJOIN_TMA", tma)
         k, a, _ = gx.hash_agg(lt, plan, ht).fetch()
         order = np.argsort(k[:, 0])
         res[sw] = (k[order], a[order])
-    for sw in ("seg", "tma", "tma2"):
+    for sw in ("seg", "tma", "tma2", "tma3"):
         np.testing.assert_array_equal(res["0"][0], res[sw][0])
         np.testing.assert_array_equal(res["0"][1][:, 0].view(np.int64), res[sw][1][:, 0].view(np.int64))
         np.testing.assert_allclose(res["0"][1][:, 1], res[sw][1][:, 1], rtol=1e-9, atol=0)
         assert res[sw][1][:, 0].view(np.int64).sum() == lt.nrows
     for t in (ht, lt, ot):
         t.free()
+
+
+def test_one_row_per_key(gx, base, variant):
+    """Every probe row its own run (128 runs per tile): the run list is full after every tile, and the variant that keeps
+    waiting runs at the front of the list has to make room first."""
+    o, l = base
+    first = np.concatenate([[True], l[g.L_ORDERKEY][1:] != l[g.L_ORDERKEY][:-1]])
+    _run(gx, o, [c[first] for c in l], _plan(), prof=variant)
