@@ -160,9 +160,14 @@ def test_same_answer_as_the_gathering_kernel_at_sf10_slice(gx, monkeypatch):
         t.free()
 
 
-def test_one_row_per_key(gx, base, variant):
-    """Every probe row its own run (128 runs per tile): the run list is full after every tile, and the variant that keeps
-    waiting runs at the front of the list has to make room first."""
+@pytest.mark.parametrize("layout", ["all", "blocks"])
+def test_one_row_per_key(gx, base, variant, layout):
+    """Every probe row its own run (128 runs per tile): the run list is full after every tile.  In blocks of 300 orders
+    alternating with ordinary ones, tiles of 128 runs follow tiles that left runs waiting at the front of the list, and the
+    variant that keeps them there has to make room first."""
     o, l = base
     first = np.concatenate([[True], l[g.L_ORDERKEY][1:] != l[g.L_ORDERKEY][:-1]])
+    if layout == "blocks":
+        order_no = np.cumsum(first) - 1
+        first = first | ((order_no // 300) % 2 == 0)
     _run(gx, o, [c[first] for c in l], _plan(), prof=variant)
