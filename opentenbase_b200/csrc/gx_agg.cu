@@ -2592,8 +2592,9 @@ static int launch_runjoin_t(gx_ctx *ctx, const gx_agg_dev &A, const gx_fast_args
     return GX_OK;
 }
 // Measured at SF100 on one B200 (profiles/r02_runjoin_variants.txt): gx_k_runjoin 2.787 ms, gx_k_runjoin_tma 2.660 ms, with the
-// branch-free fold 2.617 ms (parity suite and bench checks green under it) -> 2 is the default; GX_RUNJOIN_TMA=0 restores gx_k_runjoin
-#define GX_RUNJOIN_TMA_DEFAULT 2          /* 0 off, 1 gx_k_runjoin_tma, 2 the same with the branch-free fold */
+// branch-free fold 2.617 ms, with full probe rounds only 2.514 ms (parity suite, the whole GPU suite, smoke and the bench checks
+// green under it) -> 3 is the default; GX_RUNJOIN_TMA=0 restores gx_k_runjoin
+#define GX_RUNJOIN_TMA_DEFAULT 3          /* 0 off, 1 gx_k_runjoin_tma, 2 + branch-free fold, 3 + probe rounds of 32 lanes only */
 // gx_k_runjoin_seg: 31 consumer warps + 1 producer warp, the rest of the CTA's shared memory is the two-deep ring of
 // join-table pieces.  0 slots = the ring does not fit next to this group table (the caller keeps gx_k_runjoin).
 // Ring depth 3 when three buffers of the size a chunk is expected to need fit (table slots per outer row x 3968 rows, + 15 %

@@ -9,6 +9,9 @@ themselves are tested against the oracle by tests/test_gpu_parity.py.
    the compact one and its position.
 4. The window gx_k_runjoin_seg's producer stages for a chunk of key-ordered probe rows contains the
    home slot group of every key of the chunk, and windows of consecutive chunks tile the table.
+5. gx_k_runjoin_tma's branch-free fold (select chains + predicated stores + one continuation add per lane)
+   produces the run list of the sequential definition, and the "newest entries first" probe rounds of its
+   carry variant visit every run exactly once, always with 32 lanes except for the final flush.
 """
 import numpy as np
 import pytest
@@ -256,3 +259,104 @@ def test_unordered_chunks_stage_nothing_or_little():
         skipped += ln == 0
         nchunks += 1
     assert skipped >= 0.9 * nchunks
+
+
+# ------------------------------------------------------------------ 5. the branch-free fold and the carry rounds
+def fold_tile_branch_free(keys, vals, nrows, off=0):
+    """One 128-row tile as the 32 lanes of gx_k_runjoin_tma<FOLD2> see it (csrc/gx_agg.cu): returns the run list
+    (key, count, sum) written at positions off..off+NR-1, built from per-lane select chains, predicated stores and
+    one continuation add per lane — the arithmetic of the kernel, lane by lane."""
+    K = {}; C = {}; S = {}
+    cont = []                                            # (run index, count, sum) added after the stores (second phase)
+    inc = 0
+    bases = []
+    heads = []
+    for lane in range(32):
+        act = lane * 4 < nrows
+        k = [int(keys[lane * 4 + i]) if lane * 4 + i < len(keys) else 0 for i in range(4)]
+        prevk = int(keys[lane * 4 - 1]) if lane > 0 else None
+        h = [act and (lane == 0 or k[0] != prevk), act and k[1] != k[0], act and k[2] != k[1], act and k[3] != k[2]]
+        heads.append(h)
+        bases.append(inc + off)
+        inc += sum(h)
+    NR = inc
+    for lane in range(32):
+        act = lane * 4 < nrows
+        if not act:
+            continue
+        k = [int(keys[lane * 4 + i]) for i in range(4)]
+        v = [float(vals[lane * 4 + i]) for i in range(4)]
+        h0, h1, h2, h3 = heads[lane]
+        base = bases[lane]
+        r0 = base + int(h0) - 1; r1 = r0 + int(h1); r2 = r1 + int(h2); r3 = r2 + int(h3)
+        c1 = 1 if h1 else 2; c2 = 1 if h2 else c1 + 1; c3 = 1 if h3 else c2 + 1
+        s0 = v[0]; s1 = v[1] if h1 else s0 + v[1]; s2 = v[2] if h2 else s1 + v[2]; s3 = v[3] if h3 else s2 + v[3]
+        q0 = h0; q1 = q0 or h1; q2 = q1 or h2; q3 = q2 or h3
+        for hh, r, kk in ((h0, r0, k[0]), (h1, r1, k[1]), (h2, r2, k[2]), (h3, r3, k[3])):
+            if hh:
+                K[r] = kk
+        if h1 and q0: C[r0], S[r0] = 1, s0
+        if h2 and q1: C[r1], S[r1] = c1, s1
+        if h3 and q2: C[r2], S[r2] = c2, s2
+        if q3: C[r3], S[r3] = c3, s3
+        if not h0:
+            cc = 1 if h1 else c1 if h2 else c2 if h3 else c3
+            sc = s0 if h1 else s1 if h2 else s2 if h3 else s3
+            cont.append((base - 1, cc, sc))
+    for r, cc, sc in cont:                               # after __syncwarp(): atomicAdd onto the run's own entry
+        C[r] += cc; S[r] += sc
+    assert sorted(K) == sorted(C) == list(range(off, off + NR))
+    return [(K[r], C[r], S[r]) for r in range(off, off + NR)]
+
+
+def fold_tile_sequential(keys, vals, nrows):
+    out = []
+    for i in range(nrows):
+        if i == 0 or keys[i] != keys[i - 1]:
+            out.append([int(keys[i]), 0, 0.0])
+        out[-1][1] += 1; out[-1][2] += float(vals[i])
+    return [tuple(x) for x in out]
+
+
+@pytest.mark.parametrize("seed,maxrun", [(1, 7), (2, 1), (3, 40), (4, 300), (5, 2)])
+def test_branch_free_fold_equals_the_sequential_fold(seed, maxrun):
+    rng = np.random.default_rng(seed)
+    for _ in range(40):
+        runs = rng.integers(1, maxrun + 1, 200)
+        keys = np.repeat(np.cumsum(rng.integers(1, 5, 200)), runs)[:128 + 64]
+        start = int(rng.integers(0, 64))                 # tiles begin mid-run
+        nrows = int(rng.choice([128, 128, 128, 4 * rng.integers(1, 32)]))      # full tiles and partial last tiles
+        tile = keys[start:start + 128]
+        vals = rng.integers(1, 1000, 128).astype(np.float64)                    # integers: float sums are exact in any order
+        got = fold_tile_branch_free(tile, vals, nrows)
+        want = fold_tile_sequential(tile, vals, nrows)
+        assert got == want
+
+
+def test_carry_rounds_visit_every_run_once_in_full_rounds():
+    """GX_RUNJOIN_TMA=3: T = waiting + new runs; the rounds take entries [T mod 32, T), the first T mod 32 entries wait;
+    a tile that would not fit behind the waiting entries (capacity 128) has them probed first."""
+    rng = np.random.default_rng(9)
+    for regime in ("tpch", "one_row_keys", "mixed"):
+        lst = [None] * 128
+        nc = 0
+        seen = []
+        rounds = []
+        produced = 0
+        for t in range(400):
+            NR = {"tpch": int(rng.integers(20, 46)), "one_row_keys": 128, "mixed": int(rng.choice([30, 33, 128, 100, 1]))}[regime]
+            if nc + NR > 128:
+                seen += lst[:nc]; rounds.append(nc); nc = 0
+            for j in range(NR):
+                lst[nc + j] = produced; produced += 1
+            T = nc + NR
+            first = T & 31
+            for j0 in range(first, T, 32):
+                seen += lst[j0:j0 + 32]; rounds.append(32)
+            nc = first
+        seen += lst[:nc]
+        assert sorted(seen) == list(range(produced))     # every run exactly once
+        partial = [r for r in rounds if r != 32]
+        assert all(r < 32 for r in partial)
+        if regime == "tpch":
+            assert not partial and len(rounds) <= produced // 32
