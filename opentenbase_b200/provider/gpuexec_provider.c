@@ -54,6 +54,7 @@
 #include "nodes/makefuncs.h"
 #include "nodes/nodeFuncs.h"
 #include "optimizer/clauses.h"
+#include "optimizer/cost.h"
 #include "optimizer/distribution.h"
 #include "optimizer/pathnode.h"
 #include "optimizer/paths.h"
@@ -75,6 +76,7 @@
 #include "utils/snapmgr.h"
 
 #include "gpuexec.h"
+#include "gpuexec_cost.h"
 
 PG_MODULE_MAGIC;
 
@@ -84,6 +86,12 @@ static bool gpuexec_enabled = true;
 static int	gpuexec_device = 0;
 static int	gpuexec_pool_reserve_mb = 0;	/* HBM mapped into the library's pool when the backend's context is created */
 static int	gpuexec_hbm_limit_mb = 150 * 1024;	/* decline plans whose staged columns + join table would not fit */
+/* the cost model's rates (gpuexec_cost.h); defaults = what bench.py measured on a B200 host */
+static double gpuexec_cost_unit_us = 10.0;
+static double gpuexec_host_page_us = 0.6;
+static double gpuexec_pcie_gb_s = 50.0;
+static double gpuexec_hbm_gb_s = 4000.0;
+static double gpuexec_startup_us = 1500.0;
 static create_upper_paths_hook_type prev_upper_paths_hook = NULL;
 
 /* one CUDA context per backend process, created lazily (never in the postmaster:
@@ -1083,7 +1091,7 @@ grouping_covers_distribution(Query *parse, Distribution *d)
 
 static bool
 gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_rel, GpuExecState *out,
-				   List **agg_refs, double *est_rows, double *est_groups, double *est_bytes)
+				   List **agg_refs, double *est_rows, double *est_groups, double *est_bytes, double *est_pages)
 {
 	Query	   *parse = root->parse;
 	Path	   *in = input_rel->cheapest_total_path;
@@ -1102,6 +1110,7 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 			!match_quals(input_rel->baserestrictinfo, &out->outer, plan->preds, &plan->n_preds))
 			return false;
 		*est_bytes = input_rel->tuples;
+		*est_pages = input_rel->pages;
 	}
 	else if (IsA(in, HashPath))
 	{
@@ -1151,6 +1160,7 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 			!match_quals(ip->parent->baserestrictinfo, &out->inner, out->inner_preds, &out->n_inner_preds))
 			return false;
 		*est_bytes = op->parent->tuples;
+		*est_pages = (double) op->parent->pages + (double) ip->parent->pages;
 	}
 	else
 		return false;
@@ -1285,7 +1295,8 @@ gpuexec_upper_paths_hook(PlannerInfo *root, UpperRelationKind stage, RelOptInfo 
 	List	   *scan_exprs = NIL;
 	double		rows,
 				groups,
-				bytes = 0;
+				bytes = 0,
+				pages = 0;
 	ListCell   *lc;
 
 	if (prev_upper_paths_hook)
@@ -1293,7 +1304,7 @@ gpuexec_upper_paths_hook(PlannerInfo *root, UpperRelationKind stage, RelOptInfo 
 	if (!gpuexec_enabled || stage != UPPERREL_GROUP_AGG)
 		return;
 	memset(&desc, 0, sizeof(desc));
-	if (!gpuexec_match_plan(root, input_rel, output_rel, &desc, &agg_refs, &rows, &groups, &bytes))
+	if (!gpuexec_match_plan(root, input_rel, output_rel, &desc, &agg_refs, &rows, &groups, &bytes, &pages))
 		return;					/* decline: the CPU paths stay as they are */
 	/* capacity (the analogue of ExecChooseHashTableSize deciding on batches, nodeHash.c:864): there is
 	 * no spill path on the device, so a plan that would not fit is left to the CPU executor */
@@ -1337,11 +1348,30 @@ gpuexec_upper_paths_hook(PlannerInfo *root, UpperRelationKind stage, RelOptInfo 
 		cpath->path.parallel_aware = false;
 		cpath->path.parallel_safe = false;	/* the GPU replaces intra-node parallelism */
 		cpath->path.rows = groups;
-		/* staging dominates: charge the sequential page reads, nothing per tuple */
-		cpath->path.startup_cost = cheapest_in->total_cost * 0.25;
-		cpath->path.total_cost = cpath->path.startup_cost + groups * 0.01;
 		/* the aggregate runs where the data lives */
 		cpath->path.distribution = cheapest_in->distribution;
+		/* priced like the reference's own paths — per datanode, in units of a sequential page fetch — so that add_path()
+		 * compares like with like: the disk term of cost_seqscan (costsize.c:359), then per page on the host instead of
+		 * per tuple, PCIe, HBM passes and a fixed start-up price (gpuexec_cost.h) */
+		{
+			gpuexec_cost_params cp;
+			double		num_nodes = path_count_datanodes(cheapest_in);
+			Cost		startup,
+						total;
+
+			cp.seq_page_cost = seq_page_cost;
+			cp.cpu_tuple_cost = cpu_tuple_cost;
+			cp.cost_unit_us = gpuexec_cost_unit_us;
+			cp.host_page_us = gpuexec_host_page_us;
+			cp.pcie_gb_s = gpuexec_pcie_gb_s;
+			cp.hbm_gb_s = gpuexec_hbm_gb_s;
+			cp.startup_us = gpuexec_startup_us;
+			if (num_nodes < 1)
+				num_nodes = 1;
+			gpuexec_path_cost(&cp, pages / num_nodes, bytes / num_nodes, groups, &startup, &total);
+			cpath->path.startup_cost = startup;
+			cpath->path.total_cost = total;
+		}
 		cpath->flags = 0;
 		cpath->custom_paths = NIL;
 		cpath->custom_private = list_make2(gpuexec_serialise(&desc), scan_exprs);
@@ -1382,6 +1412,16 @@ _PG_init(void)
 							&gpuexec_pool_reserve_mb, 0, 0, 1024 * 1024, PGC_BACKEND, 0, NULL, NULL, NULL);
 	DefineCustomIntVariable("gpuexec.hbm_limit_mb", "Decline plans whose staged columns and join table are estimated above this many MB of HBM.", NULL,
 							&gpuexec_hbm_limit_mb, 150 * 1024, 64, 1024 * 1024, PGC_USERSET, 0, NULL, NULL, NULL);
+	DefineCustomRealVariable("gpuexec.cost_unit_us", "Microseconds one unit of planner cost (a sequential page fetch) stands for.", NULL,
+							 &gpuexec_cost_unit_us, 10.0, 0.01, 1e6, PGC_USERSET, 0, NULL, NULL, NULL);
+	DefineCustomRealVariable("gpuexec.host_page_us", "Host microseconds per heap page on the loader's path (visibility pass + copy into the pinned ring).", NULL,
+							 &gpuexec_host_page_us, 0.6, 0.0, 1e6, PGC_USERSET, 0, NULL, NULL, NULL);
+	DefineCustomRealVariable("gpuexec.pcie_gb_s", "Host-to-device copy rate of pinned memory in GB/s.", NULL,
+							 &gpuexec_pcie_gb_s, 50.0, 0.1, 1e4, PGC_USERSET, 0, NULL, NULL, NULL);
+	DefineCustomRealVariable("gpuexec.hbm_gb_s", "What the kernels sustain over the staged columns in GB/s.", NULL,
+							 &gpuexec_hbm_gb_s, 4000.0, 1.0, 1e5, PGC_USERSET, 0, NULL, NULL, NULL);
+	DefineCustomRealVariable("gpuexec.startup_us", "Fixed price of one GPU sub-plan in microseconds (plan compile, launches, result fetch).", NULL,
+							 &gpuexec_startup_us, 1500.0, 0.0, 1e9, PGC_USERSET, 0, NULL, NULL, NULL);
 	RegisterCustomScanMethods(&gpuexec_scan_methods);
 	RegisterResourceReleaseCallback(gpuexec_resowner_callback, NULL);
 	prev_upper_paths_hook = create_upper_paths_hook;

@@ -89,6 +89,9 @@ bool cls_check_table_has_policy(Oid r) { return false; }
 bool datamask_check_table_has_datamask(Oid r) { return false; }
 bool get_audit_fga_quals(Oid rel, char *cmd, List *tl, List **out) { return false; }
 void DefineCustomBoolVariable(const char *n, const char *s, const char *l, bool *v, bool b, GucContext c, int f, GucBoolCheckHook a, GucBoolAssignHook g, GucShowHook h) { }
+void DefineCustomRealVariable(const char *n, const char *s, const char *l, double *v, double b, double mn, double mx, GucContext c, int f, GucRealCheckHook a, GucRealAssignHook g, GucShowHook h) { }
+double		seq_page_cost = 1.0, cpu_tuple_cost = 0.01;		/* costsize.c:100-104 */
+double path_count_datanodes(Path *p) { NOT_REACHED("path_count_datanodes"); return 1; }
 void DefineCustomIntVariable(const char *n, const char *s, const char *l, int *v, int b, int mn, int mx, GucContext c, int f, GucIntCheckHook a, GucIntAssignHook g, GucShowHook h) { }
 static const CustomScanMethods *registered_methods = NULL;
 void RegisterCustomScanMethods(const CustomScanMethods *m) { registered_methods = m; }
