@@ -136,6 +136,14 @@ def test_switch_off_keeps_the_gathering_kernel(gx, base, monkeypatch):
     _run(gx, o, l, _plan(), expect_seg=False, prof="probe_agg_tma")
 
 
+def test_default_is_the_copy_engine_kernel(gx, base, monkeypatch):
+    """No switch set: gx_k_runjoin_tma (GX_RUNJOIN_TMA_DEFAULT in csrc/gx_agg.cu) answers config 3."""
+    monkeypatch.delenv("GX_RUNJOIN_TMA", raising=False)
+    monkeypatch.delenv("GX_RUNJOIN_SEG", raising=False)
+    o, l = base
+    _run(gx, o, l, _plan(), expect_seg=True, prof="probe_agg_tma")
+
+
 def test_same_answer_as_the_gathering_kernel_at_sf10_slice(gx, monkeypatch):
     """10 M orders generated on the device (no oracle at this size): all variants must agree bit for bit
     on the counts and to 1e-9 on the sums, and count(*) must equal the lineitem rows."""
