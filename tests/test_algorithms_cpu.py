@@ -12,6 +12,9 @@ themselves are tested against the oracle by tests/test_gpu_parity.py.
 5. gx_k_runjoin_tma's branch-free fold (select chains + predicated stores + one continuation add per lane)
    produces the run list of the sequential definition, and the "newest entries first" probe rounds of its
    carry variant visit every run exactly once, always with 32 lanes except for the final flush.
+6. The full/empty mbarrier protocol of gx_k_runjoin_seg's ring (one producer, 31 consumer warps, phase parities
+   derived from a per-buffer use count) neither deadlocks nor lets a buffer be refilled while a consumer still
+   reads it, under arbitrary interleavings; gx_k_runjoin_tma's per-warp barrier is the one-consumer special case.
 """
 import numpy as np
 import pytest
@@ -360,3 +363,89 @@ def test_carry_rounds_visit_every_run_once_in_full_rounds():
         assert all(r < 32 for r in partial)
         if regime == "tpch":
             assert not partial and len(rounds) <= produced // 32
+
+
+# ------------------------------------------------------------------ 6. the mbarrier ring protocol
+class MBar:
+    """An mbarrier as the kernels use it: `count` arrivals (+ outstanding transaction bytes) complete a phase;
+    try_wait.parity(p) is true once the phase with parity p has completed (i.e. the current phase has the other parity)."""
+    def __init__(self, count):
+        self.count, self.pending, self.tx, self.phase = count, count, 0, 0
+
+    def _maybe_complete(self):
+        if self.pending == 0 and self.tx == 0:
+            self.phase ^= 1
+            self.pending = self.count
+
+    def arrive(self, expect_tx=0):
+        assert self.pending > 0, "more arrivals than the barrier was initialised for"
+        self.tx += expect_tx
+        self.pending -= 1
+        self._maybe_complete()
+
+    def complete_tx(self, nbytes):
+        self.tx -= nbytes
+        self._maybe_complete()
+
+    def try_wait(self, parity):
+        return self.phase != parity
+
+
+@pytest.mark.parametrize("nbuf,nconsumers,seed", [(2, 31, 1), (3, 31, 2), (4, 31, 3), (2, 1, 4), (3, 5, 5)])
+def test_ring_protocol_is_deadlock_free_and_never_overwrites_a_buffer_in_use(nbuf, nconsumers, seed):
+    """Random scheduling of the producer, the copy engine and the consumers of gx_k_runjoin_seg (csrc/gx_agg.cu):
+    producer: for chunk j: (use > 0) wait empty[b] parity (use-1)&1; write lo/len; arrive.expect_tx(full[b]); bulk copy
+    consumer: for chunk j: wait full[b] parity use&1; read lo/len + the buffer; arrive(empty[b])
+    with b = j % nbuf, use = j // nbuf on both sides."""
+    rng = np.random.default_rng(seed)
+    niter = 40
+    full = [MBar(1) for _ in range(nbuf)]
+    empty = [MBar(nconsumers) for _ in range(nbuf)]
+    content = [None] * nbuf                   # which chunk a buffer holds (written by the copy engine)
+    meta = [None] * nbuf                      # lo/len words written by the producer before its arrive
+    inflight = []                             # (buffer, chunk) bulk copies issued and not yet landed
+    readers = [0] * nbuf                      # consumers between "wait full" and "arrive empty" on a buffer
+    pj = 0
+    cj = [0] * nconsumers
+    cstate = ["wait"] * nconsumers            # wait -> reading -> (arrive) wait
+    consumed = [[] for _ in range(nconsumers)]
+    steps = 0
+    while pj < niter or any(c < niter for c in cj) or inflight:
+        steps += 1
+        assert steps < 200_000, "no progress: deadlock"
+        actors = []
+        if pj < niter:
+            actors.append(("p", 0))
+        actors += [("e", i) for i in range(len(inflight))]
+        actors += [("c", w) for w in range(nconsumers) if cj[w] < niter]
+        kind, idx = actors[int(rng.integers(len(actors)))]
+        if kind == "p":
+            b, use = pj % nbuf, pj // nbuf
+            if use > 0 and not empty[b].try_wait((use - 1) & 1):
+                continue                      # still waiting for the consumers of chunk pj - nbuf
+            assert readers[b] == 0, "refilling a buffer a consumer still reads"
+            meta[b] = pj
+            full[b].arrive(expect_tx=100)
+            inflight.append((b, pj))
+            pj += 1
+        elif kind == "e":                     # the copy engine lands one outstanding copy
+            b, chunk = inflight.pop(idx)
+            assert readers[b] == 0
+            content[b] = chunk
+            full[b].complete_tx(100)
+        else:
+            w = idx
+            b, use = cj[w] % nbuf, cj[w] // nbuf
+            if cstate[w] == "wait":
+                if full[b].try_wait(use & 1):
+                    assert meta[b] == cj[w] and content[b] == cj[w], "consumer sees another chunk's window"
+                    readers[b] += 1
+                    cstate[w] = "reading"
+            else:
+                assert content[b] == cj[w]    # nothing changed the buffer while it was being read
+                consumed[w].append(cj[w])
+                readers[b] -= 1
+                empty[b].arrive()
+                cstate[w] = "wait"
+                cj[w] += 1
+    assert all(c == list(range(niter)) for c in consumed)
