@@ -350,21 +350,27 @@ put_int64(List *l, int64 v)
 	snprintf(buf, sizeof(buf), INT64_FORMAT, v);
 	return lappend(l, makeFloat(pstrdup(buf)));
 }
+/* ... and the other way round: a value that does fit int32 ("10") comes back from nodeRead() as a T_Integer node, whatever
+ * node type it was sent as, so the reader takes both (tests/test_provider_ship_cpu.py runs the reference's read.c over it) */
 static int64
 get_int64(ListCell **lc)
 {
-	int64		v = (int64) strtoll(strVal(lfirst(*lc)), NULL, 10);
+	Value	   *n = (Value *) lfirst(*lc);
+	int64		v = IsA(n, Integer) ? (int64) intVal(n) : (int64) strtoll(strVal(n), NULL, 10);
 
 	*lc = lnext(*lc);
 	return v;
 }
+/* doubles travel as their bit pattern (a decimal int64 string like the integers above): "%.17g" round-trips finite values, but
+ * NaN and the infinities print as "nan" / "inf", which nodeRead() (nodes/read.c:nodeTokenType) does not take for a number —
+ * a qual such as  x < 'Infinity'  would make every datanode fail to read the plan */
 static List *
 put_double(List *l, double v)
 {
-	char		buf[64];
+	int64		bits;
 
-	snprintf(buf, sizeof(buf), "%.17g", v);
-	return lappend(l, makeFloat(pstrdup(buf)));
+	memcpy(&bits, &v, sizeof(bits));
+	return put_int64(l, bits);
 }
 static int
 get_int(ListCell **lc)
@@ -377,9 +383,10 @@ get_int(ListCell **lc)
 static double
 get_double(ListCell **lc)
 {
-	double		v = floatVal(lfirst(*lc));
+	int64		bits = get_int64(lc);
+	double		v;
 
-	*lc = lnext(*lc);
+	memcpy(&v, &bits, sizeof(v));
 	return v;
 }
 

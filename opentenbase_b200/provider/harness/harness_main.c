@@ -218,8 +218,40 @@ static void read_relinfo(FILE *f, GpuRelInfo *r)
 	for (i = 0; i < r->ncols; i++) { r->attnums[i] = rd32(f); r->types[i] = rd32(f); }
 }
 
+/* read.c calls this for '{' nodes; custom_private only ever holds Value nodes */
+Node *parseNodeString(void) { NOT_REACHED("parseNodeString"); return NULL; }
+
+/* What nodeToString() writes for a List of Value nodes: _outList (nodes/outfuncs.c:443-477) around _outValue (:5103-5117:
+ * T_Integer as %d, T_Float as its string, unquoted). */
+static char *
+out_value_list(List *l)
+{
+	size_t		cap = 64 + (size_t) list_length(l) * 40, n = 0;
+	char	   *buf = (char *) malloc(cap);
+	ListCell   *lc;
+
+	buf[n++] = '(';
+	foreach(lc, l)
+	{
+		Value	   *v = (Value *) lfirst(lc);
+
+		if (IsA(v, Integer))
+			n += snprintf(buf + n, cap - n, "%d", (int) intVal(v));
+		else if (IsA(v, Float))
+			n += snprintf(buf + n, cap - n, "%s", strVal(v));
+		else
+			NOT_REACHED("out_value_list: node type");
+		if (lnext(lc))
+			buf[n++] = ' ';
+	}
+	buf[n++] = ')';
+	buf[n] = 0;
+	return buf;
+}
+
 int main(int argc, char **argv)
 {
+	bool		ship_only = false;
 	FILE	   *f;
 	char		magic[4];
 	int			nrels, i, r, nout, total_pages = 0;
@@ -233,7 +265,8 @@ int main(int argc, char **argv)
 	TupleTableSlot *slot;
 	int64		nrows = 0;
 
-	if (argc < 2) { fprintf(stderr, "usage: %s <case file>\n", argv[0]); return 2; }
+	if (argc >= 3 && strcmp(argv[1], "--ship-only") == 0) { ship_only = true; argv++; argc--; }
+	if (argc < 2) { fprintf(stderr, "usage: %s [--ship-only] <case file>\n", argv[0]); return 2; }
 	f = fopen(argv[1], "rb");
 	if (!f) { perror(argv[1]); return 2; }
 	rd(f, magic, 4);
@@ -295,6 +328,29 @@ int main(int argc, char **argv)
 	for (i = 0; i < nout; i++) out_types[i] = (Oid) rd32(f);
 	fclose(f);
 
+	if (ship_only)
+	{
+		/* CN -> DN plan shipping without a GPU: the descriptor as Value nodes, written the way nodeToString() writes them,
+		 * read back by the reference's OWN nodes/read.c (stringToNode), deserialised and serialised again */
+		List	   *priv = gpuexec_serialise(&desc);
+		char	   *wire = out_value_list(priv);
+		List	   *back = (List *) stringToNode(wire);
+		GpuExecState got;
+		char	   *again;
+
+		if (!IsA(back, List) || list_length(back) != list_length(priv)) { fprintf(stderr, "harness: %d nodes sent, %d read back\n", list_length(priv), back ? list_length(back) : -1); return 3; }
+		memset(&got, 0, sizeof(got));
+		gpuexec_deserialise(back, &got);
+		again = out_value_list(gpuexec_serialise(&got));
+		if (strcmp(wire, again) != 0) { fprintf(stderr, "harness: descriptor changed in transit\n sent %s\n got  %s\n", wire, again); return 3; }
+		for (i = 0; i < desc.plan.n_preds; i++)
+			if (desc.plan.preds[i].ival != got.plan.preds[i].ival || memcmp(&desc.plan.preds[i].fval, &got.plan.preds[i].fval, 8) != 0) { fprintf(stderr, "harness: qual constant %d changed\n", i); return 3; }
+		for (i = 0; i < desc.n_inner_preds; i++)
+			if (desc.inner_preds[i].ival != got.inner_preds[i].ival || memcmp(&desc.inner_preds[i].fval, &got.inner_preds[i].fval, 8) != 0) { fprintf(stderr, "harness: inner qual constant %d changed\n", i); return 3; }
+		if (desc.plan.est_groups != got.plan.est_groups) { fprintf(stderr, "harness: est_groups changed\n"); return 3; }
+		printf("ship ok: %d nodes, %zu bytes\n%s\n", list_length(priv), strlen(wire), wire);
+		return 0;
+	}
 	/* ---- what the planner + ExecInitCustomScan would have done */
 	_PG_init();
 	if (!registered_methods) { fprintf(stderr, "harness: _PG_init registered nothing\n"); return 3; }
