@@ -18,7 +18,11 @@
  *     descriptor, BeginCustomScan, ExecCustomScan until TupIsNull, EndCustomScan;
  *   - lists and Value nodes are the reference's own object code (nodes/list.c, nodes/value.c,
  *     compiled from where they lie).
- * libgpuexec.so is the real thing: the harness needs a GPU.
+ * libgpuexec.so is the real thing: executing a case needs a GPU.  Two modes need none (CPU tests):
+ *   --ship-only <case file>   the plan descriptor as custom_private Value nodes, written as nodeToString() writes them and read
+ *                             back by the reference's own nodes/read.c (tests/test_provider_ship_cpu.py)
+ *   --plan <scenario file>    a hand-built Query through gpuexec_upper_paths_hook + PlanCustomPath; the planner-side helpers
+ *                             are small restatements of the reference's (tests/test_provider_planner_cpu.py)
  *
  * usage: gpuexec_harness <case file>     -> one text line per result row on stdout
  */
@@ -71,27 +75,119 @@ void elog_start(const char *filename, int lineno, const char *funcname) { }
 void elog_finish(int elevel, const char *fmt,...) { if (elevel >= ERROR) { fprintf(stderr, "harness: elog(ERROR): %s\n", fmt); exit(3); } }
 void ExceptionalCondition(const char *a, const char *b, const char *c, int d) { fprintf(stderr, "harness: Assert(%s) at %s:%d\n", a, c, d); abort(); }
 
-/* planner-side entry points: linked, never reached (the harness hands the provider a finished descriptor) */
-#define NOT_REACHED(name) do { fprintf(stderr, "harness: %s() is planner-side and must not be reached\n", name); abort(); } while (0)
-void add_path(RelOptInfo *r, Path *p) { NOT_REACHED("add_path"); }
+/* planner-side entry points.  The executor test never reaches them; `--plan` mode does, so they are small working
+ * restatements of what the reference does (file:line each), enough for a hand-built Query. */
+#define NOT_REACHED(name) do { fprintf(stderr, "harness: %s() must not be reached\n", name); abort(); } while (0)
+static List *added_paths = NIL;
+static CustomPath *last_custom_path;
+void add_path(RelOptInfo *r, Path *p) { added_paths = lappend(added_paths, p); if (IsA(p, CustomPath)) last_custom_path = (CustomPath *) p; }		/* pathnode.c:423: here, just remember it */
+/* pathnode.c:3178 create_agg_path: only what the test inspects */
 AggPath *create_agg_path(PlannerInfo *root, RelOptInfo *rel, Path *subpath, PathTarget *target, AggStrategy s, AggSplit sp, List *g, List *q,
-						 const AggClauseCosts *c, double n) { NOT_REACHED("create_agg_path"); return NULL; }
-PathTarget *create_empty_pathtarget(void) { NOT_REACHED("create_empty_pathtarget"); return NULL; }
-void add_column_to_pathtarget(PathTarget *t, Expr *e, Index r) { NOT_REACHED("add_column_to_pathtarget"); }
-Path *create_redistribute_grouping_path(PlannerInfo *root, Query *parse, Path *path) { NOT_REACHED("create_redistribute_grouping_path"); return NULL; }
-void get_agg_clause_costs(PlannerInfo *root, Node *clause, AggSplit s, AggClauseCosts *c) { NOT_REACHED("get_agg_clause_costs"); }
-TargetEntry *get_sortgroupclause_tle(SortGroupClause *s, List *t) { NOT_REACHED("get_sortgroupclause_tle"); return NULL; }
-void mark_partial_aggref(Aggref *a, AggSplit s) { NOT_REACHED("mark_partial_aggref"); }
-TargetEntry *makeTargetEntry(Expr *e, AttrNumber r, char *n, bool j) { NOT_REACHED("makeTargetEntry"); return NULL; }
-void *copyObjectImpl(const void *o) { NOT_REACHED("copyObject"); return NULL; }
-bool equal(const void *a, const void *b) { NOT_REACHED("equal"); return false; }
-bool cls_check_table_has_policy(Oid r) { return false; }
+						 const AggClauseCosts *c, double n)
+{
+	AggPath    *ap = makeNode(AggPath);
+
+	ap->path.pathtype = T_Agg; ap->path.parent = rel; ap->path.pathtarget = target; ap->path.rows = n;
+	ap->subpath = subpath; ap->aggstrategy = s; ap->aggsplit = sp; ap->groupClause = g; ap->numGroups = n;
+	ap->path.startup_cost = subpath->total_cost; ap->path.total_cost = subpath->total_cost + cpu_tuple_cost * n;
+	return ap;
+}
+/* tlist.c:create_empty_pathtarget / add_column_to_pathtarget (optimizer/util/tlist.c:608,647) */
+PathTarget *create_empty_pathtarget(void) { return makeNode(PathTarget); }
+void add_column_to_pathtarget(PathTarget *t, Expr *e, Index r)
+{
+	t->exprs = lappend(t->exprs, e);
+	if (r)
+	{
+		int			n = list_length(t->exprs);
+
+		t->sortgrouprefs = (Index *) realloc(t->sortgrouprefs, n * sizeof(Index));
+		memset(t->sortgrouprefs, 0, (n - 1) * sizeof(Index));	/* good enough for a fresh target filled front to back */
+		t->sortgrouprefs[n - 1] = r;
+	}
+}
+/* the reference wraps the partial path in a RemoteSubplan distributed by the group key (pathnode.c:6091) */
+Path *create_redistribute_grouping_path(PlannerInfo *root, Query *parse, Path *path)
+{
+	Path	   *p = makeNode(Path);
+
+	if (IsA(path, CustomPath)) last_custom_path = (CustomPath *) path;
+	p->pathtype = T_RemoteSubplan; p->parent = path->parent; p->pathtarget = path->pathtarget; p->rows = path->rows;
+	p->startup_cost = path->startup_cost; p->total_cost = path->total_cost + 1.0;
+	return p;
+}
+void get_agg_clause_costs(PlannerInfo *root, Node *clause, AggSplit s, AggClauseCosts *c) { }	/* all supported aggregates are partial + serial-free */
+/* tlist.c:get_sortgroupref_tle (optimizer/util/tlist.c:367) */
+TargetEntry *get_sortgroupclause_tle(SortGroupClause *s, List *t)
+{
+	ListCell   *l;
+
+	foreach(l, t)
+		if (((TargetEntry *) lfirst(l))->ressortgroupref == s->tleSortGroupRef)
+			return (TargetEntry *) lfirst(l);
+	fprintf(stderr, "harness: ORDER/GROUP BY expression not found in targetlist\n"); abort();
+}
+/* planner.c:mark_partial_aggref (optimizer/plan/planner.c): the partial aggregate returns its transition type */
+void mark_partial_aggref(Aggref *a, AggSplit s)
+{
+	a->aggsplit = s;
+	if (DO_AGGSPLIT_SKIPFINAL(s))
+		a->aggtype = (DO_AGGSPLIT_SERIALIZE(s) && a->aggtranstype == INTERNALOID) ? BYTEAOID : a->aggtranstype;
+}
+/* makefuncs.c:237 */
+TargetEntry *makeTargetEntry(Expr *e, AttrNumber r, char *n, bool j)
+{
+	TargetEntry *t = makeNode(TargetEntry);
+
+	t->expr = e; t->resno = r; t->resname = n; t->resjunk = j;
+	return t;
+}
+/* copyObject / equal for the handful of node types a hand-built Query holds (nodes/copyfuncs.c, equalfuncs.c): shallow copies -
+ * the test only looks at the result */
+static size_t fake_node_size(const void *o)
+{
+	switch (nodeTag(o))
+	{
+		case T_Var: return sizeof(Var);
+		case T_Const: return sizeof(Const);
+		case T_Aggref: return sizeof(Aggref);
+		case T_OpExpr: return sizeof(OpExpr);
+		case T_TargetEntry: return sizeof(TargetEntry);
+		case T_RelabelType: return sizeof(RelabelType);
+		default: fprintf(stderr, "harness: copyObject of node type %d\n", (int) nodeTag(o)); abort();
+	}
+}
+void *copyObjectImpl(const void *o)
+{
+	void	   *c;
+
+	if (o == NULL) return NULL;
+	if (IsA(o, List)) return list_copy((const List *) o);
+	c = malloc(fake_node_size(o));
+	memcpy(c, o, fake_node_size(o));
+	return c;
+}
+bool equal(const void *a, const void *b)
+{
+	if (a == b) return true;
+	if (a == NULL || b == NULL || nodeTag(a) != nodeTag(b)) return false;
+	if (IsA(a, Var))
+	{
+		const Var  *x = (const Var *) a, *y = (const Var *) b;
+
+		return x->varno == y->varno && x->varattno == y->varattno && x->vartype == y->vartype && x->vartypmod == y->vartypmod && x->varlevelsup == y->varlevelsup;
+	}
+	return false;
+}
+static bool fake_cls_policy = false;		/* --plan scenario "protected": the relation has a CLS policy */
+bool cls_check_table_has_policy(Oid r) { return fake_cls_policy; }
 bool datamask_check_table_has_datamask(Oid r) { return false; }
 bool get_audit_fga_quals(Oid rel, char *cmd, List *tl, List **out) { return false; }
 void DefineCustomBoolVariable(const char *n, const char *s, const char *l, bool *v, bool b, GucContext c, int f, GucBoolCheckHook a, GucBoolAssignHook g, GucShowHook h) { }
 void DefineCustomRealVariable(const char *n, const char *s, const char *l, double *v, double b, double mn, double mx, GucContext c, int f, GucRealCheckHook a, GucRealAssignHook g, GucShowHook h) { }
 double		seq_page_cost = 1.0, cpu_tuple_cost = 0.01;		/* costsize.c:100-104 */
-double path_count_datanodes(Path *p) { NOT_REACHED("path_count_datanodes"); return 1; }
+static double fake_datanodes = 1;
+double path_count_datanodes(Path *p) { return fake_datanodes; }
 void DefineCustomIntVariable(const char *n, const char *s, const char *l, int *v, int b, int mn, int mx, GucContext c, int f, GucIntCheckHook a, GucIntAssignHook g, GucShowHook h) { }
 static const CustomScanMethods *registered_methods = NULL;
 void RegisterCustomScanMethods(const CustomScanMethods *m) { registered_methods = m; }
@@ -249,6 +345,255 @@ out_value_list(List *l)
 	return buf;
 }
 
+static char *out_value_list(List *l);
+/* ------------------------------------------------------------ --plan: a hand-built Query through the planner hook
+ * The scenario file (written by tests/test_provider_planner_cpu.py) describes base relations, the input path (SeqScan or
+ * HashJoin of two SeqScans), quals, GROUP BY, the target list and the input's distribution; this builds the PlannerInfo /
+ * Query / RelOptInfo / Path nodes the hook reads, calls gpuexec_upper_paths_hook and PlanCustomPath, and prints what
+ * came out: the path shape and costs, the descriptor as it would travel, and the scan tuple. */
+typedef struct PlanRel { RelOptInfo *rel; RangeTblEntry *rte; int ncols; Oid types[GX_MAX_COLS * 2]; int32 typmods[GX_MAX_COLS * 2]; } PlanRel;
+static PlanRel plan_rels[3];
+
+static bool type_by_name(const char *n, Oid *t, int32 *m)
+{
+	*m = -1;
+	if (!strcmp(n, "int8")) *t = INT8OID; else if (!strcmp(n, "int4")) *t = INT4OID; else if (!strcmp(n, "date")) *t = DATEOID;
+	else if (!strcmp(n, "float8")) *t = FLOAT8OID; else if (!strcmp(n, "char")) *t = CHAROID; else if (!strcmp(n, "text")) *t = TEXTOID;
+	else if (!strcmp(n, "numeric")) *t = NUMERICOID;
+	else if (!strcmp(n, "bpchar1")) { *t = BPCHAROID; *m = VARHDRSZ + 1; } else if (!strcmp(n, "bpchar3")) { *t = BPCHAROID; *m = VARHDRSZ + 3; }
+	else return false;
+	return true;
+}
+static Var *plan_var(int rti, int att)
+{
+	Var		   *v = makeNode(Var);
+
+	if (rti < 1 || rti > 2 || att < 1 || att > plan_rels[rti].ncols) { fprintf(stderr, "harness: no column %d.%d\n", rti, att); exit(2); }
+	v->varno = rti; v->varattno = att; v->vartype = plan_rels[rti].types[att - 1]; v->vartypmod = plan_rels[rti].typmods[att - 1];
+	v->varnoold = rti; v->varoattno = att;
+	return v;
+}
+static Const *plan_const(Oid t, const char *val)
+{
+	Const	   *c = makeNode(Const);
+
+	c->consttype = t; c->consttypmod = -1; c->constlen = 8; c->constbyval = true;
+	if (!strcmp(val, "null")) { c->constisnull = true; return c; }
+	switch (t)
+	{
+		case INT8OID: c->constvalue = Int64GetDatum(strtoll(val, NULL, 10)); break;
+		case INT4OID: case DATEOID: c->constvalue = Int32GetDatum((int32) strtol(val, NULL, 10)); break;
+		case FLOAT8OID: c->constvalue = Float8GetDatum(strtod(val, NULL)); break;
+		case CHAROID: c->constvalue = CharGetDatum(val[0]); break;
+		default: c->constvalue = PointerGetDatum(cstring_to_text_with_len(val, (int) strlen(val))); c->constbyval = false; c->constlen = -1; break;
+	}
+	return c;
+}
+static Oid fn_by_name(const char *n)
+{
+	static const struct { const char *n; Oid f; } tab[] = {
+		{"int4lt", F_INT4LT}, {"int4le", F_INT4LE}, {"int4eq", F_INT4EQ}, {"int4ge", F_INT4GE}, {"int4gt", F_INT4GT}, {"int4ne", F_INT4NE},
+		{"int8lt", F_INT8LT}, {"int8le", F_INT8LE}, {"int8eq", F_INT8EQ}, {"int8ge", F_INT8GE}, {"int8gt", F_INT8GT}, {"int8ne", F_INT8NE},
+		{"date_lt", F_DATE_LT}, {"date_le", F_DATE_LE}, {"date_eq", F_DATE_EQ}, {"date_ge", F_DATE_GE}, {"date_gt", F_DATE_GT}, {"date_ne", F_DATE_NE},
+		{"float8lt", F_FLOAT8LT}, {"float8le", F_FLOAT8LE}, {"float8eq", F_FLOAT8EQ}, {"float8ge", F_FLOAT8GE}, {"float8gt", F_FLOAT8GT}, {"float8ne", F_FLOAT8NE},
+		{"chareq", F_CHAREQ}, {"charlt", F_CHARLT}, {"bpchareq", F_BPCHAREQ}, {"bpcharne", F_BPCHARNE}, {"int84lt", F_INT84LT}, {"texteq", F_TEXTEQ},
+	};
+	int			i;
+
+	for (i = 0; i < (int) lengthof(tab); i++) if (!strcmp(tab[i].n, n)) return tab[i].f;
+	fprintf(stderr, "harness: unknown function %s\n", n); exit(2);
+}
+static Expr *plan_op(Oid fn, Node *l, Node *r) { OpExpr *o = makeNode(OpExpr); o->opfuncid = fn; o->args = list_make2(l, r); return (Expr *) o; }
+/* postfix tokens: v<rti>.<att>  k<float>  + - *  */
+static Node *plan_expr(char *toks)
+{
+	Node	   *stack[16];
+	int			sp = 0;
+	char	   *t;
+
+	for (t = strtok(toks, " \n"); t; t = strtok(NULL, " \n"))
+	{
+		if (t[0] == 'v') { int r, a; sscanf(t + 1, "%d.%d", &r, &a); stack[sp++] = (Node *) plan_var(r, a); }
+		else if (t[0] == 'k') stack[sp++] = (Node *) plan_const(FLOAT8OID, t + 1);
+		else { Node *y = stack[--sp], *x = stack[--sp]; stack[sp++] = (Node *) plan_op(t[0] == '+' ? F_FLOAT8PL : t[0] == '-' ? F_FLOAT8MI : t[0] == '*' ? F_FLOAT8MUL : F_FLOAT8DIV, x, y); }
+	}
+	return sp == 1 ? stack[0] : NULL;
+}
+static int plan_main(const char *path)
+{
+	FILE	   *f = fopen(path, "r");
+	char		line[1024];
+	PlannerInfo *root = makeNode(PlannerInfo);
+	Query	   *parse = makeNode(Query);
+	RelOptInfo *input_rel = NULL, *output_rel = makeNode(RelOptInfo);
+	Distribution *dist = NULL;
+	List	   *groups = NIL;		/* Var per GROUP BY column */
+	ListCell   *lc;
+	int			i;
+
+	if (!f) { perror(path); return 2; }
+	root->parse = parse;
+	root->simple_rel_array_size = 3;
+	root->simple_rte_array = (RangeTblEntry **) calloc(3, sizeof(RangeTblEntry *));
+	output_rel->reltarget = makeNode(PathTarget);
+	output_rel->rows = 100;
+	_PG_init();
+	while (fgets(line, sizeof(line), f))
+	{
+		char		w[64], ty[16][16];
+		int			r, a, r2, a2, n, u;
+		double		t, pg;
+
+		if (line[0] == '#' || line[0] == '\n') continue;
+		if (sscanf(line, "rel %d tuples %lf pages %lf cols %n", &r, &t, &pg, &n) == 3)
+		{
+			PlanRel    *pr = &plan_rels[r];
+			char	   *tok;
+
+			pr->rel = makeNode(RelOptInfo); pr->rel->relid = r; pr->rel->reloptkind = RELOPT_BASEREL; pr->rel->tuples = t; pr->rel->pages = (BlockNumber) pg; pr->rel->rows = t;
+			pr->rte = makeNode(RangeTblEntry); pr->rte->rtekind = RTE_RELATION; pr->rte->relid = 16384 + r;
+			root->simple_rte_array[r] = pr->rte;
+			for (tok = strtok(line + n, " \n"); tok; tok = strtok(NULL, " \n"))
+				if (!type_by_name(tok, &pr->types[pr->ncols], &pr->typmods[pr->ncols])) { fprintf(stderr, "harness: type %s\n", tok); return 2; } else pr->ncols++;
+			(void) ty;
+		}
+		else if (sscanf(line, "scan %d", &r) == 1)
+		{
+			Path	   *p = makeNode(Path);
+
+			input_rel = plan_rels[r].rel;
+			p->pathtype = T_SeqScan; p->parent = input_rel; p->rows = input_rel->tuples; p->total_cost = input_rel->pages + 0.01 * input_rel->tuples;
+			input_rel->cheapest_total_path = p;
+		}
+		else if (sscanf(line, "join %d.%d %d.%d unique %d %63s", &r, &a, &r2, &a2, &u, w) >= 5)
+		{
+			HashPath   *hp = makeNode(HashPath);
+			Path	   *op = makeNode(Path), *ip = makeNode(Path);
+			RestrictInfo *ri = makeNode(RestrictInfo);
+			Var		   *lv = plan_var(r, a), *rv = plan_var(r2, a2);
+			bool		remote = strstr(line, "remote_inner") != NULL, swap = strstr(line, "swapped") != NULL;
+
+			op->pathtype = T_SeqScan; op->parent = plan_rels[r].rel; op->rows = op->parent->tuples; op->total_cost = op->parent->pages + 0.01 * op->rows;
+			ip->pathtype = remote ? T_RemoteSubplan : T_SeqScan; ip->parent = plan_rels[r2].rel; ip->rows = ip->parent->tuples; ip->total_cost = ip->parent->pages + 0.01 * ip->rows;
+			ri->clause = plan_op(lv->vartype == INT8OID ? F_INT8EQ : lv->vartype == INT4OID ? F_INT4EQ : F_TEXTEQ, swap ? (Node *) rv : (Node *) lv, swap ? (Node *) lv : (Node *) rv);
+			hp->jpath.path.pathtype = T_HashJoin; hp->jpath.jointype = strstr(line, "left") ? JOIN_LEFT : JOIN_INNER; hp->jpath.inner_unique = u != 0;
+			hp->jpath.outerjoinpath = op; hp->jpath.innerjoinpath = ip; hp->jpath.joinrestrictinfo = list_make1(ri); hp->path_hashclauses = list_make1(ri);
+			input_rel = makeNode(RelOptInfo); input_rel->reloptkind = RELOPT_JOINREL; input_rel->rows = op->rows;
+			hp->jpath.path.parent = input_rel; hp->jpath.path.rows = op->rows; hp->jpath.path.total_cost = op->total_cost + ip->total_cost + 0.02 * op->rows;
+			input_rel->cheapest_total_path = &hp->jpath.path;
+		}
+		else if (sscanf(line, "qual %d %d %63s %15s %n", &r, &a, w, ty[0], &n) == 4)
+		{
+			RestrictInfo *ri = makeNode(RestrictInfo);
+			Oid			ct; int32 cm;
+			char		val[128] = "";
+			bool		flip = strstr(line + n, " flip") != NULL;
+
+			sscanf(line + n, "%127s", val);
+			type_by_name(ty[0], &ct, &cm);
+			ri->clause = flip ? plan_op(fn_by_name(w), (Node *) plan_const(ct, val), (Node *) plan_var(r, a)) : plan_op(fn_by_name(w), (Node *) plan_var(r, a), (Node *) plan_const(ct, val));
+			plan_rels[r].rel->baserestrictinfo = lappend(plan_rels[r].rel->baserestrictinfo, ri);
+		}
+		else if (sscanf(line, "group %d.%d", &r, &a) == 2)
+			groups = lappend(groups, plan_var(r, a));
+		else if (sscanf(line, "target var %d.%d", &r, &a) == 2)
+			parse->targetList = lappend(parse->targetList, makeTargetEntry((Expr *) plan_var(r, a), list_length(parse->targetList) + 1, NULL, false));
+		else if (sscanf(line, "target agg %63s %n", w, &n) == 1)
+		{
+			Aggref	   *ag = makeNode(Aggref);
+			static const struct { const char *n; Oid fn, ty, tr; } tab[] = {
+				{"count_star", 2803, INT8OID, INT8OID}, {"count", 2147, INT8OID, INT8OID}, {"sum_f8", 2111, FLOAT8OID, FLOAT8OID}, {"avg_f8", 2105, FLOAT8OID, FLOAT8ARRAYOID},
+				{"min_f8", 2136, FLOAT8OID, FLOAT8OID}, {"max_f8", 2120, FLOAT8OID, FLOAT8OID}, {"sum_i4", 2108, INT8OID, INT8OID}, {"sum_numeric", 2114, NUMERICOID, INTERNALOID},
+				{"stddev_f8", 2158, FLOAT8OID, FLOAT8ARRAYOID},
+			};
+
+			for (i = 0; i < (int) lengthof(tab); i++) if (!strcmp(tab[i].n, w)) break;
+			if (i == (int) lengthof(tab)) { fprintf(stderr, "harness: aggregate %s\n", w); return 2; }
+			ag->aggfnoid = tab[i].fn; ag->aggtype = tab[i].ty; ag->aggtranstype = tab[i].tr; ag->aggsplit = AGGSPLIT_SIMPLE; ag->aggkind = 'n';
+			if (strstr(line + n, "distinct")) ag->aggdistinct = list_make1(makeNode(SortGroupClause));
+			else if (tab[i].fn == 2803) ag->aggstar = true;
+			else { Node *e = plan_expr(line + n); if (!e) { fprintf(stderr, "harness: bad expression\n"); return 2; } ag->args = list_make1(makeTargetEntry((Expr *) e, 1, NULL, false)); }
+			parse->targetList = lappend(parse->targetList, makeTargetEntry((Expr *) ag, list_length(parse->targetList) + 1, NULL, false));
+		}
+		else if (sscanf(line, "dist %63s", w) == 1)
+		{
+			if (strcmp(w, "none") != 0)
+			{
+				dist = makeNode(Distribution);
+				dist->distributionType = !strcmp(w, "replicated") ? LOCATOR_TYPE_REPLICATED : LOCATOR_TYPE_SHARD;
+				if (sscanf(line, "dist shard %d.%d nodes %d", &r, &a, &n) == 3)
+				{
+					dist->nExprs = 1; dist->disExprs = (Node **) calloc(1, sizeof(Node *)); dist->disExprs[0] = (Node *) plan_var(r, a);
+					fake_datanodes = n;
+				}
+			}
+		}
+		else if (!strncmp(line, "having", 6)) parse->havingQual = (Node *) plan_const(INT4OID, "1");
+		else if (!strncmp(line, "groupingsets", 12)) parse->groupingSets = list_make1(makeNode(GroupingSet));
+		else if (sscanf(line, "groups %lf", &t) == 1) output_rel->rows = t;
+		else if (!strncmp(line, "protected", 9)) { g_enable_cls = true; fake_cls_policy = true; }
+		else { fprintf(stderr, "harness: scenario line not understood: %s", line); return 2; }
+	}
+	fclose(f);
+	if (!input_rel) { fprintf(stderr, "harness: scenario without input\n"); return 2; }
+	input_rel->cheapest_total_path->distribution = dist;
+	/* GROUP BY columns: mark the matching target entry, or add a resjunk one (parse_clause.c:findTargetlistEntrySQL99) */
+	i = 0;
+	foreach(lc, groups)
+	{
+		Var		   *gv = (Var *) lfirst(lc);
+		SortGroupClause *sgc = makeNode(SortGroupClause);
+		ListCell   *tl;
+		TargetEntry *found = NULL;
+
+		sgc->tleSortGroupRef = ++i;
+		foreach(tl, parse->targetList)
+			if (equal(((TargetEntry *) lfirst(tl))->expr, gv) && ((TargetEntry *) lfirst(tl))->ressortgroupref == 0) { found = (TargetEntry *) lfirst(tl); break; }
+		if (!found) { found = makeTargetEntry((Expr *) gv, list_length(parse->targetList) + 1, NULL, true); parse->targetList = lappend(parse->targetList, found); }
+		found->ressortgroupref = sgc->tleSortGroupRef;
+		parse->groupClause = lappend(parse->groupClause, sgc);
+	}
+	foreach(lc, parse->targetList)
+		if (!((TargetEntry *) lfirst(lc))->resjunk)
+			output_rel->reltarget->exprs = lappend(output_rel->reltarget->exprs, ((TargetEntry *) lfirst(lc))->expr);
+
+	gpuexec_upper_paths_hook(root, UPPERREL_GROUP_AGG, input_rel, output_rel);
+	if (added_paths == NIL) { printf("declined\n"); return 0; }
+	{
+		Path	   *top = (Path *) linitial(added_paths);
+		CustomPath *cp;
+		CustomScan *cs;
+		AttrNumber	k = 0;
+
+		if (IsA(top, AggPath))
+		{
+			AggPath    *ap = (AggPath *) top;
+
+			if (ap->subpath->pathtype != T_RemoteSubplan) { fprintf(stderr, "harness: Finalize Agg without a redistribute below it\n"); return 3; }
+			printf("path partial: Finalize Agg (split %d, strategy %d) <- RemoteSubplan <- CustomScan\n", (int) ap->aggsplit, (int) ap->aggstrategy);
+			cp = NULL;
+			/* the fake create_redistribute_grouping_path does not keep its input: the hook built exactly one CustomPath */
+		}
+		else printf("path pushdown: CustomScan\n");
+		cp = last_custom_path;
+		if (!cp) { fprintf(stderr, "harness: no CustomPath was built\n"); return 3; }
+		printf("cost startup %.3f total %.3f rows %.0f\n", cp->path.startup_cost, cp->path.total_cost, cp->path.rows);
+		cs = (CustomScan *) cp->methods->PlanCustomPath(root, output_rel, cp, parse->targetList, NIL, NIL);
+		printf("desc %s\n", out_value_list(cs->custom_private));
+		foreach(lc, cs->custom_scan_tlist)
+		{
+			TargetEntry *te = (TargetEntry *) lfirst(lc);
+
+			if (te->resno != ++k) { fprintf(stderr, "harness: custom_scan_tlist resno %d at position %d\n", te->resno, k); return 3; }
+			if (IsA(te->expr, Var)) printf("scan %d var %d.%d type %u\n", k, ((Var *) te->expr)->varno, ((Var *) te->expr)->varattno, ((Var *) te->expr)->vartype);
+			else if (IsA(te->expr, Aggref)) printf("scan %d agg %u type %u split %d\n", k, ((Aggref *) te->expr)->aggfnoid, ((Aggref *) te->expr)->aggtype, (int) ((Aggref *) te->expr)->aggsplit);
+			else printf("scan %d node %d\n", k, (int) nodeTag(te->expr));
+		}
+		printf("plan_tlist %d scanrelid %u\n", list_length(cs->scan.plan.targetlist), cs->scan.scanrelid);
+	}
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	bool		ship_only = false;
@@ -265,6 +610,7 @@ int main(int argc, char **argv)
 	TupleTableSlot *slot;
 	int64		nrows = 0;
 
+	if (argc >= 3 && strcmp(argv[1], "--plan") == 0) return plan_main(argv[2]);
 	if (argc >= 3 && strcmp(argv[1], "--ship-only") == 0) { ship_only = true; argv++; argc--; }
 	if (argc < 2) { fprintf(stderr, "usage: %s [--ship-only] <case file>\n", argv[0]); return 2; }
 	f = fopen(argv[1], "rb");
