@@ -74,6 +74,7 @@
 #include "utils/rel.h"
 #include "utils/resowner.h"
 #include "utils/snapmgr.h"
+#include "utils/syscache.h"
 
 #include "gpuexec.h"
 #include "gpuexec_cost.h"
@@ -1096,6 +1097,29 @@ grouping_covers_distribution(Query *parse, Distribution *d)
 	return true;
 }
 
+/* bytes of a staged column */
+static int
+gx_type_bytes(int32 t)
+{
+	return (t == GX_INT8 || t == GX_FLOAT8) ? 8 : t == GX_CHAR ? 1 : 4;
+}
+
+/* pg_attribute.attnotnull of (relation of rti, attno): the join payload has no NULL representation */
+static bool
+column_is_not_null(PlannerInfo *root, Index rti, AttrNumber attno)
+{
+	RangeTblEntry *rte = planner_rt_fetch(rti, root);
+	HeapTuple	tp = SearchSysCache2(ATTNUM, ObjectIdGetDatum(rte->relid), Int16GetDatum(attno));
+	bool		res = false;
+
+	if (HeapTupleIsValid(tp))
+	{
+		res = ((Form_pg_attribute) GETSTRUCT(tp))->attnotnull;
+		ReleaseSysCache(tp);
+	}
+	return res;
+}
+
 static bool
 gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_rel, GpuExecState *out,
 				   List **agg_refs, double *est_rows, double *est_groups, double *est_bytes, double *est_pages)
@@ -1195,6 +1219,8 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 			c = rel_column(&out->inner, v->varno, v->varattno, v->vartype, v->vartypmod);
 			if (c < 0)
 				return false;
+			if (!column_is_not_null(root, v->varno, v->varattno))
+				return false;		/* gx_hash_build carries payload columns inside the slot: no room for a NULL flag */
 			out->payload_cols[out->n_payload] = c;
 			plan->group_cols[plan->n_group_cols].side = 1;
 			plan->group_cols[plan->n_group_cols].col = out->n_payload++;
@@ -1202,6 +1228,30 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 		else
 			return false;
 		plan->n_group_cols++;
+	}
+
+	/* Limits the library would only report at execution time (GX_ERR_ARG -> ERROR): decline here instead, the CPU plan stays.
+	 * The join payload is one 8-byte word (gx_hash_build, csrc/gx_join.cu); the group key is two 8-byte words filled first-fit
+	 * in GROUP BY order (compile_plan, csrc/gx_agg.cu). */
+	{
+		int			payload_bytes = 0,
+					used[2] = {0, 0};
+
+		for (i = 0; i < out->n_payload; i++)
+			payload_bytes += gx_type_bytes(out->inner.types[out->payload_cols[i]]);
+		if (payload_bytes > 8)
+			return false;
+		for (i = 0; i < plan->n_group_cols; i++)
+		{
+			int32		t = plan->group_cols[i].side == 0 ? out->outer.types[plan->group_cols[i].col]
+				: out->inner.types[out->payload_cols[plan->group_cols[i].col]];
+			int			b = gx_type_bytes(t),
+						w = used[0] + b <= 8 ? 0 : 1;
+
+			if (used[w] + b > 8)
+				return false;
+			used[w] += b;
+		}
 	}
 
 	/* every target-list entry is either one of the GROUP BY expressions or a bare Aggref; the

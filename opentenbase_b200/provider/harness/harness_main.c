@@ -351,8 +351,29 @@ static char *out_value_list(List *l);
  * HashJoin of two SeqScans), quals, GROUP BY, the target list and the input's distribution; this builds the PlannerInfo /
  * Query / RelOptInfo / Path nodes the hook reads, calls gpuexec_upper_paths_hook and PlanCustomPath, and prints what
  * came out: the path shape and costs, the descriptor as it would travel, and the scan tuple. */
-typedef struct PlanRel { RelOptInfo *rel; RangeTblEntry *rte; int ncols; Oid types[GX_MAX_COLS * 2]; int32 typmods[GX_MAX_COLS * 2]; } PlanRel;
+typedef struct PlanRel { RelOptInfo *rel; RangeTblEntry *rte; int ncols; Oid types[GX_MAX_COLS * 2]; int32 typmods[GX_MAX_COLS * 2]; bool notnull[GX_MAX_COLS * 2]; } PlanRel;
 static PlanRel plan_rels[3];
+
+/* pg_attribute through the syscache, for column_is_not_null(): the scenario's "rel" line marks NOT NULL columns with a '!' */
+static struct { HeapTupleData tup; HeapTupleHeaderData hdr; char pad[64]; FormData_pg_attribute att; } fake_att_tuple;
+HeapTuple SearchSysCache2(int cacheId, Datum key1, Datum key2)
+{
+	int			r, a = DatumGetInt16(key2);
+
+	if (cacheId != ATTNUM) NOT_REACHED("SearchSysCache2 of another cache");
+	for (r = 1; r <= 2; r++)
+		if (plan_rels[r].rte && plan_rels[r].rte->relid == DatumGetObjectId(key1) && a >= 1 && a <= plan_rels[r].ncols)
+		{
+			memset(&fake_att_tuple, 0, sizeof(fake_att_tuple));
+			fake_att_tuple.hdr.t_hoff = (uint8) ((char *) &fake_att_tuple.att - (char *) &fake_att_tuple.hdr);
+			fake_att_tuple.tup.t_data = &fake_att_tuple.hdr;
+			fake_att_tuple.att.attnotnull = plan_rels[r].notnull[a - 1];
+			fake_att_tuple.att.attnum = a;
+			return &fake_att_tuple.tup;
+		}
+	return NULL;
+}
+void ReleaseSysCache(HeapTuple tuple) { }
 
 static bool type_by_name(const char *n, Oid *t, int32 *m)
 {
@@ -454,7 +475,13 @@ static int plan_main(const char *path)
 			pr->rte = makeNode(RangeTblEntry); pr->rte->rtekind = RTE_RELATION; pr->rte->relid = 16384 + r;
 			root->simple_rte_array[r] = pr->rte;
 			for (tok = strtok(line + n, " \n"); tok; tok = strtok(NULL, " \n"))
+			{
+				size_t		L = strlen(tok);
+
+				pr->notnull[pr->ncols] = L > 0 && tok[L - 1] == '!';
+				if (pr->notnull[pr->ncols]) tok[L - 1] = 0;
 				if (!type_by_name(tok, &pr->types[pr->ncols], &pr->typmods[pr->ncols])) { fprintf(stderr, "harness: type %s\n", tok); return 2; } else pr->ncols++;
+			}
 			(void) ty;
 		}
 		else if (sscanf(line, "scan %d", &r) == 1)

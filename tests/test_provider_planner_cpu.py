@@ -25,7 +25,7 @@ from test_provider_harness import HARNESS
 pytestmark = pytest.mark.skipif(not os.path.exists(HARNESS), reason="harness binary not built (needs /root/reference at build time)")
 
 LINEITEM = "rel 1 tuples 6000000 pages 110000 cols int8 float8 float8 float8 float8 date bpchar1 bpchar1"   # orderkey qty price disc tax shipdate flag status
-ORDERS = "rel 2 tuples 1500000 pages 26000 cols int8 int4 date int4"                                         # orderkey custkey orderdate shippriority
+ORDERS = "rel 2 tuples 1500000 pages 26000 cols int8! int4! date! int4! float8! int8"                       # orderkey custkey orderdate shippriority totalprice (all NOT NULL), a nullable int8
 INT8, FLOAT8, DATE, BPCHAR = 20, 701, 1082, 1042
 F8ARRAY = 1022
 
@@ -207,3 +207,20 @@ def test_costs_follow_the_cost_model():
     want = pages + (feed + 3 * staged / 4000e3 + 1500.0) / 10.0
     assert r["startup"] == pytest.approx(want, rel=1e-6)
     assert r["total"] == pytest.approx(want + 0.01 * 2526, rel=1e-6) and r["rows"] == 2526
+
+
+def test_limits_of_the_library_decline_at_plan_time_instead_of_failing_at_run_time():
+    """gx_hash_build carries the inner GROUP BY columns in ONE 8-byte payload word without NULL flags, gx_hash_agg packs the
+    group key first-fit into two 8-byte words: what does not fit would be GX_ERR_ARG (an ERROR) at execution."""
+    head = [LINEITEM, ORDERS, "join 1.1 2.1 unique 1"]
+    tail = ["target agg count_star", "dist none"]
+    ok = plan(*head, "group 2.3", "group 2.4", "target var 2.3", "target var 2.4", *tail)          # date + int4 = 8 bytes of payload
+    assert ok is not None and parse_desc(ok["desc"])["group_cols"] == [(1, 0), (1, 1)]
+    assert plan(*head, "group 2.2", "group 2.5", "target var 2.2", "target var 2.5", *tail) is None   # int4 + float8 = 12 bytes of payload
+    assert plan(*head, "group 2.6", "target var 2.6", *tail) is None                                  # a nullable inner column
+    three = plan(*head, "group 2.2", "group 2.3", "group 2.4", "target var 2.2", *tail)              # more than GX_MAX_PAYLOAD columns
+    assert three is None
+    # outer-side keys: int8 + int8 + date does not fit 8 + 8 first-fit; date + date + int8 does
+    wide = "rel 1 tuples 1000 pages 10 cols int8 int8 date date float8"
+    assert plan(wide, "scan 1", "group 1.1", "group 1.2", "group 1.3", "target agg sum_f8 v1.5", "dist none") is None
+    assert plan(wide, "scan 1", "group 1.3", "group 1.4", "group 1.1", "target agg sum_f8 v1.5", "dist none") is not None
