@@ -1099,7 +1099,7 @@ grouping_covers_distribution(Query *parse, Distribution *d)
 
 /* bytes of a staged column */
 static int
-gx_type_bytes(int32 t)
+staged_type_bytes(int32 t)
 {
 	return (t == GX_INT8 || t == GX_FLOAT8) ? 8 : t == GX_CHAR ? 1 : 4;
 }
@@ -1238,14 +1238,14 @@ gpuexec_match_plan(PlannerInfo *root, RelOptInfo *input_rel, RelOptInfo *output_
 					used[2] = {0, 0};
 
 		for (i = 0; i < out->n_payload; i++)
-			payload_bytes += gx_type_bytes(out->inner.types[out->payload_cols[i]]);
+			payload_bytes += staged_type_bytes(out->inner.types[out->payload_cols[i]]);
 		if (payload_bytes > 8)
 			return false;
 		for (i = 0; i < plan->n_group_cols; i++)
 		{
 			int32		t = plan->group_cols[i].side == 0 ? out->outer.types[plan->group_cols[i].col]
 				: out->inner.types[out->payload_cols[plan->group_cols[i].col]];
-			int			b = gx_type_bytes(t),
+			int			b = staged_type_bytes(t),
 						w = used[0] + b <= 8 ? 0 : 1;
 
 			if (used[w] + b > 8)
