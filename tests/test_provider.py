@@ -37,3 +37,15 @@ def test_provider_uses_only_declared_abi():
     src = open(os.path.join(PROV, "gpuexec_provider.c")).read()
     called = set(re.findall(r"\b(gx_[a-z0-9_]+)\s*\(", src))
     assert called <= set(g.declared_symbols()), called - set(g.declared_symbols())
+
+
+def test_product_libraries_do_not_contain_the_test_double():
+    """harness/gx_double.c stands in for libgpuexec.so in ONE test binary; neither product library may carry it."""
+    import subprocess
+    for so in (os.path.join(ROOT, "opentenbase_b200", "libgpuexec.so"), os.path.join(PROV, "gpuexec_provider.so")):
+        if not os.path.exists(so):
+            continue
+        assert "double:" not in subprocess.run(["strings", so], capture_output=True, text=True).stdout, so
+    mk = open(os.path.join(PROV, "Makefile")).read()
+    lib_rule = mk[mk.index("lib:"):mk.index("harness:")]
+    assert "gx_double" not in lib_rule
