@@ -224,3 +224,33 @@ def test_limits_of_the_library_decline_at_plan_time_instead_of_failing_at_run_ti
     wide = "rel 1 tuples 1000 pages 10 cols int8 int8 date date float8"
     assert plan(wide, "scan 1", "group 1.1", "group 1.2", "group 1.3", "target agg sum_f8 v1.5", "dist none") is None
     assert plan(wide, "scan 1", "group 1.3", "group 1.4", "group 1.1", "target agg sum_f8 v1.5", "dist none") is not None
+
+
+@pytest.mark.parametrize("name,lines,accepted", [
+    ("8 aggregates", [LINEITEM, "scan 1", "group 1.7", "target var 1.7"] + ["target agg sum_f8 v1.2"] * 8 + ["dist none"], True),
+    ("9 aggregates", [LINEITEM, "scan 1", "group 1.7", "target var 1.7"] + ["target agg sum_f8 v1.2"] * 9 + ["dist none"], False),
+    ("5 group columns", [LINEITEM, "scan 1"] + [f"group 1.{i}" for i in (6, 7, 8, 1, 2)] + ["target agg count_star", "dist none"], False),
+    ("an argument of 11 operations", [LINEITEM, "scan 1", "group 1.7", "target agg sum_f8 v1.2 v1.3 + v1.4 + v1.5 + v1.2 + v1.3 +", "dist none"], True),
+    ("an argument of 15 operations", [LINEITEM, "scan 1", "group 1.7", "target agg sum_f8 v1.2 v1.3 + v1.4 + v1.5 + v1.2 + v1.3 + v1.4 + v1.5 +", "dist none"], False),
+    ("4 quals", [LINEITEM, "scan 1"] + ["qual 1 6 date_lt date 5"] * 4 + ["group 1.7", "target agg count_star", "dist none"], True),
+    ("5 quals", [LINEITEM, "scan 1"] + ["qual 1 6 date_lt date 5"] * 5 + ["group 1.7", "target agg count_star", "dist none"], False),
+    ("no aggregate, no GROUP BY", [LINEITEM, "scan 1", "target var 1.1", "dist none"], False),
+    ("aggregates without GROUP BY", [LINEITEM, "scan 1", "target agg count_star", "target agg sum_f8 v1.3", "dist none"], True),
+    ("GROUP BY a relation that is not scanned", [LINEITEM, ORDERS, "scan 1", "group 2.3", "target agg count_star", "dist none"], False),
+    ("count(bpchar)", [LINEITEM, "scan 1", "group 1.6", "target agg count v1.7", "dist none"], False),
+    ("GROUP BY bpchar(3)", ["rel 1 tuples 10 pages 1 cols bpchar3 float8", "scan 1", "group 1.1", "target agg sum_f8 v1.2", "dist none"], False),
+    ("GROUP BY text", ["rel 1 tuples 10 pages 1 cols text float8", "scan 1", "group 1.1", "target agg sum_f8 v1.2", "dist none"], False),
+    ("bpchar(1) = 'R'", [LINEITEM, "scan 1", "qual 1 7 bpchareq bpchar1 R", "group 1.8", "target agg count_star", "dist none"], True),
+    ("bpchar(1) = 'RX'", [LINEITEM, "scan 1", "qual 1 7 bpchareq bpchar1 RX", "group 1.8", "target agg count_star", "dist none"], False),
+], ids=lambda x: x if isinstance(x, str) else None)
+def test_capacity_edges_decline_cleanly(name, lines, accepted):
+    """The descriptor's fixed capacities (GX_MAX_AGGS 8, GX_MAX_GROUP_COLS 4, GX_MAX_PREDS 4, GX_MAX_EXPR_OPS 12) and type limits:
+    at the edge the plan is taken, one past it the hook declines — it never overruns the descriptor and never raises."""
+    assert (plan(*lines) is not None) == accepted, name
+
+
+def test_plain_aggregate_on_a_sharded_table_is_two_phase():
+    """No GROUP BY, shard-distributed input: every datanode holds part of the one group -> Partial + Finalize (AGG_PLAIN)."""
+    r = plan(LINEITEM, "scan 1", "target agg count_star", "target agg avg_f8 v1.3", "dist shard 1.1 nodes 2")
+    assert r["path"].startswith("path partial: Finalize Agg (split 9, strategy 0)")          # AGGSPLIT_FINAL_DESERIAL, AGG_PLAIN
+    assert [s[:4] for s in r["scan"]] == [("agg", "2803", "type", str(INT8)), ("agg", "2105", "type", str(F8ARRAY))]
